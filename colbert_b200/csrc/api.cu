@@ -1,0 +1,199 @@
+// extern "C" entry points of libcolbert_b200.so (declared in include/colbert_b200.h) plus the small
+// amount of host state they share: thread-local last-error string, launch counter, cached SM count,
+// and the driver entry point used to encode TMA tensor maps (resolved at run time so that the
+// library links against the CUDA runtime only).
+#include <atomic>
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+
+#include "cbk_common.cuh"
+
+namespace cbk {
+
+// dispatchers implemented in the kernel translation units
+int rerank_dispatch(const void*, int, int64_t, int, const int64_t*, const int32_t*, int64_t, const int32_t*, int,
+                    const float*, int, int64_t, const int64_t*, const int64_t*, int64_t, float*, void*, cudaStream_t);
+int topk_dispatch(const float*, const int64_t*, const int64_t*, int64_t, int64_t, int, float*, int64_t*, cudaStream_t);
+int64_t topk_max_candidates();
+int gather_dispatch(const void*, int, int64_t, int, const int64_t*, const int32_t*, int64_t, const int64_t*, int64_t,
+                    int, float*, uint8_t*, cudaStream_t);
+
+int mask_cast_dispatch(const void*, int, int64_t, int, const void*, int, void*, int, cudaStream_t);
+
+namespace {
+thread_local char g_err[512] = "";
+std::atomic<uint64_t> g_launches{0};
+}  // namespace
+
+void set_error(const char* fmt, ...) {
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(g_err, sizeof(g_err), fmt, ap);
+  va_end(ap);
+}
+
+void count_launch(int n) { g_launches.fetch_add(static_cast<uint64_t>(n), std::memory_order_relaxed); }
+
+int sm_count() {
+  static thread_local int cached_dev = -1;
+  static thread_local int cached = 0;
+  int dev = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess) return 148;
+  if (dev != cached_dev) {
+    int n = 0;
+    if (cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || n <= 0) n = 148;
+    cached = n;
+    cached_dev = dev;
+  }
+  return cached;
+}
+
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+static EncodeTiledFn encode_tiled_fn() {
+  static EncodeTiledFn fn = nullptr;
+  if (fn) return fn;
+  void* p = nullptr;
+  cudaDriverEntryPointQueryResult qres;
+  if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &qres) != cudaSuccess ||
+      qres != cudaDriverEntryPointSuccess || p == nullptr)
+    return nullptr;
+  fn = reinterpret_cast<EncodeTiledFn>(p);
+  return fn;
+}
+
+int make_store_tensor_map(CUtensorMap* out, const void* base, int64_t rows, int dim, int box_cols, int box_rows) {
+  EncodeTiledFn fn = encode_tiled_fn();
+  if (!fn) {
+    set_error("cuTensorMapEncodeTiled is not available from the installed driver");
+    return CBK_ERR_CUDA;
+  }
+  const cuuint64_t gdim[2] = {static_cast<cuuint64_t>(dim), static_cast<cuuint64_t>(rows)};
+  const cuuint64_t gstride[1] = {static_cast<cuuint64_t>(dim) * 2};  // bytes between consecutive rows
+  const cuuint32_t box[2] = {static_cast<cuuint32_t>(box_cols), static_cast<cuuint32_t>(box_rows)};
+  const cuuint32_t estride[2] = {1, 1};
+  // 16-bit payload: the TMA only moves bits, so fp16 and bf16 share one descriptor type
+  CUresult r = fn(out, CU_TENSOR_MAP_DATA_TYPE_UINT16, 2, const_cast<void*>(base), gdim, gstride, box, estride,
+                  CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                  CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) {
+    set_error("cuTensorMapEncodeTiled failed with CUresult %d (base %p rows %lld dim %d box %dx%d)", static_cast<int>(r),
+              base, static_cast<long long>(rows), dim, box_cols, box_rows);
+    return CBK_ERR_CUDA;
+  }
+  return CBK_OK;
+}
+
+static int check_device() {
+  int dev = 0;
+  CBK_CUDA(cudaGetDevice(&dev));
+  int major = 0;
+  CBK_CUDA(cudaDeviceGetAttribute(&major, cudaDevAttrComputeCapabilityMajor, dev));
+  CBK_CHECK_SUPPORTED(major == 10, "device %d has compute capability major %d; this library is sm_100a only", dev, major);
+  return CBK_OK;
+}
+
+}  // namespace cbk
+
+using namespace cbk;
+
+extern "C" {
+
+const char* cbk_last_error(void) { return g_err; }
+
+int cbk_abi_version(void) { return CBK_ABI_VERSION; }
+
+int cbk_device_supported(int device) {
+  int major = 0;
+  cudaError_t e = cudaDeviceGetAttribute(&major, cudaDevAttrComputeCapabilityMajor, device);
+  if (e != cudaSuccess) {
+    set_error("cudaDeviceGetAttribute failed: %s", cudaGetErrorString(e));
+    return CBK_ERR_CUDA;
+  }
+  return major == 10 ? 1 : 0;
+}
+
+uint64_t cbk_launch_count(void) { return g_launches.load(std::memory_order_relaxed); }
+
+size_t cbk_maxsim_rerank_workspace_bytes(void) { return 256; }
+
+int cbk_maxsim_rerank(const void* d_store, int store_dtype, int64_t n_store_rows, int dim, const int64_t* d_pfxsum,
+                      const int32_t* d_doclens, int64_t n_docs, const int32_t* strides, int n_strides, const float* d_Q,
+                      int q_len, int64_t n_queries, const int64_t* d_cand_pids, const int64_t* d_cand_rowptr,
+                      int64_t n_cand_total, float* d_out_scores, void* d_workspace, size_t workspace_bytes,
+                      void* stream) {
+  CBK_CHECK_ARG(d_store && d_pfxsum && d_doclens && d_Q && d_cand_pids && d_cand_rowptr && d_out_scores,
+                "cbk_maxsim_rerank: null pointer argument");
+  CBK_CHECK_ARG(store_dtype == CBK_F16 || store_dtype == CBK_BF16, "cbk_maxsim_rerank: unknown store dtype %d", store_dtype);
+  CBK_CHECK_ARG(n_store_rows > 0 && n_docs > 0 && n_queries > 0 && n_cand_total >= 0,
+                "cbk_maxsim_rerank: sizes must be positive (rows %lld docs %lld queries %lld cands %lld)",
+                (long long)n_store_rows, (long long)n_docs, (long long)n_queries, (long long)n_cand_total);
+  CBK_CHECK_ARG(n_strides >= 0 && n_strides <= CBK_MAX_STRIDES && (n_strides == 0 || strides),
+                "cbk_maxsim_rerank: n_strides %d outside [0, %d] or strides is NULL", n_strides, CBK_MAX_STRIDES);
+  CBK_CHECK_SUPPORTED(dim == 128, "cbk_maxsim_rerank: dim %d not supported (128 only)", dim);
+  CBK_CHECK_SUPPORTED(q_len >= 1 && q_len <= CBK_MAX_QLEN, "cbk_maxsim_rerank: q_len %d outside [1, %d]", q_len,
+                      CBK_MAX_QLEN);
+  CBK_CHECK_SUPPORTED(n_store_rows < (1ll << 31), "cbk_maxsim_rerank: store of %lld rows exceeds 2^31-1",
+                      (long long)n_store_rows);
+  CBK_CHECK_ARG((reinterpret_cast<uintptr_t>(d_store) & 0xff) == 0, "cbk_maxsim_rerank: store base must be 256-byte aligned");
+  if (!d_workspace || workspace_bytes < cbk_maxsim_rerank_workspace_bytes()) {
+    set_error("cbk_maxsim_rerank: workspace of %zu bytes, need %zu", workspace_bytes, cbk_maxsim_rerank_workspace_bytes());
+    return CBK_ERR_WORKSPACE;
+  }
+  int rc = check_device();
+  if (rc != CBK_OK) return rc;
+  if (n_cand_total == 0) return CBK_OK;
+  return rerank_dispatch(d_store, store_dtype, n_store_rows, dim, d_pfxsum, d_doclens, n_docs, strides, n_strides, d_Q,
+                         q_len, n_queries, d_cand_pids, d_cand_rowptr, n_cand_total, d_out_scores, d_workspace,
+                         static_cast<cudaStream_t>(stream));
+}
+
+int64_t cbk_topk_max_candidates(void) { return topk_max_candidates(); }
+
+int cbk_topk_per_query(const float* d_scores, const int64_t* d_cand_pids, const int64_t* d_cand_rowptr,
+                       int64_t n_queries, int64_t max_cand_per_query, int k, float* d_out_scores, int64_t* d_out_pids,
+                       void* stream) {
+  CBK_CHECK_ARG(d_scores && d_cand_pids && d_cand_rowptr && d_out_scores && d_out_pids,
+                "cbk_topk_per_query: null pointer argument");
+  CBK_CHECK_ARG(n_queries > 0 && k > 0 && max_cand_per_query > 0, "cbk_topk_per_query: n_queries %lld, k %d, max_cand %lld",
+                (long long)n_queries, k, (long long)max_cand_per_query);
+  CBK_CHECK_SUPPORTED(max_cand_per_query <= topk_max_candidates(),
+                      "cbk_topk_per_query: %lld candidates per query exceeds the limit of %lld",
+                      (long long)max_cand_per_query, (long long)topk_max_candidates());
+  CBK_CHECK_SUPPORTED(n_queries < (1ll << 31), "cbk_topk_per_query: too many queries");
+  int rc = check_device();
+  if (rc != CBK_OK) return rc;
+  return topk_dispatch(d_scores, d_cand_pids, d_cand_rowptr, n_queries, max_cand_per_query, k, d_out_scores, d_out_pids,
+                       static_cast<cudaStream_t>(stream));
+}
+
+int cbk_gather_rows(const void* d_store, int store_dtype, int64_t n_store_rows, int dim, const int64_t* d_pfxsum,
+                    const int32_t* d_doclens, int64_t n_docs, const int64_t* d_pids, int64_t n, int stride,
+                    float* d_out_D, uint8_t* d_out_mask, void* stream) {
+  CBK_CHECK_ARG(d_store && d_pfxsum && d_doclens && d_pids && d_out_D && d_out_mask, "cbk_gather_rows: null pointer argument");
+  CBK_CHECK_ARG(store_dtype == CBK_F16 || store_dtype == CBK_BF16, "cbk_gather_rows: unknown store dtype %d", store_dtype);
+  CBK_CHECK_ARG(n > 0 && stride > 0 && n_docs > 0 && n_store_rows > 0, "cbk_gather_rows: sizes must be positive");
+  CBK_CHECK_SUPPORTED(dim > 0 && dim % 8 == 0, "cbk_gather_rows: dim %d must be a multiple of 8", dim);
+  CBK_CHECK_ARG((reinterpret_cast<uintptr_t>(d_store) & 0xf) == 0, "cbk_gather_rows: store base must be 16-byte aligned");
+  int rc = check_device();
+  if (rc != CBK_OK) return rc;
+  return gather_dispatch(d_store, store_dtype, n_store_rows, dim, d_pfxsum, d_doclens, n_docs, d_pids, n, stride,
+                         d_out_D, d_out_mask, static_cast<cudaStream_t>(stream));
+}
+
+int cbk_mask_cast_rows(const void* d_src, int src_dtype, int64_t n_rows, int dim, const void* d_mask, int mask_dtype,
+                       void* d_out, int out_dtype, void* stream) {
+  CBK_CHECK_ARG(d_src && d_out, "cbk_mask_cast_rows: null pointer argument");
+  CBK_CHECK_ARG(n_rows > 0 && dim > 0, "cbk_mask_cast_rows: sizes must be positive");
+  CBK_CHECK_ARG(mask_dtype == CBK_MASK_NONE || d_mask, "cbk_mask_cast_rows: mask dtype %d given but mask is NULL", mask_dtype);
+  CBK_CHECK_SUPPORTED(dim % 4 == 0, "cbk_mask_cast_rows: dim %d must be a multiple of 4", dim);
+  int rc = check_device();
+  if (rc != CBK_OK) return rc;
+  return mask_cast_dispatch(d_src, src_dtype, n_rows, dim, mask_dtype == CBK_MASK_NONE ? nullptr : d_mask, mask_dtype,
+                            d_out, out_dtype, static_cast<cudaStream_t>(stream));
+}
+
+}  // extern "C"

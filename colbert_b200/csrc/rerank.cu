@@ -1,0 +1,306 @@
+// MaxSim rerank kernel (sm_100a): doclen-offset gather by TMA + 16-bit tensor-core MaxSim with the
+// max-over-tokens / sum-over-query-tokens reductions fused in registers.
+//
+// Replaces reference colbert/ranking/colbert_ranker.py:88-118 (lookup, stride-bucket gather, H2D,
+// cast, mask) and colbert/modeling/BaseModel.py:41-45 (mask-mul, einsum, max, sum).
+//
+// Design (DESIGN.md §"rerank kernel"):
+//   * every warp is an autonomous streaming unit: it owns a 4-stage ring of 16-row × 256-B document
+//     tiles in shared memory, issues its own TMA loads (2-D tensor map over the flat store, row
+//     coordinate = pfxsum[pid] + 16·tile, 128-byte swizzle) and waits on its own mbarriers — there is
+//     no block-wide barrier anywhere in the main loop;
+//   * the query matrix (≤ 32 × 128) lives in REGISTERS as mma.sync A-fragments (64 regs) for as long
+//     as the warp keeps scoring candidates of the same query;
+//   * document tiles are read with conflict-free ldmatrix.x4 straight out of the swizzled layout the
+//     TMA wrote, multiplied with m16n8k16 MMAs (fp32 accumulate); the epilogue keeps a running
+//     max per query row in registers, masks tokens ≥ doclen, applies the reference's zero floor and
+//     reduces with warp shuffles; only one fp32 per candidate is ever written;
+//   * work is handed out in segments of 64 consecutive candidates through one atomic counter.
+#include <algorithm>
+
+#include "cbk_common.cuh"
+
+namespace cbk {
+
+namespace {
+
+constexpr int kDim = 128;
+constexpr int kTileRows = 16;
+constexpr int kStages = 4;
+constexpr int kWarps = 4;
+constexpr int kCtasPerSm = 3;
+constexpr int kSegCands = 64;
+constexpr int kTileBytes = kTileRows * kDim * 2;  // 4096
+constexpr int kHalfBytes = kTileRows * 128;       // one 64-column half of a tile
+
+struct StrideSet {
+  int n;
+  int v[CBK_MAX_STRIDES];
+};
+
+struct __align__(1024) WarpSmem {
+  uint8_t tiles[kStages][kTileBytes];
+  int2 meta[kSegCands];  // .x = first store row, .y = doclen (-1: pid out of range)
+  uint64_t full[kStages];
+};
+static_assert(sizeof(WarpSmem) % 1024 == 0, "per-warp smem must keep 1024-B swizzle-atom alignment");
+
+template <typename T>
+__global__ void __launch_bounds__(kWarps * 32, kCtasPerSm)
+maxsim_rerank_kernel(const __grid_constant__ CUtensorMap tmap, const int64_t* __restrict__ pfxsum,
+                     const int32_t* __restrict__ doclens, int64_t n_docs, StrideSet strides,
+                     const float* __restrict__ Q, int q_len, int64_t n_queries,
+                     const int64_t* __restrict__ cand_pids, const int64_t* __restrict__ rowptr,
+                     int64_t n_cand, float* __restrict__ out, unsigned int* __restrict__ seg_counter) {
+  extern __shared__ uint8_t smem_raw[];
+  const int lane = threadIdx.x & 31;
+  const int warp = threadIdx.x >> 5;
+  const uint32_t raw_addr = smem_u32(smem_raw);
+  const uint32_t pad = ((raw_addr + 1023u) & ~1023u) - raw_addr;
+  WarpSmem* ws = reinterpret_cast<WarpSmem*>(smem_raw + pad) + warp;
+  const uint32_t tiles_addr = smem_u32(&ws->tiles[0][0]);
+  const uint32_t full_addr = smem_u32(&ws->full[0]);
+
+  if (lane == 0) {
+    tma_prefetch_desc(&tmap);
+    for (int s = 0; s < kStages; ++s) mbar_init(full_addr + 8 * s, 1);
+    fence_mbar_init();
+  }
+  __syncwarp();
+
+  const int n_mt = q_len > 16 ? 2 : 1;
+  const int64_t n_segs = (n_cand + kSegCands - 1) / kSegCands;
+  uint32_t issued = 0;    // tiles handed to the TMA so far   → stage = issued % kStages
+  uint32_t consumed = 0;  // tiles multiplied so far          → stage / parity of the next wait
+  int64_t cur_q = -1;
+  uint32_t qa[2][8][4];   // A fragments of the current query: [m-tile][k-step][reg]
+
+  // ldmatrix addressing that does not depend on the tile: row (lane & 7) of matrix (lane >> 3)
+  const int lrow = lane & 7;
+  const int lmat = lane >> 3;
+
+  while (true) {
+    unsigned int seg = 0;
+    if (lane == 0) seg = atomicAdd(seg_counter, 1u);
+    seg = __shfl_sync(0xffffffffu, seg, 0);
+    if (static_cast<int64_t>(seg) >= n_segs) break;
+    const int64_t c0 = static_cast<int64_t>(seg) * kSegCands;
+    const int nc = static_cast<int>(min(static_cast<int64_t>(kSegCands), n_cand - c0));
+
+    // ---- segment prologue: pid → (first row, doclen)   [colbert_ranker.py:88] --------------------
+    __syncwarp();
+    for (int i = lane; i < nc; i += 32) {
+      const int64_t pid = cand_pids[c0 + i];
+      int2 m = make_int2(0, -1);
+      if (pid >= 0 && pid < n_docs) m = make_int2(static_cast<int>(pfxsum[pid]), doclens[pid]);
+      ws->meta[i] = m;
+    }
+    __syncwarp();
+
+    // ---- which query owns candidate c0: uniform guess, else binary search over rowptr -----------
+    int64_t q = static_cast<int64_t>((static_cast<double>(c0) * n_queries) / static_cast<double>(n_cand));
+    q = max(static_cast<int64_t>(0), min(q, n_queries - 1));
+    if (!(rowptr[q] <= c0 && c0 < rowptr[q + 1])) {
+      int64_t lo = 0, hi = n_queries - 1;  // last q with rowptr[q] <= c0
+      while (lo < hi) {
+        const int64_t mid = (lo + hi + 1) >> 1;
+        if (rowptr[mid] <= c0) lo = mid; else hi = mid - 1;
+      }
+      q = lo;
+    }
+    int64_t q_end = rowptr[q + 1];
+
+    // ---- producer cursor (runs kStages-1 tiles ahead of the consumer inside the segment) ---------
+    int pc = 0, pt = 0;
+    while (pc < nc && ws->meta[pc].y <= 0) ++pc;
+    auto issue_tile = [&]() {
+      if (pc >= nc) return;
+      const int2 m = ws->meta[pc];
+      if (lane == 0) {
+        const uint32_t st = issued % kStages;
+        const uint32_t bar = full_addr + 8 * st;
+        const uint32_t dst = tiles_addr + st * kTileBytes;
+        const int row = m.x + pt * kTileRows;
+        mbar_arrive_expect_tx(bar, kTileBytes);
+        tma_load_2d(dst, &tmap, 0, row, bar, kEvictFirst);
+        tma_load_2d(dst + kHalfBytes, &tmap, 64, row, bar, kEvictFirst);
+      }
+      ++issued;
+      ++pt;
+      if (pt * kTileRows >= m.y) {
+        pt = 0;
+        ++pc;
+        while (pc < nc && ws->meta[pc].y <= 0) ++pc;
+      }
+    };
+#pragma unroll
+    for (int s = 0; s < kStages - 1; ++s) issue_tile();
+
+    for (int ci = 0; ci < nc; ++ci) {
+      const int64_t c = c0 + ci;
+      while (c >= q_end) {
+        ++q;
+        q_end = rowptr[q + 1];
+      }
+      if (q != cur_q) {
+        // ---- (re)load the query as A fragments, fp32 → T with round-to-nearest ------------------
+        cur_q = q;
+        const float* Qq = Q + q * static_cast<int64_t>(q_len) * kDim;
+#pragma unroll
+        for (int mt = 0; mt < 2; ++mt) {
+          const int r0 = mt * 16 + (lane >> 2);
+          const int r1 = r0 + 8;
+#pragma unroll
+          for (int ks = 0; ks < 8; ++ks) {
+            const int k0 = ks * 16 + 2 * (lane & 3);
+            float2 v00 = make_float2(0.f, 0.f), v10 = v00, v01 = v00, v11 = v00;
+            if (r0 < q_len) {
+              v00 = *reinterpret_cast<const float2*>(Qq + r0 * kDim + k0);
+              v01 = *reinterpret_cast<const float2*>(Qq + r0 * kDim + k0 + 8);
+            }
+            if (r1 < q_len) {
+              v10 = *reinterpret_cast<const float2*>(Qq + r1 * kDim + k0);
+              v11 = *reinterpret_cast<const float2*>(Qq + r1 * kDim + k0 + 8);
+            }
+            qa[mt][ks][0] = pack2<T>(v00.x, v00.y);
+            qa[mt][ks][1] = pack2<T>(v10.x, v10.y);
+            qa[mt][ks][2] = pack2<T>(v01.x, v01.y);
+            qa[mt][ks][3] = pack2<T>(v11.x, v11.y);
+          }
+        }
+      }
+
+      const int2 m = ws->meta[ci];
+      const int len = m.y;
+      const int ntiles = len > 0 ? (len + kTileRows - 1) / kTileRows : 0;
+      float rmax[2][2] = {{-INFINITY, -INFINITY}, {-INFINITY, -INFINITY}};
+
+      for (int t = 0; t < ntiles; ++t) {
+        issue_tile();
+        const uint32_t st = consumed % kStages;
+        mbar_wait(full_addr + 8 * st, (consumed / kStages) & 1u);
+        const uint32_t sbase = tiles_addr + st * kTileBytes;
+
+        float acc[2][2][4];  // [sub-tile of 8 tokens][m-tile][reg]
+#pragma unroll
+        for (int s = 0; s < 2; ++s)
+#pragma unroll
+          for (int mt = 0; mt < 2; ++mt)
+#pragma unroll
+            for (int r = 0; r < 4; ++r) acc[s][mt][r] = 0.f;
+
+#pragma unroll
+        for (int p = 0; p < 4; ++p) {  // 32 columns (two k-steps) per ldmatrix.x4
+          const int chunk = (p & 1) * 4 + lmat;
+          const uint32_t coff = (p >> 1) * kHalfBytes + (((chunk ^ lrow) & 7) << 4);
+#pragma unroll
+          for (int s = 0; s < 2; ++s) {
+            uint32_t b0, b1, b2, b3;
+            ldmatrix_x4(sbase + coff + (s * 8 + lrow) * 128, b0, b1, b2, b3);
+            mma_16816<T>(acc[s][0], qa[0][2 * p], b0, b1);
+            mma_16816<T>(acc[s][0], qa[0][2 * p + 1], b2, b3);
+            if (n_mt > 1) {
+              mma_16816<T>(acc[s][1], qa[1][2 * p], b0, b1);
+              mma_16816<T>(acc[s][1], qa[1][2 * p + 1], b2, b3);
+            }
+          }
+        }
+
+        // ---- running max over this tile's tokens; tokens ≥ doclen are ignored -------------------
+        const int tok0 = t * kTileRows + 2 * (lane & 3);
+        if ((t + 1) * kTileRows <= len) {
+#pragma unroll
+          for (int s = 0; s < 2; ++s)
+#pragma unroll
+            for (int mt = 0; mt < 2; ++mt) {
+              rmax[mt][0] = fmaxf(rmax[mt][0], fmaxf(acc[s][mt][0], acc[s][mt][1]));
+              rmax[mt][1] = fmaxf(rmax[mt][1], fmaxf(acc[s][mt][2], acc[s][mt][3]));
+            }
+        } else {
+#pragma unroll
+          for (int s = 0; s < 2; ++s) {
+            const bool v0 = tok0 + s * 8 < len;
+            const bool v1 = tok0 + s * 8 + 1 < len;
+#pragma unroll
+            for (int mt = 0; mt < 2; ++mt) {
+              rmax[mt][0] = fmaxf(rmax[mt][0], fmaxf(v0 ? acc[s][mt][0] : -INFINITY, v1 ? acc[s][mt][1] : -INFINITY));
+              rmax[mt][1] = fmaxf(rmax[mt][1], fmaxf(v0 ? acc[s][mt][2] : -INFINITY, v1 ? acc[s][mt][3] : -INFINITY));
+            }
+          }
+        }
+        __syncwarp();  // every lane is done reading this stage before it is refilled
+        ++consumed;
+      }
+
+      // ---- per-candidate epilogue: max across the 4 lanes of a row, floor, sum over query rows ----
+      bool do_floor = strides.n > 0;
+#pragma unroll
+      for (int i = 0; i < CBK_MAX_STRIDES; ++i)
+        if (i < strides.n && strides.v[i] == len) do_floor = false;
+      float total = 0.f;
+#pragma unroll
+      for (int mt = 0; mt < 2; ++mt) {
+        if (mt < n_mt) {
+#pragma unroll
+          for (int i = 0; i < 2; ++i) {
+            float v = rmax[mt][i];
+            v = fmaxf(v, __shfl_xor_sync(0xffffffffu, v, 1));
+            v = fmaxf(v, __shfl_xor_sync(0xffffffffu, v, 2));
+            if (do_floor) v = fmaxf(v, 0.f);
+            total += v;
+          }
+        }
+      }
+      total += __shfl_xor_sync(0xffffffffu, total, 4);
+      total += __shfl_xor_sync(0xffffffffu, total, 8);
+      total += __shfl_xor_sync(0xffffffffu, total, 16);
+      if (lane == 0) {
+        float r = total;
+        if (len == 0) r = 0.f;                       // empty document: nothing but padding
+        if (len < 0) r = __int_as_float(0x7fc00000);  // pid out of range
+        out[c] = r;
+      }
+    }
+  }
+}
+
+template <typename T>
+int launch(const CUtensorMap& tmap, const int64_t* pfxsum, const int32_t* doclens, int64_t n_docs,
+           const StrideSet& strides, const float* Q, int q_len, int64_t n_queries, const int64_t* cand_pids,
+           const int64_t* rowptr, int64_t n_cand, float* out, unsigned int* counter, cudaStream_t stream) {
+  const size_t smem = kWarps * sizeof(WarpSmem) + 1024;
+  CBK_CUDA(cudaFuncSetAttribute(maxsim_rerank_kernel<T>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                static_cast<int>(smem)));
+  const int64_t n_segs = (n_cand + kSegCands - 1) / kSegCands;
+  const int64_t want = (n_segs + kWarps - 1) / kWarps;
+  const int grid = static_cast<int>(std::max<int64_t>(1, std::min<int64_t>(want, static_cast<int64_t>(sm_count()) * kCtasPerSm)));
+  maxsim_rerank_kernel<T><<<grid, kWarps * 32, smem, stream>>>(tmap, pfxsum, doclens, n_docs, strides, Q, q_len,
+                                                              n_queries, cand_pids, rowptr, n_cand, out, counter);
+  CBK_CUDA(cudaGetLastError());
+  count_launch();
+  return CBK_OK;
+}
+
+}  // namespace
+
+int rerank_dispatch(const void* d_store, int store_dtype, int64_t n_store_rows, int dim, const int64_t* d_pfxsum,
+                    const int32_t* d_doclens, int64_t n_docs, const int32_t* strides, int n_strides,
+                    const float* d_Q, int q_len, int64_t n_queries, const int64_t* d_cand_pids,
+                    const int64_t* d_cand_rowptr, int64_t n_cand_total, float* d_out_scores, void* d_workspace,
+                    cudaStream_t stream) {
+  CUtensorMap tmap;
+  int rc = make_store_tensor_map(&tmap, d_store, n_store_rows, dim, 64, kTileRows);
+  if (rc != CBK_OK) return rc;
+  StrideSet ss;
+  ss.n = n_strides;
+  for (int i = 0; i < CBK_MAX_STRIDES; ++i) ss.v[i] = i < n_strides ? strides[i] : -1;
+  unsigned int* counter = static_cast<unsigned int*>(d_workspace);
+  CBK_CUDA(cudaMemsetAsync(counter, 0, sizeof(unsigned int), stream));
+  if (store_dtype == CBK_F16)
+    return launch<__half>(tmap, d_pfxsum, d_doclens, n_docs, ss, d_Q, q_len, n_queries, d_cand_pids, d_cand_rowptr,
+                          n_cand_total, d_out_scores, counter, stream);
+  return launch<__nv_bfloat16>(tmap, d_pfxsum, d_doclens, n_docs, ss, d_Q, q_len, n_queries, d_cand_pids,
+                               d_cand_rowptr, n_cand_total, d_out_scores, counter, stream);
+}
+
+}  // namespace cbk

@@ -1,0 +1,141 @@
+"""Thin tensor-level wrappers over the C ABI (include/colbert_b200.h).
+
+Each function checks devices / dtypes / contiguity, passes raw device pointers, sizes and the
+current CUDA stream to libcolbert_b200.so, and returns CUDA tensors.  Nothing here computes on the
+host and nothing falls back to torch ops: a missing library or an unsupported shape raises.
+"""
+from __future__ import annotations
+
+import ctypes as C
+from typing import Optional, Sequence
+
+import torch
+
+from . import _lib
+
+
+def _ptr(t: Optional[torch.Tensor]) -> C.c_void_p:
+    return C.c_void_p(0 if t is None else t.data_ptr())
+
+
+def _need(t: torch.Tensor, name: str, dtype, device) -> None:
+    if not t.is_cuda or t.device != device:
+        raise ValueError(f"{name} must live on {device}, got {t.device}")
+    if t.dtype != dtype:
+        raise TypeError(f"{name} must be {dtype}, got {t.dtype}")
+    if not t.is_contiguous():
+        raise ValueError(f"{name} must be contiguous")
+
+
+_workspaces = {}
+
+
+def _workspace(device: torch.device) -> torch.Tensor:
+    key = (device.index, torch.cuda.current_stream(device).cuda_stream)
+    ws = _workspaces.get(key)
+    if ws is None:
+        nbytes = int(_lib.load().cbk_maxsim_rerank_workspace_bytes())
+        ws = torch.zeros(nbytes, dtype=torch.uint8, device=device)
+        _workspaces[key] = ws
+    return ws
+
+
+def maxsim_rerank(store: torch.Tensor, pfxsum: torch.Tensor, doclens: torch.Tensor, strides: Sequence[int],
+                  Q: torch.Tensor, cand_pids: torch.Tensor, cand_rowptr: torch.Tensor,
+                  out: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """scores[c] for the CSR candidate lists; see cbk_maxsim_rerank in include/colbert_b200.h.
+
+    store [rows, dim] fp16|bf16 · pfxsum [n_docs+1] int64 · doclens [n_docs] int32 · Q [B, q_len, dim] fp32
+    cand_pids [n] int64 · cand_rowptr [B+1] int64  → fp32 [n] (all on the store's device)."""
+    lib = _lib.load()
+    dev = store.device
+    _need(store, "store", store.dtype, dev)
+    _need(pfxsum, "pfxsum", torch.int64, dev)
+    _need(doclens, "doclens", torch.int32, dev)
+    _need(Q, "Q", torch.float32, dev)
+    _need(cand_pids, "cand_pids", torch.int64, dev)
+    _need(cand_rowptr, "cand_rowptr", torch.int64, dev)
+    if Q.dim() != 3 or store.dim() != 2 or Q.size(2) != store.size(1):
+        raise ValueError(f"Q must be [B, q_len, dim={store.size(1)}], got {tuple(Q.shape)}")
+    n_q, q_len, dim = Q.shape
+    if cand_rowptr.numel() != n_q + 1:
+        raise ValueError("cand_rowptr must have B+1 entries")
+    n = cand_pids.numel()
+    if out is None:
+        out = torch.empty(n, dtype=torch.float32, device=dev)
+    else:
+        _need(out, "out", torch.float32, dev)
+        if out.numel() != n:
+            raise ValueError("out must have one entry per candidate")
+    st = (C.c_int32 * max(1, len(strides)))(*[int(s) for s in strides])
+    ws = _workspace(dev)
+    with torch.cuda.device(dev):
+        rc = lib.cbk_maxsim_rerank(_ptr(store), _lib.dtype_code(store.dtype), store.size(0), dim, _ptr(pfxsum),
+                                   _ptr(doclens), doclens.numel(), C.cast(st, C.c_void_p), len(strides), _ptr(Q),
+                                   q_len, n_q, _ptr(cand_pids), _ptr(cand_rowptr), n, _ptr(out), _ptr(ws),
+                                   ws.numel(), C.c_void_p(_lib.current_stream_ptr(dev)))
+    _lib.check("cbk_maxsim_rerank", rc)
+    return out
+
+
+def topk_per_query(scores: torch.Tensor, cand_pids: torch.Tensor, cand_rowptr: torch.Tensor, k: int,
+                   max_cand_per_query: int):
+    """(top scores [B,k] fp32, top pids [B,k] int64), score-descending, ties by ascending pid;
+    lists shorter than k are padded with (-inf, -1).  See cbk_topk_per_query."""
+    lib = _lib.load()
+    dev = scores.device
+    _need(scores, "scores", torch.float32, dev)
+    _need(cand_pids, "cand_pids", torch.int64, dev)
+    _need(cand_rowptr, "cand_rowptr", torch.int64, dev)
+    n_q = cand_rowptr.numel() - 1
+    out_s = torch.empty((n_q, k), dtype=torch.float32, device=dev)
+    out_p = torch.empty((n_q, k), dtype=torch.int64, device=dev)
+    with torch.cuda.device(dev):
+        rc = lib.cbk_topk_per_query(_ptr(scores), _ptr(cand_pids), _ptr(cand_rowptr), n_q, int(max_cand_per_query),
+                                    int(k), _ptr(out_s), _ptr(out_p), C.c_void_p(_lib.current_stream_ptr(dev)))
+    _lib.check("cbk_topk_per_query", rc)
+    return out_s, out_p
+
+
+def gather_rows(store: torch.Tensor, pfxsum: torch.Tensor, doclens: torch.Tensor, pids: torch.Tensor, stride: int):
+    """(D fp32 [n, stride, dim], mask bool [n, stride]) — bit-exact copies of `stride` store rows per
+    pid starting at its offset (reference colbert_ranker.py:105-109).  See cbk_gather_rows."""
+    lib = _lib.load()
+    dev = store.device
+    _need(store, "store", store.dtype, dev)
+    _need(pfxsum, "pfxsum", torch.int64, dev)
+    _need(doclens, "doclens", torch.int32, dev)
+    _need(pids, "pids", torch.int64, dev)
+    n, dim = pids.numel(), store.size(1)
+    D = torch.empty((n, stride, dim), dtype=torch.float32, device=dev)
+    mask = torch.empty((n, stride), dtype=torch.uint8, device=dev)
+    with torch.cuda.device(dev):
+        rc = lib.cbk_gather_rows(_ptr(store), _lib.dtype_code(store.dtype), store.size(0), dim, _ptr(pfxsum),
+                                 _ptr(doclens), doclens.numel(), _ptr(pids), n, int(stride), _ptr(D), _ptr(mask),
+                                 C.c_void_p(_lib.current_stream_ptr(dev)))
+    _lib.check("cbk_gather_rows", rc)
+    return D, mask.view(torch.bool)
+
+
+def mask_cast_rows(src: torch.Tensor, mask: Optional[torch.Tensor], out_dtype: torch.dtype) -> torch.Tensor:
+    """out[r, :] = out_dtype(float(src[r, :]) * float(mask[r])) for a 2-D ``src`` (fp16/bf16/fp32) and a
+    1-D per-row mask (bool/uint8/int64/fp32, or None for a plain cast).  See cbk_mask_cast_rows."""
+    lib = _lib.load()
+    dev = src.device
+    _need(src, "src", src.dtype, dev)
+    if src.dim() != 2:
+        raise ValueError("src must be 2-D [rows, dim]")
+    n_rows, dim = src.shape
+    mcode = _lib.CBK_MASK_NONE
+    if mask is not None:
+        _need(mask, "mask", mask.dtype, dev)
+        if mask.numel() != n_rows:
+            raise ValueError("mask must have one entry per row")
+        mcode = _lib.mask_code(mask.dtype)
+    out = torch.empty((n_rows, dim), dtype=out_dtype, device=dev)
+    with torch.cuda.device(dev):
+        rc = lib.cbk_mask_cast_rows(_ptr(src), _lib.dtype_code(src.dtype, True), n_rows, dim, _ptr(mask), mcode,
+                                    _ptr(out), _lib.dtype_code(out_dtype, True),
+                                    C.c_void_p(_lib.current_stream_ptr(dev)))
+    _lib.check("cbk_mask_cast_rows", rc)
+    return out

@@ -1,0 +1,227 @@
+"""GPU-resident ``ColbertRanker`` — the host-side mirror of the reference's ranking API
+(reference colbert/ranking/colbert_ranker.py:15-137, 238-241).
+
+Same constructor, attributes and ``rank_forward`` contract as the reference class; the work the
+reference does per query on the CPU + over PCIe (stride-bucket gather, cast, mask, einsum/max/sum,
+un-permute, full sort) is one fused MaxSim launch and one top-k launch of libcolbert_b200.so over
+a store that lives in HBM.  There is no torch-op or CPU fallback.
+
+What changed relative to the reference and why:
+  * ``self.tensor`` (the flat fp16 store, still ``num_embeddings + 512`` rows) lives on the GPU;
+  * ``self.buffers`` is empty — the pinned / device staging buffers of ``_create_buffers``
+    (≈1.9 GB at the reference's BSIZE) are not needed because nothing is staged;
+  * ``self.views`` (the ``as_strided`` stride-views) are still offered, lazily, for API compatibility
+    and for ``output_D_embedding``; scoring never reads through them — the kernel reads exactly
+    ``doclen`` rows per document and reproduces the reference's zero-floor through a per-document
+    flag (``doclen ∉ strides``, SURVEY.md §8 a12′);
+  * ``rank_forward_batch`` scores many queries, each with its own candidate list, in one launch.
+"""
+from __future__ import annotations
+
+from typing import List, Optional, Sequence, Tuple, Union
+
+import torch
+
+from .. import kernels
+from ..indexing.index_manager import load_index_part
+from ..indexing.loaders import get_parts, load_doclens
+
+BSIZE = 1 << 14          # reference colbert_ranker.py:11 — most candidates one query may carry
+TAIL_PAD_ROWS = 512      # reference colbert_ranker.py:62
+DEVICE = "cuda"
+
+
+def torch_percentile(tensor: torch.Tensor, p: int):
+    """k-th smallest value with k = int(p·len/100), 1-indexed (reference colbert_ranker.py:238-241)."""
+    assert p in range(1, 100 + 1)
+    assert tensor.dim() == 1
+    return tensor.kthvalue(int(p * tensor.size(0) / 100.0)).values.item()
+
+
+def flatten(L):
+    """reference colbert/utils/utils.py:133-134"""
+    return [x for y in L for x in y]
+
+
+class ColbertRanker:
+    """Drop-in for the reference ``ColbertRanker`` (upstream ColBERT: ``IndexPart`` + ``IndexRanker``)."""
+
+    def __init__(self, index_path: Optional[str], model=None, dim: Optional[int] = None,
+                 device: Union[str, torch.device, None] = None, store_dtype: torch.dtype = torch.float16,
+                 verbose: bool = False):
+        self.device = torch.device(device if device is not None else DEVICE)
+        if self.device.type != "cuda":
+            raise RuntimeError("colbert_b200.ColbertRanker needs a CUDA device (sm_100a); there is no CPU path")
+        if self.device.index is None:
+            self.device = torch.device("cuda", torch.cuda.current_device())
+        self.maxsim_dtype = torch.float32
+        self.store_dtype = store_dtype
+        self.model = model          # accepted for signature compatibility; scoring is the fused kernel
+        self.verbose = verbose
+        self.dim = dim
+        if index_path is not None:
+            _, self.parts_paths, _ = get_parts(index_path)
+            self.parts_doclens = load_doclens(index_path, flatten=False)
+            self.doclens = flatten(self.parts_doclens)
+            self.num_embeddings = sum(self.doclens)
+            self.tensor = self._load_parts(dim)
+            self.init_ranker()
+
+    # -- alternative constructor for stores that are already in memory (synthetic benches, tests) ----
+    @classmethod
+    def from_tensors(cls, embeddings: torch.Tensor, doclens: Sequence[int], device=None, model=None,
+                     store_dtype: Optional[torch.dtype] = None) -> "ColbertRanker":
+        """``embeddings`` is ``[num_embeddings, dim]`` (host or device, fp16/bf16); the 512-row zero
+        tail of the reference layout is appended here."""
+        self = cls(None, model=model, dim=embeddings.size(1), device=device,
+                   store_dtype=store_dtype or embeddings.dtype)
+        self.parts_paths, self.parts_doclens = [], [list(map(int, doclens))]
+        self.doclens = self.parts_doclens[0]
+        self.num_embeddings = int(embeddings.size(0))
+        assert sum(self.doclens) == self.num_embeddings
+        store = torch.zeros(self.num_embeddings + TAIL_PAD_ROWS, self.dim, dtype=self.store_dtype, device=self.device)
+        store[: self.num_embeddings].copy_(embeddings, non_blocking=True)
+        self.tensor = store
+        self.init_ranker()
+        return self
+
+    @classmethod
+    def from_store(cls, store: torch.Tensor, doclens, model=None) -> "ColbertRanker":
+        """Adopt (no copy) a device store that already has the reference layout
+        ``[num_embeddings + 512, dim]``; ``doclens`` is a list or an int64 tensor."""
+        assert store.is_cuda and store.dim() == 2 and store.is_contiguous()
+        self = cls(None, model=model, dim=store.size(1), device=store.device, store_dtype=store.dtype)
+        self.parts_paths, self.parts_doclens = [], []
+        self.doclens = doclens
+        self.num_embeddings = int(store.size(0)) - TAIL_PAD_ROWS
+        self.tensor = store
+        self.init_ranker()
+        assert int(self.doclens_pfxsum[-1]) == self.num_embeddings, "doclens do not add up to the store size"
+        return self
+
+    # -- reference colbert_ranker.py:61-73 ---------------------------------------------------------
+    def _load_parts(self, dim, verbose=None):
+        store = torch.zeros(self.num_embeddings + TAIL_PAD_ROWS, dim, dtype=self.store_dtype, device=self.device)
+        row = 0
+        for idx, filename in enumerate(self.parts_paths):
+            n_rows = sum(self.parts_doclens[idx])
+            part = load_index_part(filename, verbose=False)
+            assert part.size(0) == n_rows and part.size(1) == dim, (filename, tuple(part.shape), n_rows, dim)
+            store[row: row + n_rows].copy_(part.to(self.store_dtype))
+            row += n_rows
+        return store
+
+    # -- reference colbert_ranker.py:31-43 ---------------------------------------------------------
+    def init_ranker(self):
+        self.doclens = torch.as_tensor(self.doclens, dtype=torch.int64)
+        self.doclens_pfxsum = torch.zeros(self.doclens.numel() + 1, dtype=torch.int64)
+        torch.cumsum(self.doclens, 0, out=self.doclens_pfxsum[1:])
+        self.dim = self.tensor.size(-1)
+        self.strides = [torch_percentile(self.doclens, p) for p in [25, 50, 75]]
+        self.strides.append(self.doclens.max().item())
+        self.strides = sorted(list(set(self.strides)))
+        if self.verbose:
+            print(f"#> Using strides {self.strides}..", flush=True)
+        self._views = None
+        self.buffers = {}
+        # device-side copies the kernels index by pid
+        self._doclens_dev = self.doclens.to(torch.int32).to(self.device)
+        self._pfxsum_dev = self.doclens_pfxsum.to(self.device)
+        assert self.tensor.size(0) < 2 ** 31, "store exceeds 2^31-1 rows"
+
+    @property
+    def views(self) -> List[torch.Tensor]:
+        """reference colbert_ranker.py:45-51 — zero-copy stride-views of the store, built on demand."""
+        if self._views is None:
+            self._views = self._create_views(self.tensor)
+        return self._views
+
+    def _create_views(self, tensor: torch.Tensor):
+        out = []
+        for stride in self.strides:
+            rows = tensor.size(0) - stride + 1
+            out.append(torch.as_strided(tensor, (rows, stride, self.dim), (self.dim, self.dim, 1)))
+        return out
+
+    # -- the batched primitive everything else goes through -----------------------------------------
+    def score_candidates(self, Q: torch.Tensor, cand_pids: torch.Tensor, cand_rowptr: torch.Tensor) -> torch.Tensor:
+        """fp32 scores, one per candidate, in candidate order.  ``Q`` is ``[B, q_len, dim]`` fp32 on the
+        device; query rows beyond 32 are scored in 32-row slices whose partial sums are added."""
+        B, q_len, dim = Q.shape
+        if q_len <= kernels._lib.CBK_MAX_QLEN:
+            return kernels.maxsim_rerank(self.tensor, self._pfxsum_dev, self._doclens_dev, self.strides, Q,
+                                         cand_pids, cand_rowptr)
+        total = None
+        for lo in range(0, q_len, kernels._lib.CBK_MAX_QLEN):
+            part = kernels.maxsim_rerank(self.tensor, self._pfxsum_dev, self._doclens_dev, self.strides,
+                                         Q[:, lo: lo + kernels._lib.CBK_MAX_QLEN].contiguous(), cand_pids, cand_rowptr)
+            total = part if total is None else total.add_(part)
+        return total
+
+    def rank_forward_batch(self, Q: torch.Tensor, cand_pids: torch.Tensor, cand_rowptr: Optional[torch.Tensor] = None,
+                           depth: Optional[int] = 10, max_cand: Optional[int] = None
+                           ) -> Tuple[torch.Tensor, torch.Tensor]:
+        """Many queries, each with its own candidates, in one MaxSim launch + one top-k launch.
+
+        ``Q``: ``[B, q_len, dim]`` fp32 (host — ideally pinned — or device).  ``cand_pids``: ``[B, n]``
+        int64 for equal-length lists, or flat ``[N]`` with ``cand_rowptr`` ``[B+1]``.
+        → ``(pids [B, k] int64, scores [B, k] fp32)`` on the device, score-descending; k = depth
+        (None: the longest list); shorter lists are padded with (-1, -inf)."""
+        Q = Q.to(self.device, dtype=self.maxsim_dtype, non_blocking=True).contiguous()
+        B = Q.size(0)
+        cand_pids = cand_pids.to(self.device, non_blocking=True)
+        if cand_rowptr is None:
+            assert cand_pids.dim() == 2 and cand_pids.size(0) == B
+            n = cand_pids.size(1)
+            cand_rowptr = torch.arange(0, (B + 1) * n, n, dtype=torch.int64, device=self.device)
+            max_cand = n
+            cand_pids = cand_pids.reshape(-1)
+        else:
+            cand_rowptr = cand_rowptr.to(self.device, non_blocking=True)
+            if max_cand is None:
+                max_cand = int((cand_rowptr[1:] - cand_rowptr[:-1]).max().item())
+        cand_pids = cand_pids.contiguous()
+        scores = self.score_candidates(Q, cand_pids, cand_rowptr)
+        k = max_cand if depth is None else min(int(depth), max_cand)
+        top_scores, top_pids = kernels.topk_per_query(scores, cand_pids, cand_rowptr, k, max_cand)
+        return top_pids, top_scores
+
+    # -- reference colbert_ranker.py:75-137 ----------------------------------------------------------
+    def rank_forward(self, Q, pids, views=None, depth=10, output_D_embedding=False):
+        """``Q``: ``[1, dim, q_len]`` (as ``ColbertRetriever.search`` passes it, faiss_indexers.py:232-234);
+        ``pids``: list or int64 tensor.  → ``(pids, scores)`` Python lists, score-descending, at most
+        ``depth`` long; with ``output_D_embedding`` → ``(pids, D fp32 [depth, stride, dim], mask bool)``."""
+        assert len(pids) > 0
+        assert Q.size(0) in [1, len(pids)]
+        if Q.size(0) != 1:
+            # the reference accepts one query per candidate here but then only ever scores row 0 of
+            # each bucket (colbert_ranker.py:111-112 `[0]`); that path has no defined meaning to mirror
+            raise ValueError("rank_forward expects Q of shape [1, dim, q_len]")
+        if len(pids) > BSIZE:
+            raise ValueError(f"{len(pids)} candidates exceed BSIZE={BSIZE} (reference colbert_ranker.py:11)")
+        Qb = Q.to(self.device, dtype=self.maxsim_dtype).permute(0, 2, 1).contiguous()   # [1, q_len, dim]
+        pids_t = torch.as_tensor(pids, dtype=torch.int64).to(self.device)
+        n = pids_t.numel()
+        rowptr = torch.tensor([0, n], dtype=torch.int64, device=self.device)
+        scores = self.score_candidates(Qb, pids_t, rowptr)
+        k = n if depth is None else min(int(depth), n)
+        top_scores, top_pids = kernels.topk_per_query(scores, pids_t, rowptr, k, n)
+        if not output_D_embedding:
+            return top_pids[0].tolist(), top_scores[0].tolist()
+        # output_D_embedding: the reference can only concatenate when every candidate fell into one
+        # stride bucket (colbert_ranker.py:131-132), i.e. multi-view / fixed-length indexes
+        dl = self.doclens[pids_t.cpu()]
+        buckets = (dl.unsqueeze(1) > torch.tensor(self.strides).unsqueeze(0) + 1e-6).sum(-1)
+        if int(buckets.min()) != int(buckets.max()):
+            raise RuntimeError("output_D_embedding needs all candidates in one stride bucket "
+                               f"(got buckets {sorted(set(buckets.tolist()))}); the reference fails here too")
+        stride = self.strides[int(buckets[0])]
+        D, mask = kernels.gather_rows(self.tensor, self._pfxsum_dev, self._doclens_dev, top_pids[0].contiguous(), stride)
+        return top_pids[0].tolist(), D, mask
+
+    # upstream ColBERT name for the same call (IndexRanker.rank)
+    def rank(self, Q, pids, views=None, depth=10):
+        return self.rank_forward(Q, pids, views=views, depth=depth)
+
+
+IndexRanker = ColbertRanker

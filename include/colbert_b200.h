@@ -1,0 +1,153 @@
+/*
+ * colbert_b200.h — C ABI of the B200-native late-interaction scoring path.
+ *
+ * Drop-in boundary for ONE path of wuyaoxuehun/colbert: doclen-offset gather of per-token document
+ * embeddings from the flat index store → MaxSim (Q·Dᵀ, max over document tokens / views, sum over
+ * query tokens) → top-k.  The reference has no FFI for this path (it is pure Python calling torch);
+ * the seam this library sits behind is the pair of Python call signatures
+ *     ColbertRanker.rank_forward(Q, pids, views, depth, output_D_embedding)   colbert/ranking/colbert_ranker.py:75-137
+ *     BaseModel.score(Q, D, q_mask, d_mask)                                   colbert/modeling/BaseModel.py:39-46
+ * and every entry point below names the reference lines whose work it replaces.  INTEGRATION.md
+ * shows the ctypes binding a maintainer of the reference would add.
+ *
+ * Conventions
+ *   - plain C: pointers + sizes, no C++ / torch types; every function returns a cbk_status
+ *     (0 = OK, negative = error) and never throws; cbk_last_error() gives the message of the last
+ *     failure on the calling thread.
+ *   - every pointer named d_* is DEVICE memory owned by the caller; nothing is allocated, freed or
+ *     retained by the library; scratch comes from a caller-supplied workspace whose size is given by
+ *     the matching *_workspace_bytes().
+ *   - every launch takes an explicit cudaStream_t (passed as void*; 0 = legacy default stream) and is
+ *     asynchronous with respect to the host.  Calls are thread-safe when they use distinct
+ *     workspaces.
+ *   - the library targets sm_100a only and reports CBK_ERR_UNSUPPORTED on any other device; there is
+ *     no CPU fallback.
+ *
+ * Store layout (reference colbert_ranker.py:61-73, loaders.py:7-32): one flat row-major matrix
+ * [n_store_rows, dim] of 16-bit floats (fp16 as the reference writes it, or bf16), the embeddings
+ * of document p occupying rows pfxsum[p] .. pfxsum[p]+doclens[p]-1; the reference appends 512 zero
+ * rows, this library does not need them but tolerates them (n_store_rows counts them).
+ */
+#ifndef COLBERT_B200_H
+#define COLBERT_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define CBK_ABI_VERSION 1
+#define CBK_MAX_STRIDES 8      /* the reference produces at most 4 (percentiles 25/50/75 + max) */
+#define CBK_MAX_QLEN 32        /* query rows per launch; longer queries are split by the caller  */
+
+typedef enum cbk_status {
+  CBK_OK = 0,
+  CBK_ERR_INVALID_ARG = -1,
+  CBK_ERR_UNSUPPORTED = -2,   /* shape/dtype/device outside what the kernels implement */
+  CBK_ERR_CUDA = -3,          /* a CUDA runtime/driver call failed; see cbk_last_error() */
+  CBK_ERR_WORKSPACE = -4      /* workspace missing or too small */
+} cbk_status;
+
+typedef enum cbk_dtype {
+  CBK_F16 = 0,                /* IEEE half — the reference's store dtype (encoder.py:175) */
+  CBK_BF16 = 1,
+  CBK_F32 = 2                 /* only as a source/destination of cbk_mask_cast_rows */
+} cbk_dtype;
+
+typedef enum cbk_mask_dtype {
+  CBK_MASK_NONE = 0,          /* no mask: plain cast */
+  CBK_MASK_U8 = 1,            /* bool / uint8 */
+  CBK_MASK_I64 = 2,           /* torch.long, what the reference passes (colbert_ranker.py:112) */
+  CBK_MASK_F32 = 3
+} cbk_mask_dtype;
+
+/* Message of the last error raised on this thread ("" if none). Never NULL. */
+const char* cbk_last_error(void);
+
+/* CBK_ABI_VERSION the library was built with. */
+int cbk_abi_version(void);
+
+/* 1 when device `device` is an sm_100 part the kernels can run on, else 0 (or a negative cbk_status). */
+int cbk_device_supported(int device);
+
+/* How many kernels this library has launched in this process since load (for bench accounting). */
+uint64_t cbk_launch_count(void);
+
+/* ------------------------------------------------------------------------------------------------
+ * MaxSim rerank — replaces colbert_ranker.py:88-118 (pid→(doclen,offset) lookup, stride-bucket
+ * gather, H2D, fp16→fp32 cast, length mask) and BaseModel.py:41-45 (mask-mul, einsum, max, sum),
+ * for a BATCH of queries each with its own candidate list (CSR).
+ *
+ *   score[c] = Σ_{m<q_len} max( max_{t<doclen[p]} Q[q(c)][m]·store[pfxsum[p]+t] , floor[p] ),  p = cand_pids[c]
+ *   floor[p] = 0 when doclens[p] is NOT one of `strides` (the reference's multiplicative mask gives a
+ *              padded slot similarity 0, SURVEY.md §8 a12′), −inf otherwise; n_strides == 0 ⇒ no floor.
+ *
+ *   d_store        [n_store_rows, dim] store_dtype, 256-byte aligned base
+ *   d_pfxsum       [n_docs + 1] int64    (colbert_ranker.py:32)
+ *   d_doclens      [n_docs] int32
+ *   strides        host array of n_strides ints (colbert_ranker.py:36-40), may be NULL when n_strides == 0
+ *   d_Q            [n_queries, q_len, dim] fp32 row-major (the reference's Q.permute(0,2,1), l.111)
+ *   d_cand_pids    [n_cand_total] int64, concatenated candidate lists
+ *   d_cand_rowptr  [n_queries + 1] int64, query q owns candidates rowptr[q] .. rowptr[q+1]-1;
+ *                  rowptr[n_queries] == n_cand_total
+ *   d_out_scores   [n_cand_total] fp32, written at the candidate's own position (the reference's
+ *                  un-permute, colbert_ranker.py:120-122, is therefore not needed)
+ *   d_workspace    ≥ cbk_maxsim_rerank_workspace_bytes() bytes
+ *
+ * Supported: dim == 128, 1 ≤ q_len ≤ CBK_MAX_QLEN, n_store_rows < 2^31.  pids are range-checked on
+ * the device; an out-of-range pid yields NaN at its position.
+ * ------------------------------------------------------------------------------------------------ */
+size_t cbk_maxsim_rerank_workspace_bytes(void);
+
+int cbk_maxsim_rerank(const void* d_store, int store_dtype, int64_t n_store_rows, int dim,
+                      const int64_t* d_pfxsum, const int32_t* d_doclens, int64_t n_docs,
+                      const int32_t* strides, int n_strides,
+                      const float* d_Q, int q_len, int64_t n_queries,
+                      const int64_t* d_cand_pids, const int64_t* d_cand_rowptr, int64_t n_cand_total,
+                      float* d_out_scores, void* d_workspace, size_t workspace_bytes, void* stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * Per-query top-k — replaces colbert_ranker.py:128-130 (full sort, descending, truncate to depth).
+ * Total order: score descending, then pid ascending (the reference's torch.sort is unstable, so its
+ * order among exact ties is unspecified).
+ *
+ *   d_scores, d_cand_pids, d_cand_rowptr as above; each query may hold at most
+ *   cbk_topk_max_candidates() candidates; pids must be < 2^32.
+ *   d_out_scores [n_queries, k] fp32, d_out_pids [n_queries, k] int64; when a query has fewer than k
+ *   candidates the tail is filled with (−inf, −1).
+ * ------------------------------------------------------------------------------------------------ */
+int64_t cbk_topk_max_candidates(void);
+
+int cbk_topk_per_query(const float* d_scores, const int64_t* d_cand_pids, const int64_t* d_cand_rowptr,
+                       int64_t n_queries, int64_t max_cand_per_query, int k,
+                       float* d_out_scores, int64_t* d_out_pids, void* stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * Row gather — replaces colbert_ranker.py:105-109 as exposed by rank_forward(output_D_embedding=True)
+ * (l.131-136): for each pid, `stride` consecutive store rows starting at pfxsum[pid] (rows past the
+ * document's own length belong to the next document, exactly as the reference's stride-view reads
+ * them), upcast to fp32, plus the length mask  mask[i][t] = (t + 1 <= doclens[pid_i]).
+ *
+ *   d_out_D [n, stride, dim] fp32, d_out_mask [n, stride] uint8 (0/1).  Rows at or past n_store_rows read as 0.
+ * ------------------------------------------------------------------------------------------------ */
+int cbk_gather_rows(const void* d_store, int store_dtype, int64_t n_store_rows, int dim,
+                    const int64_t* d_pfxsum, const int32_t* d_doclens, int64_t n_docs,
+                    const int64_t* d_pids, int64_t n, int stride,
+                    float* d_out_D, uint8_t* d_out_mask, void* stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * Masked row cast — the multiplicative masks of BaseModel.score (BaseModel.py:41-42: D * d_mask[...,None],
+ * Q * q_mask[...,None]) fused with the cast to the tensor-core input type:
+ *     out[r, :] = (out_dtype)( (float)src[r, :] * (float)mask[r] )          mask == NULL ⇒ plain cast
+ *   d_src [n_rows, dim] of src_dtype (CBK_F16 | CBK_BF16 | CBK_F32), d_mask [n_rows] of mask_dtype,
+ *   d_out [n_rows, dim] of out_dtype.  dim must be a multiple of 4.
+ * ------------------------------------------------------------------------------------------------ */
+int cbk_mask_cast_rows(const void* d_src, int src_dtype, int64_t n_rows, int dim, const void* d_mask, int mask_dtype,
+                       void* d_out, int out_dtype, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* COLBERT_B200_H */

@@ -1,0 +1,253 @@
+"""Parity of the CUDA path (through the C ABI) against the oracle and the committed golden vectors
+produced by the unmodified reference.  Needs a B200: ``pytest -m gpu``.
+
+Bars (BASELINE.json north_star): pids, doc offsets and gathered rows bit-exact; scores within 1e-3
+relative of the reference's fp32 result; identical top-k except for ties inside that tolerance."""
+import os
+
+import numpy as np
+import pytest
+import torch
+
+from golden_cases import CASES, build_case
+from oracle import maxsim_oracle as O
+from parity_utils import SCORE_RTOL, check_topk
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def dev():
+    assert torch.cuda.is_available(), "GPU tests need a CUDA device"
+    from colbert_b200 import _lib
+    lib = _lib.load()                                   # raises if the extension is missing
+    assert lib.cbk_device_supported(0) == 1, "not an sm_100 device"
+    return torch.device("cuda", 0)
+
+
+def make_ranker(index, dev, store_dtype=torch.float16):
+    from colbert_b200.ranking import ColbertRanker
+    return ColbertRanker.from_tensors(torch.from_numpy(index.emb), index.doclens.tolist(), device=dev,
+                                      store_dtype=store_dtype)
+
+
+# ------------------------------------------------------------------------------------------------
+# rank_forward against the reference's golden vectors
+# ------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("case", CASES, ids=[c["name"] for c in CASES])
+def test_rank_forward_golden(dev, golden_dir, case):
+    g = np.load(os.path.join(golden_dir, f"rank_{case['name']}.npz"))
+    index, queries, cands = build_case(case)
+    ranker = make_ranker(index, dev)
+    assert ranker.strides == g["strides"].tolist()
+    assert ranker.tensor.size(0) == int(g["store_rows"][0])
+    assert ranker.doclens_pfxsum[-4:].tolist() == g["pfxsum_tail"].tolist()
+    worst = 0.0
+    for qi, (Q, pids) in enumerate(zip(queries, cands)):
+        Qt = torch.from_numpy(Q).unsqueeze(0).permute(0, 2, 1)       # [1, dim, q_len], as the caller passes it
+        full_p, full_s = g[f"q{qi}_all_pids"], g[f"q{qi}_all_scores"]
+        for dname, depth in case["depths"]:
+            p, s = ranker.rank_forward(Qt, [int(x) for x in pids], depth=depth)
+            assert isinstance(p, list) and isinstance(s, list)
+            worst = max(worst, check_topk(p, s, g[f"q{qi}_{dname}_pids"], g[f"q{qi}_{dname}_scores"], SCORE_RTOL,
+                                          full_p, full_s))
+            assert all(s[i] >= s[i + 1] for i in range(len(s) - 1))
+        if case.get("output_D"):
+            p, D, M = ranker.rank_forward(Qt, [int(x) for x in pids], depth=case["output_D"], output_D_embedding=True)
+            assert p == g[f"q{qi}_D_pids"].tolist()
+            assert D.dtype == torch.float32 and M.dtype == torch.bool
+            assert np.array_equal(D.cpu().numpy().astype(np.float16), g[f"q{qi}_D_rows"])      # bit-exact rows
+            assert np.array_equal(D.cpu().numpy(), g[f"q{qi}_D_rows"].astype(np.float32))
+            assert np.array_equal(M.cpu().numpy(), g[f"q{qi}_D_mask"])
+    print(f"[{case['name']}] worst relative score error vs reference fp32: {worst:.3e}")
+
+
+def test_rank_forward_from_disk_index(dev, tmp_path, golden_dir):
+    """Same answers when the store is loaded from the reference's on-disk layout (3 parts)."""
+    from colbert_b200 import synthetic
+    from colbert_b200.ranking import ColbertRanker
+    case = CASES[0]
+    g = np.load(os.path.join(golden_dir, "rank_small.npz"))
+    index, queries, cands = build_case(case)
+    synthetic.write_index(index, str(tmp_path))
+    ranker = ColbertRanker(str(tmp_path), model=None, dim=128, device=dev)
+    assert ranker.strides == g["strides"].tolist()
+    ref_store = O.pad_store(index.emb)
+    assert np.array_equal(ranker.tensor.cpu().numpy(), ref_store)              # bit-exact store incl. zero tail
+    assert np.array_equal(ranker.doclens_pfxsum.numpy(), O.doclens_pfxsum(index.doclens))
+    Qt = torch.from_numpy(queries[0]).unsqueeze(0).permute(0, 2, 1)
+    p, s = ranker.rank_forward(Qt, cands[0].tolist(), depth=10)
+    check_topk(p, s, g["q0_d10_pids"], g["q0_d10_scores"], SCORE_RTOL, g["q0_all_pids"], g["q0_all_scores"])
+
+
+def test_rank_forward_asserts_like_reference(dev):
+    index, queries, cands = build_case(CASES[0])
+    ranker = make_ranker(index, dev)
+    Qt = torch.from_numpy(queries[0]).unsqueeze(0).permute(0, 2, 1)
+    with pytest.raises(AssertionError):
+        ranker.rank_forward(Qt, [])                                            # colbert_ranker.py:76
+    with pytest.raises(AssertionError):
+        ranker.rank_forward(Qt.repeat(3, 1, 1), [1, 2])                        # colbert_ranker.py:77
+    # candidates in several stride buckets cannot return D (the reference's torch.cat fails as well)
+    with pytest.raises(RuntimeError):
+        ranker.rank_forward(Qt, cands[0].tolist(), depth=5, output_D_embedding=True)
+
+
+# ------------------------------------------------------------------------------------------------
+# kernels against the oracle on seeded inputs
+# ------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("store_dtype", [torch.float16, torch.bfloat16], ids=["fp16", "bf16"])
+@pytest.mark.parametrize("q_len", [32, 16, 8, 3])
+def test_batched_scores_match_oracle(dev, store_dtype, q_len):
+    from colbert_b200 import synthetic
+    index = synthetic.make_index(101, 3000, dim=128, lo=1, hi=180)
+    emb = torch.from_numpy(index.emb)
+    if store_dtype == torch.bfloat16:
+        emb = emb.to(torch.bfloat16)                        # the bf16 store holds bf16-rounded values
+    from colbert_b200.ranking import ColbertRanker
+    ranker = ColbertRanker.from_tensors(emb, index.doclens.tolist(), device=dev, store_dtype=store_dtype)
+    B, n = 7, 333
+    Q = synthetic.make_queries(202, B, q_len, 128)
+    cand = synthetic.make_candidates(303, B, index.num_docs, n)
+    rowptr = torch.arange(0, (B + 1) * n, n, dtype=torch.int64, device=dev)
+    scores = ranker.score_candidates(torch.from_numpy(Q).to(dev), torch.from_numpy(cand).reshape(-1).to(dev), rowptr)
+    scores = scores.cpu().numpy().reshape(B, n)
+    store = O.pad_store(emb.float().numpy().astype(np.float32))   # oracle on the exact stored values, in fp32
+    pf = O.doclens_pfxsum(index.doclens)
+    strides = O.compute_strides(index.doclens)
+    assert strides == ranker.strides
+    worst = 0.0
+    for b in range(B):
+        ref = O.maxsim_exact(store, index.doclens, pf, strides, Q[b], cand[b])
+        rel = np.abs(scores[b] - ref) / np.maximum(np.abs(ref), 1.0)
+        worst = max(worst, float(rel.max()))
+    print(f"[{store_dtype}, q_len={q_len}] worst relative score error: {worst:.3e}")
+    assert worst <= SCORE_RTOL
+
+
+def test_ragged_candidate_lists_and_empty_queries(dev):
+    """CSR candidate lists of very different lengths (incl. empty and 1-candidate queries)."""
+    from colbert_b200 import synthetic
+    index = synthetic.make_index(7, 500, dim=128, lo=1, hi=90)
+    ranker = make_ranker(index, dev)
+    rng = np.random.default_rng(3)
+    lens = [0, 1, 130, 0, 64, 65, 700, 2, 0]
+    Q = synthetic.make_queries(8, len(lens), 32, 128)
+    cands = [rng.integers(0, index.num_docs, size=l) for l in lens]     # duplicates allowed
+    flat = np.concatenate(cands).astype(np.int64)
+    rowptr = np.concatenate([[0], np.cumsum(lens)]).astype(np.int64)
+    pids, scores = ranker.rank_forward_batch(torch.from_numpy(Q), torch.from_numpy(flat), torch.from_numpy(rowptr), depth=5)
+    pids, scores = pids.cpu().numpy(), scores.cpu().numpy()
+    store, pf = O.pad_store(index.emb), O.doclens_pfxsum(index.doclens)
+    for b, l in enumerate(lens):
+        k = min(5, l)
+        if l:
+            ref = O.maxsim_exact(store, index.doclens, pf, ranker.strides, Q[b], cands[b])
+            rp, rs = O.topk_desc(ref, cands[b].astype(np.int64), 5)
+            full_p, full_s = O.topk_desc(ref, cands[b].astype(np.int64), None)
+            check_topk(pids[b, :k], scores[b, :k], rp, rs, SCORE_RTOL, full_p, full_s)
+        assert np.all(pids[b, k:] == -1) and np.all(np.isneginf(scores[b, k:]))
+
+
+def test_out_of_range_pid_yields_nan_not_a_fault(dev):
+    from colbert_b200 import synthetic
+    index = synthetic.make_index(7, 50, dim=128, lo=1, hi=20)
+    ranker = make_ranker(index, dev)
+    Q = torch.from_numpy(synthetic.make_queries(1, 1, 32, 128)).to(dev)
+    cand = torch.tensor([3, 50, -1, 49], dtype=torch.int64, device=dev)
+    rowptr = torch.tensor([0, 4], dtype=torch.int64, device=dev)
+    s = ranker.score_candidates(Q, cand, rowptr).cpu().numpy()
+    assert np.isfinite(s[0]) and np.isfinite(s[3]) and np.isnan(s[1]) and np.isnan(s[2])
+
+
+def test_topk_kernel_total_order_and_padding(dev):
+    """score desc, then pid asc; -inf / negative / tied scores; n from 1 to 16384 (the reference's BSIZE)."""
+    from colbert_b200 import kernels
+    rng = np.random.default_rng(5)
+    lens = [1, 31, 32, 33, 1000, 1024, 4097, 16384]
+    sc = [np.round(rng.standard_normal(l), 1).astype(np.float32) for l in lens]   # rounding → many exact ties
+    sc[3][:5] = -np.inf
+    ids = [rng.permutation(1_000_000)[:l].astype(np.int64) for l in lens]
+    rowptr = np.concatenate([[0], np.cumsum(lens)]).astype(np.int64)
+    for k in (1, 10, 1000):
+        ts, tp = kernels.topk_per_query(torch.from_numpy(np.concatenate(sc)).to(dev),
+                                        torch.from_numpy(np.concatenate(ids)).to(dev),
+                                        torch.from_numpy(rowptr).to(dev), k, max(lens))
+        ts, tp = ts.cpu().numpy(), tp.cpu().numpy()
+        for b, l in enumerate(lens):
+            rp, rs = O.topk_desc(sc[b], ids[b], k)
+            kk = min(k, l)
+            assert np.array_equal(tp[b, :kk], rp) and np.array_equal(ts[b, :kk], rs)   # bit-exact incl. tie order
+            assert np.all(tp[b, kk:] == -1) and np.all(np.isneginf(ts[b, kk:]))
+
+
+def test_gather_rows_bit_exact(dev):
+    from colbert_b200 import kernels, synthetic
+    index = synthetic.make_index(17, 200, dim=128, lo=1, hi=50)
+    ranker = make_ranker(index, dev)
+    pids = np.array([0, 199, 7, 7, 42], dtype=np.int64)             # 199 = last doc: over-read runs into the zero tail
+    store, pf = O.pad_store(index.emb), O.doclens_pfxsum(index.doclens)
+    for stride in (1, 8, 50, 180):
+        D, M = kernels.gather_rows(ranker.tensor, ranker._pfxsum_dev, ranker._doclens_dev,
+                                   torch.from_numpy(pids).to(dev), stride)
+        rD, rM = O.gather_rows(store, index.doclens, pf, pids, stride)
+        assert np.array_equal(D.cpu().numpy(), rD) and np.array_equal(M.cpu().numpy(), rM)
+
+
+# ------------------------------------------------------------------------------------------------
+# BaseModel.score (all-pairs, multiplicative masks)
+# ------------------------------------------------------------------------------------------------
+def test_score_known_answer_shape(dev, golden_dir):
+    """The reference's only KAT has h=3, outside the kernel's dim=128: embed it in 128 dims (zeros
+    elsewhere do not change any dot product) and expect exactly [[21., 41.]]."""
+    from colbert_b200.modeling.BaseModel import BaseModel
+    sc = np.load(os.path.join(golden_dir, "score_cases.npz"))
+    Q = np.zeros((1, 2, 128), np.float32); Q[..., :3] = sc["kat_Q"]
+    D = np.zeros((2, 2, 128), np.float32); D[..., :3] = sc["kat_D"]
+    out = BaseModel.score(torch.from_numpy(Q).to(dev), torch.from_numpy(D).to(dev),
+                          torch.ones(1, 2, device=dev), torch.ones(2, 2, device=dev))
+    assert out.cpu().tolist() == [[21.0, 41.0]]
+
+
+@pytest.mark.parametrize("name", ["ap_mid", "ap_views"])
+def test_score_allpairs_golden(dev, golden_dir, name):
+    from colbert_b200.modeling.BaseModel import BaseModel
+    sc = np.load(os.path.join(golden_dir, "score_cases.npz"))
+    Q = torch.from_numpy(sc[name + "_Q"].astype(np.float32)).to(dev)
+    D = torch.from_numpy(sc[name + "_D"].astype(np.float32)).to(dev)
+    out = BaseModel.score(Q, D, torch.from_numpy(sc[name + "_qmask"]).to(dev), torch.from_numpy(sc[name + "_dmask"]).to(dev))
+    ref = sc[name + "_score"]
+    rel = np.abs(out.cpu().numpy() - ref) / np.maximum(np.abs(ref), 1.0)
+    print(f"[{name}] worst relative error {rel.max():.3e}")
+    assert out.shape == ref.shape and rel.max() <= SCORE_RTOL
+
+
+# ------------------------------------------------------------------------------------------------
+# BASELINE-sized run: properties that do not need the oracle on every candidate
+# ------------------------------------------------------------------------------------------------
+def test_baseline_scale_properties(dev):
+    """512 queries × 1000 candidates over a 200k-doc store (≈18 M tokens, 4.6 GB ≫ L2):
+       - a sample of queries matches the oracle within tolerance;
+       - scoring is invariant to candidate order (permutation property);
+       - the top-k of the scores equals a sort of the scores (sortedness, idempotence)."""
+    from colbert_b200 import synthetic
+    index = synthetic.make_index(2024, 200_000, dim=128, lo=1, hi=180)
+    ranker = make_ranker(index, dev)
+    B, n = 512, 1000
+    Q = synthetic.make_queries(11, B, 32, 128)
+    cand = synthetic.make_candidates(12, B, index.num_docs, n)
+    Qd, cd = torch.from_numpy(Q).to(dev), torch.from_numpy(cand).to(dev)
+    rowptr = torch.arange(0, (B + 1) * n, n, dtype=torch.int64, device=dev)
+    s1 = ranker.score_candidates(Qd, cd.reshape(-1), rowptr).reshape(B, n)
+    perm = torch.from_numpy(np.random.default_rng(1).permutation(n)).to(dev)
+    s2 = ranker.score_candidates(Qd, cd[:, perm].contiguous().reshape(-1), rowptr).reshape(B, n)
+    assert torch.equal(s1[:, perm], s2)                                   # bit-identical under permutation
+    pids, top = ranker.rank_forward_batch(Qd, cd, depth=1000)
+    assert torch.equal(top, torch.sort(s1, dim=1, descending=True).values)   # same multiset, sorted
+    assert torch.all(top[:, :-1] >= top[:, 1:])
+    store, pf = O.pad_store(index.emb), O.doclens_pfxsum(index.doclens)
+    for b in (0, 17, 511):
+        ref = O.maxsim_exact(store, index.doclens, pf, ranker.strides, Q[b], cand[b])
+        rp, rs = O.topk_desc(ref, cand[b], 10)
+        fp, fs = O.topk_desc(ref, cand[b], None)
+        check_topk(pids[b, :10].cpu().numpy(), top[b, :10].cpu().numpy(), rp, rs, SCORE_RTOL, fp, fs)

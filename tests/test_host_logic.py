@@ -1,0 +1,63 @@
+"""Host-side mirror of the reference interface, CPU-checkable parts: index-directory readers,
+percentile strides, and that the product package never imports the oracle."""
+import ast
+import os
+
+import numpy as np
+import pytest
+import torch
+
+from colbert_b200 import synthetic
+from colbert_b200.indexing.index_manager import IndexManager, load_index_part
+from colbert_b200.indexing.loaders import get_parts, load_doclens
+from colbert_b200.ranking.colbert_ranker import torch_percentile
+from oracle import maxsim_oracle as O
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def test_loaders_match_oracle(tmp_path):
+    idx = synthetic.make_index(9, 40, dim=128, lo=1, hi=12, num_parts=12)
+    synthetic.write_index(idx, str(tmp_path))
+    assert get_parts(str(tmp_path)) == O.get_parts(str(tmp_path))
+    assert load_doclens(str(tmp_path), flatten=True) == O.load_doclens(str(tmp_path), flatten=True)
+    assert load_doclens(str(tmp_path), flatten=False) == O.load_doclens(str(tmp_path), flatten=False)
+    part = load_index_part(os.path.join(str(tmp_path), "11.pt"))
+    assert part.dtype == torch.float16 and part.shape[1] == 128
+
+
+def test_get_parts_asserts_contiguous_numbering(tmp_path):
+    torch.save(torch.zeros(1, 4), tmp_path / "0.pt")
+    torch.save(torch.zeros(1, 4), tmp_path / "2.pt")
+    with pytest.raises(AssertionError):
+        get_parts(str(tmp_path))
+
+
+def test_legacy_list_part_is_concatenated(tmp_path):
+    a, b = torch.ones(2, 4, dtype=torch.float16), torch.zeros(3, 4, dtype=torch.float16)
+    IndexManager(4).save([a, b], str(tmp_path / "0.pt"))
+    assert load_index_part(str(tmp_path / "0.pt")).shape == (5, 4)
+
+
+def test_torch_percentile_matches_oracle():
+    rng = np.random.default_rng(0)
+    for n in (4, 7, 100, 1001):
+        d = rng.integers(1, 181, size=n)
+        for p in (25, 50, 75, 100):
+            assert torch_percentile(torch.from_numpy(d), p) == O.percentile_kth(d, p)
+
+
+def test_product_never_imports_the_oracle():
+    """colbert_b200/ must not import, call or link anything under oracle/ (it is test infrastructure)."""
+    for dirpath, _, files in os.walk(os.path.join(ROOT, "colbert_b200")):
+        for f in files:
+            if not f.endswith(".py"):
+                continue
+            tree = ast.parse(open(os.path.join(dirpath, f)).read())
+            for node in ast.walk(tree):
+                names = []
+                if isinstance(node, ast.Import):
+                    names = [a.name for a in node.names]
+                elif isinstance(node, ast.ImportFrom):
+                    names = [node.module or ""]
+                assert not any(n.split(".")[0] == "oracle" for n in names), (f, names)
