@@ -13,7 +13,7 @@ namespace cbk {
 
 // dispatchers implemented in the kernel translation units
 int rerank_dispatch(const void*, int, int64_t, int, const int64_t*, const int32_t*, int64_t, const int32_t*, int,
-                    const float*, int, int64_t, const int64_t*, const int64_t*, int64_t, float*, void*, cudaStream_t);
+                    const float*, int, int64_t, const int64_t*, const int64_t*, int64_t, float*, void*, int, cudaStream_t);
 int topk_dispatch(const float*, const int64_t*, const int64_t*, int64_t, int64_t, int, float*, int64_t*, cudaStream_t);
 int64_t topk_max_candidates();
 int gather_dispatch(const void*, int, int64_t, int, const int64_t*, const int32_t*, int64_t, const int64_t*, int64_t,
@@ -124,7 +124,7 @@ int cbk_maxsim_rerank(const void* d_store, int store_dtype, int64_t n_store_rows
                       const int32_t* d_doclens, int64_t n_docs, const int32_t* strides, int n_strides, const float* d_Q,
                       int q_len, int64_t n_queries, const int64_t* d_cand_pids, const int64_t* d_cand_rowptr,
                       int64_t n_cand_total, float* d_out_scores, void* d_workspace, size_t workspace_bytes,
-                      void* stream) {
+                      int flags, void* stream) {
   CBK_CHECK_ARG(d_store && d_pfxsum && d_doclens && d_Q && d_cand_pids && d_cand_rowptr && d_out_scores,
                 "cbk_maxsim_rerank: null pointer argument");
   CBK_CHECK_ARG(store_dtype == CBK_F16 || store_dtype == CBK_BF16, "cbk_maxsim_rerank: unknown store dtype %d", store_dtype);
@@ -147,7 +147,7 @@ int cbk_maxsim_rerank(const void* d_store, int store_dtype, int64_t n_store_rows
   if (rc != CBK_OK) return rc;
   if (n_cand_total == 0) return CBK_OK;
   return rerank_dispatch(d_store, store_dtype, n_store_rows, dim, d_pfxsum, d_doclens, n_docs, strides, n_strides, d_Q,
-                         q_len, n_queries, d_cand_pids, d_cand_rowptr, n_cand_total, d_out_scores, d_workspace,
+                         q_len, n_queries, d_cand_pids, d_cand_rowptr, n_cand_total, d_out_scores, d_workspace, flags,
                          static_cast<cudaStream_t>(stream));
 }
 

@@ -45,7 +45,19 @@ struct __align__(1024) WarpSmem {
 };
 static_assert(sizeof(WarpSmem) % 1024 == 0, "per-warp smem must keep 1024-B swizzle-atom alignment");
 
-template <typename T>
+// two bf16 packed in a 32-bit register → two fp16 (exact for |x| in fp16's normal range, i.e. for
+// the unit-norm embeddings ColBERT stores; tiny values land on fp16 subnormals)
+__device__ __forceinline__ uint32_t bf16x2_to_f16x2(uint32_t v) {
+  const float lo = __uint_as_float(v << 16);
+  const float hi = __uint_as_float(v & 0xffff0000u);
+  uint32_t r;
+  asm("cvt.rn.f16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(hi), "f"(lo));
+  return r;
+}
+
+// T = type fed to the tensor cores.  kCvtBf16: the store holds bf16 but is multiplied as fp16
+// (converted in registers after ldmatrix) so that the query keeps 11 significant bits instead of 8.
+template <typename T, bool kCvtBf16>
 __global__ void __launch_bounds__(kWarps * 32, kCtasPerSm)
 maxsim_rerank_kernel(const __grid_constant__ CUtensorMap tmap, const int64_t* __restrict__ pfxsum,
                      const int32_t* __restrict__ doclens, int64_t n_docs, StrideSet strides,
@@ -197,6 +209,12 @@ maxsim_rerank_kernel(const __grid_constant__ CUtensorMap tmap, const int64_t* __
           for (int s = 0; s < 2; ++s) {
             uint32_t b0, b1, b2, b3;
             ldmatrix_x4(sbase + coff + (s * 8 + lrow) * 128, b0, b1, b2, b3);
+            if (kCvtBf16) {
+              b0 = bf16x2_to_f16x2(b0);
+              b1 = bf16x2_to_f16x2(b1);
+              b2 = bf16x2_to_f16x2(b2);
+              b3 = bf16x2_to_f16x2(b3);
+            }
             mma_16816<T>(acc[s][0], qa[0][2 * p], b0, b1);
             mma_16816<T>(acc[s][0], qa[0][2 * p + 1], b2, b3);
             if (n_mt > 1) {
@@ -264,17 +282,17 @@ maxsim_rerank_kernel(const __grid_constant__ CUtensorMap tmap, const int64_t* __
   }
 }
 
-template <typename T>
+template <typename T, bool kCvtBf16>
 int launch(const CUtensorMap& tmap, const int64_t* pfxsum, const int32_t* doclens, int64_t n_docs,
            const StrideSet& strides, const float* Q, int q_len, int64_t n_queries, const int64_t* cand_pids,
            const int64_t* rowptr, int64_t n_cand, float* out, unsigned int* counter, cudaStream_t stream) {
   const size_t smem = kWarps * sizeof(WarpSmem) + 1024;
-  CBK_CUDA(cudaFuncSetAttribute(maxsim_rerank_kernel<T>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+  CBK_CUDA(cudaFuncSetAttribute(maxsim_rerank_kernel<T, kCvtBf16>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                 static_cast<int>(smem)));
   const int64_t n_segs = (n_cand + kSegCands - 1) / kSegCands;
   const int64_t want = (n_segs + kWarps - 1) / kWarps;
   const int grid = static_cast<int>(std::max<int64_t>(1, std::min<int64_t>(want, static_cast<int64_t>(sm_count()) * kCtasPerSm)));
-  maxsim_rerank_kernel<T><<<grid, kWarps * 32, smem, stream>>>(tmap, pfxsum, doclens, n_docs, strides, Q, q_len,
+  maxsim_rerank_kernel<T, kCvtBf16><<<grid, kWarps * 32, smem, stream>>>(tmap, pfxsum, doclens, n_docs, strides, Q, q_len,
                                                               n_queries, cand_pids, rowptr, n_cand, out, counter);
   CBK_CUDA(cudaGetLastError());
   count_launch();
@@ -287,7 +305,7 @@ int rerank_dispatch(const void* d_store, int store_dtype, int64_t n_store_rows, 
                     const int32_t* d_doclens, int64_t n_docs, const int32_t* strides, int n_strides,
                     const float* d_Q, int q_len, int64_t n_queries, const int64_t* d_cand_pids,
                     const int64_t* d_cand_rowptr, int64_t n_cand_total, float* d_out_scores, void* d_workspace,
-                    cudaStream_t stream) {
+                    int flags, cudaStream_t stream) {
   CUtensorMap tmap;
   int rc = make_store_tensor_map(&tmap, d_store, n_store_rows, dim, 64, kTileRows);
   if (rc != CBK_OK) return rc;
@@ -297,10 +315,13 @@ int rerank_dispatch(const void* d_store, int store_dtype, int64_t n_store_rows, 
   unsigned int* counter = static_cast<unsigned int*>(d_workspace);
   CBK_CUDA(cudaMemsetAsync(counter, 0, sizeof(unsigned int), stream));
   if (store_dtype == CBK_F16)
-    return launch<__half>(tmap, d_pfxsum, d_doclens, n_docs, ss, d_Q, q_len, n_queries, d_cand_pids, d_cand_rowptr,
-                          n_cand_total, d_out_scores, counter, stream);
-  return launch<__nv_bfloat16>(tmap, d_pfxsum, d_doclens, n_docs, ss, d_Q, q_len, n_queries, d_cand_pids,
-                               d_cand_rowptr, n_cand_total, d_out_scores, counter, stream);
+    return launch<__half, false>(tmap, d_pfxsum, d_doclens, n_docs, ss, d_Q, q_len, n_queries, d_cand_pids,
+                                 d_cand_rowptr, n_cand_total, d_out_scores, counter, stream);
+  if (flags & CBK_FLAG_BF16_NATIVE_MMA)
+    return launch<__nv_bfloat16, false>(tmap, d_pfxsum, d_doclens, n_docs, ss, d_Q, q_len, n_queries, d_cand_pids,
+                                        d_cand_rowptr, n_cand_total, d_out_scores, counter, stream);
+  return launch<__half, true>(tmap, d_pfxsum, d_doclens, n_docs, ss, d_Q, q_len, n_queries, d_cand_pids,
+                              d_cand_rowptr, n_cand_total, d_out_scores, counter, stream);
 }
 
 }  // namespace cbk

@@ -42,7 +42,7 @@ def _workspace(device: torch.device) -> torch.Tensor:
 
 def maxsim_rerank(store: torch.Tensor, pfxsum: torch.Tensor, doclens: torch.Tensor, strides: Sequence[int],
                   Q: torch.Tensor, cand_pids: torch.Tensor, cand_rowptr: torch.Tensor,
-                  out: Optional[torch.Tensor] = None) -> torch.Tensor:
+                  out: Optional[torch.Tensor] = None, flags: int = 0) -> torch.Tensor:
     """scores[c] for the CSR candidate lists; see cbk_maxsim_rerank in include/colbert_b200.h.
 
     store [rows, dim] fp16|bf16 · pfxsum [n_docs+1] int64 · doclens [n_docs] int32 · Q [B, q_len, dim] fp32
@@ -73,7 +73,7 @@ def maxsim_rerank(store: torch.Tensor, pfxsum: torch.Tensor, doclens: torch.Tens
         rc = lib.cbk_maxsim_rerank(_ptr(store), _lib.dtype_code(store.dtype), store.size(0), dim, _ptr(pfxsum),
                                    _ptr(doclens), doclens.numel(), C.cast(st, C.c_void_p), len(strides), _ptr(Q),
                                    q_len, n_q, _ptr(cand_pids), _ptr(cand_rowptr), n, _ptr(out), _ptr(ws),
-                                   ws.numel(), C.c_void_p(_lib.current_stream_ptr(dev)))
+                                   ws.numel(), int(flags), C.c_void_p(_lib.current_stream_ptr(dev)))
     _lib.check("cbk_maxsim_rerank", rc)
     return out
 

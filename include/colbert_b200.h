@@ -41,6 +41,7 @@ extern "C" {
 #define CBK_ABI_VERSION 1
 #define CBK_MAX_STRIDES 8      /* the reference produces at most 4 (percentiles 25/50/75 + max) */
 #define CBK_MAX_QLEN 32        /* query rows per launch; longer queries are split by the caller  */
+#define CBK_FLAG_BF16_NATIVE_MMA 1
 
 typedef enum cbk_status {
   CBK_OK = 0,
@@ -96,6 +97,13 @@ uint64_t cbk_launch_count(void);
  *                  un-permute, colbert_ranker.py:120-122, is therefore not needed)
  *   d_workspace    ≥ cbk_maxsim_rerank_workspace_bytes() bytes
  *
+ *   flags          0, or CBK_FLAG_BF16_NATIVE_MMA.  By default a bf16 store is converted to fp16 in
+ *                  registers (exact for values in fp16's normal range — ColBERT embeddings are
+ *                  L2-normalised, BaseModel.py:26) and multiplied with the query rounded to fp16
+ *                  (11 significant bits; measured worst relative score error 2e-4).  With the flag the
+ *                  bf16 values are multiplied directly with the query rounded to bf16 (8 bits; 1.2e-3,
+ *                  outside the 1e-3 parity tolerance but safe for stores beyond fp16's range).
+ *
  * Supported: dim == 128, 1 ≤ q_len ≤ CBK_MAX_QLEN, n_store_rows < 2^31.  pids are range-checked on
  * the device; an out-of-range pid yields NaN at its position.
  * ------------------------------------------------------------------------------------------------ */
@@ -106,7 +114,7 @@ int cbk_maxsim_rerank(const void* d_store, int store_dtype, int64_t n_store_rows
                       const int32_t* strides, int n_strides,
                       const float* d_Q, int q_len, int64_t n_queries,
                       const int64_t* d_cand_pids, const int64_t* d_cand_rowptr, int64_t n_cand_total,
-                      float* d_out_scores, void* d_workspace, size_t workspace_bytes, void* stream);
+                      float* d_out_scores, void* d_workspace, size_t workspace_bytes, int flags, void* stream);
 
 /* ------------------------------------------------------------------------------------------------
  * Per-query top-k — replaces colbert_ranker.py:128-130 (full sort, descending, truncate to depth).

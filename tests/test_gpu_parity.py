@@ -125,6 +125,29 @@ def test_batched_scores_match_oracle(dev, store_dtype, q_len):
     assert worst <= SCORE_RTOL
 
 
+def test_bf16_native_mma_flag(dev):
+    """CBK_FLAG_BF16_NATIVE_MMA multiplies bf16 x bf16 directly: query rounded to 8 significant bits,
+    documented error ~1.2e-3 (outside the parity tolerance, hence not the default)."""
+    from colbert_b200 import _lib, synthetic
+    from colbert_b200.ranking import ColbertRanker
+    index = synthetic.make_index(101, 3000, dim=128, lo=1, hi=180)
+    emb = torch.from_numpy(index.emb).to(torch.bfloat16)
+    ranker = ColbertRanker.from_tensors(emb, index.doclens.tolist(), device=dev, store_dtype=torch.bfloat16)
+    Q = synthetic.make_queries(202, 2, 32, 128)
+    cand = synthetic.make_candidates(303, 2, index.num_docs, 333)
+    rowptr = torch.arange(0, 3 * 333, 333, dtype=torch.int64, device=dev)
+    args = (torch.from_numpy(Q).to(dev), torch.from_numpy(cand).reshape(-1).to(dev), rowptr)
+    default = ranker.score_candidates(*args).cpu().numpy()
+    ranker.kernel_flags = _lib.CBK_FLAG_BF16_NATIVE_MMA
+    native = ranker.score_candidates(*args).cpu().numpy()
+    store, pf = O.pad_store(emb.float().numpy()), O.doclens_pfxsum(index.doclens)
+    ref = np.concatenate([O.maxsim_exact(store, index.doclens, pf, ranker.strides, Q[b], cand[b]) for b in range(2)])
+    e_def = np.max(np.abs(default - ref) / np.maximum(np.abs(ref), 1.0))
+    e_nat = np.max(np.abs(native - ref) / np.maximum(np.abs(ref), 1.0))
+    print(f"bf16 store: default (fp16 MMA) {e_def:.3e}, native bf16 MMA {e_nat:.3e}")
+    assert e_def <= SCORE_RTOL and e_nat <= 4e-3 and e_def < e_nat
+
+
 def test_ragged_candidate_lists_and_empty_queries(dev):
     """CSR candidate lists of very different lengths (incl. empty and 1-candidate queries)."""
     from colbert_b200 import synthetic
