@@ -6,9 +6,10 @@
 //
 // Design (DESIGN.md §"rerank kernel"):
 //   * every warp is an autonomous streaming unit: it owns a 4-stage ring of 16-row × 256-B document
-//     tiles in shared memory, issues its own TMA loads (2-D tensor map over the flat store, row
-//     coordinate = pfxsum[pid] + 16·tile, 128-byte swizzle) and waits on its own mbarriers — there is
-//     no block-wide barrier anywhere in the main loop;
+//     tiles in shared memory, issues its own TMA loads (2-D tensor maps over the flat store, row
+//     coordinate = pfxsum[pid] + 16·tile, 128-byte swizzle; one map per box height 1..16 so a
+//     document's tail tile reads exactly its remaining rows) and waits on its own mbarriers — there
+//     is no block-wide barrier anywhere in the main loop;
 //   * the query matrix (≤ 32 × 128) lives in REGISTERS as mma.sync A-fragments (64 regs) for as long
 //     as the warp keeps scoring candidates of the same query;
 //   * document tiles are read with conflict-free ldmatrix.x4 straight out of the swizzled layout the
@@ -38,6 +39,12 @@ struct StrideSet {
   int v[CBK_MAX_STRIDES];
 };
 
+// one tensor map per box height 1..16: the last tile of a document is fetched with exactly the rows
+// it still has, so no byte beyond the document is read from HBM
+struct TmapSet {
+  CUtensorMap m[kTileRows];
+};
+
 struct __align__(1024) WarpSmem {
   uint8_t tiles[kStages][kTileBytes];
   int2 meta[kSegCands];  // .x = first store row, .y = doclen (-1: pid out of range)
@@ -59,7 +66,7 @@ __device__ __forceinline__ uint32_t bf16x2_to_f16x2(uint32_t v) {
 // (converted in registers after ldmatrix) so that the query keeps 11 significant bits instead of 8.
 template <typename T, bool kCvtBf16>
 __global__ void __launch_bounds__(kWarps * 32, kCtasPerSm)
-maxsim_rerank_kernel(const __grid_constant__ CUtensorMap tmap, const int64_t* __restrict__ pfxsum,
+maxsim_rerank_kernel(const __grid_constant__ TmapSet tmaps, const int64_t* __restrict__ pfxsum,
                      const int32_t* __restrict__ doclens, int64_t n_docs, StrideSet strides,
                      const float* __restrict__ Q, int q_len, int64_t n_queries,
                      const int64_t* __restrict__ cand_pids, const int64_t* __restrict__ rowptr,
@@ -73,8 +80,8 @@ maxsim_rerank_kernel(const __grid_constant__ CUtensorMap tmap, const int64_t* __
   const uint32_t tiles_addr = smem_u32(&ws->tiles[0][0]);
   const uint32_t full_addr = smem_u32(&ws->full[0]);
 
+  if (lane < kTileRows) tma_prefetch_desc(&tmaps.m[lane]);
   if (lane == 0) {
-    tma_prefetch_desc(&tmap);
     for (int s = 0; s < kStages; ++s) mbar_init(full_addr + 8 * s, 1);
     fence_mbar_init();
   }
@@ -133,9 +140,11 @@ maxsim_rerank_kernel(const __grid_constant__ CUtensorMap tmap, const int64_t* __
         const uint32_t bar = full_addr + 8 * st;
         const uint32_t dst = tiles_addr + st * kTileBytes;
         const int row = m.x + pt * kTileRows;
-        mbar_arrive_expect_tx(bar, kTileBytes);
-        tma_load_2d(dst, &tmap, 0, row, bar, kEvictFirst);
-        tma_load_2d(dst + kHalfBytes, &tmap, 64, row, bar, kEvictFirst);
+        const int rows = min(kTileRows, m.y - pt * kTileRows);   // exact: the tail tile is shorter
+        const CUtensorMap* tm = &tmaps.m[rows - 1];
+        mbar_arrive_expect_tx(bar, rows * kDim * 2);
+        tma_load_2d(dst, tm, 0, row, bar, kEvictFirst);
+        tma_load_2d(dst + kHalfBytes, tm, 64, row, bar, kEvictFirst);
       }
       ++issued;
       ++pt;
@@ -193,6 +202,7 @@ maxsim_rerank_kernel(const __grid_constant__ CUtensorMap tmap, const int64_t* __
         mbar_wait(full_addr + 8 * st, (consumed / kStages) & 1u);
         const uint32_t sbase = tiles_addr + st * kTileBytes;
 
+        const int n_sub = (len - t * kTileRows > 8) ? 2 : 1;   // a short tail tile has one 8-token sub-tile
         float acc[2][2][4];  // [sub-tile of 8 tokens][m-tile][reg]
 #pragma unroll
         for (int s = 0; s < 2; ++s)
@@ -207,6 +217,7 @@ maxsim_rerank_kernel(const __grid_constant__ CUtensorMap tmap, const int64_t* __
           const uint32_t coff = (p >> 1) * kHalfBytes + (((chunk ^ lrow) & 7) << 4);
 #pragma unroll
           for (int s = 0; s < 2; ++s) {
+            if (s >= n_sub) break;
             uint32_t b0, b1, b2, b3;
             ldmatrix_x4(sbase + coff + (s * 8 + lrow) * 128, b0, b1, b2, b3);
             if (kCvtBf16) {
@@ -237,6 +248,7 @@ maxsim_rerank_kernel(const __grid_constant__ CUtensorMap tmap, const int64_t* __
         } else {
 #pragma unroll
           for (int s = 0; s < 2; ++s) {
+            if (s >= n_sub) break;
             const bool v0 = tok0 + s * 8 < len;
             const bool v1 = tok0 + s * 8 + 1 < len;
 #pragma unroll
@@ -283,7 +295,7 @@ maxsim_rerank_kernel(const __grid_constant__ CUtensorMap tmap, const int64_t* __
 }
 
 template <typename T, bool kCvtBf16>
-int launch(const CUtensorMap& tmap, const int64_t* pfxsum, const int32_t* doclens, int64_t n_docs,
+int launch(const TmapSet& tmaps, const int64_t* pfxsum, const int32_t* doclens, int64_t n_docs,
            const StrideSet& strides, const float* Q, int q_len, int64_t n_queries, const int64_t* cand_pids,
            const int64_t* rowptr, int64_t n_cand, float* out, unsigned int* counter, cudaStream_t stream) {
   const size_t smem = kWarps * sizeof(WarpSmem) + 1024;
@@ -292,7 +304,7 @@ int launch(const CUtensorMap& tmap, const int64_t* pfxsum, const int32_t* doclen
   const int64_t n_segs = (n_cand + kSegCands - 1) / kSegCands;
   const int64_t want = (n_segs + kWarps - 1) / kWarps;
   const int grid = static_cast<int>(std::max<int64_t>(1, std::min<int64_t>(want, static_cast<int64_t>(sm_count()) * kCtasPerSm)));
-  maxsim_rerank_kernel<T, kCvtBf16><<<grid, kWarps * 32, smem, stream>>>(tmap, pfxsum, doclens, n_docs, strides, Q, q_len,
+  maxsim_rerank_kernel<T, kCvtBf16><<<grid, kWarps * 32, smem, stream>>>(tmaps, pfxsum, doclens, n_docs, strides, Q, q_len,
                                                               n_queries, cand_pids, rowptr, n_cand, out, counter);
   CBK_CUDA(cudaGetLastError());
   count_launch();
@@ -306,21 +318,31 @@ int rerank_dispatch(const void* d_store, int store_dtype, int64_t n_store_rows, 
                     const float* d_Q, int q_len, int64_t n_queries, const int64_t* d_cand_pids,
                     const int64_t* d_cand_rowptr, int64_t n_cand_total, float* d_out_scores, void* d_workspace,
                     int flags, cudaStream_t stream) {
-  CUtensorMap tmap;
-  int rc = make_store_tensor_map(&tmap, d_store, n_store_rows, dim, 64, kTileRows);
-  if (rc != CBK_OK) return rc;
+  // tensor maps depend only on (base, rows): keep the last set per thread instead of re-encoding
+  static thread_local TmapSet tmaps;
+  static thread_local const void* cached_base = nullptr;
+  static thread_local int64_t cached_rows = -1;
+  if (cached_base != d_store || cached_rows != n_store_rows) {
+    cached_base = nullptr;
+    for (int r = 1; r <= kTileRows; ++r) {
+      int rc = make_store_tensor_map(&tmaps.m[r - 1], d_store, n_store_rows, dim, 64, r);
+      if (rc != CBK_OK) return rc;
+    }
+    cached_base = d_store;
+    cached_rows = n_store_rows;
+  }
   StrideSet ss;
   ss.n = n_strides;
   for (int i = 0; i < CBK_MAX_STRIDES; ++i) ss.v[i] = i < n_strides ? strides[i] : -1;
   unsigned int* counter = static_cast<unsigned int*>(d_workspace);
   CBK_CUDA(cudaMemsetAsync(counter, 0, sizeof(unsigned int), stream));
   if (store_dtype == CBK_F16)
-    return launch<__half, false>(tmap, d_pfxsum, d_doclens, n_docs, ss, d_Q, q_len, n_queries, d_cand_pids,
+    return launch<__half, false>(tmaps, d_pfxsum, d_doclens, n_docs, ss, d_Q, q_len, n_queries, d_cand_pids,
                                  d_cand_rowptr, n_cand_total, d_out_scores, counter, stream);
   if (flags & CBK_FLAG_BF16_NATIVE_MMA)
-    return launch<__nv_bfloat16, false>(tmap, d_pfxsum, d_doclens, n_docs, ss, d_Q, q_len, n_queries, d_cand_pids,
+    return launch<__nv_bfloat16, false>(tmaps, d_pfxsum, d_doclens, n_docs, ss, d_Q, q_len, n_queries, d_cand_pids,
                                         d_cand_rowptr, n_cand_total, d_out_scores, counter, stream);
-  return launch<__half, true>(tmap, d_pfxsum, d_doclens, n_docs, ss, d_Q, q_len, n_queries, d_cand_pids,
+  return launch<__half, true>(tmaps, d_pfxsum, d_doclens, n_docs, ss, d_Q, q_len, n_queries, d_cand_pids,
                               d_cand_rowptr, n_cand_total, d_out_scores, counter, stream);
 }
 

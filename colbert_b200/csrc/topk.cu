@@ -36,7 +36,7 @@ topk_per_query_kernel(const float* __restrict__ scores, const int64_t* __restric
   for (int i = tid; i < P; i += kTopkThreads) {
     uint64_t key = 0;  // padding: below every real key
     if (i < n) {
-      const uint32_t s = float_to_ordered(scores[beg + i]);
+      const uint32_t s = float_to_ordered(scores[beg + i] + 0.0f);  // -0.0 → +0.0: they tie
       const uint32_t p = ~static_cast<uint32_t>(cand_pids[beg + i]);
       key = (static_cast<uint64_t>(s) << 32) | p;
     }
