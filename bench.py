@@ -208,15 +208,32 @@ def run_ours(args, rank, world, local_rank):
     dtype = torch.bfloat16 if args.dtype == "bf16" else torch.float16
     dim, q_len = 128, 32
 
+    # Weak scaling: every GPU holds a shard of `--docs` documents (pids [rank*docs, (rank+1)*docs)); the job
+    # scores `--queries * world` queries, each with `--cands` candidates drawn over the WHOLE corpus, so every
+    # GPU scores ~queries*cands candidates per step.  All ranks see the same (replicated) queries and lists.
     store, doclens = build_store(torch, dev, args.docs, dim, dtype, seed=1234 + rank)
     ranker = ColbertRanker.from_store(store, doclens)
-    Q_host, cand_host = build_queries(torch, args.queries, q_len, dim, args.docs, args.cands, seed=4321 + rank)
+    n_queries = args.queries * world
+    Q_host, cand_host = build_queries(torch, n_queries, q_len, dim, args.docs * world, args.cands, seed=4321)
     Q_pin, cand_pin = Q_host.pin_memory(), cand_host.pin_memory()
     Q_dev, cand_dev = Q_host.to(dev), cand_host.to(dev).reshape(-1).contiguous()
-    n_cand_total = args.queries * args.cands
+    n_cand_total = n_queries * args.cands
     rowptr = torch.arange(0, n_cand_total + 1, args.cands, dtype=torch.int64, device=dev)
-    algo_bytes = int(ranker._doclens_dev[cand_dev].to(torch.int64).sum().item()) * dim * 2   # Σ doclen · dim · 2 B
     k = min(args.depth, args.cands)
+    sharded = None
+    if world > 1:
+        from colbert_b200.sharding import ShardedColbertRanker
+        from colbert_b200.ranking.colbert_ranker import torch_percentile
+        all_dl = [torch.empty_like(doclens, device=dev) for _ in range(world)]
+        dist.all_gather(all_dl, doclens.to(dev))
+        gdl = torch.cat(all_dl).cpu()
+        gstrides = sorted({torch_percentile(gdl, p) for p in (25, 50, 75)} | {int(gdl.max())})
+        sharded = ShardedColbertRanker(ranker, rank * args.docs, gstrides)
+    local = cand_dev - rank * args.docs
+    mine = (local >= 0) & (local < args.docs)
+    algo_bytes = int(ranker._doclens_dev[local[mine]].to(torch.int64).sum().item()) * dim * 2   # Σ doclen · dim · 2 B
+    n_local_cands = int(mine.sum().item())
+    del local, mine
     torch.cuda.synchronize()
 
     def barrier():
@@ -234,7 +251,11 @@ def run_ours(args, rank, world, local_rank):
         scores = ranker.score_candidates(Q_dev, cand_dev, rowptr)
         if i is not None:
             ev_k1[i].record()
-        return kernels.topk_per_query(scores, cand_dev, rowptr, k, args.cands)
+        if sharded is None:
+            return kernels.topk_per_query(scores, cand_dev, rowptr, k, args.cands)
+        keys = kernels.topk_per_query(scores, cand_dev, rowptr, k, args.cands,
+                                      flags=_lib.CBK_TOPK_NEG_INF_IS_PADDING, as_keys=True)
+        return sharded._merge(sharded._exchange(keys), k)          # NCCL all-gather of packed keys + merge
 
     for _ in range(args.warmup):
         step_device()
@@ -254,7 +275,7 @@ def run_ours(args, rank, world, local_rank):
 
     # ---- end to end through the public API with host buffers: `e2e` ---------------------------------
     def step_e2e():
-        pids, scores = ranker.rank_forward_batch(Q_pin, cand_pin, depth=args.depth)
+        pids, scores = (sharded or ranker).rank_forward_batch(Q_pin, cand_pin, depth=args.depth)
         return pids.cpu(), scores.cpu()                 # device→host read of the step's result (synchronises)
 
     for _ in range(args.warmup):
@@ -270,10 +291,16 @@ def run_ours(args, rank, world, local_rank):
     clocks = sampler.stop()
 
     times = torch.tensor([ms_total, e2e_ms_total, kern_ms], dtype=torch.float64, device=dev)
+    sums = torch.tensor([float(algo_bytes), float(n_local_cands), float(launches)], dtype=torch.float64, device=dev)
     if world > 1:
         dist.all_reduce(times, op=dist.ReduceOp.MAX)
+        dist.all_reduce(sums, op=dist.ReduceOp.SUM)
     ms_total, e2e_ms_total, kern_ms = times.tolist()
-    total_cands = n_cand_total * world
+    algo_bytes_all, scored_all, launches_all = sums.tolist()
+    total_cands = n_cand_total                      # every candidate of every query is scored by exactly one GPU
+    assert int(scored_all) == total_cands, (scored_all, total_cands)
+    algo_bytes = algo_bytes_all / world             # per-GPU (per-launch) average for the roofline line
+    launches = int(launches_all)
 
     if rank == 0:
         peaks_path = os.path.join(ROOT, "MEASURED_PEAKS.json")
@@ -287,20 +314,21 @@ def run_ours(args, rank, world, local_rank):
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_total / args.steps,
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": args.dtype, "data": "synthetic",
             "config": {
-                "workload": f"rerank: {args.queries} queries x {args.cands} candidates per GPU, q_len 32, dim 128, "
-                            f"doclen U[1,180], {args.dtype} store of {args.docs} docs per GPU, top-{k} per query "
-                            f"(BASELINE.json configs[1])",
+                "workload": f"rerank: {n_queries} queries x {args.cands} candidates ({args.queries}x{args.cands} per GPU), "
+                            f"q_len 32, dim 128, doclen U[1,180], {args.dtype} store of {args.docs} docs per GPU, "
+                            f"top-{k} per query (BASELINE.json configs[1])",
                 "store_bytes_per_gpu": int(store.numel() * 2),
                 "l2_policy": "inputs larger than L2: each step gathers "
                              f"{algo_bytes / 1e9:.1f} GB of distinct document rows from a {store.numel() * 2 / 1e9:.1f} GB store",
-                "parallelism": f"doc-sharded x{world}" if world > 1 else "single GPU",
+                "parallelism": (f"store sharded by pid range over {world} GPUs, queries replicated, one NCCL all-gather "
+                                f"of packed top-{k} keys per step + replicated merge") if world > 1 else "single GPU",
             },
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                          "traffic": None, "kernel": "maxsim_rerank_kernel", "algorithmic_bytes_per_launch": algo_bytes,
                          "kernel_ms": kern_ms, "peak_source": peak_src},
             "e2e": {"value": total_cands * args.steps / (e2e_ms_total * 1e-3), "unit": UNIT,
-                    "h2d_bytes_per_step": int(Q_pin.numel() * 4 + cand_pin.numel() * 8),
-                    "d2h_bytes_per_step": int(args.queries * k * (8 + 4)), "ms_per_step": e2e_ms_total / args.steps},
+                    "h2d_bytes_per_step": int(Q_pin.numel() * 4 + cand_pin.numel() * 8) * world,
+                    "d2h_bytes_per_step": int(n_queries * k * (8 + 4)) * world, "ms_per_step": e2e_ms_total / args.steps},
             "gpu_launches": int(launches),
             "clocks": clocks,
         }

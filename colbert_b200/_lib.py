@@ -19,6 +19,8 @@ CBK_MASK_NONE, CBK_MASK_U8, CBK_MASK_I64, CBK_MASK_F32 = 0, 1, 2, 3
 CBK_MAX_STRIDES = 8
 CBK_MAX_QLEN = 32
 CBK_FLAG_BF16_NATIVE_MMA = 1
+CBK_FLAG_SKIP_FOREIGN_PIDS = 2
+CBK_TOPK_NEG_INF_IS_PADDING = 1
 
 # name → (restype, argtypes); mirrors include/colbert_b200.h one to one
 _vp, _i64, _i32, _sz = C.c_void_p, C.c_int64, C.c_int, C.c_size_t
@@ -28,10 +30,12 @@ SIGNATURES = {
     "cbk_device_supported": (C.c_int, [C.c_int]),
     "cbk_launch_count": (C.c_uint64, []),
     "cbk_maxsim_rerank_workspace_bytes": (_sz, []),
-    "cbk_maxsim_rerank": (C.c_int, [_vp, _i32, _i64, _i32, _vp, _vp, _i64, _vp, _i32, _vp, _i32, _i64,
+    "cbk_maxsim_rerank": (C.c_int, [_vp, _i32, _i64, _i32, _vp, _vp, _i64, _i64, _vp, _i32, _vp, _i32, _i64,
                                     _vp, _vp, _i64, _vp, _vp, _sz, _i32, _vp]),
     "cbk_topk_max_candidates": (_i64, []),
-    "cbk_topk_per_query": (C.c_int, [_vp, _vp, _vp, _i64, _i64, _i32, _vp, _vp, _vp]),
+    "cbk_topk_per_query": (C.c_int, [_vp, _vp, _vp, _i64, _i64, _i32, _i32, _vp, _vp, _vp]),
+    "cbk_topk_per_query_keys": (C.c_int, [_vp, _vp, _vp, _i64, _i64, _i32, _i32, _vp, _vp]),
+    "cbk_merge_topk_keys": (C.c_int, [_vp, _i32, _i64, _i32, _i32, _vp, _vp, _vp]),
     "cbk_gather_rows": (C.c_int, [_vp, _i32, _i64, _i32, _vp, _vp, _i64, _vp, _i64, _i32, _vp, _vp, _vp]),
     "cbk_mask_cast_rows": (C.c_int, [_vp, _i32, _i64, _i32, _vp, _i32, _vp, _i32, _vp]),
 }

@@ -12,9 +12,11 @@
 namespace cbk {
 
 // dispatchers implemented in the kernel translation units
-int rerank_dispatch(const void*, int, int64_t, int, const int64_t*, const int32_t*, int64_t, const int32_t*, int,
+int rerank_dispatch(const void*, int, int64_t, int, const int64_t*, const int32_t*, int64_t, int64_t, const int32_t*, int,
                     const float*, int, int64_t, const int64_t*, const int64_t*, int64_t, float*, void*, int, cudaStream_t);
-int topk_dispatch(const float*, const int64_t*, const int64_t*, int64_t, int64_t, int, float*, int64_t*, cudaStream_t);
+int topk_dispatch(const float*, const int64_t*, const int64_t*, int64_t, int64_t, int, int, float*, int64_t*, uint64_t*,
+                  cudaStream_t);
+int merge_dispatch(const uint64_t*, int, int64_t, int, int, float*, int64_t*, cudaStream_t);
 int64_t topk_max_candidates();
 int gather_dispatch(const void*, int, int64_t, int, const int64_t*, const int32_t*, int64_t, const int64_t*, int64_t,
                     int, float*, uint8_t*, cudaStream_t);
@@ -121,7 +123,8 @@ uint64_t cbk_launch_count(void) { return g_launches.load(std::memory_order_relax
 size_t cbk_maxsim_rerank_workspace_bytes(void) { return 256; }
 
 int cbk_maxsim_rerank(const void* d_store, int store_dtype, int64_t n_store_rows, int dim, const int64_t* d_pfxsum,
-                      const int32_t* d_doclens, int64_t n_docs, const int32_t* strides, int n_strides, const float* d_Q,
+                      const int32_t* d_doclens, int64_t n_docs, int64_t pid_base, const int32_t* strides, int n_strides,
+                      const float* d_Q,
                       int q_len, int64_t n_queries, const int64_t* d_cand_pids, const int64_t* d_cand_rowptr,
                       int64_t n_cand_total, float* d_out_scores, void* d_workspace, size_t workspace_bytes,
                       int flags, void* stream) {
@@ -146,28 +149,56 @@ int cbk_maxsim_rerank(const void* d_store, int store_dtype, int64_t n_store_rows
   int rc = check_device();
   if (rc != CBK_OK) return rc;
   if (n_cand_total == 0) return CBK_OK;
-  return rerank_dispatch(d_store, store_dtype, n_store_rows, dim, d_pfxsum, d_doclens, n_docs, strides, n_strides, d_Q,
+  return rerank_dispatch(d_store, store_dtype, n_store_rows, dim, d_pfxsum, d_doclens, n_docs, pid_base, strides, n_strides, d_Q,
                          q_len, n_queries, d_cand_pids, d_cand_rowptr, n_cand_total, d_out_scores, d_workspace, flags,
                          static_cast<cudaStream_t>(stream));
 }
 
 int64_t cbk_topk_max_candidates(void) { return topk_max_candidates(); }
 
-int cbk_topk_per_query(const float* d_scores, const int64_t* d_cand_pids, const int64_t* d_cand_rowptr,
-                       int64_t n_queries, int64_t max_cand_per_query, int k, float* d_out_scores, int64_t* d_out_pids,
-                       void* stream) {
-  CBK_CHECK_ARG(d_scores && d_cand_pids && d_cand_rowptr && d_out_scores && d_out_pids,
-                "cbk_topk_per_query: null pointer argument");
-  CBK_CHECK_ARG(n_queries > 0 && k > 0 && max_cand_per_query > 0, "cbk_topk_per_query: n_queries %lld, k %d, max_cand %lld",
+static int topk_common(const char* fn, const float* d_scores, const int64_t* d_cand_pids, const int64_t* d_cand_rowptr,
+                       int64_t n_queries, int64_t max_cand_per_query, int k, int flags, float* d_out_scores,
+                       int64_t* d_out_pids, uint64_t* d_out_keys, void* stream) {
+  CBK_CHECK_ARG(d_scores && d_cand_pids && d_cand_rowptr && ((d_out_scores && d_out_pids) || d_out_keys),
+                "%s: null pointer argument", fn);
+  CBK_CHECK_ARG(n_queries > 0 && k > 0 && max_cand_per_query > 0, "%s: n_queries %lld, k %d, max_cand %lld", fn,
                 (long long)n_queries, k, (long long)max_cand_per_query);
-  CBK_CHECK_SUPPORTED(max_cand_per_query <= topk_max_candidates(),
-                      "cbk_topk_per_query: %lld candidates per query exceeds the limit of %lld",
-                      (long long)max_cand_per_query, (long long)topk_max_candidates());
-  CBK_CHECK_SUPPORTED(n_queries < (1ll << 31), "cbk_topk_per_query: too many queries");
+  CBK_CHECK_SUPPORTED(max_cand_per_query <= topk_max_candidates(), "%s: %lld candidates per query exceeds the limit of %lld",
+                      fn, (long long)max_cand_per_query, (long long)topk_max_candidates());
+  CBK_CHECK_SUPPORTED(n_queries < (1ll << 31), "%s: too many queries", fn);
   int rc = check_device();
   if (rc != CBK_OK) return rc;
-  return topk_dispatch(d_scores, d_cand_pids, d_cand_rowptr, n_queries, max_cand_per_query, k, d_out_scores, d_out_pids,
-                       static_cast<cudaStream_t>(stream));
+  return topk_dispatch(d_scores, d_cand_pids, d_cand_rowptr, n_queries, max_cand_per_query, k, flags, d_out_scores,
+                       d_out_pids, d_out_keys, static_cast<cudaStream_t>(stream));
+}
+
+int cbk_topk_per_query(const float* d_scores, const int64_t* d_cand_pids, const int64_t* d_cand_rowptr,
+                       int64_t n_queries, int64_t max_cand_per_query, int k, int flags, float* d_out_scores,
+                       int64_t* d_out_pids, void* stream) {
+  CBK_CHECK_ARG(d_out_scores && d_out_pids, "cbk_topk_per_query: null pointer argument");
+  return topk_common("cbk_topk_per_query", d_scores, d_cand_pids, d_cand_rowptr, n_queries, max_cand_per_query, k, flags,
+                     d_out_scores, d_out_pids, nullptr, stream);
+}
+
+int cbk_topk_per_query_keys(const float* d_scores, const int64_t* d_cand_pids, const int64_t* d_cand_rowptr,
+                            int64_t n_queries, int64_t max_cand_per_query, int k, int flags, uint64_t* d_out_keys,
+                            void* stream) {
+  CBK_CHECK_ARG(d_out_keys, "cbk_topk_per_query_keys: null pointer argument");
+  return topk_common("cbk_topk_per_query_keys", d_scores, d_cand_pids, d_cand_rowptr, n_queries, max_cand_per_query, k,
+                     flags, nullptr, nullptr, d_out_keys, stream);
+}
+
+int cbk_merge_topk_keys(const uint64_t* d_keys, int world, int64_t n_queries, int k_in, int k, float* d_out_scores,
+                        int64_t* d_out_pids, void* stream) {
+  CBK_CHECK_ARG(d_keys && d_out_scores && d_out_pids, "cbk_merge_topk_keys: null pointer argument");
+  CBK_CHECK_ARG(world > 0 && n_queries > 0 && k_in > 0 && k > 0, "cbk_merge_topk_keys: sizes must be positive");
+  CBK_CHECK_SUPPORTED(static_cast<int64_t>(world) * k_in <= topk_max_candidates(),
+                      "cbk_merge_topk_keys: world*k_in = %lld exceeds the limit of %lld", (long long)world * k_in,
+                      (long long)topk_max_candidates());
+  CBK_CHECK_SUPPORTED(n_queries < (1ll << 31), "cbk_merge_topk_keys: too many queries");
+  int rc = check_device();
+  if (rc != CBK_OK) return rc;
+  return merge_dispatch(d_keys, world, n_queries, k_in, k, d_out_scores, d_out_pids, static_cast<cudaStream_t>(stream));
 }
 
 int cbk_gather_rows(const void* d_store, int store_dtype, int64_t n_store_rows, int dim, const int64_t* d_pfxsum,

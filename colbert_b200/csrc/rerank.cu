@@ -47,8 +47,9 @@ struct TmapSet {
 
 struct __align__(1024) WarpSmem {
   uint8_t tiles[kStages][kTileBytes];
-  int2 meta[kSegCands];  // .x = first store row, .y = doclen (-1: pid out of range)
+  int2 meta[kSegCands];     // compacted list of scorable candidates: .x = first store row, .y = doclen (> 0)
   uint64_t full[kStages];
+  uint8_t cidx[kSegCands];  // position of each compacted entry inside the segment
 };
 static_assert(sizeof(WarpSmem) % 1024 == 0, "per-warp smem must keep 1024-B swizzle-atom alignment");
 
@@ -67,7 +68,8 @@ __device__ __forceinline__ uint32_t bf16x2_to_f16x2(uint32_t v) {
 template <typename T, bool kCvtBf16>
 __global__ void __launch_bounds__(kWarps * 32, kCtasPerSm)
 maxsim_rerank_kernel(const __grid_constant__ TmapSet tmaps, const int64_t* __restrict__ pfxsum,
-                     const int32_t* __restrict__ doclens, int64_t n_docs, StrideSet strides,
+                     const int32_t* __restrict__ doclens, int64_t n_docs, int64_t pid_base, int skip_foreign,
+                     StrideSet strides,
                      const float* __restrict__ Q, int q_len, int64_t n_queries,
                      const int64_t* __restrict__ cand_pids, const int64_t* __restrict__ rowptr,
                      int64_t n_cand, float* __restrict__ out, unsigned int* __restrict__ seg_counter) {
@@ -107,23 +109,41 @@ maxsim_rerank_kernel(const __grid_constant__ TmapSet tmaps, const int64_t* __res
     const int nc = static_cast<int>(min(static_cast<int64_t>(kSegCands), n_cand - c0));
 
     // ---- segment prologue: pid → (first row, doclen)   [colbert_ranker.py:88] --------------------
+    // Candidates that need no scoring are answered here (empty document → 0; pid outside this
+    // shard → -inf when sharded, NaN otherwise); the rest are compacted, in order, into ws->meta.
     __syncwarp();
-    for (int i = lane; i < nc; i += 32) {
-      const int64_t pid = cand_pids[c0 + i];
-      int2 m = make_int2(0, -1);
-      if (pid >= 0 && pid < n_docs) m = make_int2(static_cast<int>(pfxsum[pid]), doclens[pid]);
-      ws->meta[i] = m;
+    int nv = 0;
+    for (int i0 = 0; i0 < nc; i0 += 32) {
+      const int i = i0 + lane;
+      int row = 0, len = -1;
+      if (i < nc) {
+        const int64_t pid = cand_pids[c0 + i] - pid_base;
+        if (pid >= 0 && pid < n_docs) {
+          row = static_cast<int>(pfxsum[pid]);
+          len = doclens[pid];
+        }
+        if (len <= 0) out[c0 + i] = len == 0 ? 0.f : (skip_foreign ? -INFINITY : __int_as_float(0x7fc00000));
+      }
+      const unsigned int live = __ballot_sync(0xffffffffu, len > 0);
+      if (len > 0) {
+        const int slot = nv + __popc(live & ((1u << lane) - 1u));
+        ws->meta[slot] = make_int2(row, len);
+        ws->cidx[slot] = static_cast<uint8_t>(i);
+      }
+      nv += __popc(live);
     }
     __syncwarp();
+    if (nv == 0) continue;
 
     // ---- which query owns candidate c0: uniform guess, else binary search over rowptr -----------
-    int64_t q = static_cast<int64_t>((static_cast<double>(c0) * n_queries) / static_cast<double>(n_cand));
+    const int64_t cfirst = c0 + ws->cidx[0];
+    int64_t q = static_cast<int64_t>((static_cast<double>(cfirst) * n_queries) / static_cast<double>(n_cand));
     q = max(static_cast<int64_t>(0), min(q, n_queries - 1));
-    if (!(rowptr[q] <= c0 && c0 < rowptr[q + 1])) {
-      int64_t lo = 0, hi = n_queries - 1;  // last q with rowptr[q] <= c0
+    if (!(rowptr[q] <= cfirst && cfirst < rowptr[q + 1])) {
+      int64_t lo = 0, hi = n_queries - 1;  // last q with rowptr[q] <= cfirst
       while (lo < hi) {
         const int64_t mid = (lo + hi + 1) >> 1;
-        if (rowptr[mid] <= c0) lo = mid; else hi = mid - 1;
+        if (rowptr[mid] <= cfirst) lo = mid; else hi = mid - 1;
       }
       q = lo;
     }
@@ -131,9 +151,8 @@ maxsim_rerank_kernel(const __grid_constant__ TmapSet tmaps, const int64_t* __res
 
     // ---- producer cursor (runs kStages-1 tiles ahead of the consumer inside the segment) ---------
     int pc = 0, pt = 0;
-    while (pc < nc && ws->meta[pc].y <= 0) ++pc;
     auto issue_tile = [&]() {
-      if (pc >= nc) return;
+      if (pc >= nv) return;
       const int2 m = ws->meta[pc];
       if (lane == 0) {
         const uint32_t st = issued % kStages;
@@ -151,14 +170,13 @@ maxsim_rerank_kernel(const __grid_constant__ TmapSet tmaps, const int64_t* __res
       if (pt * kTileRows >= m.y) {
         pt = 0;
         ++pc;
-        while (pc < nc && ws->meta[pc].y <= 0) ++pc;
       }
     };
 #pragma unroll
     for (int s = 0; s < kStages - 1; ++s) issue_tile();
 
-    for (int ci = 0; ci < nc; ++ci) {
-      const int64_t c = c0 + ci;
+    for (int ci = 0; ci < nv; ++ci) {
+      const int64_t c = c0 + ws->cidx[ci];
       while (c >= q_end) {
         ++q;
         q_end = rowptr[q + 1];
@@ -193,7 +211,7 @@ maxsim_rerank_kernel(const __grid_constant__ TmapSet tmaps, const int64_t* __res
 
       const int2 m = ws->meta[ci];
       const int len = m.y;
-      const int ntiles = len > 0 ? (len + kTileRows - 1) / kTileRows : 0;
+      const int ntiles = (len + kTileRows - 1) / kTileRows;
       float rmax[2][2] = {{-INFINITY, -INFINITY}, {-INFINITY, -INFINITY}};
 
       for (int t = 0; t < ntiles; ++t) {
@@ -284,19 +302,14 @@ maxsim_rerank_kernel(const __grid_constant__ TmapSet tmaps, const int64_t* __res
       total += __shfl_xor_sync(0xffffffffu, total, 4);
       total += __shfl_xor_sync(0xffffffffu, total, 8);
       total += __shfl_xor_sync(0xffffffffu, total, 16);
-      if (lane == 0) {
-        float r = total;
-        if (len == 0) r = 0.f;                       // empty document: nothing but padding
-        if (len < 0) r = __int_as_float(0x7fc00000);  // pid out of range
-        out[c] = r;
-      }
+      if (lane == 0) out[c] = total;
     }
   }
 }
 
 template <typename T, bool kCvtBf16>
-int launch(const TmapSet& tmaps, const int64_t* pfxsum, const int32_t* doclens, int64_t n_docs,
-           const StrideSet& strides, const float* Q, int q_len, int64_t n_queries, const int64_t* cand_pids,
+int launch(const TmapSet& tmaps, const int64_t* pfxsum, const int32_t* doclens, int64_t n_docs, int64_t pid_base,
+           int skip_foreign, const StrideSet& strides, const float* Q, int q_len, int64_t n_queries, const int64_t* cand_pids,
            const int64_t* rowptr, int64_t n_cand, float* out, unsigned int* counter, cudaStream_t stream) {
   const size_t smem = kWarps * sizeof(WarpSmem) + 1024;
   CBK_CUDA(cudaFuncSetAttribute(maxsim_rerank_kernel<T, kCvtBf16>, cudaFuncAttributeMaxDynamicSharedMemorySize,
@@ -304,7 +317,7 @@ int launch(const TmapSet& tmaps, const int64_t* pfxsum, const int32_t* doclens, 
   const int64_t n_segs = (n_cand + kSegCands - 1) / kSegCands;
   const int64_t want = (n_segs + kWarps - 1) / kWarps;
   const int grid = static_cast<int>(std::max<int64_t>(1, std::min<int64_t>(want, static_cast<int64_t>(sm_count()) * kCtasPerSm)));
-  maxsim_rerank_kernel<T, kCvtBf16><<<grid, kWarps * 32, smem, stream>>>(tmaps, pfxsum, doclens, n_docs, strides, Q, q_len,
+  maxsim_rerank_kernel<T, kCvtBf16><<<grid, kWarps * 32, smem, stream>>>(tmaps, pfxsum, doclens, n_docs, pid_base, skip_foreign, strides, Q, q_len,
                                                               n_queries, cand_pids, rowptr, n_cand, out, counter);
   CBK_CUDA(cudaGetLastError());
   count_launch();
@@ -314,7 +327,7 @@ int launch(const TmapSet& tmaps, const int64_t* pfxsum, const int32_t* doclens, 
 }  // namespace
 
 int rerank_dispatch(const void* d_store, int store_dtype, int64_t n_store_rows, int dim, const int64_t* d_pfxsum,
-                    const int32_t* d_doclens, int64_t n_docs, const int32_t* strides, int n_strides,
+                    const int32_t* d_doclens, int64_t n_docs, int64_t pid_base, const int32_t* strides, int n_strides,
                     const float* d_Q, int q_len, int64_t n_queries, const int64_t* d_cand_pids,
                     const int64_t* d_cand_rowptr, int64_t n_cand_total, float* d_out_scores, void* d_workspace,
                     int flags, cudaStream_t stream) {
@@ -334,15 +347,16 @@ int rerank_dispatch(const void* d_store, int store_dtype, int64_t n_store_rows, 
   StrideSet ss;
   ss.n = n_strides;
   for (int i = 0; i < CBK_MAX_STRIDES; ++i) ss.v[i] = i < n_strides ? strides[i] : -1;
+  const int skip = (flags & CBK_FLAG_SKIP_FOREIGN_PIDS) ? 1 : 0;
   unsigned int* counter = static_cast<unsigned int*>(d_workspace);
   CBK_CUDA(cudaMemsetAsync(counter, 0, sizeof(unsigned int), stream));
   if (store_dtype == CBK_F16)
-    return launch<__half, false>(tmaps, d_pfxsum, d_doclens, n_docs, ss, d_Q, q_len, n_queries, d_cand_pids,
+    return launch<__half, false>(tmaps, d_pfxsum, d_doclens, n_docs, pid_base, skip, ss, d_Q, q_len, n_queries, d_cand_pids,
                                  d_cand_rowptr, n_cand_total, d_out_scores, counter, stream);
   if (flags & CBK_FLAG_BF16_NATIVE_MMA)
-    return launch<__nv_bfloat16, false>(tmaps, d_pfxsum, d_doclens, n_docs, ss, d_Q, q_len, n_queries, d_cand_pids,
+    return launch<__nv_bfloat16, false>(tmaps, d_pfxsum, d_doclens, n_docs, pid_base, skip, ss, d_Q, q_len, n_queries, d_cand_pids,
                                         d_cand_rowptr, n_cand_total, d_out_scores, counter, stream);
-  return launch<__half, true>(tmaps, d_pfxsum, d_doclens, n_docs, ss, d_Q, q_len, n_queries, d_cand_pids,
+  return launch<__half, true>(tmaps, d_pfxsum, d_doclens, n_docs, pid_base, skip, ss, d_Q, q_len, n_queries, d_cand_pids,
                               d_cand_rowptr, n_cand_total, d_out_scores, counter, stream);
 }
 

@@ -22,28 +22,8 @@ __device__ __forceinline__ uint64_t shfl_xor_u64(uint64_t v, int mask) {
   return (static_cast<uint64_t>(hi) << 32) | lo;
 }
 
-// keys sorted DESCENDING.  P = padded power-of-two length (≥ 32).
-__global__ void __launch_bounds__(kTopkThreads)
-topk_per_query_kernel(const float* __restrict__ scores, const int64_t* __restrict__ cand_pids,
-                      const int64_t* __restrict__ rowptr, int P, int k, float* __restrict__ out_scores,
-                      int64_t* __restrict__ out_pids) {
-  extern __shared__ uint64_t keys[];
-  const int64_t q = blockIdx.x;
-  const int64_t beg = rowptr[q];
-  const int n = static_cast<int>(min(rowptr[q + 1] - beg, static_cast<int64_t>(P)));
-  const int tid = threadIdx.x;
-
-  for (int i = tid; i < P; i += kTopkThreads) {
-    uint64_t key = 0;  // padding: below every real key
-    if (i < n) {
-      const uint32_t s = float_to_ordered(scores[beg + i] + 0.0f);  // -0.0 → +0.0: they tie
-      const uint32_t p = ~static_cast<uint32_t>(cand_pids[beg + i]);
-      key = (static_cast<uint64_t>(s) << 32) | p;
-    }
-    keys[i] = key;
-  }
-  __syncthreads();
-
+// Sort the P keys held in shared memory, descending.  P = power of two ≥ 32.
+__device__ __forceinline__ void bitonic_sort_desc(uint64_t* keys, int P, int tid) {
   for (int size = 2; size <= P; size <<= 1) {
     int stride = size >> 1;
     // distances ≥ 32: one compare-exchange per pair through shared memory
@@ -76,33 +56,102 @@ topk_per_query_kernel(const float* __restrict__ scores, const int64_t* __restric
     }
     __syncthreads();
   }
+}
 
-  for (int i = tid; i < k; i += kTopkThreads) {
-    float s = -INFINITY;
-    int64_t pid = -1;
-    if (i < n) {
-      const uint64_t key = keys[i];
-      s = ordered_to_float(static_cast<uint32_t>(key >> 32));
-      pid = static_cast<int64_t>(~static_cast<uint32_t>(key));
-    }
-    out_scores[q * k + i] = s;
-    out_pids[q * k + i] = pid;
+// key 0 is padding (sorts below every real key): decoded as (−inf, −1)
+__device__ __forceinline__ void emit(uint64_t key, int64_t pos, float* out_scores, int64_t* out_pids,
+                                     uint64_t* out_keys) {
+  if (out_keys) {
+    out_keys[pos] = key;
+  } else {
+    out_scores[pos] = key ? ordered_to_float(static_cast<uint32_t>(key >> 32)) : -INFINITY;
+    out_pids[pos] = key ? static_cast<int64_t>(~static_cast<uint32_t>(key)) : -1;
   }
+}
+
+// One CTA per query: candidates (scores + pids, CSR) → top-k as (scores, pids) or as packed keys.
+__global__ void __launch_bounds__(kTopkThreads)
+topk_per_query_kernel(const float* __restrict__ scores, const int64_t* __restrict__ cand_pids,
+                      const int64_t* __restrict__ rowptr, int P, int k, int neg_inf_is_padding,
+                      float* __restrict__ out_scores, int64_t* __restrict__ out_pids,
+                      uint64_t* __restrict__ out_keys) {
+  extern __shared__ uint64_t keys[];
+  const int64_t q = blockIdx.x;
+  const int64_t beg = rowptr[q];
+  const int n = static_cast<int>(min(rowptr[q + 1] - beg, static_cast<int64_t>(P)));
+  const int tid = threadIdx.x;
+  for (int i = tid; i < P; i += kTopkThreads) {
+    uint64_t key = 0;
+    if (i < n) {
+      const float sc = scores[beg + i] + 0.0f;  // -0.0 → +0.0: they tie
+      if (!(neg_inf_is_padding && sc == -INFINITY)) {
+        const uint32_t p = ~static_cast<uint32_t>(cand_pids[beg + i]);
+        key = (static_cast<uint64_t>(float_to_ordered(sc)) << 32) | p;
+      }
+    }
+    keys[i] = key;
+  }
+  __syncthreads();
+  bitonic_sort_desc(keys, P, tid);
+  for (int i = tid; i < k; i += kTopkThreads) emit(i < n ? keys[i] : 0ull, q * k + i, out_scores, out_pids, out_keys);
+}
+
+// One CTA per query: W rank-major lists of k_in packed keys each ([W, n_queries, k_in]) → global top-k.
+// Replicated on every rank after the all-gather; the key order is a total order, so
+// the result does not depend on W.
+__global__ void __launch_bounds__(kTopkThreads)
+merge_topk_keys_kernel(const uint64_t* __restrict__ in_keys, int W, int64_t n_queries, int k_in, int P, int k,
+                       float* __restrict__ out_scores, int64_t* __restrict__ out_pids) {
+  extern __shared__ uint64_t keys[];
+  const int64_t q = blockIdx.x;
+  const int n = W * k_in;
+  const int tid = threadIdx.x;
+  for (int i = tid; i < P; i += kTopkThreads) {
+    uint64_t key = 0;
+    if (i < n) {
+      const int w = i / k_in, j = i - w * k_in;
+      key = in_keys[(static_cast<int64_t>(w) * n_queries + q) * k_in + j];
+    }
+    keys[i] = key;
+  }
+  __syncthreads();
+  bitonic_sort_desc(keys, P, tid);
+  for (int i = tid; i < k; i += kTopkThreads) emit(i < n ? keys[i] : 0ull, q * k + i, out_scores, out_pids, nullptr);
 }
 
 }  // namespace
 
 int64_t topk_max_candidates() { return kTopkMaxCand; }
 
-int topk_dispatch(const float* d_scores, const int64_t* d_cand_pids, const int64_t* d_cand_rowptr, int64_t n_queries,
-                  int64_t max_cand_per_query, int k, float* d_out_scores, int64_t* d_out_pids, cudaStream_t stream) {
+static int padded_pow2(int64_t n) {
   int P = 32;
-  while (P < max_cand_per_query) P <<= 1;
+  while (P < n) P <<= 1;
+  return P;
+}
+
+int topk_dispatch(const float* d_scores, const int64_t* d_cand_pids, const int64_t* d_cand_rowptr, int64_t n_queries,
+                  int64_t max_cand_per_query, int k, int flags, float* d_out_scores, int64_t* d_out_pids,
+                  uint64_t* d_out_keys, cudaStream_t stream) {
+  const int P = padded_pow2(max_cand_per_query);
   const size_t smem = static_cast<size_t>(P) * sizeof(uint64_t);
   CBK_CUDA(cudaFuncSetAttribute(topk_per_query_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                 static_cast<int>(smem)));
   topk_per_query_kernel<<<static_cast<unsigned int>(n_queries), kTopkThreads, smem, stream>>>(
-      d_scores, d_cand_pids, d_cand_rowptr, P, k, d_out_scores, d_out_pids);
+      d_scores, d_cand_pids, d_cand_rowptr, P, k, (flags & CBK_TOPK_NEG_INF_IS_PADDING) ? 1 : 0, d_out_scores,
+      d_out_pids, d_out_keys);
+  CBK_CUDA(cudaGetLastError());
+  count_launch();
+  return CBK_OK;
+}
+
+int merge_dispatch(const uint64_t* d_keys, int world, int64_t n_queries, int k_in, int k, float* d_out_scores,
+                   int64_t* d_out_pids, cudaStream_t stream) {
+  const int P = padded_pow2(static_cast<int64_t>(world) * k_in);
+  const size_t smem = static_cast<size_t>(P) * sizeof(uint64_t);
+  CBK_CUDA(cudaFuncSetAttribute(merge_topk_keys_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                static_cast<int>(smem)));
+  merge_topk_keys_kernel<<<static_cast<unsigned int>(n_queries), kTopkThreads, smem, stream>>>(
+      d_keys, world, n_queries, k_in, P, k, d_out_scores, d_out_pids);
   CBK_CUDA(cudaGetLastError());
   count_launch();
   return CBK_OK;

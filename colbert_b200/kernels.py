@@ -42,7 +42,7 @@ def _workspace(device: torch.device) -> torch.Tensor:
 
 def maxsim_rerank(store: torch.Tensor, pfxsum: torch.Tensor, doclens: torch.Tensor, strides: Sequence[int],
                   Q: torch.Tensor, cand_pids: torch.Tensor, cand_rowptr: torch.Tensor,
-                  out: Optional[torch.Tensor] = None, flags: int = 0) -> torch.Tensor:
+                  out: Optional[torch.Tensor] = None, flags: int = 0, pid_base: int = 0) -> torch.Tensor:
     """scores[c] for the CSR candidate lists; see cbk_maxsim_rerank in include/colbert_b200.h.
 
     store [rows, dim] fp16|bf16 · pfxsum [n_docs+1] int64 · doclens [n_docs] int32 · Q [B, q_len, dim] fp32
@@ -71,7 +71,8 @@ def maxsim_rerank(store: torch.Tensor, pfxsum: torch.Tensor, doclens: torch.Tens
     ws = _workspace(dev)
     with torch.cuda.device(dev):
         rc = lib.cbk_maxsim_rerank(_ptr(store), _lib.dtype_code(store.dtype), store.size(0), dim, _ptr(pfxsum),
-                                   _ptr(doclens), doclens.numel(), C.cast(st, C.c_void_p), len(strides), _ptr(Q),
+                                   _ptr(doclens), doclens.numel(), int(pid_base), C.cast(st, C.c_void_p),
+                                   len(strides), _ptr(Q),
                                    q_len, n_q, _ptr(cand_pids), _ptr(cand_rowptr), n, _ptr(out), _ptr(ws),
                                    ws.numel(), int(flags), C.c_void_p(_lib.current_stream_ptr(dev)))
     _lib.check("cbk_maxsim_rerank", rc)
@@ -79,21 +80,45 @@ def maxsim_rerank(store: torch.Tensor, pfxsum: torch.Tensor, doclens: torch.Tens
 
 
 def topk_per_query(scores: torch.Tensor, cand_pids: torch.Tensor, cand_rowptr: torch.Tensor, k: int,
-                   max_cand_per_query: int):
+                   max_cand_per_query: int, flags: int = 0, as_keys: bool = False):
     """(top scores [B,k] fp32, top pids [B,k] int64), score-descending, ties by ascending pid;
-    lists shorter than k are padded with (-inf, -1).  See cbk_topk_per_query."""
+    lists shorter than k are padded with (-inf, -1).  With ``as_keys`` the winners come back as packed
+    int64 keys [B,k] (see cbk_topk_per_query_keys) ready for an all-gather."""
     lib = _lib.load()
     dev = scores.device
     _need(scores, "scores", torch.float32, dev)
     _need(cand_pids, "cand_pids", torch.int64, dev)
     _need(cand_rowptr, "cand_rowptr", torch.int64, dev)
     n_q = cand_rowptr.numel() - 1
-    out_s = torch.empty((n_q, k), dtype=torch.float32, device=dev)
-    out_p = torch.empty((n_q, k), dtype=torch.int64, device=dev)
+    stream = C.c_void_p(_lib.current_stream_ptr(dev))
     with torch.cuda.device(dev):
+        if as_keys:
+            out_k = torch.empty((n_q, k), dtype=torch.int64, device=dev)
+            rc = lib.cbk_topk_per_query_keys(_ptr(scores), _ptr(cand_pids), _ptr(cand_rowptr), n_q,
+                                             int(max_cand_per_query), int(k), int(flags), _ptr(out_k), stream)
+            _lib.check("cbk_topk_per_query_keys", rc)
+            return out_k
+        out_s = torch.empty((n_q, k), dtype=torch.float32, device=dev)
+        out_p = torch.empty((n_q, k), dtype=torch.int64, device=dev)
         rc = lib.cbk_topk_per_query(_ptr(scores), _ptr(cand_pids), _ptr(cand_rowptr), n_q, int(max_cand_per_query),
-                                    int(k), _ptr(out_s), _ptr(out_p), C.c_void_p(_lib.current_stream_ptr(dev)))
+                                    int(k), int(flags), _ptr(out_s), _ptr(out_p), stream)
     _lib.check("cbk_topk_per_query", rc)
+    return out_s, out_p
+
+
+def merge_topk_keys(keys: torch.Tensor, k: int):
+    """keys [W, B, k_in] int64 (packed, rank-major, as all-gathered) → (scores [B,k] fp32, pids [B,k] int64):
+    the global top-k per query under the total order (score desc, pid asc).  See cbk_merge_topk_keys."""
+    lib = _lib.load()
+    dev = keys.device
+    _need(keys, "keys", torch.int64, dev)
+    W, B, k_in = keys.shape
+    out_s = torch.empty((B, k), dtype=torch.float32, device=dev)
+    out_p = torch.empty((B, k), dtype=torch.int64, device=dev)
+    with torch.cuda.device(dev):
+        rc = lib.cbk_merge_topk_keys(_ptr(keys), W, B, k_in, int(k), _ptr(out_s), _ptr(out_p),
+                                     C.c_void_p(_lib.current_stream_ptr(dev)))
+    _lib.check("cbk_merge_topk_keys", rc)
     return out_s, out_p
 
 

@@ -62,6 +62,7 @@ class ColbertRanker:
         # bf16 stores are multiplied as fp16 by default (see cbk_maxsim_rerank `flags`); set to
         # kernels._lib.CBK_FLAG_BF16_NATIVE_MMA to multiply bf16 directly
         self.kernel_flags = 0
+        self.pid_base = 0           # first global pid of this store (non-zero only for a shard, see sharding.py)
         if index_path is not None:
             _, self.parts_paths, _ = get_parts(index_path)
             self.parts_doclens = load_doclens(index_path, flatten=False)
@@ -153,12 +154,12 @@ class ColbertRanker:
         B, q_len, dim = Q.shape
         if q_len <= kernels._lib.CBK_MAX_QLEN:
             return kernels.maxsim_rerank(self.tensor, self._pfxsum_dev, self._doclens_dev, self.strides, Q,
-                                         cand_pids, cand_rowptr, flags=self.kernel_flags)
+                                         cand_pids, cand_rowptr, flags=self.kernel_flags, pid_base=self.pid_base)
         total = None
         for lo in range(0, q_len, kernels._lib.CBK_MAX_QLEN):
             part = kernels.maxsim_rerank(self.tensor, self._pfxsum_dev, self._doclens_dev, self.strides,
                                          Q[:, lo: lo + kernels._lib.CBK_MAX_QLEN].contiguous(), cand_pids, cand_rowptr,
-                                         flags=self.kernel_flags)
+                                         flags=self.kernel_flags, pid_base=self.pid_base)
             total = part if total is None else total.add_(part)
         return total
 

@@ -1,0 +1,126 @@
+"""Document-range sharding of the embedding store across the GPUs of one box.
+
+The reference's ranker is single-GPU (`DEVICE = "cuda"`, colbert/ranking/colbert_ranker.py:12); this
+is the multi-GPU layout of the same path: contiguous pid ranges balanced by TOKEN count (the store is
+what fills HBM), one process per GPU, queries replicated, every rank scores the candidates that fall
+in its range, and the per-rank top-k lists are exchanged with ONE all-gather of packed
+(score, pid) keys and merged identically on every rank.
+"""
+from __future__ import annotations
+
+from typing import List, Optional, Tuple
+
+import torch
+import torch.distributed as dist
+
+from . import kernels
+from ._lib import CBK_FLAG_SKIP_FOREIGN_PIDS, CBK_TOPK_NEG_INF_IS_PADDING
+
+
+def plan_shards(doclens_pfxsum: torch.Tensor, world: int) -> List[int]:
+    """→ pid boundaries ``b[0]=0 ≤ b[1] ≤ … ≤ b[world]=N``; rank r owns pids ``[b[r], b[r+1])`` and store
+    rows ``[pfxsum[b[r]], pfxsum[b[r+1]])``.  Boundaries are the pids whose prefix sum is closest to
+    ``r/world`` of the token total, so shards differ by at most one document's worth of tokens."""
+    assert doclens_pfxsum.dim() == 1 and doclens_pfxsum.numel() >= 1 and world >= 1
+    n_docs = doclens_pfxsum.numel() - 1
+    total = int(doclens_pfxsum[-1])
+    bounds = [0]
+    for r in range(1, world):
+        target = (total * r) // world
+        j = int(torch.searchsorted(doclens_pfxsum, torch.tensor(target, dtype=doclens_pfxsum.dtype)))
+        j = min(max(j, 0), n_docs)
+        if j > 0 and abs(int(doclens_pfxsum[j - 1]) - target) <= abs(int(doclens_pfxsum[j]) - target):
+            j -= 1
+        bounds.append(max(j, bounds[-1]))
+    bounds.append(n_docs)
+    return bounds
+
+
+def owner_of(pids: torch.Tensor, bounds: List[int]) -> torch.Tensor:
+    """Rank owning each global pid."""
+    b = torch.as_tensor(bounds[1:-1], dtype=pids.dtype, device=pids.device)
+    return torch.searchsorted(b, pids, right=True)
+
+
+class ShardedColbertRanker:
+    """One rank's view of a pid-range-sharded store.
+
+    ``local`` is a :class:`colbert_b200.ranking.ColbertRanker` holding only this rank's documents;
+    ``pid_base`` its first global pid; ``global_strides`` the strides of the WHOLE corpus (the
+    reference's zero-floor rule, SURVEY.md §8 a12′, depends on them, so every shard must use the same
+    list).  ``rank_forward_batch`` returns the same (pids, scores) on every rank, equal to what a
+    single-GPU ranker over the whole corpus returns."""
+
+    def __init__(self, local, pid_base: int, global_strides, group: Optional[dist.ProcessGroup] = None):
+        self.local = local
+        self.pid_base = int(pid_base)
+        self.strides = [int(s) for s in global_strides]
+        self.group = group
+        self.world = dist.get_world_size(group) if dist.is_initialized() else 1
+        self.rank = dist.get_rank(group) if dist.is_initialized() else 0
+        if local is not None:
+            local.strides = self.strides
+            local.pid_base = self.pid_base
+            local.kernel_flags |= CBK_FLAG_SKIP_FOREIGN_PIDS
+
+    @classmethod
+    def from_global_tensors(cls, embeddings: torch.Tensor, doclens, device, group=None, store_dtype=None):
+        """Every rank is handed the whole (host) corpus and keeps its own pid range — for tests and
+        small indexes; large stores are loaded shard by shard instead."""
+        from .ranking.colbert_ranker import ColbertRanker, torch_percentile
+        doclens = torch.as_tensor(doclens, dtype=torch.int64)
+        pfx = torch.zeros(doclens.numel() + 1, dtype=torch.int64)
+        torch.cumsum(doclens, 0, out=pfx[1:])
+        world = dist.get_world_size(group) if dist.is_initialized() else 1
+        rank = dist.get_rank(group) if dist.is_initialized() else 0
+        bounds = plan_shards(pfx, world)
+        lo, hi = bounds[rank], bounds[rank + 1]
+        strides = sorted({torch_percentile(doclens, p) for p in (25, 50, 75)} | {int(doclens.max())})
+        local = ColbertRanker.from_tensors(embeddings[int(pfx[lo]): int(pfx[hi])], doclens[lo:hi].tolist(),
+                                           device=device, store_dtype=store_dtype)
+        self = cls(local, lo, strides, group)
+        self.bounds = bounds
+        return self
+
+    # ---- the four stages; the CPU (gloo) tests override the two device stages -----------------------
+    def _local_topk_keys(self, Q: torch.Tensor, cand_pids: torch.Tensor, cand_rowptr: torch.Tensor, k: int,
+                         max_cand: int) -> torch.Tensor:
+        """Score this shard's share of every candidate list and keep the local top-k as packed keys."""
+        scores = self.local.score_candidates(Q, cand_pids, cand_rowptr)
+        return kernels.topk_per_query(scores, cand_pids, cand_rowptr, k, max_cand,
+                                      flags=CBK_TOPK_NEG_INF_IS_PADDING, as_keys=True)
+
+    def _exchange(self, keys: torch.Tensor) -> torch.Tensor:
+        """[B, k] → [world, B, k]: one all-gather (NCCL over NVLink on GPUs, gloo in the CPU tests)."""
+        if self.world == 1:
+            return keys.unsqueeze(0)
+        B, k = keys.shape
+        gathered = torch.empty((self.world * B, k), dtype=keys.dtype, device=keys.device)   # rank-major concat
+        dist.all_gather_into_tensor(gathered, keys.contiguous(), group=self.group)
+        return gathered.view(self.world, B, k)
+
+    def _merge(self, gathered: torch.Tensor, k: int) -> Tuple[torch.Tensor, torch.Tensor]:
+        scores, pids = kernels.merge_topk_keys(gathered, k)
+        return pids, scores
+
+    def rank_forward_batch(self, Q: torch.Tensor, cand_pids: torch.Tensor, cand_rowptr: Optional[torch.Tensor] = None,
+                           depth: Optional[int] = 10, max_cand: Optional[int] = None):
+        """Same contract as ``ColbertRanker.rank_forward_batch`` with GLOBAL pids; identical on all ranks."""
+        dev = self.local.device if self.local is not None else Q.device
+        Q = Q.to(dev, dtype=torch.float32, non_blocking=True).contiguous()
+        B = Q.size(0)
+        cand_pids = cand_pids.to(dev, non_blocking=True)
+        if cand_rowptr is None:
+            assert cand_pids.dim() == 2 and cand_pids.size(0) == B
+            n = cand_pids.size(1)
+            cand_rowptr = torch.arange(0, (B + 1) * n, n, dtype=torch.int64, device=dev)
+            max_cand = n
+            cand_pids = cand_pids.reshape(-1)
+        else:
+            cand_rowptr = cand_rowptr.to(dev, non_blocking=True)
+            if max_cand is None:
+                max_cand = int((cand_rowptr[1:] - cand_rowptr[:-1]).max().item())
+        cand_pids = cand_pids.contiguous()
+        k = max_cand if depth is None else min(int(depth), max_cand)
+        keys = self._local_topk_keys(Q, cand_pids, cand_rowptr, k, max_cand)
+        return self._merge(self._exchange(keys), k)

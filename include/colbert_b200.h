@@ -42,6 +42,8 @@ extern "C" {
 #define CBK_MAX_STRIDES 8      /* the reference produces at most 4 (percentiles 25/50/75 + max) */
 #define CBK_MAX_QLEN 32        /* query rows per launch; longer queries are split by the caller  */
 #define CBK_FLAG_BF16_NATIVE_MMA 1
+#define CBK_FLAG_SKIP_FOREIGN_PIDS 2   /* sharded stores: a pid outside this shard scores -inf, not NaN */
+#define CBK_TOPK_NEG_INF_IS_PADDING 1  /* top-k: candidates scored -inf are dropped (sharded rerank) */
 
 typedef enum cbk_status {
   CBK_OK = 0,
@@ -88,6 +90,8 @@ uint64_t cbk_launch_count(void);
  *   d_store        [n_store_rows, dim] store_dtype, 256-byte aligned base
  *   d_pfxsum       [n_docs + 1] int64    (colbert_ranker.py:32)
  *   d_doclens      [n_docs] int32
+ *   pid_base       first GLOBAL pid held by this store (0 unless the corpus is sharded by pid range,
+ *                  SURVEY.md §8e); candidates carry global pids, document p is local row block p - pid_base
  *   strides        host array of n_strides ints (colbert_ranker.py:36-40), may be NULL when n_strides == 0
  *   d_Q            [n_queries, q_len, dim] fp32 row-major (the reference's Q.permute(0,2,1), l.111)
  *   d_cand_pids    [n_cand_total] int64, concatenated candidate lists
@@ -97,7 +101,9 @@ uint64_t cbk_launch_count(void);
  *                  un-permute, colbert_ranker.py:120-122, is therefore not needed)
  *   d_workspace    ≥ cbk_maxsim_rerank_workspace_bytes() bytes
  *
- *   flags          0, or CBK_FLAG_BF16_NATIVE_MMA.  By default a bf16 store is converted to fp16 in
+ *   flags          bit-or of CBK_FLAG_*.  CBK_FLAG_SKIP_FOREIGN_PIDS: a pid outside
+ *                  [pid_base, pid_base + n_docs) scores -inf (it belongs to another shard) instead of NaN.
+ *                  CBK_FLAG_BF16_NATIVE_MMA: by default a bf16 store is converted to fp16 in
  *                  registers (exact for values in fp16's normal range — ColBERT embeddings are
  *                  L2-normalised, BaseModel.py:26) and multiplied with the query rounded to fp16
  *                  (11 significant bits; measured worst relative score error 2e-4).  With the flag the
@@ -110,7 +116,7 @@ uint64_t cbk_launch_count(void);
 size_t cbk_maxsim_rerank_workspace_bytes(void);
 
 int cbk_maxsim_rerank(const void* d_store, int store_dtype, int64_t n_store_rows, int dim,
-                      const int64_t* d_pfxsum, const int32_t* d_doclens, int64_t n_docs,
+                      const int64_t* d_pfxsum, const int32_t* d_doclens, int64_t n_docs, int64_t pid_base,
                       const int32_t* strides, int n_strides,
                       const float* d_Q, int q_len, int64_t n_queries,
                       const int64_t* d_cand_pids, const int64_t* d_cand_rowptr, int64_t n_cand_total,
@@ -122,15 +128,31 @@ int cbk_maxsim_rerank(const void* d_store, int store_dtype, int64_t n_store_rows
  * order among exact ties is unspecified).
  *
  *   d_scores, d_cand_pids, d_cand_rowptr as above; each query may hold at most
- *   cbk_topk_max_candidates() candidates; pids must be < 2^32.
+ *   cbk_topk_max_candidates() candidates; pids must be < 2^32.  flags: CBK_TOPK_NEG_INF_IS_PADDING.
  *   d_out_scores [n_queries, k] fp32, d_out_pids [n_queries, k] int64; when a query has fewer than k
  *   candidates the tail is filled with (−inf, −1).
  * ------------------------------------------------------------------------------------------------ */
 int64_t cbk_topk_max_candidates(void);
 
 int cbk_topk_per_query(const float* d_scores, const int64_t* d_cand_pids, const int64_t* d_cand_rowptr,
-                       int64_t n_queries, int64_t max_cand_per_query, int k,
+                       int64_t n_queries, int64_t max_cand_per_query, int k, int flags,
                        float* d_out_scores, int64_t* d_out_pids, void* stream);
+
+/* Same selection, but the k winners of each query are returned as packed 64-bit keys
+ * [ordered(score) : 32 | ~pid : 32] (0 = padding) — the unit the shards exchange: one all-gather of
+ * [n_queries, k] uint64 per rank instead of separate score and pid buffers.  d_out_keys [n_queries, k]. */
+int cbk_topk_per_query_keys(const float* d_scores, const int64_t* d_cand_pids, const int64_t* d_cand_rowptr,
+                            int64_t n_queries, int64_t max_cand_per_query, int k, int flags,
+                            uint64_t* d_out_keys, void* stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * Merge of per-shard top-k lists (no counterpart in the reference, whose ranker is
+ * single-GPU): d_keys [world, n_queries, k_in] packed keys as all-gathered from the ranks → the global
+ * top-k per query under the same total order, decoded to d_out_scores / d_out_pids [n_queries, k]
+ * ((−inf, −1) padding).  world * k_in ≤ cbk_topk_max_candidates().
+ * ------------------------------------------------------------------------------------------------ */
+int cbk_merge_topk_keys(const uint64_t* d_keys, int world, int64_t n_queries, int k_in, int k,
+                        float* d_out_scores, int64_t* d_out_pids, void* stream);
 
 /* ------------------------------------------------------------------------------------------------
  * Row gather — replaces colbert_ranker.py:105-109 as exposed by rank_forward(output_D_embedding=True)

@@ -275,3 +275,28 @@ def merge_topk(list_scores: Sequence[np.ndarray], list_pids: Sequence[np.ndarray
     sc, pid = sc[keep], pid[keep]
     order = np.lexsort((pid, -sc))[:k]
     return pid[order], sc[order]
+
+
+def pack_keys(scores: np.ndarray, pids: np.ndarray) -> np.ndarray:
+    """The 64-bit key the shards exchange (include/colbert_b200.h, cbk_topk_per_query_keys):
+    [ordered(score) : 32 | ~pid : 32]; sorting keys descending = (score desc, pid asc); 0 = padding.
+    -0.0 is canonicalised to +0.0 first."""
+    s = (np.asarray(scores, dtype=np.float32) + np.float32(0.0)).view(np.uint32).astype(np.uint64)
+    neg = (s & np.uint64(0x80000000)) != 0
+    ordered = np.where(neg, (~s) & np.uint64(0xFFFFFFFF), s | np.uint64(0x80000000))
+    low = (~np.asarray(pids, dtype=np.int64).astype(np.uint64)) & np.uint64(0xFFFFFFFF)
+    return (ordered << np.uint64(32)) | low
+
+
+def unpack_keys(keys: np.ndarray):
+    """Inverse of :func:`pack_keys`; key 0 → (-inf, -1)."""
+    keys = np.asarray(keys).astype(np.uint64)
+    hi = (keys >> np.uint64(32)).astype(np.uint32)
+    pos = (hi & np.uint32(0x80000000)) != 0
+    bits = np.where(pos, hi & np.uint32(0x7FFFFFFF), ~hi).astype(np.uint32)
+    scores = bits.view(np.float32).copy()
+    pids = ((~keys) & np.uint64(0xFFFFFFFF)).astype(np.int64)
+    pad = keys == 0
+    scores[pad] = -np.inf
+    pids[pad] = -1
+    return scores, pids

@@ -21,7 +21,7 @@ def declared_symbols():
 def test_header_declares_the_path():
     syms = declared_symbols()
     for must in ("cbk_maxsim_rerank", "cbk_topk_per_query", "cbk_gather_rows", "cbk_mask_cast_rows",
-                 "cbk_last_error", "cbk_abi_version"):
+                 "cbk_topk_per_query_keys", "cbk_merge_topk_keys", "cbk_last_error", "cbk_abi_version"):
         assert must in syms
 
 
@@ -52,9 +52,9 @@ def test_library_is_sm100a_and_uses_tma(built_lib):
 def test_invalid_arguments_are_reported_not_crashed(built_lib):
     from colbert_b200 import _lib
     lib = _lib.load()
-    rc = lib.cbk_maxsim_rerank(None, 0, 10, 128, None, None, 1, None, 0, None, 32, 1, None, None, 0, None, None, 0, 0, None)
+    rc = lib.cbk_maxsim_rerank(None, 0, 10, 128, None, None, 1, 0, None, 0, None, 32, 1, None, None, 0, None, None, 0, 0, None)
     assert rc == -1 and b"null pointer" in lib.cbk_last_error()
-    rc = lib.cbk_topk_per_query(None, None, None, 1, 1, 1, None, None, None)
+    rc = lib.cbk_topk_per_query(None, None, None, 1, 1, 1, 0, None, None, None)
     assert rc == -1
     rc = lib.cbk_gather_rows(None, 0, 1, 128, None, None, 1, None, 1, 1, None, None, None)
     assert rc == -1

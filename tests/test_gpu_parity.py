@@ -274,3 +274,54 @@ def test_baseline_scale_properties(dev):
         rp, rs = O.topk_desc(ref, cand[b], 10)
         fp, fs = O.topk_desc(ref, cand[b], None)
         check_topk(pids[b, :10].cpu().numpy(), top[b, :10].cpu().numpy(), rp, rs, SCORE_RTOL, fp, fs)
+
+
+# ------------------------------------------------------------------------------------------------
+# sharded path, exercised on ONE GPU: W shard rankers side by side, the packed-key
+# exchange emulated by stacking, merged by the device kernel
+# ------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("world", [2, 3, 8])
+def test_sharded_path_matches_single_store(dev, world):
+    from colbert_b200 import _lib, kernels, synthetic
+    from colbert_b200.ranking import ColbertRanker
+    from colbert_b200.sharding import plan_shards
+    index = synthetic.make_index(909, 4000, dim=128, lo=1, hi=120)
+    single = make_ranker(index, dev)
+    B, n, k = 9, 400, 25
+    Q = torch.from_numpy(synthetic.make_queries(910, B, 32, 128)).to(dev)
+    cand = torch.from_numpy(synthetic.make_candidates(911, B, index.num_docs, n)).to(dev)
+    ref_pids, ref_scores = single.rank_forward_batch(Q, cand, depth=k)
+    rowptr = torch.arange(0, (B + 1) * n, n, dtype=torch.int64, device=dev)
+    bounds = plan_shards(single.doclens_pfxsum, world)
+    pf = single.doclens_pfxsum
+    keys = []
+    for r in range(world):
+        lo, hi = bounds[r], bounds[r + 1]
+        shard = ColbertRanker.from_tensors(torch.from_numpy(index.emb[int(pf[lo]): int(pf[hi])]),
+                                           index.doclens[lo:hi].tolist(), device=dev)
+        shard.strides, shard.pid_base = single.strides, lo                # global strides, global pid base
+        shard.kernel_flags |= _lib.CBK_FLAG_SKIP_FOREIGN_PIDS
+        s = shard.score_candidates(Q, cand.reshape(-1), rowptr)
+        own = (cand.reshape(-1) >= lo) & (cand.reshape(-1) < hi)
+        assert torch.isneginf(s[~own]).all() and torch.isfinite(s[own]).all()
+        kk = kernels.topk_per_query(s, cand.reshape(-1), rowptr, k, n, flags=_lib.CBK_TOPK_NEG_INF_IS_PADDING, as_keys=True)
+        # the device key format is the oracle's pack_keys, bit for bit
+        sc, pp = O.unpack_keys(kk.cpu().numpy().view(np.uint64))
+        assert np.array_equal(O.pack_keys(sc[pp >= 0], pp[pp >= 0]), kk.cpu().numpy().view(np.uint64)[pp >= 0])
+        keys.append(kk)
+    scores, pids = kernels.merge_topk_keys(torch.stack(keys).contiguous(), k)
+    assert torch.equal(pids, ref_pids) and torch.equal(scores, ref_scores)     # independent of the world size
+
+
+def test_sharded_ranker_world1(dev):
+    """ShardedColbertRanker without a process group behaves like the plain ranker."""
+    from colbert_b200 import synthetic
+    from colbert_b200.sharding import ShardedColbertRanker
+    index = synthetic.make_index(31, 1500, dim=128, lo=1, hi=100)
+    single = make_ranker(index, dev)
+    sharded = ShardedColbertRanker.from_global_tensors(torch.from_numpy(index.emb), index.doclens, dev)
+    Q = torch.from_numpy(synthetic.make_queries(32, 4, 32, 128))
+    cand = torch.from_numpy(synthetic.make_candidates(33, 4, index.num_docs, 300))
+    p1, s1 = single.rank_forward_batch(Q, cand, depth=10)
+    p2, s2 = sharded.rank_forward_batch(Q, cand, depth=10)
+    assert torch.equal(p1, p2) and torch.equal(s1, s2)
