@@ -246,14 +246,18 @@ def run_ours(args, rank, world, local_rank):
     ev_k1 = [torch.cuda.Event(enable_timing=True) for _ in range(args.steps)]
 
     def step_device(i=None):
+        if sharded is None:
+            pids_i, rowptr_i = cand_dev, rowptr
+        else:                                            # route this shard's candidates (stays on the device)
+            pids_i, rowptr_i = kernels.partition_candidates(cand_dev, rowptr, rank * args.docs, (rank + 1) * args.docs)
         if i is not None:
             ev_k0[i].record()
-        scores = ranker.score_candidates(Q_dev, cand_dev, rowptr)
+        scores = ranker.score_candidates(Q_dev, pids_i, rowptr_i)
         if i is not None:
             ev_k1[i].record()
         if sharded is None:
-            return kernels.topk_per_query(scores, cand_dev, rowptr, k, args.cands)
-        keys = kernels.topk_per_query(scores, cand_dev, rowptr, k, args.cands,
+            return kernels.topk_per_query(scores, pids_i, rowptr_i, k, args.cands)
+        keys = kernels.topk_per_query(scores, pids_i, rowptr_i, k, args.cands,
                                       flags=_lib.CBK_TOPK_NEG_INF_IS_PADDING, as_keys=True)
         return sharded._merge(sharded._exchange(keys), k)          # NCCL all-gather of packed keys + merge
 

@@ -37,6 +37,8 @@ SIGNATURES = {
     "cbk_topk_per_query_keys": (C.c_int, [_vp, _vp, _vp, _i64, _i64, _i32, _i32, _vp, _vp]),
     "cbk_merge_topk_keys": (C.c_int, [_vp, _i32, _i64, _i32, _i32, _vp, _vp, _vp]),
     "cbk_gather_rows": (C.c_int, [_vp, _i32, _i64, _i32, _vp, _vp, _i64, _vp, _i64, _i32, _vp, _vp, _vp]),
+    "cbk_partition_workspace_bytes": (_sz, [_i64]),
+    "cbk_partition_candidates": (C.c_int, [_vp, _vp, _i64, _i64, _i64, _vp, _vp, _vp, _sz, _vp]),
     "cbk_mask_cast_rows": (C.c_int, [_vp, _i32, _i64, _i32, _vp, _i32, _vp, _i32, _vp]),
 }
 

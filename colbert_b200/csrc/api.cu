@@ -21,6 +21,7 @@ int64_t topk_max_candidates();
 int gather_dispatch(const void*, int, int64_t, int, const int64_t*, const int32_t*, int64_t, const int64_t*, int64_t,
                     int, float*, uint8_t*, cudaStream_t);
 
+int partition_dispatch(const int64_t*, const int64_t*, int64_t, int64_t, int64_t, int64_t*, int64_t*, int64_t*, cudaStream_t);
 int mask_cast_dispatch(const void*, int, int64_t, int, const void*, int, void*, int, cudaStream_t);
 
 namespace {
@@ -213,6 +214,25 @@ int cbk_gather_rows(const void* d_store, int store_dtype, int64_t n_store_rows, 
   if (rc != CBK_OK) return rc;
   return gather_dispatch(d_store, store_dtype, n_store_rows, dim, d_pfxsum, d_doclens, n_docs, d_pids, n, stride,
                          d_out_D, d_out_mask, static_cast<cudaStream_t>(stream));
+}
+
+size_t cbk_partition_workspace_bytes(int64_t n_queries) { return static_cast<size_t>(n_queries > 0 ? n_queries : 1) * sizeof(int64_t); }
+
+int cbk_partition_candidates(const int64_t* d_cand_pids, const int64_t* d_cand_rowptr, int64_t n_queries, int64_t pid_lo,
+                             int64_t pid_hi, int64_t* d_out_pids, int64_t* d_out_rowptr, void* d_workspace,
+                             size_t workspace_bytes, void* stream) {
+  CBK_CHECK_ARG(d_cand_pids && d_cand_rowptr && d_out_pids && d_out_rowptr, "cbk_partition_candidates: null pointer argument");
+  CBK_CHECK_ARG(n_queries > 0 && pid_lo <= pid_hi, "cbk_partition_candidates: n_queries %lld, range [%lld, %lld)",
+                (long long)n_queries, (long long)pid_lo, (long long)pid_hi);
+  if (!d_workspace || workspace_bytes < cbk_partition_workspace_bytes(n_queries)) {
+    set_error("cbk_partition_candidates: workspace of %zu bytes, need %zu", workspace_bytes,
+              cbk_partition_workspace_bytes(n_queries));
+    return CBK_ERR_WORKSPACE;
+  }
+  int rc = check_device();
+  if (rc != CBK_OK) return rc;
+  return partition_dispatch(d_cand_pids, d_cand_rowptr, n_queries, pid_lo, pid_hi, d_out_pids, d_out_rowptr,
+                            static_cast<int64_t*>(d_workspace), static_cast<cudaStream_t>(stream));
 }
 
 int cbk_mask_cast_rows(const void* d_src, int src_dtype, int64_t n_rows, int dim, const void* d_mask, int mask_dtype,

@@ -72,7 +72,7 @@ maxsim_rerank_kernel(const __grid_constant__ TmapSet tmaps, const int64_t* __res
                      StrideSet strides,
                      const float* __restrict__ Q, int q_len, int64_t n_queries,
                      const int64_t* __restrict__ cand_pids, const int64_t* __restrict__ rowptr,
-                     int64_t n_cand, float* __restrict__ out, unsigned int* __restrict__ seg_counter) {
+                     int64_t n_cand_bound, float* __restrict__ out, unsigned int* __restrict__ seg_counter) {
   extern __shared__ uint8_t smem_raw[];
   const int lane = threadIdx.x & 31;
   const int warp = threadIdx.x >> 5;
@@ -89,6 +89,9 @@ maxsim_rerank_kernel(const __grid_constant__ TmapSet tmaps, const int64_t* __res
   }
   __syncwarp();
 
+  // the candidate count lives on the device (a routed list's length is only known there); the host
+  // passes an upper bound that sizes the grid
+  const int64_t n_cand = min(rowptr[n_queries], n_cand_bound);
   const int n_mt = q_len > 16 ? 2 : 1;
   const int64_t n_segs = (n_cand + kSegCands - 1) / kSegCands;
   uint32_t issued = 0;    // tiles handed to the TMA so far   → stage = issued % kStages

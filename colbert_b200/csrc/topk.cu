@@ -72,14 +72,16 @@ __device__ __forceinline__ void emit(uint64_t key, int64_t pos, float* out_score
 // One CTA per query: candidates (scores + pids, CSR) → top-k as (scores, pids) or as packed keys.
 __global__ void __launch_bounds__(kTopkThreads)
 topk_per_query_kernel(const float* __restrict__ scores, const int64_t* __restrict__ cand_pids,
-                      const int64_t* __restrict__ rowptr, int P, int k, int neg_inf_is_padding,
+                      const int64_t* __restrict__ rowptr, int Pmax, int k, int neg_inf_is_padding,
                       float* __restrict__ out_scores, int64_t* __restrict__ out_pids,
                       uint64_t* __restrict__ out_keys) {
   extern __shared__ uint64_t keys[];
   const int64_t q = blockIdx.x;
   const int64_t beg = rowptr[q];
-  const int n = static_cast<int>(min(rowptr[q + 1] - beg, static_cast<int64_t>(P)));
+  const int n = static_cast<int>(min(rowptr[q + 1] - beg, static_cast<int64_t>(Pmax)));
   const int tid = threadIdx.x;
+  int P = 32;  // sort only as many slots as this query needs (routed lists are short)
+  while (P < n) P <<= 1;
   for (int i = tid; i < P; i += kTopkThreads) {
     uint64_t key = 0;
     if (i < n) {

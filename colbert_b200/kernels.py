@@ -164,3 +164,22 @@ def mask_cast_rows(src: torch.Tensor, mask: Optional[torch.Tensor], out_dtype: t
                                     C.c_void_p(_lib.current_stream_ptr(dev)))
     _lib.check("cbk_mask_cast_rows", rc)
     return out
+
+
+def partition_candidates(cand_pids: torch.Tensor, cand_rowptr: torch.Tensor, pid_lo: int, pid_hi: int):
+    """Keep, per query and in order, the candidates with pid in [pid_lo, pid_hi) → (pids [n_total] int64 of
+    which the first rowptr[-1] are valid, rowptr [B+1] int64); no host synchronisation.
+    See cbk_partition_candidates."""
+    lib = _lib.load()
+    dev = cand_pids.device
+    _need(cand_pids, "cand_pids", torch.int64, dev)
+    _need(cand_rowptr, "cand_rowptr", torch.int64, dev)
+    n_q = cand_rowptr.numel() - 1
+    out_p = torch.empty_like(cand_pids)
+    out_r = torch.empty_like(cand_rowptr)
+    ws = torch.empty(int(lib.cbk_partition_workspace_bytes(n_q)), dtype=torch.uint8, device=dev)
+    with torch.cuda.device(dev):
+        rc = lib.cbk_partition_candidates(_ptr(cand_pids), _ptr(cand_rowptr), n_q, int(pid_lo), int(pid_hi), _ptr(out_p),
+                                          _ptr(out_r), _ptr(ws), ws.numel(), C.c_void_p(_lib.current_stream_ptr(dev)))
+    _lib.check("cbk_partition_candidates", rc)
+    return out_p, out_r

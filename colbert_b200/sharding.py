@@ -85,9 +85,11 @@ class ShardedColbertRanker:
     # ---- the four stages; the CPU (gloo) tests override the two device stages -----------------------
     def _local_topk_keys(self, Q: torch.Tensor, cand_pids: torch.Tensor, cand_rowptr: torch.Tensor, k: int,
                          max_cand: int) -> torch.Tensor:
-        """Score this shard's share of every candidate list and keep the local top-k as packed keys."""
-        scores = self.local.score_candidates(Q, cand_pids, cand_rowptr)
-        return kernels.topk_per_query(scores, cand_pids, cand_rowptr, k, max_cand,
+        """Route this shard's share of every candidate list, score it, keep the local top-k as packed keys."""
+        n_docs = self.local.doclens.numel()
+        my_pids, my_rowptr = kernels.partition_candidates(cand_pids, cand_rowptr, self.pid_base, self.pid_base + n_docs)
+        scores = self.local.score_candidates(Q, my_pids, my_rowptr)
+        return kernels.topk_per_query(scores, my_pids, my_rowptr, k, max_cand,
                                       flags=CBK_TOPK_NEG_INF_IS_PADDING, as_keys=True)
 
     def _exchange(self, keys: torch.Tensor) -> torch.Tensor:

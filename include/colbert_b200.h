@@ -96,7 +96,8 @@ uint64_t cbk_launch_count(void);
  *   d_Q            [n_queries, q_len, dim] fp32 row-major (the reference's Q.permute(0,2,1), l.111)
  *   d_cand_pids    [n_cand_total] int64, concatenated candidate lists
  *   d_cand_rowptr  [n_queries + 1] int64, query q owns candidates rowptr[q] .. rowptr[q+1]-1;
- *                  rowptr[n_queries] == n_cand_total
+ *                  the number of candidates actually scored is rowptr[n_queries], read on the device;
+ *                  n_cand_total only has to be an upper bound of it (it sizes the launch)
  *   d_out_scores   [n_cand_total] fp32, written at the candidate's own position (the reference's
  *                  un-permute, colbert_ranker.py:120-122, is therefore not needed)
  *   d_workspace    ≥ cbk_maxsim_rerank_workspace_bytes() bytes
@@ -166,6 +167,22 @@ int cbk_gather_rows(const void* d_store, int store_dtype, int64_t n_store_rows, 
                     const int64_t* d_pfxsum, const int32_t* d_doclens, int64_t n_docs,
                     const int64_t* d_pids, int64_t n, int stride,
                     float* d_out_D, uint8_t* d_out_mask, void* stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * Candidate routing for a sharded store: keep, per query and in order, the candidates
+ * whose GLOBAL pid lies in [pid_lo, pid_hi).
+ *   d_cand_pids [n_cand_total] int64, d_cand_rowptr [n_queries+1] int64   (replicated inputs)
+ *   d_out_pids  [≥ n_cand_total] int64  (only the first d_out_rowptr[n_queries] entries are written)
+ *   d_out_rowptr [n_queries+1] int64
+ *   d_workspace ≥ cbk_partition_workspace_bytes(n_queries) bytes
+ * The kept count stays on the device; cbk_maxsim_rerank reads it from d_cand_rowptr[n_queries], so the
+ * outputs can be passed straight on (with n_cand_total as the upper bound) without a host sync.
+ * ------------------------------------------------------------------------------------------------ */
+size_t cbk_partition_workspace_bytes(int64_t n_queries);
+
+int cbk_partition_candidates(const int64_t* d_cand_pids, const int64_t* d_cand_rowptr, int64_t n_queries,
+                             int64_t pid_lo, int64_t pid_hi, int64_t* d_out_pids, int64_t* d_out_rowptr,
+                             void* d_workspace, size_t workspace_bytes, void* stream);
 
 /* ------------------------------------------------------------------------------------------------
  * Masked row cast — the multiplicative masks of BaseModel.score (BaseModel.py:41-42: D * d_mask[...,None],

@@ -301,10 +301,15 @@ def test_sharded_path_matches_single_store(dev, world):
                                            index.doclens[lo:hi].tolist(), device=dev)
         shard.strides, shard.pid_base = single.strides, lo                # global strides, global pid base
         shard.kernel_flags |= _lib.CBK_FLAG_SKIP_FOREIGN_PIDS
-        s = shard.score_candidates(Q, cand.reshape(-1), rowptr)
+        s = shard.score_candidates(Q, cand.reshape(-1), rowptr)          # unrouted: foreign pids score -inf
         own = (cand.reshape(-1) >= lo) & (cand.reshape(-1) < hi)
         assert torch.isneginf(s[~own]).all() and torch.isfinite(s[own]).all()
-        kk = kernels.topk_per_query(s, cand.reshape(-1), rowptr, k, n, flags=_lib.CBK_TOPK_NEG_INF_IS_PADDING, as_keys=True)
+        k_unrouted = kernels.topk_per_query(s, cand.reshape(-1), rowptr, k, n, flags=_lib.CBK_TOPK_NEG_INF_IS_PADDING,
+                                            as_keys=True)
+        my_pids, my_rowptr = kernels.partition_candidates(cand.reshape(-1).contiguous(), rowptr, lo, hi)   # routed
+        s2 = shard.score_candidates(Q, my_pids, my_rowptr)
+        kk = kernels.topk_per_query(s2, my_pids, my_rowptr, k, n, flags=_lib.CBK_TOPK_NEG_INF_IS_PADDING, as_keys=True)
+        assert torch.equal(kk, k_unrouted)
         # the device key format is the oracle's pack_keys, bit for bit
         sc, pp = O.unpack_keys(kk.cpu().numpy().view(np.uint64))
         assert np.array_equal(O.pack_keys(sc[pp >= 0], pp[pp >= 0]), kk.cpu().numpy().view(np.uint64)[pp >= 0])
@@ -325,3 +330,21 @@ def test_sharded_ranker_world1(dev):
     p1, s1 = single.rank_forward_batch(Q, cand, depth=10)
     p2, s2 = sharded.rank_forward_batch(Q, cand, depth=10)
     assert torch.equal(p1, p2) and torch.equal(s1, s2)
+
+
+def test_partition_candidates_matches_numpy(dev):
+    """Routing kernel: per query, in order, the pids inside [lo, hi); ragged lists incl. empty ones,
+    more than 1024 queries (the scan works in chunks of 1024)."""
+    from colbert_b200 import kernels
+    rng = np.random.default_rng(21)
+    lens = rng.integers(0, 70, size=2500)
+    lens[[0, 7, 1024, 2499]] = 0
+    pids = rng.integers(0, 10_000, size=int(lens.sum())).astype(np.int64)
+    rowptr = np.concatenate([[0], np.cumsum(lens)]).astype(np.int64)
+    for lo, hi in ((0, 10_000), (2_500, 5_000), (9_999, 10_000), (4_000, 4_000)):
+        op, orp = kernels.partition_candidates(torch.from_numpy(pids).to(dev), torch.from_numpy(rowptr).to(dev), lo, hi)
+        op, orp = op.cpu().numpy(), orp.cpu().numpy()
+        keep = (pids >= lo) & (pids < hi)
+        exp_rowptr = np.concatenate([[0], np.cumsum([keep[rowptr[q]: rowptr[q + 1]].sum() for q in range(len(lens))])])
+        assert np.array_equal(orp, exp_rowptr)
+        assert np.array_equal(op[: exp_rowptr[-1]], pids[keep])                 # order preserved within and across queries
