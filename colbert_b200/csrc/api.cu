@@ -22,6 +22,7 @@ int gather_dispatch(const void*, int, int64_t, int, const int64_t*, const int32_
                     int, float*, uint8_t*, cudaStream_t);
 
 int partition_dispatch(const int64_t*, const int64_t*, int64_t, int64_t, int64_t, int64_t*, int64_t*, int64_t*, cudaStream_t);
+int umma_probe_dispatch(const void*, const void*, int, int, int, float*, cudaStream_t);
 int mask_cast_dispatch(const void*, int, int64_t, int, const void*, int, void*, int, cudaStream_t);
 
 namespace {
@@ -245,6 +246,14 @@ int cbk_mask_cast_rows(const void* d_src, int src_dtype, int64_t n_rows, int dim
   if (rc != CBK_OK) return rc;
   return mask_cast_dispatch(d_src, src_dtype, n_rows, dim, mask_dtype == CBK_MASK_NONE ? nullptr : d_mask, mask_dtype,
                             d_out, out_dtype, static_cast<cudaStream_t>(stream));
+}
+
+int cbk_selftest_umma_gemm(const void* d_A, const void* d_B, int N, int a_bf16, int b_bf16, float* d_C, void* stream) {
+  CBK_CHECK_ARG(d_A && d_B && d_C, "cbk_selftest_umma_gemm: null pointer argument");
+  CBK_CHECK_SUPPORTED(N >= 16 && N <= 256 && N % 16 == 0, "cbk_selftest_umma_gemm: N %d must be a multiple of 16 in [16, 256]", N);
+  int rc = check_device();
+  if (rc != CBK_OK) return rc;
+  return umma_probe_dispatch(d_A, d_B, N, a_bf16, b_bf16, d_C, static_cast<cudaStream_t>(stream));
 }
 
 }  // extern "C"

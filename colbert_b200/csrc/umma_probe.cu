@@ -1,0 +1,97 @@
+// Self-test of the tcgen05 building blocks (TMA SW128 tiles → tcgen05.mma → TMEM → tcgen05.ld):
+//   C[128, N] = A[128, 128] · B[N, 128]^T   (16-bit inputs, fp32 accumulate), one CTA.
+// Exposed as cbk_selftest_umma_gemm; the GPU tests compare it with a float64 product, so a wrong
+// descriptor bit or TMEM lane mapping shows up here rather than inside the scoring kernels.
+#include "umma.cuh"
+
+namespace cbk {
+
+namespace {
+
+struct ProbeMaps {
+  CUtensorMap a, b;
+};
+
+__global__ void __launch_bounds__(128, 1)
+umma_probe_kernel(const __grid_constant__ ProbeMaps maps, int N, uint32_t idesc, float* __restrict__ C) {
+  extern __shared__ uint8_t smem_raw[];
+  __shared__ __align__(8) uint64_t bar_full, bar_mma;
+  __shared__ uint32_t tmem_base_smem;
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const uint32_t raw = smem_u32(smem_raw);
+  const uint32_t base = (raw + 1023u) & ~1023u;
+  const uint32_t a_addr = base;                 // 2 halves × 128 rows × 128 B
+  const uint32_t b_addr = base + 32768;         // 2 halves × N rows × 128 B
+  const uint32_t b_half = static_cast<uint32_t>(N) * 128u;
+  uint32_t ncols = 32;
+  while (ncols < static_cast<uint32_t>(N)) ncols <<= 1;
+
+  if (tid == 0) {
+    mbar_init(smem_u32(&bar_full), 1);
+    mbar_init(smem_u32(&bar_mma), 1);
+    fence_mbar_init();
+  }
+  if (warp == 1) {
+    umma::tmem_alloc(smem_u32(&tmem_base_smem), ncols);
+    umma::tmem_relinquish();
+  }
+  umma::fence_before_sync();
+  __syncthreads();
+  umma::fence_after_sync();
+  const uint32_t tmem = tmem_base_smem;
+
+  if (tid == 0) {
+    const uint32_t full = smem_u32(&bar_full);
+    mbar_arrive_expect_tx(full, 32768u + 2u * b_half);
+    tma_load_2d(a_addr, &maps.a, 0, 0, full, kEvictNormal);
+    tma_load_2d(a_addr + 16384, &maps.a, 64, 0, full, kEvictNormal);
+    tma_load_2d(b_addr, &maps.b, 0, 0, full, kEvictNormal);
+    tma_load_2d(b_addr + b_half, &maps.b, 64, 0, full, kEvictNormal);
+    mbar_wait(full, 0);
+    umma::fence_after_sync();
+#pragma unroll
+    for (int h = 0; h < 2; ++h)
+#pragma unroll
+      for (int k = 0; k < 4; ++k) {
+        const uint64_t ad = umma::make_smem_desc_sw128(a_addr + h * 16384 + k * 32);
+        const uint64_t bd = umma::make_smem_desc_sw128(b_addr + h * b_half + k * 32);
+        umma::mma_f16_ss(tmem, ad, bd, idesc, (h | k) ? 1u : 0u);
+      }
+    umma::commit(smem_u32(&bar_mma));
+  }
+  __syncwarp();
+  mbar_wait(smem_u32(&bar_mma), 0);
+  umma::fence_after_sync();
+
+  const int row = warp * 32 + lane;
+  for (int c0 = 0; c0 < N; c0 += 16) {
+    uint32_t r[16];
+    umma::tmem_ld_32x16(tmem + (static_cast<uint32_t>(warp * 32) << 16) + c0, r);
+    umma::tmem_ld_wait();
+#pragma unroll
+    for (int j = 0; j < 16; ++j) C[row * N + c0 + j] = __uint_as_float(r[j]);
+  }
+  umma::fence_before_sync();
+  __syncthreads();
+  if (warp == 1) umma::tmem_dealloc(tmem, ncols);
+}
+
+}  // namespace
+
+int umma_probe_dispatch(const void* d_A, const void* d_B, int N, int a_bf16, int b_bf16, float* d_C, cudaStream_t stream) {
+  ProbeMaps maps;
+  int rc = make_store_tensor_map(&maps.a, d_A, 128, 128, 64, 128);
+  if (rc != CBK_OK) return rc;
+  rc = make_store_tensor_map(&maps.b, d_B, N, 128, 64, N);
+  if (rc != CBK_OK) return rc;
+  const uint32_t idesc = umma::make_idesc(128, static_cast<uint32_t>(N), a_bf16 ? umma::kFmtBF16 : umma::kFmtF16,
+                                          b_bf16 ? umma::kFmtBF16 : umma::kFmtF16);
+  const size_t smem = 32768 + static_cast<size_t>(N) * 256 + 1024;
+  CBK_CUDA(cudaFuncSetAttribute(umma_probe_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
+  umma_probe_kernel<<<1, 128, smem, stream>>>(maps, N, idesc, d_C);
+  CBK_CUDA(cudaGetLastError());
+  count_launch();
+  return CBK_OK;
+}
+
+}  // namespace cbk

@@ -183,3 +183,19 @@ def partition_candidates(cand_pids: torch.Tensor, cand_rowptr: torch.Tensor, pid
                                           _ptr(out_r), _ptr(ws), ws.numel(), C.c_void_p(_lib.current_stream_ptr(dev)))
     _lib.check("cbk_partition_candidates", rc)
     return out_p, out_r
+
+
+def selftest_umma_gemm(A: torch.Tensor, B: torch.Tensor) -> torch.Tensor:
+    """C[128, N] = A[128,128] · B[N,128]^T through TMA → tcgen05.mma → TMEM → tcgen05.ld (one CTA)."""
+    lib = _lib.load()
+    dev = A.device
+    _need(A, "A", A.dtype, dev)
+    _need(B, "B", B.dtype, dev)
+    assert A.shape == (128, 128) and B.dim() == 2 and B.size(1) == 128
+    N = B.size(0)
+    Cout = torch.empty((128, N), dtype=torch.float32, device=dev)
+    with torch.cuda.device(dev):
+        rc = lib.cbk_selftest_umma_gemm(_ptr(A), _ptr(B), N, int(A.dtype == torch.bfloat16), int(B.dtype == torch.bfloat16),
+                                        _ptr(Cout), C.c_void_p(_lib.current_stream_ptr(dev)))
+    _lib.check("cbk_selftest_umma_gemm", rc)
+    return Cout

@@ -194,6 +194,13 @@ int cbk_partition_candidates(const int64_t* d_cand_pids, const int64_t* d_cand_r
 int cbk_mask_cast_rows(const void* d_src, int src_dtype, int64_t n_rows, int dim, const void* d_mask, int mask_dtype,
                        void* d_out, int out_dtype, void* stream);
 
+/* ------------------------------------------------------------------------------------------------
+ * Self-test of the tcgen05 / TMEM / TMA building blocks the query-batched kernels are made of:
+ *     C[128, N] = A[128, 128] · B[N, 128]^T      16-bit inputs (a_bf16 / b_bf16: 0 = fp16, 1 = bf16), fp32 out
+ * N a multiple of 16 in [16, 256]; one CTA.  Not part of the scoring path.
+ * ------------------------------------------------------------------------------------------------ */
+int cbk_selftest_umma_gemm(const void* d_A, const void* d_B, int N, int a_bf16, int b_bf16, float* d_C, void* stream);
+
 #ifdef __cplusplus
 }
 #endif
