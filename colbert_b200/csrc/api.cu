@@ -22,6 +22,13 @@ int gather_dispatch(const void*, int, int64_t, int, const int64_t*, const int32_
                     int, float*, uint8_t*, cudaStream_t);
 
 int partition_dispatch(const int64_t*, const int64_t*, int64_t, int64_t, int64_t, int64_t*, int64_t*, int64_t*, cudaStream_t);
+size_t doc_end_bits_bytes(int64_t);
+int doc_end_bits_dispatch(const int64_t*, int64_t, int64_t, uint32_t*, cudaStream_t);
+size_t exhaustive_workspace_bytes(int64_t);
+int exhaustive_dispatch(const void*, int, int64_t, const int64_t*, const uint32_t*, int64_t, const int32_t*, int, const float*,
+                        int, int64_t, float*, void*, int, cudaStream_t);
+size_t topk_dense_workspace_bytes(int64_t, int64_t, int);
+int topk_dense_dispatch(const float*, int64_t, int64_t, int, int64_t, int, float*, int64_t*, void*, cudaStream_t);
 int umma_probe_dispatch(const void*, const void*, int, int, int, float*, cudaStream_t);
 int mask_cast_dispatch(const void*, int, int64_t, int, const void*, int, void*, int, cudaStream_t);
 
@@ -246,6 +253,64 @@ int cbk_mask_cast_rows(const void* d_src, int src_dtype, int64_t n_rows, int dim
   if (rc != CBK_OK) return rc;
   return mask_cast_dispatch(d_src, src_dtype, n_rows, dim, mask_dtype == CBK_MASK_NONE ? nullptr : d_mask, mask_dtype,
                             d_out, out_dtype, static_cast<cudaStream_t>(stream));
+}
+
+size_t cbk_doc_end_bits_bytes(int64_t n_store_rows) { return doc_end_bits_bytes(n_store_rows > 0 ? n_store_rows : 0); }
+
+int cbk_build_doc_end_bits(const int64_t* d_pfxsum, int64_t n_docs, int64_t n_store_rows, uint32_t* d_bits, void* stream) {
+  CBK_CHECK_ARG(d_pfxsum && d_bits, "cbk_build_doc_end_bits: null pointer argument");
+  CBK_CHECK_ARG(n_docs > 0 && n_store_rows > 0, "cbk_build_doc_end_bits: sizes must be positive");
+  int rc = check_device();
+  if (rc != CBK_OK) return rc;
+  return doc_end_bits_dispatch(d_pfxsum, n_docs, n_store_rows, d_bits, static_cast<cudaStream_t>(stream));
+}
+
+size_t cbk_maxsim_exhaustive_workspace_bytes(int64_t n_queries) { return exhaustive_workspace_bytes(n_queries > 0 ? n_queries : 1); }
+
+int cbk_maxsim_exhaustive(const void* d_store, int store_dtype, int64_t n_store_rows, int dim, const int64_t* d_pfxsum,
+                          const uint32_t* d_doc_end_bits, int64_t n_docs, const int32_t* strides, int n_strides,
+                          const float* d_Q, int q_len, int64_t n_queries, float* d_out_scores, void* d_workspace,
+                          size_t workspace_bytes, int flags, void* stream) {
+  CBK_CHECK_ARG(d_store && d_pfxsum && d_doc_end_bits && d_Q && d_out_scores, "cbk_maxsim_exhaustive: null pointer argument");
+  CBK_CHECK_ARG(store_dtype == CBK_F16 || store_dtype == CBK_BF16, "cbk_maxsim_exhaustive: unknown store dtype %d", store_dtype);
+  CBK_CHECK_ARG(n_store_rows > 0 && n_docs > 0 && n_queries > 0, "cbk_maxsim_exhaustive: sizes must be positive");
+  CBK_CHECK_ARG(n_strides >= 0 && n_strides <= CBK_MAX_STRIDES && (n_strides == 0 || strides),
+                "cbk_maxsim_exhaustive: n_strides %d outside [0, %d] or strides is NULL", n_strides, CBK_MAX_STRIDES);
+  CBK_CHECK_SUPPORTED(dim == 128, "cbk_maxsim_exhaustive: dim %d not supported (128 only)", dim);
+  CBK_CHECK_SUPPORTED(q_len >= 1 && q_len <= CBK_MAX_QLEN, "cbk_maxsim_exhaustive: q_len %d outside [1, %d]", q_len, CBK_MAX_QLEN);
+  CBK_CHECK_SUPPORTED(n_store_rows < (1ll << 31) && n_queries < (1 << 20), "cbk_maxsim_exhaustive: store or batch too large");
+  CBK_CHECK_ARG((reinterpret_cast<uintptr_t>(d_store) & 0xff) == 0, "cbk_maxsim_exhaustive: store base must be 256-byte aligned");
+  if (!d_workspace || workspace_bytes < cbk_maxsim_exhaustive_workspace_bytes(n_queries) ||
+      (reinterpret_cast<uintptr_t>(d_workspace) & 0xff) != 0) {
+    set_error("cbk_maxsim_exhaustive: workspace of %zu bytes (256-byte aligned), need %zu", workspace_bytes,
+              cbk_maxsim_exhaustive_workspace_bytes(n_queries));
+    return CBK_ERR_WORKSPACE;
+  }
+  int rc = check_device();
+  if (rc != CBK_OK) return rc;
+  return exhaustive_dispatch(d_store, store_dtype, n_store_rows, d_pfxsum, d_doc_end_bits, n_docs, strides, n_strides, d_Q,
+                             q_len, n_queries, d_out_scores, d_workspace, flags, static_cast<cudaStream_t>(stream));
+}
+
+size_t cbk_topk_dense_workspace_bytes(int64_t n_queries, int64_t n_docs, int k) {
+  if (n_queries <= 0 || n_docs <= 0 || k <= 0) return 256;
+  return topk_dense_workspace_bytes(n_queries, n_docs, k);
+}
+
+int cbk_topk_dense(const float* d_scores, int64_t n_queries, int64_t n_docs, int k, int64_t pid_base, int as_keys,
+                   float* d_out_scores, int64_t* d_out_pids, void* d_workspace, size_t workspace_bytes, void* stream) {
+  CBK_CHECK_ARG(d_scores && d_out_pids && (as_keys || d_out_scores), "cbk_topk_dense: null pointer argument");
+  CBK_CHECK_ARG(n_queries > 0 && n_docs > 0 && k > 0, "cbk_topk_dense: sizes must be positive");
+  CBK_CHECK_SUPPORTED(k <= topk_max_candidates() / 2, "cbk_topk_dense: k %d exceeds %lld", k, (long long)topk_max_candidates() / 2);
+  CBK_CHECK_SUPPORTED(n_queries < 65536 && pid_base + n_docs < (1ll << 32), "cbk_topk_dense: batch or pid range too large");
+  if (!d_workspace || workspace_bytes < cbk_topk_dense_workspace_bytes(n_queries, n_docs, k)) {
+    set_error("cbk_topk_dense: workspace of %zu bytes, need %zu", workspace_bytes, cbk_topk_dense_workspace_bytes(n_queries, n_docs, k));
+    return CBK_ERR_WORKSPACE;
+  }
+  int rc = check_device();
+  if (rc != CBK_OK) return rc;
+  return topk_dense_dispatch(d_scores, n_queries, n_docs, k, pid_base, as_keys, d_out_scores, d_out_pids, d_workspace,
+                             static_cast<cudaStream_t>(stream));
 }
 
 int cbk_selftest_umma_gemm(const void* d_A, const void* d_B, int N, int a_bf16, int b_bf16, float* d_C, void* stream) {

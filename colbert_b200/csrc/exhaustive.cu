@@ -1,0 +1,369 @@
+// Query-batched exhaustive MaxSim (sm_100a, tcgen05 + TMEM + TMA): every document of the store (or
+// of this GPU's shard) is scored against a batch of queries; the document tile is read from HBM once
+// per pass of up to 16 queries and reused for all of them out of shared memory.
+//
+// This is the all-pairs shape of BaseModel.score (reference colbert/modeling/BaseModel.py:39-46,
+// "qmh,dnh->qdmn" → max over n → sum over m) applied to the flat index store of
+// colbert/ranking/colbert_ranker.py:61-73 — SURVEY.md §8d configs 4 and 5.
+//
+// Orientation: S[query rows, tokens] = Qblock[128, 128] · Dtile[128 tokens, 128]^T
+//   * A operand = a block of 4 queries × 32 rows (fp32 → 16-bit, packed once per call, resident in
+//     shared memory for a whole pass);  B operand = 128 consecutive store rows (one TMA box pair);
+//   * accumulator = 128 TMEM lanes (query rows) × 128 columns (tokens): the max over a document's
+//     tokens is a per-thread running max over columns (no cross-lane traffic), the sum over a query's
+//     32 rows is one warp reduction per (query, document);
+//   * document boundaries come from a bitmap with one bit per store row (set on the last row of each
+//     document), so the epilogue never chases pfxsum;
+//   * warp roles: warp 0 TMA producer, warp 1 MMA issuer (one thread), warps 2-5 epilogue (one TMEM
+//     lane quadrant = one query each); 3-stage smem ring for document tiles, 4 TMEM accumulator slots.
+// bf16 stores: both MMA operands must share a format (mixed fp16 × bf16 is an illegal instruction),
+// so the query is split into bf16 hi + lo parts and each tile is multiplied twice into the same
+// accumulator (K = 256); fp16 stores need one pass over K.
+#include <algorithm>
+
+#include "umma.cuh"
+
+namespace cbk {
+
+namespace {
+
+constexpr int kTileTok = 128;
+constexpr int kBStages = 3;
+constexpr int kABlocks = 4;               // 32 KB A slots in shared memory
+constexpr int kAccSlots = 4;              // × 128 TMEM columns
+constexpr int kTileBytes = kTileTok * 256;
+constexpr int kExhThreads = 192;
+
+struct StrideSet {
+  int n;
+  int v[CBK_MAX_STRIDES];
+};
+
+struct ExhMaps {
+  CUtensorMap store;  // [rows, 128] 16-bit, box {64, 128}
+  CUtensorMap q;      // packed queries [parts * n_qblocks * 128, 128] 16-bit, box {64, 128}
+};
+
+// ---- index-time metadata: bit t set ⇔ store row t is the last row of a document -------------------
+__global__ void doc_end_bits_kernel(const int64_t* __restrict__ pfxsum, int64_t n_docs, uint32_t* __restrict__ bits) {
+  const int64_t d = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (d >= n_docs) return;
+  const int64_t end = pfxsum[d + 1] - 1;
+  if (end >= pfxsum[d]) atomicOr(&bits[end >> 5], 1u << (end & 31));
+}
+
+// ---- per-launch: document-aligned, token-balanced ranges for the CTAs -------------------------------
+__global__ void plan_ranges_kernel(const int64_t* __restrict__ pfxsum, int64_t n_docs, int n_ctas,
+                                   int64_t* __restrict__ cta_doc_start) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i > n_ctas) return;
+  const int64_t total = pfxsum[n_docs];
+  const int64_t target = (total / n_ctas) * i + ((total % n_ctas) * i) / n_ctas;
+  int64_t lo = 0, hi = n_docs;  // first doc d with pfxsum[d] >= target
+  while (lo < hi) {
+    const int64_t mid = (lo + hi) >> 1;
+    if (pfxsum[mid] < target) lo = mid + 1; else hi = mid;
+  }
+  cta_doc_start[i] = i == n_ctas ? n_docs : lo;
+}
+
+// ---- per-launch: fp32 queries → 16-bit blocks of 4 queries × 32 rows, zero padded -------------------
+// out rows [part][qblock][query-in-block][row] ; part 0 = value rounded to T (hi), part 1 = residual (lo)
+template <typename T>
+__global__ void pack_queries_kernel(const float* __restrict__ Q, int n_queries, int q_len, int n_qblocks, int parts,
+                                    T* __restrict__ out) {
+  const int64_t n_rows = static_cast<int64_t>(n_qblocks) * 128;
+  const int64_t idx = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x;   // one thread per (row, 4 columns)
+  if (idx >= n_rows * 32) return;
+  const int64_t row = idx >> 5;
+  const int c = static_cast<int>(idx & 31) * 4;
+  const int q = static_cast<int>(row >> 5), r = static_cast<int>(row & 31);
+  float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+  if (q < n_queries && r < q_len) v = *reinterpret_cast<const float4*>(Q + (static_cast<int64_t>(q) * q_len + r) * 128 + c);
+  const float in[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+  for (int j = 0; j < 4; ++j) {
+    const T hi = static_cast<T>(in[j]);
+    out[row * 128 + c + j] = hi;
+    if (parts > 1) out[(n_rows + row) * 128 + c + j] = static_cast<T>(in[j] - static_cast<float>(hi));
+  }
+}
+
+__device__ __forceinline__ float warp_sum(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+
+// =====================================================================================================
+__global__ void __launch_bounds__(kExhThreads, 1)
+maxsim_exhaustive_kernel(const __grid_constant__ ExhMaps maps, const uint32_t* __restrict__ doc_end_bits,
+                         const int64_t* __restrict__ pfxsum, const int64_t* __restrict__ cta_doc_start,
+                         StrideSet strides, int n_queries, int n_qblocks, int parts, int64_t n_docs, uint32_t idesc,
+                         float* __restrict__ scores) {
+  extern __shared__ uint8_t smem_raw[];
+  __shared__ __align__(8) uint64_t bar_a_full, bar_pass_done;
+  __shared__ __align__(8) uint64_t bar_b_full[kBStages], bar_b_empty[kBStages];
+  __shared__ __align__(8) uint64_t bar_acc_full[kAccSlots], bar_acc_empty[kAccSlots];
+  __shared__ uint32_t tmem_base_smem;
+
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const uint32_t raw = smem_u32(smem_raw);
+  const uint32_t a_addr = (raw + 1023u) & ~1023u;              // kABlocks × 32 KB
+  const uint32_t b_addr = a_addr + kABlocks * kTileBytes;      // kBStages × 32 KB
+
+  if (tid == 0) {
+    mbar_init(smem_u32(&bar_a_full), 1);
+    mbar_init(smem_u32(&bar_pass_done), 1);
+    for (int s = 0; s < kBStages; ++s) {
+      mbar_init(smem_u32(&bar_b_full[s]), 1);
+      mbar_init(smem_u32(&bar_b_empty[s]), 1);
+    }
+    for (int s = 0; s < kAccSlots; ++s) {
+      mbar_init(smem_u32(&bar_acc_full[s]), 1);
+      mbar_init(smem_u32(&bar_acc_empty[s]), 4);   // one arrival per epilogue warp
+    }
+    fence_mbar_init();
+  }
+  if (warp == 1) {
+    umma::tmem_alloc(smem_u32(&tmem_base_smem), 512);
+    umma::tmem_relinquish();
+  }
+  umma::fence_before_sync();
+  __syncthreads();
+  umma::fence_after_sync();
+  const uint32_t tmem = tmem_base_smem;
+
+  const int64_t d0 = cta_doc_start[blockIdx.x], d1 = cta_doc_start[blockIdx.x + 1];
+  const int64_t tok0 = pfxsum[d0], tok1 = pfxsum[d1];
+  const int ntiles = static_cast<int>((tok1 - tok0 + kTileTok - 1) / kTileTok);
+  const int qb_max = kABlocks / parts;                          // query blocks per pass
+  const int n_passes = (n_qblocks + qb_max - 1) / qb_max;
+
+  if (warp == 0) {
+    // ===================================== TMA producer =============================================
+    if (lane == 0) {
+      tma_prefetch_desc(&maps.store);
+      tma_prefetch_desc(&maps.q);
+      uint32_t it = 0;
+      for (int p = 0; p < n_passes; ++p) {
+        if (p > 0) mbar_wait(smem_u32(&bar_pass_done), (p - 1) & 1);   // every MMA that read the old A blocks is done
+        const int qb = min(qb_max, n_qblocks - p * qb_max);
+        const uint32_t afull = smem_u32(&bar_a_full);
+        mbar_arrive_expect_tx(afull, static_cast<uint32_t>(qb * parts) * kTileBytes);
+        for (int a = 0; a < qb; ++a)
+          for (int part = 0; part < parts; ++part) {
+            const int row = (part * n_qblocks + p * qb_max + a) * 128;
+            const uint32_t dst = a_addr + (a * parts + part) * kTileBytes;
+            tma_load_2d(dst, &maps.q, 0, row, afull, kEvictLast);
+            tma_load_2d(dst + kTileBytes / 2, &maps.q, 64, row, afull, kEvictLast);
+          }
+        for (int t = 0; t < ntiles; ++t, ++it) {
+          const uint32_t st = it % kBStages;
+          mbar_wait(smem_u32(&bar_b_empty[st]), ((it / kBStages) & 1u) ^ 1u);
+          const uint32_t full = smem_u32(&bar_b_full[st]);
+          const uint32_t dst = b_addr + st * kTileBytes;
+          const int row = static_cast<int>(tok0) + t * kTileTok;
+          mbar_arrive_expect_tx(full, kTileBytes);
+          tma_load_2d(dst, &maps.store, 0, row, full, kEvictFirst);
+          tma_load_2d(dst + kTileBytes / 2, &maps.store, 64, row, full, kEvictFirst);
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ===================================== MMA issuer ===============================================
+    if (lane == 0) {
+      uint32_t it = 0, acc_it = 0;
+      for (int p = 0; p < n_passes; ++p) {
+        const int qb = min(qb_max, n_qblocks - p * qb_max);
+        mbar_wait(smem_u32(&bar_a_full), p & 1);
+        umma::fence_after_sync();
+        for (int t = 0; t < ntiles; ++t, ++it) {
+          const uint32_t st = it % kBStages;
+          mbar_wait(smem_u32(&bar_b_full[st]), (it / kBStages) & 1u);
+          umma::fence_after_sync();
+          const uint32_t bt = b_addr + st * kTileBytes;
+          for (int a = 0; a < qb; ++a, ++acc_it) {
+            const uint32_t slot = acc_it % kAccSlots;
+            mbar_wait(smem_u32(&bar_acc_empty[slot]), ((acc_it / kAccSlots) & 1u) ^ 1u);
+            umma::fence_after_sync();
+            const uint32_t d_tmem = tmem + slot * kTileTok;
+            uint32_t acc = 0;
+            for (int part = 0; part < parts; ++part) {
+              const uint32_t at = a_addr + (a * parts + part) * kTileBytes;
+#pragma unroll
+              for (int h = 0; h < 2; ++h)
+#pragma unroll
+                for (int k = 0; k < 4; ++k) {
+                  umma::mma_f16_ss(d_tmem, umma::make_smem_desc_sw128(at + h * (kTileBytes / 2) + k * 32),
+                                   umma::make_smem_desc_sw128(bt + h * (kTileBytes / 2) + k * 32), idesc, acc);
+                  acc = 1;
+                }
+            }
+            umma::commit(smem_u32(&bar_acc_full[slot]));
+          }
+          umma::commit(smem_u32(&bar_b_empty[st]));
+        }
+        umma::commit(smem_u32(&bar_pass_done));
+      }
+    }
+  } else {
+    // ===================================== epilogue (warps 2..5) ====================================
+    const int quad = warp & 3;                       // TMEM lane quadrant this warp may read = query within the block
+    const uint32_t lane_base = static_cast<uint32_t>(quad * 32) << 16;
+    uint32_t acc_it = 0;
+    for (int p = 0; p < n_passes; ++p) {
+      const int qb = min(qb_max, n_qblocks - p * qb_max);
+      int64_t doc = d0;
+      int cur_len = 0;
+      float run[kABlocks];
+#pragma unroll
+      for (int a = 0; a < kABlocks; ++a) run[a] = -INFINITY;
+
+      for (int t = 0; t < ntiles; ++t) {
+        // 128 document-end bits of this tile, shifted so that bit j of word c is column 32c + j
+        const int64_t tbase = tok0 + static_cast<int64_t>(t) * kTileTok;
+        const int64_t w0 = tbase >> 5;
+        const int sh = static_cast<int>(tbase & 31);
+        uint32_t wraw[5];
+#pragma unroll
+        for (int i = 0; i < 5; ++i) wraw[i] = doc_end_bits[w0 + i];
+        uint32_t ends[4];
+#pragma unroll
+        for (int c = 0; c < 4; ++c) {
+          ends[c] = __funnelshift_r(wraw[c], wraw[c + 1], sh);
+          const int64_t left = tok1 - (tbase + 32 * c);          // rows of this CTA's range left in the chunk
+          if (left <= 0) ends[c] = 0u;
+          else if (left < 32) ends[c] &= (1u << left) - 1u;
+        }
+        int64_t doc_next = doc;
+        int len_next = cur_len;
+#pragma unroll
+        for (int a = 0; a < kABlocks; ++a) {
+          if (a < qb) {
+            const uint32_t slot = acc_it % kAccSlots;
+            mbar_wait(smem_u32(&bar_acc_full[slot]), (acc_it / kAccSlots) & 1u);
+            umma::fence_after_sync();
+            ++acc_it;
+            const int q = (p * qb_max + a) * 4 + quad;
+            int64_t doc_a = doc;
+            int len_a = cur_len;
+            float r = run[a];
+#pragma unroll
+            for (int c = 0; c < 4; ++c) {
+              uint32_t v[32];
+              umma::tmem_ld_32x32(tmem + lane_base + slot * kTileTok + c * 32, v);
+              umma::tmem_ld_wait();
+              if (c == 3) {   // all columns of the slot are in registers: hand it back to the MMA warp
+                umma::fence_before_sync();
+                __syncwarp();
+                if (lane == 0) mbar_arrive(smem_u32(&bar_acc_empty[slot]));
+              }
+              const uint32_t m = ends[c];
+              if (m == 0u) {
+                float mx = __uint_as_float(v[0]);
+#pragma unroll
+                for (int j = 1; j < 32; ++j) mx = fmaxf(mx, __uint_as_float(v[j]));
+                r = fmaxf(r, mx);
+                len_a += 32;
+              } else {
+#pragma unroll
+                for (int j = 0; j < 32; ++j) {
+                  r = fmaxf(r, __uint_as_float(v[j]));
+                  ++len_a;
+                  if ((m >> j) & 1u) {   // column 32c + j is the last token of document doc_a (warp-uniform)
+                    bool do_floor = strides.n > 0;
+#pragma unroll
+                    for (int i = 0; i < CBK_MAX_STRIDES; ++i)
+                      if (i < strides.n && strides.v[i] == len_a) do_floor = false;
+                    const float total = warp_sum(do_floor ? fmaxf(r, 0.f) : r);
+                    if (lane == 0 && q < n_queries) scores[static_cast<int64_t>(q) * n_docs + doc_a] = total;
+                    ++doc_a;
+                    len_a = 0;
+                    r = -INFINITY;
+                  }
+                }
+              }
+            }
+            run[a] = r;
+            doc_next = doc_a;
+            len_next = len_a;
+          }
+        }
+        doc = doc_next;
+        cur_len = len_next;
+      }
+    }
+  }
+
+  umma::fence_before_sync();
+  __syncthreads();
+  if (warp == 1) umma::tmem_dealloc(tmem, 512);
+}
+
+}  // namespace
+
+size_t doc_end_bits_bytes(int64_t n_store_rows) {
+  return static_cast<size_t>((n_store_rows + 31) / 32 + 8) * sizeof(uint32_t);   // +8 words: tiles read 5 words past their start
+}
+
+int doc_end_bits_dispatch(const int64_t* d_pfxsum, int64_t n_docs, int64_t n_store_rows, uint32_t* d_bits,
+                          cudaStream_t stream) {
+  CBK_CUDA(cudaMemsetAsync(d_bits, 0, doc_end_bits_bytes(n_store_rows), stream));
+  const int threads = 256;
+  const unsigned int blocks = static_cast<unsigned int>((n_docs + threads - 1) / threads);
+  doc_end_bits_kernel<<<blocks, threads, 0, stream>>>(d_pfxsum, n_docs, d_bits);
+  CBK_CUDA(cudaGetLastError());
+  count_launch();
+  return CBK_OK;
+}
+
+size_t exhaustive_workspace_bytes(int64_t n_queries) {
+  const int64_t n_qblocks = (n_queries + 3) / 4;
+  return 4096 /* CTA ranges */ + static_cast<size_t>(2 * n_qblocks * 128 * 128 * 2) /* packed queries, ≤ 2 parts */;
+}
+
+int exhaustive_dispatch(const void* d_store, int store_dtype, int64_t n_store_rows, const int64_t* d_pfxsum,
+                        const uint32_t* d_doc_end_bits, int64_t n_docs, const int32_t* strides, int n_strides,
+                        const float* d_Q, int q_len, int64_t n_queries, float* d_out_scores, void* d_workspace,
+                        int flags, cudaStream_t stream) {
+  const int n_ctas = std::min<int64_t>(sm_count(), std::max<int64_t>(1, n_docs));
+  const int n_qblocks = static_cast<int>((n_queries + 3) / 4);
+  const bool bf16 = store_dtype == CBK_BF16;
+  const int parts = (bf16 && !(flags & CBK_FLAG_BF16_NATIVE_MMA)) ? 2 : 1;
+  int64_t* d_ranges = static_cast<int64_t*>(d_workspace);
+  void* d_qp = static_cast<uint8_t*>(d_workspace) + 4096;
+
+  plan_ranges_kernel<<<1, 256, 0, stream>>>(d_pfxsum, n_docs, n_ctas, d_ranges);
+  CBK_CUDA(cudaGetLastError());
+  const int64_t pack_threads = static_cast<int64_t>(n_qblocks) * 128 * 32;
+  const unsigned int pack_blocks = static_cast<unsigned int>((pack_threads + 255) / 256);
+  if (bf16)
+    pack_queries_kernel<__nv_bfloat16><<<pack_blocks, 256, 0, stream>>>(d_Q, static_cast<int>(n_queries), q_len, n_qblocks,
+                                                                        parts, static_cast<__nv_bfloat16*>(d_qp));
+  else
+    pack_queries_kernel<__half><<<pack_blocks, 256, 0, stream>>>(d_Q, static_cast<int>(n_queries), q_len, n_qblocks, parts,
+                                                                 static_cast<__half*>(d_qp));
+  CBK_CUDA(cudaGetLastError());
+
+  ExhMaps maps;
+  int rc = make_store_tensor_map(&maps.store, d_store, n_store_rows, 128, 64, kTileTok);
+  if (rc != CBK_OK) return rc;
+  rc = make_store_tensor_map(&maps.q, d_qp, static_cast<int64_t>(parts) * n_qblocks * 128, 128, 64, 128);
+  if (rc != CBK_OK) return rc;
+  StrideSet ss;
+  ss.n = n_strides;
+  for (int i = 0; i < CBK_MAX_STRIDES; ++i) ss.v[i] = i < n_strides ? strides[i] : -1;
+  const uint32_t fmt = bf16 ? umma::kFmtBF16 : umma::kFmtF16;
+  const uint32_t idesc = umma::make_idesc(128, kTileTok, fmt, fmt);
+  const size_t smem = 1024 + static_cast<size_t>(kABlocks + kBStages) * kTileBytes;
+  CBK_CUDA(cudaFuncSetAttribute(maxsim_exhaustive_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
+  maxsim_exhaustive_kernel<<<n_ctas, kExhThreads, smem, stream>>>(maps, d_doc_end_bits, d_pfxsum, d_ranges, ss,
+                                                                static_cast<int>(n_queries), n_qblocks, parts, n_docs, idesc,
+                                                                d_out_scores);
+  CBK_CUDA(cudaGetLastError());
+  count_launch(3);
+  return CBK_OK;
+}
+
+}  // namespace cbk

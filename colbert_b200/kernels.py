@@ -199,3 +199,59 @@ def selftest_umma_gemm(A: torch.Tensor, B: torch.Tensor) -> torch.Tensor:
                                         _ptr(Cout), C.c_void_p(_lib.current_stream_ptr(dev)))
     _lib.check("cbk_selftest_umma_gemm", rc)
     return Cout
+
+
+def build_doc_end_bits(pfxsum: torch.Tensor, n_store_rows: int) -> torch.Tensor:
+    """Index-time metadata for the exhaustive kernel: one bit per store row, set on the last row of each
+    document (int32 words).  See cbk_build_doc_end_bits."""
+    lib = _lib.load()
+    dev = pfxsum.device
+    _need(pfxsum, "pfxsum", torch.int64, dev)
+    bits = torch.empty(int(lib.cbk_doc_end_bits_bytes(int(n_store_rows))) // 4, dtype=torch.int32, device=dev)
+    with torch.cuda.device(dev):
+        rc = lib.cbk_build_doc_end_bits(_ptr(pfxsum), pfxsum.numel() - 1, int(n_store_rows), _ptr(bits),
+                                        C.c_void_p(_lib.current_stream_ptr(dev)))
+    _lib.check("cbk_build_doc_end_bits", rc)
+    return bits
+
+
+def maxsim_exhaustive(store: torch.Tensor, pfxsum: torch.Tensor, doc_end_bits: torch.Tensor, strides: Sequence[int],
+                      Q: torch.Tensor, flags: int = 0, out: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """scores [B, n_docs] fp32 of every document against every query (tcgen05 kernel); see cbk_maxsim_exhaustive."""
+    lib = _lib.load()
+    dev = store.device
+    _need(store, "store", store.dtype, dev)
+    _need(pfxsum, "pfxsum", torch.int64, dev)
+    _need(doc_end_bits, "doc_end_bits", torch.int32, dev)
+    _need(Q, "Q", torch.float32, dev)
+    n_q, q_len, dim = Q.shape
+    n_docs = pfxsum.numel() - 1
+    if out is None:
+        out = torch.empty((n_q, n_docs), dtype=torch.float32, device=dev)
+    ws = torch.empty(int(lib.cbk_maxsim_exhaustive_workspace_bytes(n_q)), dtype=torch.uint8, device=dev)
+    st = (C.c_int32 * max(1, len(strides)))(*[int(s) for s in strides])
+    with torch.cuda.device(dev):
+        rc = lib.cbk_maxsim_exhaustive(_ptr(store), _lib.dtype_code(store.dtype), store.size(0), dim, _ptr(pfxsum),
+                                       _ptr(doc_end_bits), n_docs, C.cast(st, C.c_void_p), len(strides), _ptr(Q), q_len,
+                                       n_q, _ptr(out), _ptr(ws), ws.numel(), int(flags),
+                                       C.c_void_p(_lib.current_stream_ptr(dev)))
+    _lib.check("cbk_maxsim_exhaustive", rc)
+    return out
+
+
+def topk_dense(scores: torch.Tensor, k: int, pid_base: int = 0, as_keys: bool = False):
+    """Row-wise top-k of a dense [B, n_docs] score matrix → (scores [B,k], pids [B,k]); pid = pid_base + column.
+    With ``as_keys`` → packed int64 keys [B,k] for the cross-shard merge."""
+    lib = _lib.load()
+    dev = scores.device
+    _need(scores, "scores", torch.float32, dev)
+    n_q, n_docs = scores.shape
+    ws = torch.empty(int(lib.cbk_topk_dense_workspace_bytes(n_q, n_docs, int(k))), dtype=torch.uint8, device=dev)
+    out_s = torch.empty((n_q, k), dtype=torch.float32, device=dev)
+    out_p = torch.empty((n_q, k), dtype=torch.int64, device=dev)
+    with torch.cuda.device(dev):
+        rc = lib.cbk_topk_dense(_ptr(scores), n_q, n_docs, int(k), int(pid_base), int(as_keys),
+                                None if as_keys else _ptr(out_s), _ptr(out_p), _ptr(ws), ws.numel(),
+                                C.c_void_p(_lib.current_stream_ptr(dev)))
+    _lib.check("cbk_topk_dense", rc)
+    return out_p if as_keys else (out_s, out_p)

@@ -191,6 +191,23 @@ class ColbertRanker:
         top_scores, top_pids = kernels.topk_per_query(scores, cand_pids, cand_rowptr, k, max_cand)
         return top_pids, top_scores
 
+    def score_all(self, Q: torch.Tensor) -> torch.Tensor:
+        """fp32 ``[B, n_docs]``: every document of this store against every query (``Q`` ``[B, q_len ≤ 32, dim]``
+        fp32 on the device) — the query-batched tcgen05 kernel."""
+        if getattr(self, "_doc_end_bits", None) is None:
+            assert int(self.doclens.min()) >= 1, "exhaustive scoring needs every document to have at least one row"
+            self._doc_end_bits = kernels.build_doc_end_bits(self._pfxsum_dev, self.tensor.size(0))
+        return kernels.maxsim_exhaustive(self.tensor, self._pfxsum_dev, self._doc_end_bits, self.strides, Q,
+                                         flags=self.kernel_flags & kernels._lib.CBK_FLAG_BF16_NATIVE_MMA)
+
+    def rank_exhaustive(self, Q: torch.Tensor, k: int = 1000) -> Tuple[torch.Tensor, torch.Tensor]:
+        """No candidate generation: score the whole store and keep the top ``k`` per query.
+        ``Q``: ``[B, q_len, dim]`` fp32 (host or device) → ``(pids [B,k] int64, scores [B,k] fp32)`` on the device."""
+        Q = Q.to(self.device, dtype=self.maxsim_dtype, non_blocking=True).contiguous()
+        k = min(int(k), int(self.doclens.numel()))
+        scores, pids = kernels.topk_dense(self.score_all(Q), k, pid_base=self.pid_base)
+        return pids, scores
+
     # -- reference colbert_ranker.py:75-137 ----------------------------------------------------------
     def rank_forward(self, Q, pids, views=None, depth=10, output_D_embedding=False):
         """``Q``: ``[1, dim, q_len]`` (as ``ColbertRetriever.search`` passes it, faiss_indexers.py:232-234);

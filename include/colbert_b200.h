@@ -195,6 +195,37 @@ int cbk_mask_cast_rows(const void* d_src, int src_dtype, int64_t n_rows, int dim
                        void* d_out, int out_dtype, void* stream);
 
 /* ------------------------------------------------------------------------------------------------
+ * Exhaustive, query-batched MaxSim — every document of the store against a batch of queries: the
+ * all-pairs shape of BaseModel.score (BaseModel.py:39-46) applied to the flat store of
+ * colbert_ranker.py:61-73.  Document tiles are read from HBM once per pass of
+ * up to 16 queries (8 for bf16 stores, whose query is split in hi + lo parts) and multiplied on tcgen05
+ * tensor cores with TMEM accumulators.
+ *
+ *   cbk_build_doc_end_bits   index-time metadata: bit t of d_bits set ⇔ store row t is the last row of a
+ *                            document; d_bits has cbk_doc_end_bits_bytes(n_store_rows) bytes.  Every
+ *                            document must have at least one row.
+ *   cbk_maxsim_exhaustive    d_out_scores [n_queries, n_docs] fp32 row-major: score of query q against
+ *                            document p at [q*n_docs + p], same floor rule as cbk_maxsim_rerank.
+ *                            d_Q [n_queries, q_len ≤ 32, 128] fp32; dim must be 128.
+ *   cbk_topk_dense           per-row top-k of a dense score matrix [n_queries, n_docs] (pid = pid_base +
+ *                            column), same total order as cbk_topk_per_query; k ≤ 8192.  as_keys != 0: the
+ *                            winners are written to d_out_pids as packed keys (see cbk_topk_per_query_keys)
+ *                            for the cross-shard merge, and d_out_scores may be NULL.
+ * ------------------------------------------------------------------------------------------------ */
+size_t cbk_doc_end_bits_bytes(int64_t n_store_rows);
+int cbk_build_doc_end_bits(const int64_t* d_pfxsum, int64_t n_docs, int64_t n_store_rows, uint32_t* d_bits, void* stream);
+
+size_t cbk_maxsim_exhaustive_workspace_bytes(int64_t n_queries);
+int cbk_maxsim_exhaustive(const void* d_store, int store_dtype, int64_t n_store_rows, int dim,
+                          const int64_t* d_pfxsum, const uint32_t* d_doc_end_bits, int64_t n_docs,
+                          const int32_t* strides, int n_strides, const float* d_Q, int q_len, int64_t n_queries,
+                          float* d_out_scores, void* d_workspace, size_t workspace_bytes, int flags, void* stream);
+
+size_t cbk_topk_dense_workspace_bytes(int64_t n_queries, int64_t n_docs, int k);
+int cbk_topk_dense(const float* d_scores, int64_t n_queries, int64_t n_docs, int k, int64_t pid_base, int as_keys,
+                   float* d_out_scores, int64_t* d_out_pids, void* d_workspace, size_t workspace_bytes, void* stream);
+
+/* ------------------------------------------------------------------------------------------------
  * Self-test of the tcgen05 / TMEM / TMA building blocks the query-batched kernels are made of:
  *     C[128, N] = A[128, 128] · B[N, 128]^T      16-bit inputs (a_bf16 / b_bf16: 0 = fp16, 1 = bf16), fp32 out
  * N a multiple of 16 in [16, 256]; one CTA.  Not part of the scoring path.

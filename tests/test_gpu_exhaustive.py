@@ -1,0 +1,82 @@
+"""Query-batched exhaustive scoring (tcgen05 kernel) and the dense top-k against the oracle."""
+import numpy as np
+import pytest
+import torch
+
+from oracle import maxsim_oracle as O
+from parity_utils import SCORE_RTOL, check_topk
+
+pytestmark = pytest.mark.gpu
+DEV = torch.device("cuda", 0)
+
+
+def _index(seed, doclens):
+    from colbert_b200 import synthetic
+    return synthetic.make_index(seed, len(doclens), dim=128, doclens=doclens)
+
+
+def _oracle_scores(index, strides, Q, store_values):
+    store, pf = O.pad_store(store_values), O.doclens_pfxsum(index.doclens)
+    all_pids = np.arange(index.num_docs)
+    return np.stack([O.maxsim_exact(store, index.doclens, pf, strides, Q[b], all_pids) for b in range(Q.shape[0])])
+
+
+@pytest.mark.parametrize("dt", [torch.float16, torch.bfloat16], ids=["fp16", "bf16"])
+@pytest.mark.parametrize("n_q,q_len", [(1, 32), (4, 32), (5, 8), (17, 32), (40, 20)])
+def test_exhaustive_scores_match_oracle(dt, n_q, q_len):
+    from colbert_b200 import synthetic
+    from colbert_b200.ranking import ColbertRanker
+    rng = np.random.default_rng(n_q)
+    # long documents (span several 128-token tiles), runs of 1-token documents, ordinary ones
+    doclens = np.concatenate([rng.integers(1, 181, size=1500), np.ones(300, np.int64), rng.integers(200, 513, size=40),
+                              rng.integers(1, 181, size=1200)]).astype(np.int64)
+    rng.shuffle(doclens)
+    index = _index(1000 + n_q, doclens)
+    emb = torch.from_numpy(index.emb).to(dt)
+    ranker = ColbertRanker.from_tensors(emb, index.doclens.tolist(), device=DEV, store_dtype=dt)
+    Q = synthetic.make_queries(50 + n_q, n_q, q_len, 128)
+    got = ranker.score_all(torch.from_numpy(Q).to(DEV)).cpu().numpy()
+    ref = _oracle_scores(index, ranker.strides, Q, emb.float().numpy())
+    rel = np.abs(got - ref) / np.maximum(np.abs(ref), 1.0)
+    print(f"[{dt}, n_q={n_q}, q_len={q_len}] worst relative error {rel.max():.3e}")
+    assert got.shape == ref.shape and rel.max() <= SCORE_RTOL
+
+
+def test_exhaustive_equals_rerank_of_everything():
+    """The tcgen05 path and the mma.sync rerank path are two kernels for the same function."""
+    from colbert_b200 import synthetic
+    from colbert_b200.ranking import ColbertRanker
+    index = synthetic.make_index(4, 2500, dim=128, lo=1, hi=180)
+    ranker = ColbertRanker.from_tensors(torch.from_numpy(index.emb), index.doclens.tolist(), device=DEV)
+    Q = torch.from_numpy(synthetic.make_queries(5, 6, 32, 128)).to(DEV)
+    dense = ranker.score_all(Q)
+    cand = torch.arange(index.num_docs, dtype=torch.int64, device=DEV).repeat(6)
+    rowptr = torch.arange(0, 7 * index.num_docs, index.num_docs, dtype=torch.int64, device=DEV)
+    rer = ranker.score_candidates(Q, cand, rowptr).reshape(6, -1)
+    assert torch.allclose(dense, rer, rtol=2e-5, atol=2e-5)
+
+
+@pytest.mark.parametrize("n_docs,k", [(50, 10), (5000, 1000), (40_000, 1000), (300_000, 100)])
+def test_topk_dense_matches_oracle(n_docs, k):
+    from colbert_b200 import kernels
+    rng = np.random.default_rng(n_docs)
+    sc = np.round(rng.standard_normal((3, n_docs)), 2).astype(np.float32)      # rounding → exact ties
+    ts, tp = kernels.topk_dense(torch.from_numpy(sc).to(DEV), min(k, n_docs), pid_base=1000)
+    for b in range(3):
+        rp, rs = O.topk_desc(sc[b], np.arange(n_docs, dtype=np.int64) + 1000, min(k, n_docs))
+        assert np.array_equal(tp[b].cpu().numpy(), rp) and np.array_equal(ts[b].cpu().numpy(), rs)
+
+
+def test_rank_exhaustive_topk():
+    from colbert_b200 import synthetic
+    from colbert_b200.ranking import ColbertRanker
+    index = synthetic.make_index(8, 20_000, dim=128, lo=20, hi=120)
+    ranker = ColbertRanker.from_tensors(torch.from_numpy(index.emb), index.doclens.tolist(), device=DEV)
+    Q = synthetic.make_queries(9, 3, 32, 128)
+    pids, scores = ranker.rank_exhaustive(torch.from_numpy(Q), k=100)
+    store, pf = O.pad_store(index.emb), O.doclens_pfxsum(index.doclens)
+    for b in range(3):
+        ref = O.maxsim_exact(store, index.doclens, pf, ranker.strides, Q[b], np.arange(index.num_docs))
+        rp, rs = O.topk_desc(ref, np.arange(index.num_docs, dtype=np.int64), 100)
+        fp, fs = O.topk_desc(ref, np.arange(index.num_docs, dtype=np.int64), None)
+        check_topk(pids[b].cpu().numpy(), scores[b].cpu().numpy(), rp, rs, SCORE_RTOL, fp, fs)
