@@ -95,6 +95,18 @@ __device__ __forceinline__ float warp_sum(float v) {
   return v;
 }
 
+// End of a document reached by a whole warp (lane = query row): apply the reference's zero floor
+// (doclen ∉ strides, SURVEY.md §8 a12'), sum the 32 rows, store one score.  Deliberately NOT inlined:
+// it is reached from 32 unrolled column positions and the epilogue must stay inside the instruction cache.
+__device__ __noinline__ void finish_document(float row_max, int doclen, const int* s_strides, int n_strides,
+                                             float* __restrict__ dst, bool write) {
+  bool do_floor = n_strides > 0;
+  for (int i = 0; i < n_strides; ++i)
+    if (s_strides[i] == doclen) do_floor = false;
+  const float total = warp_sum(do_floor ? fmaxf(row_max, 0.f) : row_max);
+  if (write && (threadIdx.x & 31) == 0) *dst = total;
+}
+
 // =====================================================================================================
 __global__ void __launch_bounds__(kExhThreads, 1)
 maxsim_exhaustive_kernel(const __grid_constant__ ExhMaps maps, const uint32_t* __restrict__ doc_end_bits,
@@ -106,8 +118,12 @@ maxsim_exhaustive_kernel(const __grid_constant__ ExhMaps maps, const uint32_t* _
   __shared__ __align__(8) uint64_t bar_b_full[kBStages], bar_b_empty[kBStages];
   __shared__ __align__(8) uint64_t bar_acc_full[kAccSlots], bar_acc_empty[kAccSlots];
   __shared__ uint32_t tmem_base_smem;
+  __shared__ int s_strides[CBK_MAX_STRIDES];
+  __shared__ int s_n_strides;
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  if (tid < CBK_MAX_STRIDES) s_strides[tid] = strides.v[tid];
+  if (tid == 0) s_n_strides = strides.n;
   const uint32_t raw = smem_u32(smem_raw);
   const uint32_t a_addr = (raw + 1023u) & ~1023u;              // kABlocks × 32 KB
   const uint32_t b_addr = a_addr + kABlocks * kTileBytes;      // kBStages × 32 KB
@@ -209,6 +225,8 @@ maxsim_exhaustive_kernel(const __grid_constant__ ExhMaps maps, const uint32_t* _
     }
   } else {
     // ===================================== epilogue (warps 2..5) ====================================
+    // Code-size discipline: the loops over query blocks (a) and 32-column chunks (c) are real loops;
+    // only the 32 columns of a chunk are unrolled (register array), and the per-document tail is a call.
     const int quad = warp & 3;                       // TMEM lane quadrant this warp may read = query within the block
     const uint32_t lane_base = static_cast<uint32_t>(quad * 32) << 16;
     uint32_t acc_it = 0;
@@ -216,9 +234,7 @@ maxsim_exhaustive_kernel(const __grid_constant__ ExhMaps maps, const uint32_t* _
       const int qb = min(qb_max, n_qblocks - p * qb_max);
       int64_t doc = d0;
       int cur_len = 0;
-      float run[kABlocks];
-#pragma unroll
-      for (int a = 0; a < kABlocks; ++a) run[a] = -INFINITY;
+      float run0 = -INFINITY, run1 = -INFINITY, run2 = -INFINITY, run3 = -INFINITY;
 
       for (int t = 0; t < ntiles; ++t) {
         // 128 document-end bits of this tile, shifted so that bit j of word c is column 32c + j
@@ -238,57 +254,55 @@ maxsim_exhaustive_kernel(const __grid_constant__ ExhMaps maps, const uint32_t* _
         }
         int64_t doc_next = doc;
         int len_next = cur_len;
+#pragma unroll 1
+        for (int a = 0; a < qb; ++a) {
+          const uint32_t slot = acc_it % kAccSlots;
+          mbar_wait(smem_u32(&bar_acc_full[slot]), (acc_it / kAccSlots) & 1u);
+          umma::fence_after_sync();
+          ++acc_it;
+          const int q = (p * qb_max + a) * 4 + quad;
+          float* const dst_row = scores + static_cast<int64_t>(q < n_queries ? q : 0) * n_docs;
+          int64_t doc_a = doc;
+          int len_a = cur_len;
+          float r = a == 0 ? run0 : (a == 1 ? run1 : (a == 2 ? run2 : run3));
+#pragma unroll 1
+          for (int c = 0; c < 4; ++c) {
+            uint32_t v[32];
+            umma::tmem_ld_32x32(tmem + lane_base + slot * kTileTok + c * 32, v);
+            umma::tmem_ld_wait();
+            if (c == 3) {   // all columns of the slot are in registers: hand it back to the MMA warp
+              umma::fence_before_sync();
+              __syncwarp();
+              if (lane == 0) mbar_arrive(smem_u32(&bar_acc_empty[slot]));
+            }
+            const uint32_t m = c == 0 ? ends[0] : (c == 1 ? ends[1] : (c == 2 ? ends[2] : ends[3]));
+            if (m == 0u) {
+              float mx0 = fmaxf(__uint_as_float(v[0]), __uint_as_float(v[1]));
+              float mx1 = fmaxf(__uint_as_float(v[2]), __uint_as_float(v[3]));
 #pragma unroll
-        for (int a = 0; a < kABlocks; ++a) {
-          if (a < qb) {
-            const uint32_t slot = acc_it % kAccSlots;
-            mbar_wait(smem_u32(&bar_acc_full[slot]), (acc_it / kAccSlots) & 1u);
-            umma::fence_after_sync();
-            ++acc_it;
-            const int q = (p * qb_max + a) * 4 + quad;
-            int64_t doc_a = doc;
-            int len_a = cur_len;
-            float r = run[a];
-#pragma unroll
-            for (int c = 0; c < 4; ++c) {
-              uint32_t v[32];
-              umma::tmem_ld_32x32(tmem + lane_base + slot * kTileTok + c * 32, v);
-              umma::tmem_ld_wait();
-              if (c == 3) {   // all columns of the slot are in registers: hand it back to the MMA warp
-                umma::fence_before_sync();
-                __syncwarp();
-                if (lane == 0) mbar_arrive(smem_u32(&bar_acc_empty[slot]));
+              for (int j = 4; j < 32; j += 2) {
+                mx0 = fmaxf(mx0, __uint_as_float(v[j]));
+                mx1 = fmaxf(mx1, __uint_as_float(v[j + 1]));
               }
-              const uint32_t m = ends[c];
-              if (m == 0u) {
-                float mx = __uint_as_float(v[0]);
+              r = fmaxf(r, fmaxf(mx0, mx1));
+              len_a += 32;
+            } else {
 #pragma unroll
-                for (int j = 1; j < 32; ++j) mx = fmaxf(mx, __uint_as_float(v[j]));
-                r = fmaxf(r, mx);
-                len_a += 32;
-              } else {
-#pragma unroll
-                for (int j = 0; j < 32; ++j) {
-                  r = fmaxf(r, __uint_as_float(v[j]));
-                  ++len_a;
-                  if ((m >> j) & 1u) {   // column 32c + j is the last token of document doc_a (warp-uniform)
-                    bool do_floor = strides.n > 0;
-#pragma unroll
-                    for (int i = 0; i < CBK_MAX_STRIDES; ++i)
-                      if (i < strides.n && strides.v[i] == len_a) do_floor = false;
-                    const float total = warp_sum(do_floor ? fmaxf(r, 0.f) : r);
-                    if (lane == 0 && q < n_queries) scores[static_cast<int64_t>(q) * n_docs + doc_a] = total;
-                    ++doc_a;
-                    len_a = 0;
-                    r = -INFINITY;
-                  }
+              for (int j = 0; j < 32; ++j) {
+                r = fmaxf(r, __uint_as_float(v[j]));
+                if ((m >> j) & 1u) {   // column 32c + j is the last token of document doc_a (warp-uniform)
+                  finish_document(r, len_a + j + 1, s_strides, s_n_strides, dst_row + doc_a, q < n_queries);
+                  ++doc_a;
+                  len_a = -(j + 1);
+                  r = -INFINITY;
                 }
               }
+              len_a += 32;
             }
-            run[a] = r;
-            doc_next = doc_a;
-            len_next = len_a;
           }
+          if (a == 0) run0 = r; else if (a == 1) run1 = r; else if (a == 2) run2 = r; else run3 = r;
+          doc_next = doc_a;
+          len_next = len_a;
         }
         doc = doc_next;
         cur_len = len_next;
