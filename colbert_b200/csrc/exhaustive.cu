@@ -14,8 +14,11 @@
 //     32 rows is one warp reduction per (query, document);
 //   * document boundaries come from a bitmap with one bit per store row (set on the last row of each
 //     document), so the epilogue never chases pfxsum;
-//   * warp roles: warp 0 TMA producer, warp 1 MMA issuer (one thread), warps 2-5 epilogue (one TMEM
-//     lane quadrant = one query each); 3-stage smem ring for document tiles, 4 TMEM accumulator slots.
+//   * warp roles: warp 0 TMA producer, warp 1 MMA issuer (one thread), warps 2-17 epilogue: four groups of
+//     four warps (one TMEM lane quadrant = one query each).  A CTA owns four document-aligned token
+//     sub-ranges and interleaves their tiles; group g drains the accumulators of sub-range g, so four
+//     accumulators are being reduced while the next ones are being multiplied.  3-stage smem ring for
+//     document tiles, 4 TMEM accumulator slots of 128 columns.
 // bf16 stores: both MMA operands must share a format (mixed fp16 × bf16 is an illegal instruction),
 // so the query is split into bf16 hi + lo parts and each tile is multiplied twice into the same
 // accumulator (K = 256); fp16 stores need one pass over K.
@@ -32,7 +35,8 @@ constexpr int kBStages = 3;
 constexpr int kABlocks = 4;               // 32 KB A slots in shared memory
 constexpr int kAccSlots = 4;              // × 128 TMEM columns
 constexpr int kTileBytes = kTileTok * 256;
-constexpr int kExhThreads = 192;
+constexpr int kEpiGroups = 4;             // epilogue warp groups (4 warps each, one per TMEM lane quadrant)
+constexpr int kExhThreads = 64 + kEpiGroups * 128;
 
 struct StrideSet {
   int n;
@@ -150,9 +154,19 @@ maxsim_exhaustive_kernel(const __grid_constant__ ExhMaps maps, const uint32_t* _
   umma::fence_after_sync();
   const uint32_t tmem = tmem_base_smem;
 
-  const int64_t d0 = cta_doc_start[blockIdx.x], d1 = cta_doc_start[blockIdx.x + 1];
-  const int64_t tok0 = pfxsum[d0], tok1 = pfxsum[d1];
-  const int ntiles = static_cast<int>((tok1 - tok0 + kTileTok - 1) / kTileTok);
+  // four document-aligned sub-ranges per CTA; item (t, g) = tile t of sub-range g, visited t-major
+  int64_t sub_d0[kEpiGroups], sub_tok0[kEpiGroups], sub_tok1[kEpiGroups];
+  int sub_nt[kEpiGroups];
+  int max_nt = 0;
+#pragma unroll
+  for (int g = 0; g < kEpiGroups; ++g) {
+    sub_d0[g] = cta_doc_start[blockIdx.x * kEpiGroups + g];
+    const int64_t dend = cta_doc_start[blockIdx.x * kEpiGroups + g + 1];
+    sub_tok0[g] = pfxsum[sub_d0[g]];
+    sub_tok1[g] = pfxsum[dend];
+    sub_nt[g] = static_cast<int>((sub_tok1[g] - sub_tok0[g] + kTileTok - 1) / kTileTok);
+    max_nt = max(max_nt, sub_nt[g]);
+  }
   const int qb_max = kABlocks / parts;                          // query blocks per pass
   const int n_passes = (n_qblocks + qb_max - 1) / qb_max;
 
@@ -174,16 +188,20 @@ maxsim_exhaustive_kernel(const __grid_constant__ ExhMaps maps, const uint32_t* _
             tma_load_2d(dst, &maps.q, 0, row, afull, kEvictLast);
             tma_load_2d(dst + kTileBytes / 2, &maps.q, 64, row, afull, kEvictLast);
           }
-        for (int t = 0; t < ntiles; ++t, ++it) {
-          const uint32_t st = it % kBStages;
-          mbar_wait(smem_u32(&bar_b_empty[st]), ((it / kBStages) & 1u) ^ 1u);
-          const uint32_t full = smem_u32(&bar_b_full[st]);
-          const uint32_t dst = b_addr + st * kTileBytes;
-          const int row = static_cast<int>(tok0) + t * kTileTok;
-          mbar_arrive_expect_tx(full, kTileBytes);
-          tma_load_2d(dst, &maps.store, 0, row, full, kEvictFirst);
-          tma_load_2d(dst + kTileBytes / 2, &maps.store, 64, row, full, kEvictFirst);
-        }
+        for (int t = 0; t < max_nt; ++t)
+#pragma unroll
+          for (int g = 0; g < kEpiGroups; ++g) {
+            if (t >= sub_nt[g]) continue;
+            const uint32_t st = it % kBStages;
+            mbar_wait(smem_u32(&bar_b_empty[st]), ((it / kBStages) & 1u) ^ 1u);
+            const uint32_t full = smem_u32(&bar_b_full[st]);
+            const uint32_t dst = b_addr + st * kTileBytes;
+            const int row = static_cast<int>(sub_tok0[g]) + t * kTileTok;
+            mbar_arrive_expect_tx(full, kTileBytes);
+            tma_load_2d(dst, &maps.store, 0, row, full, kEvictFirst);
+            tma_load_2d(dst + kTileBytes / 2, &maps.store, 64, row, full, kEvictFirst);
+            ++it;
+          }
       }
     }
   } else if (warp == 1) {
@@ -194,51 +212,80 @@ maxsim_exhaustive_kernel(const __grid_constant__ ExhMaps maps, const uint32_t* _
         const int qb = min(qb_max, n_qblocks - p * qb_max);
         mbar_wait(smem_u32(&bar_a_full), p & 1);
         umma::fence_after_sync();
-        for (int t = 0; t < ntiles; ++t, ++it) {
-          const uint32_t st = it % kBStages;
-          mbar_wait(smem_u32(&bar_b_full[st]), (it / kBStages) & 1u);
-          umma::fence_after_sync();
-          const uint32_t bt = b_addr + st * kTileBytes;
-          for (int a = 0; a < qb; ++a, ++acc_it) {
-            const uint32_t slot = acc_it % kAccSlots;
-            mbar_wait(smem_u32(&bar_acc_empty[slot]), ((acc_it / kAccSlots) & 1u) ^ 1u);
+        for (int t = 0; t < max_nt; ++t)
+#pragma unroll
+          for (int g = 0; g < kEpiGroups; ++g) {
+            if (t >= sub_nt[g]) continue;
+            const uint32_t st = it % kBStages;
+            mbar_wait(smem_u32(&bar_b_full[st]), (it / kBStages) & 1u);
             umma::fence_after_sync();
-            const uint32_t d_tmem = tmem + slot * kTileTok;
-            uint32_t acc = 0;
-            for (int part = 0; part < parts; ++part) {
-              const uint32_t at = a_addr + (a * parts + part) * kTileBytes;
+            const uint32_t bt = b_addr + st * kTileBytes;
+            for (int a = 0; a < qb; ++a, ++acc_it) {
+              const uint32_t slot = acc_it % kAccSlots;
+              mbar_wait(smem_u32(&bar_acc_empty[slot]), ((acc_it / kAccSlots) & 1u) ^ 1u);
+              umma::fence_after_sync();
+              const uint32_t d_tmem = tmem + slot * kTileTok;
+              uint32_t acc = 0;
+              for (int part = 0; part < parts; ++part) {
+                const uint32_t at = a_addr + (a * parts + part) * kTileBytes;
 #pragma unroll
-              for (int h = 0; h < 2; ++h)
+                for (int h = 0; h < 2; ++h)
 #pragma unroll
-                for (int k = 0; k < 4; ++k) {
-                  umma::mma_f16_ss(d_tmem, umma::make_smem_desc_sw128(at + h * (kTileBytes / 2) + k * 32),
-                                   umma::make_smem_desc_sw128(bt + h * (kTileBytes / 2) + k * 32), idesc, acc);
-                  acc = 1;
-                }
+                  for (int k = 0; k < 4; ++k) {
+                    umma::mma_f16_ss(d_tmem, umma::make_smem_desc_sw128(at + h * (kTileBytes / 2) + k * 32),
+                                     umma::make_smem_desc_sw128(bt + h * (kTileBytes / 2) + k * 32), idesc, acc);
+                    acc = 1;
+                  }
+              }
+              umma::commit(smem_u32(&bar_acc_full[slot]));
             }
-            umma::commit(smem_u32(&bar_acc_full[slot]));
+            umma::commit(smem_u32(&bar_b_empty[st]));
+            ++it;
           }
-          umma::commit(smem_u32(&bar_b_empty[st]));
-        }
         umma::commit(smem_u32(&bar_pass_done));
       }
     }
   } else {
-    // ===================================== epilogue (warps 2..5) ====================================
+    // ===================================== epilogue (warps 2..17) ===================================
     // Code-size discipline: the loops over query blocks (a) and 32-column chunks (c) are real loops;
-    // only the 32 columns of a chunk are unrolled (register array), and the per-document tail is a call.
+    // only the columns of a chunk are unrolled (register array), and the per-document tail is a call.
+    const int grp = (warp - 2) >> 2;                 // sub-range this warp group drains
     const int quad = warp & 3;                       // TMEM lane quadrant this warp may read = query within the block
     const uint32_t lane_base = static_cast<uint32_t>(quad * 32) << 16;
+    int64_t my_d0 = 0, my_tok0 = 0, my_tok1 = 0;
+#pragma unroll
+    for (int g = 0; g < kEpiGroups; ++g)
+      if (g == grp) {
+        my_d0 = sub_d0[g];
+        my_tok0 = sub_tok0[g];
+        my_tok1 = sub_tok1[g];
+      }
     uint32_t acc_it = 0;
     for (int p = 0; p < n_passes; ++p) {
       const int qb = min(qb_max, n_qblocks - p * qb_max);
-      int64_t doc = d0;
+      int64_t doc = my_d0;
       int cur_len = 0;
       float run0 = -INFINITY, run1 = -INFINITY, run2 = -INFINITY, run3 = -INFINITY;
 
-      for (int t = 0; t < ntiles; ++t) {
+      for (int t = 0; t < max_nt; ++t) {
+        // accumulator slots are handed out in item order: skip over the other groups' items of this round
+        bool mine = false;
+#pragma unroll
+        for (int g = 0; g < kEpiGroups; ++g) {
+          if (t >= sub_nt[g]) continue;
+          if (g < grp) acc_it += qb;
+          if (g == grp) mine = true;
+        }
+        uint32_t after = 0;
+#pragma unroll
+        for (int g = 0; g < kEpiGroups; ++g)
+          if (t < sub_nt[g] && g > grp) after += qb;
+        if (!mine) {
+          acc_it += after;
+          continue;
+        }
         // 128 document-end bits of this tile, shifted so that bit j of word c is column 32c + j
-        const int64_t tbase = tok0 + static_cast<int64_t>(t) * kTileTok;
+        const int64_t tbase = my_tok0 + static_cast<int64_t>(t) * kTileTok;
         const int64_t w0 = tbase >> 5;
         const int sh = static_cast<int>(tbase & 31);
         uint32_t wraw[5];
@@ -248,7 +295,7 @@ maxsim_exhaustive_kernel(const __grid_constant__ ExhMaps maps, const uint32_t* _
 #pragma unroll
         for (int c = 0; c < 4; ++c) {
           ends[c] = __funnelshift_r(wraw[c], wraw[c + 1], sh);
-          const int64_t left = tok1 - (tbase + 32 * c);          // rows of this CTA's range left in the chunk
+          const int64_t left = my_tok1 - (tbase + 32 * c);       // rows of this sub-range left in the chunk
           if (left <= 0) ends[c] = 0u;
           else if (left < 32) ends[c] &= (1u << left) - 1u;
         }
@@ -276,29 +323,28 @@ maxsim_exhaustive_kernel(const __grid_constant__ ExhMaps maps, const uint32_t* _
               if (lane == 0) mbar_arrive(smem_u32(&bar_acc_empty[slot]));
             }
             const uint32_t m = c == 0 ? ends[0] : (c == 1 ? ends[1] : (c == 2 ? ends[2] : ends[3]));
-            if (m == 0u) {
-              float mx0 = fmaxf(__uint_as_float(v[0]), __uint_as_float(v[1]));
-              float mx1 = fmaxf(__uint_as_float(v[2]), __uint_as_float(v[3]));
 #pragma unroll
-              for (int j = 4; j < 32; j += 2) {
-                mx0 = fmaxf(mx0, __uint_as_float(v[j]));
-                mx1 = fmaxf(mx1, __uint_as_float(v[j + 1]));
-              }
-              r = fmaxf(r, fmaxf(mx0, mx1));
-              len_a += 32;
-            } else {
+            for (int s8 = 0; s8 < 4; ++s8) {   // 8 columns at a time: most groups of 8 hold no document end
+              const uint32_t m8 = (m >> (8 * s8)) & 0xffu;
+              if (m8 == 0u) {
+                const float x0 = fmaxf(fmaxf(__uint_as_float(v[8 * s8]), __uint_as_float(v[8 * s8 + 1])), __uint_as_float(v[8 * s8 + 2]));
+                const float x1 = fmaxf(fmaxf(__uint_as_float(v[8 * s8 + 3]), __uint_as_float(v[8 * s8 + 4])), __uint_as_float(v[8 * s8 + 5]));
+                const float x2 = fmaxf(fmaxf(__uint_as_float(v[8 * s8 + 6]), __uint_as_float(v[8 * s8 + 7])), r);
+                r = fmaxf(fmaxf(x0, x1), x2);
+              } else {
 #pragma unroll
-              for (int j = 0; j < 32; ++j) {
-                r = fmaxf(r, __uint_as_float(v[j]));
-                if ((m >> j) & 1u) {   // column 32c + j is the last token of document doc_a (warp-uniform)
-                  finish_document(r, len_a + j + 1, s_strides, s_n_strides, dst_row + doc_a, q < n_queries);
-                  ++doc_a;
-                  len_a = -(j + 1);
-                  r = -INFINITY;
+                for (int j = 0; j < 8; ++j) {
+                  r = fmaxf(r, __uint_as_float(v[8 * s8 + j]));
+                  if ((m8 >> j) & 1u) {   // this column is the last token of document doc_a (warp-uniform)
+                    finish_document(r, len_a + 8 * s8 + j + 1, s_strides, s_n_strides, dst_row + doc_a, q < n_queries);
+                    ++doc_a;
+                    len_a = -(8 * s8 + j + 1);
+                    r = -INFINITY;
+                  }
                 }
               }
-              len_a += 32;
             }
+            len_a += 32;
           }
           if (a == 0) run0 = r; else if (a == 1) run1 = r; else if (a == 2) run2 = r; else run3 = r;
           doc_next = doc_a;
@@ -306,6 +352,7 @@ maxsim_exhaustive_kernel(const __grid_constant__ ExhMaps maps, const uint32_t* _
         }
         doc = doc_next;
         cur_len = len_next;
+        acc_it += after;
       }
     }
   }
@@ -334,21 +381,21 @@ int doc_end_bits_dispatch(const int64_t* d_pfxsum, int64_t n_docs, int64_t n_sto
 
 size_t exhaustive_workspace_bytes(int64_t n_queries) {
   const int64_t n_qblocks = (n_queries + 3) / 4;
-  return 4096 /* CTA ranges */ + static_cast<size_t>(2 * n_qblocks * 128 * 128 * 2) /* packed queries, ≤ 2 parts */;
+  return 8192 /* CTA sub-ranges */ + static_cast<size_t>(2 * n_qblocks * 128 * 128 * 2) /* packed queries, ≤ 2 parts */;
 }
 
 int exhaustive_dispatch(const void* d_store, int store_dtype, int64_t n_store_rows, const int64_t* d_pfxsum,
                         const uint32_t* d_doc_end_bits, int64_t n_docs, const int32_t* strides, int n_strides,
                         const float* d_Q, int q_len, int64_t n_queries, float* d_out_scores, void* d_workspace,
                         int flags, cudaStream_t stream) {
-  const int n_ctas = std::min<int64_t>(sm_count(), std::max<int64_t>(1, n_docs));
+  const int n_ctas = static_cast<int>(std::min<int64_t>(sm_count(), std::max<int64_t>(1, n_docs / kEpiGroups)));
   const int n_qblocks = static_cast<int>((n_queries + 3) / 4);
   const bool bf16 = store_dtype == CBK_BF16;
   const int parts = (bf16 && !(flags & CBK_FLAG_BF16_NATIVE_MMA)) ? 2 : 1;
   int64_t* d_ranges = static_cast<int64_t*>(d_workspace);
-  void* d_qp = static_cast<uint8_t*>(d_workspace) + 4096;
+  void* d_qp = static_cast<uint8_t*>(d_workspace) + 8192;
 
-  plan_ranges_kernel<<<1, 256, 0, stream>>>(d_pfxsum, n_docs, n_ctas, d_ranges);
+  plan_ranges_kernel<<<(n_ctas * kEpiGroups + 256) / 256, 256, 0, stream>>>(d_pfxsum, n_docs, n_ctas * kEpiGroups, d_ranges);
   CBK_CUDA(cudaGetLastError());
   const int64_t pack_threads = static_cast<int64_t>(n_qblocks) * 128 * 32;
   const unsigned int pack_blocks = static_cast<unsigned int>((pack_threads + 255) / 256);
