@@ -120,7 +120,9 @@ maxsim_exhaustive_kernel(const __grid_constant__ ExhMaps maps, const uint32_t* _
   extern __shared__ uint8_t smem_raw[];
   __shared__ __align__(8) uint64_t bar_a_full, bar_pass_done;
   __shared__ __align__(8) uint64_t bar_b_full[kBStages], bar_b_empty[kBStages];
-  __shared__ __align__(8) uint64_t bar_acc_full[kAccSlots], bar_acc_empty[kAccSlots];
+  // acc_full is per (consuming epilogue group, slot): an mbarrier wait only tells phases apart by parity, so a
+  // barrier must never have two waiters that are a whole phase apart (two groups sharing one slot would be)
+  __shared__ __align__(8) uint64_t bar_acc_full[kEpiGroups * kAccSlots], bar_acc_empty[kAccSlots];
   __shared__ uint32_t tmem_base_smem;
   __shared__ int s_strides[CBK_MAX_STRIDES];
   __shared__ int s_n_strides;
@@ -139,10 +141,8 @@ maxsim_exhaustive_kernel(const __grid_constant__ ExhMaps maps, const uint32_t* _
       mbar_init(smem_u32(&bar_b_full[s]), 1);
       mbar_init(smem_u32(&bar_b_empty[s]), 1);
     }
-    for (int s = 0; s < kAccSlots; ++s) {
-      mbar_init(smem_u32(&bar_acc_full[s]), 1);
-      mbar_init(smem_u32(&bar_acc_empty[s]), 4);   // one arrival per epilogue warp
-    }
+    for (int s = 0; s < kEpiGroups * kAccSlots; ++s) mbar_init(smem_u32(&bar_acc_full[s]), 1);
+    for (int s = 0; s < kAccSlots; ++s) mbar_init(smem_u32(&bar_acc_empty[s]), 4);   // one arrival per epilogue warp
     fence_mbar_init();
   }
   if (warp == 1) {
@@ -237,7 +237,7 @@ maxsim_exhaustive_kernel(const __grid_constant__ ExhMaps maps, const uint32_t* _
                     acc = 1;
                   }
               }
-              umma::commit(smem_u32(&bar_acc_full[slot]));
+              umma::commit(smem_u32(&bar_acc_full[g * kAccSlots + slot]));
             }
             umma::commit(smem_u32(&bar_b_empty[st]));
             ++it;
@@ -261,6 +261,7 @@ maxsim_exhaustive_kernel(const __grid_constant__ ExhMaps maps, const uint32_t* _
         my_tok1 = sub_tok1[g];
       }
     uint32_t acc_it = 0;
+    uint32_t full_parity = 0;                        // bit s = parity of this group's next wait on its barrier of slot s
     for (int p = 0; p < n_passes; ++p) {
       const int qb = min(qb_max, n_qblocks - p * qb_max);
       int64_t doc = my_d0;
@@ -304,7 +305,8 @@ maxsim_exhaustive_kernel(const __grid_constant__ ExhMaps maps, const uint32_t* _
 #pragma unroll 1
         for (int a = 0; a < qb; ++a) {
           const uint32_t slot = acc_it % kAccSlots;
-          mbar_wait(smem_u32(&bar_acc_full[slot]), (acc_it / kAccSlots) & 1u);
+          mbar_wait(smem_u32(&bar_acc_full[grp * kAccSlots + slot]), (full_parity >> slot) & 1u);
+          full_parity ^= 1u << slot;
           umma::fence_after_sync();
           ++acc_it;
           const int q = (p * qb_max + a) * 4 + quad;
