@@ -105,6 +105,23 @@ class ShardedColbertRanker:
         scores, pids = kernels.merge_topk_keys(gathered, k)
         return pids, scores
 
+    def _local_exhaustive_keys(self, Q: torch.Tensor, k: int) -> torch.Tensor:
+        """Every document of this shard against every query; local top-k as packed keys (global pids)."""
+        return kernels.topk_dense(self.local.score_all(Q), k, pid_base=self.pid_base, as_keys=True)
+
+    def rank_exhaustive(self, Q: torch.Tensor, k: int = 1000):
+        """Exhaustive scoring over the whole sharded corpus: every rank scans its own
+        shard, one all-gather of [B, k] packed keys, replicated merge → (pids [B,k], scores [B,k]), identical on
+        all ranks and equal to a single-GPU ``ColbertRanker.rank_exhaustive`` over the whole corpus."""
+        dev = self.local.device if self.local is not None else Q.device
+        Q = Q.to(dev, dtype=torch.float32, non_blocking=True).contiguous()
+        k_local = min(int(k), int(self.local.doclens.numel())) if self.local is not None else int(k)
+        keys = self._local_exhaustive_keys(Q, k_local)
+        if k_local < k:   # a shard smaller than k: pad its list so that every rank contributes [B, k]
+            pad = torch.zeros((keys.size(0), k - k_local), dtype=keys.dtype, device=keys.device)
+            keys = torch.cat([keys, pad], dim=1)
+        return self._merge(self._exchange(keys), int(k))
+
     def rank_forward_batch(self, Q: torch.Tensor, cand_pids: torch.Tensor, cand_rowptr: Optional[torch.Tensor] = None,
                            depth: Optional[int] = 10, max_cand: Optional[int] = None):
         """Same contract as ``ColbertRanker.rank_forward_batch`` with GLOBAL pids; identical on all ranks."""

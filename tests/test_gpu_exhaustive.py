@@ -80,3 +80,28 @@ def test_rank_exhaustive_topk():
         rp, rs = O.topk_desc(ref, np.arange(index.num_docs, dtype=np.int64), 100)
         fp, fs = O.topk_desc(ref, np.arange(index.num_docs, dtype=np.int64), None)
         check_topk(pids[b].cpu().numpy(), scores[b].cpu().numpy(), rp, rs, SCORE_RTOL, fp, fs)
+
+
+@pytest.mark.parametrize("world", [2, 4])
+def test_sharded_exhaustive_matches_single_store(world):
+    """Config 4 layout on one GPU: W shard stores side by side, packed-key lists stacked as the all-gather would,
+    merged by the device kernel → identical to the single-store result."""
+    from colbert_b200 import kernels, synthetic
+    from colbert_b200.ranking import ColbertRanker
+    from colbert_b200.sharding import plan_shards
+    index = synthetic.make_index(515, 30_000, dim=128, lo=20, hi=120)
+    single = ColbertRanker.from_tensors(torch.from_numpy(index.emb), index.doclens.tolist(), device=DEV)
+    Q = torch.from_numpy(synthetic.make_queries(516, 5, 32, 128)).to(DEV)
+    k = 200
+    ref_pids, ref_scores = single.rank_exhaustive(Q, k=k)
+    pf = single.doclens_pfxsum
+    bounds = plan_shards(pf, world)
+    keys = []
+    for r in range(world):
+        lo, hi = bounds[r], bounds[r + 1]
+        shard = ColbertRanker.from_tensors(torch.from_numpy(index.emb[int(pf[lo]): int(pf[hi])]),
+                                           index.doclens[lo:hi].tolist(), device=DEV)
+        shard.strides, shard.pid_base = single.strides, lo
+        keys.append(kernels.topk_dense(shard.score_all(Q), k, pid_base=lo, as_keys=True))
+    scores, pids = kernels.merge_topk_keys(torch.stack(keys).contiguous(), k)
+    assert torch.equal(pids, ref_pids) and torch.equal(scores, ref_scores)
