@@ -40,6 +40,9 @@ def parse_args():
     ap.add_argument("--docs", type=int, default=2_000_000, help="documents per GPU shard")
     ap.add_argument("--depth", type=int, default=10)
     ap.add_argument("--dtype", default="bf16", choices=["bf16", "fp16"])
+    ap.add_argument("--doclen-fixed", type=int, default=0,
+                    help="every document has exactly this many rows (configs[2], multi-view: 8); 0 = U[1,180]")
+    ap.add_argument("--q-len", type=int, default=32, help="query rows (multi-view: q_view)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--cpu-queries", type=int, default=128, help="bounded CPU-baseline sample (queries)")
     return ap.parse_args()
@@ -97,9 +100,12 @@ class ClockSampler:
 # --------------------------------------------------------------------------------------------------
 # synthetic workload: unit-norm rows, doclen U[1,180], candidates uniform w/o replacement
 # --------------------------------------------------------------------------------------------------
-def build_store(torch, dev, n_docs, dim, dtype, seed):
+def build_store(torch, dev, n_docs, dim, dtype, seed, doclen_fixed=0):
     g = torch.Generator(device="cpu"); g.manual_seed(seed)
-    doclens = torch.randint(1, 181, (n_docs,), generator=g, dtype=torch.int64)
+    if doclen_fixed:
+        doclens = torch.full((n_docs,), int(doclen_fixed), dtype=torch.int64)
+    else:
+        doclens = torch.randint(1, 181, (n_docs,), generator=g, dtype=torch.int64)
     total = int(doclens.sum())
     store = torch.zeros(total + 512, dim, dtype=dtype, device=dev)       # reference layout: +512 zero rows
     gg = torch.Generator(device=dev); gg.manual_seed(seed + 1)
@@ -206,12 +212,12 @@ def run_ours(args, rank, world, local_rank):
     lib = _lib.load()
     assert lib.cbk_device_supported(local_rank) == 1, "bench.py needs an sm_100 device"
     dtype = torch.bfloat16 if args.dtype == "bf16" else torch.float16
-    dim, q_len = 128, 32
+    dim, q_len = 128, args.q_len
 
     # Weak scaling: every GPU holds a shard of `--docs` documents (pids [rank*docs, (rank+1)*docs)); the job
     # scores `--queries * world` queries, each with `--cands` candidates drawn over the WHOLE corpus, so every
     # GPU scores ~queries*cands candidates per step.  All ranks see the same (replicated) queries and lists.
-    store, doclens = build_store(torch, dev, args.docs, dim, dtype, seed=1234 + rank)
+    store, doclens = build_store(torch, dev, args.docs, dim, dtype, seed=1234 + rank, doclen_fixed=args.doclen_fixed)
     ranker = ColbertRanker.from_store(store, doclens)
     n_queries = args.queries * world
     Q_host, cand_host = build_queries(torch, n_queries, q_len, dim, args.docs * world, args.cands, seed=4321)
@@ -319,8 +325,9 @@ def run_ours(args, rank, world, local_rank):
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": args.dtype, "data": "synthetic",
             "config": {
                 "workload": f"rerank: {n_queries} queries x {args.cands} candidates ({args.queries}x{args.cands} per GPU), "
-                            f"q_len 32, dim 128, doclen U[1,180], {args.dtype} store of {args.docs} docs per GPU, "
-                            f"top-{k} per query (BASELINE.json configs[1])",
+                            f"q_len {q_len}, dim 128, doclen {args.doclen_fixed or 'U[1,180]'}, {args.dtype} store of "
+                            f"{args.docs} docs per GPU, top-{k} per query "
+                            f"(BASELINE.json configs[{2 if args.doclen_fixed else 1}])",
                 "store_bytes_per_gpu": int(store.numel() * 2),
                 "l2_policy": "inputs larger than L2: each step gathers "
                              f"{algo_bytes / 1e9:.1f} GB of distinct document rows from a {store.numel() * 2 / 1e9:.1f} GB store",
