@@ -39,6 +39,9 @@ SIGNATURES = {
     "cbk_gather_rows": (C.c_int, [_vp, _i32, _i64, _i32, _vp, _vp, _i64, _vp, _i64, _i32, _vp, _vp, _vp]),
     "cbk_partition_workspace_bytes": (_sz, [_i64]),
     "cbk_partition_candidates": (C.c_int, [_vp, _vp, _i64, _i64, _i64, _vp, _vp, _vp, _sz, _vp]),
+    "cbk_build_emb2pid": (C.c_int, [_vp, _i64, _vp, _vp]),
+    "cbk_embedding_ids_to_pids_workspace_bytes": (_sz, [_i64, _i32]),
+    "cbk_embedding_ids_to_pids": (C.c_int, [_vp, _i64, _i32, _vp, _i64, _vp, _vp, _vp, _sz, _vp]),
     "cbk_doc_end_bits_bytes": (_sz, [_i64]),
     "cbk_build_doc_end_bits": (C.c_int, [_vp, _i64, _i64, _vp, _vp]),
     "cbk_maxsim_exhaustive_workspace_bytes": (_sz, [_i64]),

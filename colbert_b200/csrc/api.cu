@@ -29,6 +29,8 @@ int exhaustive_dispatch(const void*, int, int64_t, const int64_t*, const uint32_
                         int, int64_t, float*, void*, int, cudaStream_t);
 size_t topk_dense_workspace_bytes(int64_t, int64_t, int);
 int topk_dense_dispatch(const float*, int64_t, int64_t, int, int64_t, int, float*, int64_t*, void*, cudaStream_t);
+int emb2pid_dispatch(const int64_t*, int64_t, int32_t*, cudaStream_t);
+int unique_pids_dispatch(const int64_t*, int64_t, int, const int32_t*, int64_t, int64_t*, int64_t*, void*, cudaStream_t);
 int umma_probe_dispatch(const void*, const void*, int, int, int, float*, cudaStream_t);
 int mask_cast_dispatch(const void*, int, int64_t, int, const void*, int, void*, int, cudaStream_t);
 
@@ -253,6 +255,36 @@ int cbk_mask_cast_rows(const void* d_src, int src_dtype, int64_t n_rows, int dim
   if (rc != CBK_OK) return rc;
   return mask_cast_dispatch(d_src, src_dtype, n_rows, dim, mask_dtype == CBK_MASK_NONE ? nullptr : d_mask, mask_dtype,
                             d_out, out_dtype, static_cast<cudaStream_t>(stream));
+}
+
+int cbk_build_emb2pid(const int64_t* d_pfxsum, int64_t n_docs, int32_t* d_emb2pid, void* stream) {
+  CBK_CHECK_ARG(d_pfxsum && d_emb2pid && n_docs > 0, "cbk_build_emb2pid: bad argument");
+  CBK_CHECK_SUPPORTED(n_docs < (1ll << 31), "cbk_build_emb2pid: too many documents for int32 pids");
+  int rc = check_device();
+  if (rc != CBK_OK) return rc;
+  return emb2pid_dispatch(d_pfxsum, n_docs, d_emb2pid, static_cast<cudaStream_t>(stream));
+}
+
+size_t cbk_embedding_ids_to_pids_workspace_bytes(int64_t n_queries, int n_ids) {
+  if (n_queries <= 0 || n_ids <= 0) return 8;
+  return static_cast<size_t>(n_queries) * (static_cast<size_t>(n_ids) + 1) * sizeof(int64_t);
+}
+
+int cbk_embedding_ids_to_pids(const int64_t* d_emb_ids, int64_t n_queries, int n_ids, const int32_t* d_emb2pid,
+                              int64_t n_tokens, int64_t* d_out_pids, int64_t* d_out_rowptr, void* d_workspace,
+                              size_t workspace_bytes, void* stream) {
+  CBK_CHECK_ARG(d_emb_ids && d_emb2pid && d_out_pids && d_out_rowptr, "cbk_embedding_ids_to_pids: null pointer argument");
+  CBK_CHECK_ARG(n_queries > 0 && n_ids > 0 && n_tokens > 0, "cbk_embedding_ids_to_pids: sizes must be positive");
+  CBK_CHECK_SUPPORTED(n_ids <= 16384 && n_queries < (1ll << 31), "cbk_embedding_ids_to_pids: n_ids %d exceeds 16384", n_ids);
+  if (!d_workspace || workspace_bytes < cbk_embedding_ids_to_pids_workspace_bytes(n_queries, n_ids)) {
+    set_error("cbk_embedding_ids_to_pids: workspace of %zu bytes, need %zu", workspace_bytes,
+              cbk_embedding_ids_to_pids_workspace_bytes(n_queries, n_ids));
+    return CBK_ERR_WORKSPACE;
+  }
+  int rc = check_device();
+  if (rc != CBK_OK) return rc;
+  return unique_pids_dispatch(d_emb_ids, n_queries, n_ids, d_emb2pid, n_tokens, d_out_pids, d_out_rowptr, d_workspace,
+                              static_cast<cudaStream_t>(stream));
 }
 
 size_t cbk_doc_end_bits_bytes(int64_t n_store_rows) { return doc_end_bits_bytes(n_store_rows > 0 ? n_store_rows : 0); }

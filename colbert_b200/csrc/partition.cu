@@ -88,7 +88,115 @@ scatter_in_range_kernel(const int64_t* __restrict__ pids, const int64_t* __restr
   }
 }
 
+// ---- candidate-generation post-processing (reference colbert_ranker.py:163-174, 212-235) ----------------
+// emb2pid[t] = document that owns store row t (ColbertIndex.build_emb2pid): one warp per document.
+__global__ void __launch_bounds__(256)
+build_emb2pid_kernel(const int64_t* __restrict__ pfxsum, int64_t n_docs, int32_t* __restrict__ emb2pid) {
+  const int lane = threadIdx.x & 31;
+  const int64_t warps = static_cast<int64_t>(gridDim.x) * (blockDim.x >> 5);
+  for (int64_t d = static_cast<int64_t>(blockIdx.x) * (blockDim.x >> 5) + (threadIdx.x >> 5); d < n_docs; d += warps) {
+    const int64_t beg = pfxsum[d], end = pfxsum[d + 1];
+    for (int64_t t = beg + lane; t < end; t += 32) emb2pid[t] = static_cast<int32_t>(d);
+  }
+}
+
+// One CTA per query: embedding ids → pids (emb2pid lookup) → sorted unique pids (the reference's per-query
+// `list(set(...))`, ColbertIndex.embedding_ids_to_pids + uniq).  Ids outside [0, n_tokens) are dropped (faiss
+// pads missing neighbours with -1).  Output: padded row of `n_ids` slots + count.
+__global__ void __launch_bounds__(256)
+unique_pids_kernel(const int64_t* __restrict__ emb_ids, int n_ids, const int32_t* __restrict__ emb2pid, int64_t n_tokens,
+                   int P, int64_t* __restrict__ out_padded, int64_t* __restrict__ counts) {
+  extern __shared__ uint32_t skeys[];          // P keys, then 8 warp totals
+  __shared__ int warp_tot[8];
+  const int64_t q = blockIdx.x;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  for (int i = tid; i < P; i += 256) {
+    uint32_t key = 0xffffffffu;                // padding sorts last (ascending)
+    if (i < n_ids) {
+      const int64_t e = emb_ids[q * n_ids + i];
+      if (e >= 0 && e < n_tokens) key = static_cast<uint32_t>(emb2pid[e]);
+    }
+    skeys[i] = key;
+  }
+  __syncthreads();
+  // bitonic sort, ascending
+  for (int size = 2; size <= P; size <<= 1)
+    for (int stride = size >> 1; stride > 0; stride >>= 1) {
+      for (int t = tid; t < (P >> 1); t += 256) {
+        const int lo = ((t & ~(stride - 1)) << 1) | (t & (stride - 1));
+        const int hi = lo + stride;
+        const bool asc = (lo & size) == 0;
+        const uint32_t a = skeys[lo], b = skeys[hi];
+        if ((a > b) == asc) {
+          skeys[lo] = b;
+          skeys[hi] = a;
+        }
+      }
+      __syncthreads();
+    }
+  // ordered compaction of first occurrences: each thread owns a contiguous run of P/256 keys
+  const int per = P / 256 > 0 ? P / 256 : 1;
+  const int beg = tid * per, end = min(P, beg + per);
+  int mine = 0;
+  for (int i = beg; i < end && tid * per < P; ++i) {
+    const uint32_t k = skeys[i];
+    if (k != 0xffffffffu && (i == 0 || skeys[i - 1] != k)) ++mine;
+  }
+  int incl = mine;
+#pragma unroll
+  for (int o = 1; o < 32; o <<= 1) {
+    const int t = __shfl_up_sync(0xffffffffu, incl, o);
+    if (lane >= o) incl += t;
+  }
+  if (lane == 31) warp_tot[warp] = incl;
+  __syncthreads();
+  int base = 0;
+  for (int w = 0; w < warp; ++w) base += warp_tot[w];
+  int pos = base + incl - mine;
+  for (int i = beg; i < end && tid * per < P; ++i) {
+    const uint32_t k = skeys[i];
+    if (k != 0xffffffffu && (i == 0 || skeys[i - 1] != k)) out_padded[q * n_ids + pos++] = static_cast<int64_t>(k);
+  }
+  if (tid == 255) counts[q] = base + incl;
+}
+
+// padded rows + rowptr → CSR
+__global__ void __launch_bounds__(256)
+pack_rows_kernel(const int64_t* __restrict__ padded, int n_ids, const int64_t* __restrict__ rowptr, int64_t n_queries,
+                 int64_t* __restrict__ out) {
+  const int64_t q = blockIdx.x;
+  const int64_t beg = rowptr[q], n = rowptr[q + 1] - beg;
+  for (int64_t i = threadIdx.x; i < n; i += blockDim.x) out[beg + i] = padded[q * n_ids + i];
+}
+
 }  // namespace
+
+int emb2pid_dispatch(const int64_t* d_pfxsum, int64_t n_docs, int32_t* d_emb2pid, cudaStream_t stream) {
+  const int grid = static_cast<int>(std::max<int64_t>(1, std::min<int64_t>((n_docs + 7) / 8, static_cast<int64_t>(sm_count()) * 16)));
+  build_emb2pid_kernel<<<grid, 256, 0, stream>>>(d_pfxsum, n_docs, d_emb2pid);
+  CBK_CUDA(cudaGetLastError());
+  count_launch();
+  return CBK_OK;
+}
+
+int unique_pids_dispatch(const int64_t* d_emb_ids, int64_t n_queries, int n_ids, const int32_t* d_emb2pid, int64_t n_tokens,
+                         int64_t* d_out_pids, int64_t* d_out_rowptr, void* d_workspace, cudaStream_t stream) {
+  int P = 256;
+  while (P < n_ids) P <<= 1;
+  int64_t* padded = static_cast<int64_t*>(d_workspace);
+  int64_t* counts = padded + n_queries * n_ids;
+  const size_t smem = static_cast<size_t>(P) * sizeof(uint32_t);
+  CBK_CUDA(cudaFuncSetAttribute(unique_pids_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
+  unique_pids_kernel<<<static_cast<unsigned int>(n_queries), 256, smem, stream>>>(d_emb_ids, n_ids, d_emb2pid, n_tokens, P,
+                                                                                  padded, counts);
+  CBK_CUDA(cudaGetLastError());
+  exclusive_scan_kernel<<<1, 1024, 0, stream>>>(counts, n_queries, d_out_rowptr);
+  CBK_CUDA(cudaGetLastError());
+  pack_rows_kernel<<<static_cast<unsigned int>(n_queries), 256, 0, stream>>>(padded, n_ids, d_out_rowptr, n_queries, d_out_pids);
+  CBK_CUDA(cudaGetLastError());
+  count_launch(3);
+  return CBK_OK;
+}
 
 int partition_dispatch(const int64_t* d_pids, const int64_t* d_rowptr, int64_t n_queries, int64_t lo, int64_t hi,
                        int64_t* d_out_pids, int64_t* d_out_rowptr, int64_t* d_counts, cudaStream_t stream) {

@@ -255,3 +255,34 @@ def topk_dense(scores: torch.Tensor, k: int, pid_base: int = 0, as_keys: bool = 
                                 C.c_void_p(_lib.current_stream_ptr(dev)))
     _lib.check("cbk_topk_dense", rc)
     return out_p if as_keys else (out_s, out_p)
+
+
+def build_emb2pid(pfxsum: torch.Tensor) -> torch.Tensor:
+    """int32 [n_tokens]: the document owning each store row (reference ColbertIndex.build_emb2pid)."""
+    lib = _lib.load()
+    dev = pfxsum.device
+    _need(pfxsum, "pfxsum", torch.int64, dev)
+    n_tokens = int(pfxsum[-1].item())
+    out = torch.empty(n_tokens, dtype=torch.int32, device=dev)
+    with torch.cuda.device(dev):
+        rc = lib.cbk_build_emb2pid(_ptr(pfxsum), pfxsum.numel() - 1, _ptr(out), C.c_void_p(_lib.current_stream_ptr(dev)))
+    _lib.check("cbk_build_emb2pid", rc)
+    return out
+
+
+def embedding_ids_to_pids(emb_ids: torch.Tensor, emb2pid: torch.Tensor):
+    """emb_ids [B, n_ids] int64 (-1 = no neighbour) → per query the sorted unique pids as CSR
+    (pids [B*n_ids] int64 of which rowptr[-1] are valid, rowptr [B+1] int64).  See cbk_embedding_ids_to_pids."""
+    lib = _lib.load()
+    dev = emb_ids.device
+    _need(emb_ids, "emb_ids", torch.int64, dev)
+    _need(emb2pid, "emb2pid", torch.int32, dev)
+    B, n_ids = emb_ids.shape
+    out_p = torch.empty(B * n_ids, dtype=torch.int64, device=dev)
+    out_r = torch.empty(B + 1, dtype=torch.int64, device=dev)
+    ws = torch.empty(int(lib.cbk_embedding_ids_to_pids_workspace_bytes(B, n_ids)), dtype=torch.uint8, device=dev)
+    with torch.cuda.device(dev):
+        rc = lib.cbk_embedding_ids_to_pids(_ptr(emb_ids), B, n_ids, _ptr(emb2pid), emb2pid.numel(), _ptr(out_p), _ptr(out_r),
+                                           _ptr(ws), ws.numel(), C.c_void_p(_lib.current_stream_ptr(dev)))
+    _lib.check("cbk_embedding_ids_to_pids", rc)
+    return out_p, out_r

@@ -185,6 +185,23 @@ int cbk_partition_candidates(const int64_t* d_cand_pids, const int64_t* d_cand_r
                              void* d_workspace, size_t workspace_bytes, void* stream);
 
 /* ------------------------------------------------------------------------------------------------
+ * Candidate-generation post-processing — the step just before the scoring path:
+ *   cbk_build_emb2pid           replaces ColbertIndex.build_emb2pid (colbert_ranker.py:163-174):
+ *                               d_emb2pid[t] = document owning store row t, int32 [n_tokens].
+ *   cbk_embedding_ids_to_pids   replaces ColbertIndex.embedding_ids_to_pids + uniq (colbert_ranker.py:212-235):
+ *                               d_emb_ids [n_queries, n_ids] int64 (the ANN search's neighbour ids, -1 = none) →
+ *                               per query the SORTED UNIQUE pids as CSR (d_out_pids capacity n_queries*n_ids,
+ *                               d_out_rowptr [n_queries+1]); the reference returns the same set in Python
+ *                               `set` order.  n_ids ≤ 16384 (= 32 query tokens × faiss_depth 512).  The CSR pair
+ *                               feeds cbk_maxsim_rerank directly, with no host round trip.
+ * ------------------------------------------------------------------------------------------------ */
+int cbk_build_emb2pid(const int64_t* d_pfxsum, int64_t n_docs, int32_t* d_emb2pid, void* stream);
+size_t cbk_embedding_ids_to_pids_workspace_bytes(int64_t n_queries, int n_ids);
+int cbk_embedding_ids_to_pids(const int64_t* d_emb_ids, int64_t n_queries, int n_ids, const int32_t* d_emb2pid,
+                              int64_t n_tokens, int64_t* d_out_pids, int64_t* d_out_rowptr, void* d_workspace,
+                              size_t workspace_bytes, void* stream);
+
+/* ------------------------------------------------------------------------------------------------
  * Masked row cast — the multiplicative masks of BaseModel.score (BaseModel.py:41-42: D * d_mask[...,None],
  * Q * q_mask[...,None]) fused with the cast to the tensor-core input type:
  *     out[r, :] = (out_dtype)( (float)src[r, :] * (float)mask[r] )          mask == NULL ⇒ plain cast

@@ -21,7 +21,7 @@ def declared_symbols():
 def test_header_declares_the_path():
     syms = declared_symbols()
     for must in ("cbk_maxsim_rerank", "cbk_topk_per_query", "cbk_gather_rows", "cbk_mask_cast_rows",
-                 "cbk_topk_per_query_keys", "cbk_merge_topk_keys", "cbk_partition_candidates", "cbk_maxsim_exhaustive", "cbk_build_doc_end_bits", "cbk_topk_dense", "cbk_last_error", "cbk_abi_version"):
+                 "cbk_topk_per_query_keys", "cbk_merge_topk_keys", "cbk_partition_candidates", "cbk_maxsim_exhaustive", "cbk_build_emb2pid", "cbk_embedding_ids_to_pids", "cbk_build_doc_end_bits", "cbk_topk_dense", "cbk_last_error", "cbk_abi_version"):
         assert must in syms
 
 

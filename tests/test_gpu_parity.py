@@ -348,3 +348,56 @@ def test_partition_candidates_matches_numpy(dev):
         exp_rowptr = np.concatenate([[0], np.cumsum([keep[rowptr[q]: rowptr[q + 1]].sum() for q in range(len(lens))])])
         assert np.array_equal(orp, exp_rowptr)
         assert np.array_equal(op[: exp_rowptr[-1]], pids[keep])                 # order preserved within and across queries
+
+
+# ------------------------------------------------------------------------------------------------
+# the caller (ColbertRetriever.search) and the candidate post-processing (emb2pid + per-query unique)
+# ------------------------------------------------------------------------------------------------
+def _brute_force_searcher(store, n_tokens):
+    """Test stand-in for the reference's faiss search: exact inner-product top-`depth` rows per query row."""
+    emb = store[:n_tokens].float()
+
+    def search(Q_rows, depth):
+        return torch.topk(Q_rows @ emb.T, depth, dim=1).indices
+    return search
+
+
+def test_emb2pid_and_unique_pids(dev):
+    from colbert_b200 import kernels, synthetic
+    index = synthetic.make_index(61, 700, dim=128, lo=1, hi=40)
+    ranker = make_ranker(index, dev)
+    emb2pid = kernels.build_emb2pid(ranker._pfxsum_dev)
+    ref = np.repeat(np.arange(index.num_docs), index.doclens)                       # colbert_ranker.py:169-172
+    assert np.array_equal(emb2pid.cpu().numpy(), ref.astype(np.int32))
+    rng = np.random.default_rng(62)
+    for n_ids in (1, 37, 256, 1000, 16384):
+        ids = rng.integers(0, index.num_tokens, size=(5, n_ids)).astype(np.int64)
+        ids[1, : n_ids // 2] = -1                                                    # faiss pads with -1
+        ids[2, :] = ids[2, 0]                                                        # a single distinct id
+        pids, rowptr = kernels.embedding_ids_to_pids(torch.from_numpy(ids).to(dev), emb2pid)
+        pids, rowptr = pids.cpu().numpy(), rowptr.cpu().numpy()
+        for b in range(5):
+            valid = ids[b][ids[b] >= 0]
+            expect = np.array(sorted(set(ref[valid].tolist())), dtype=np.int64)     # the reference's uniq(), sorted
+            assert np.array_equal(pids[rowptr[b]: rowptr[b + 1]], expect)
+
+
+def test_retriever_search_matches_oracle(dev):
+    from colbert_b200 import synthetic
+    from colbert_b200.indexing.faiss_indexers import ColbertRetriever
+    index = synthetic.make_index(71, 1200, dim=128, lo=1, hi=60)
+    ranker = make_ranker(index, dev)
+    retr = ColbertRetriever(dim=128, faiss_depth=16, searcher=_brute_force_searcher(ranker.tensor, index.num_tokens))
+    retr.load_index(ranker)
+    Q = synthetic.make_queries(72, 3, 32, 128)
+    store, pf = O.pad_store(index.emb), O.doclens_pfxsum(index.doclens)
+    batch_pids, batch_scores = retr.search_batch(torch.from_numpy(Q).to(dev), topk_doc=10)
+    for b in range(3):
+        pids, scores = retr.search(torch.from_numpy(Q[b]).to(dev), topk_doc=10)      # reference signature
+        cands = retr.faiss_index.retrieve(16, torch.from_numpy(Q[b:b + 1]).to(dev))[0]
+        assert cands == sorted(set(cands)) and len(cands) > 10
+        ref = O.maxsim_exact(store, index.doclens, pf, ranker.strides, Q[b], cands)
+        rp, rs = O.topk_desc(ref, np.asarray(cands, dtype=np.int64), 10)
+        fp, fs = O.topk_desc(ref, np.asarray(cands, dtype=np.int64), None)
+        check_topk(pids, scores, rp, rs, SCORE_RTOL, fp, fs)
+        assert batch_pids[b].tolist() == pids
