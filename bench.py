@@ -28,6 +28,12 @@ sys.path.insert(0, ROOT)
 METRIC = "candidates MaxSim-scored/sec (k=1000 rerank)"
 UNIT = "candidates/s"
 
+# dram__bytes_read.sum + dram__bytes_write.sum of ONE maxsim_rerank_kernel launch of the default workload, from the
+# `ncu --set full` capture summarised in profiles/r01_v2_rerank_ncu_full_summary.csv (94.949 GB read + 0.018 GB
+# written; algorithmic 94.869 GB — the difference is candidate/query metadata).  Only valid for the default
+# arguments (same seeds → same candidate lists).
+NCU_TRAFFIC_DEFAULT_BYTES = 94_967_255_528
+
 
 def parse_args():
     ap = argparse.ArgumentParser()
@@ -335,7 +341,10 @@ def run_ours(args, rank, world, local_rank):
                                 f"of packed top-{k} keys per step + replicated merge") if world > 1 else "single GPU",
             },
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                         "traffic": None, "kernel": "maxsim_rerank_kernel", "algorithmic_bytes_per_launch": algo_bytes,
+                         "traffic": (NCU_TRAFFIC_DEFAULT_BYTES if (world == 1 and args.queries == 4096 and args.cands == 1000
+                                                                     and args.docs == 2_000_000 and not args.doclen_fixed
+                                                                     and args.q_len == 32) else None),
+                         "kernel": "maxsim_rerank_kernel", "algorithmic_bytes_per_launch": algo_bytes,
                          "kernel_ms": kern_ms, "peak_source": peak_src},
             "e2e": {"value": total_cands * args.steps / (e2e_ms_total * 1e-3), "unit": UNIT,
                     "h2d_bytes_per_step": int(Q_pin.numel() * 4 + cand_pin.numel() * 8) * world,

@@ -268,6 +268,15 @@ maxsim_exhaustive_kernel(const __grid_constant__ ExhMaps maps, const uint32_t* _
       int cur_len = 0;
       float run0 = -INFINITY, run1 = -INFINITY, run2 = -INFINITY, run3 = -INFINITY;
 
+      // document-end bits of a tile: 5 words starting at the tile's first row (prefetched one tile ahead)
+      uint32_t wraw[5];
+      auto load_end_bits = [&](int t) {
+        const int64_t w0 = (my_tok0 + static_cast<int64_t>(t) * kTileTok) >> 5;
+#pragma unroll
+        for (int i = 0; i < 5; ++i) wraw[i] = doc_end_bits[w0 + i];
+      };
+      load_end_bits(0);
+
       for (int t = 0; t < max_nt; ++t) {
         // accumulator slots are handed out in item order: skip over the other groups' items of this round
         bool mine = false;
@@ -285,21 +294,19 @@ maxsim_exhaustive_kernel(const __grid_constant__ ExhMaps maps, const uint32_t* _
           acc_it += after;
           continue;
         }
-        // 128 document-end bits of this tile, shifted so that bit j of word c is column 32c + j
+        // shift so that bit j of word c is column 32c + j; drop the rows past this sub-range
         const int64_t tbase = my_tok0 + static_cast<int64_t>(t) * kTileTok;
-        const int64_t w0 = tbase >> 5;
         const int sh = static_cast<int>(tbase & 31);
-        uint32_t wraw[5];
-#pragma unroll
-        for (int i = 0; i < 5; ++i) wraw[i] = doc_end_bits[w0 + i];
         uint32_t ends[4];
 #pragma unroll
         for (int c = 0; c < 4; ++c) {
           ends[c] = __funnelshift_r(wraw[c], wraw[c + 1], sh);
-          const int64_t left = my_tok1 - (tbase + 32 * c);       // rows of this sub-range left in the chunk
+          const int64_t left = my_tok1 - (tbase + 32 * c);
           if (left <= 0) ends[c] = 0u;
           else if (left < 32) ends[c] &= (1u << left) - 1u;
         }
+        load_end_bits(t + 1);   // in flight while this tile is reduced (the bitmap is padded past the store)
+
         int64_t doc_next = doc;
         int len_next = cur_len;
 #pragma unroll 1
@@ -314,19 +321,12 @@ maxsim_exhaustive_kernel(const __grid_constant__ ExhMaps maps, const uint32_t* _
           int64_t doc_a = doc;
           int len_a = cur_len;
           float r = a == 0 ? run0 : (a == 1 ? run1 : (a == 2 ? run2 : run3));
-#pragma unroll 1
-          for (int c = 0; c < 4; ++c) {
-            uint32_t v[32];
-            umma::tmem_ld_32x32(tmem + lane_base + slot * kTileTok + c * 32, v);
-            umma::tmem_ld_wait();
-            if (c == 3) {   // all columns of the slot are in registers: hand it back to the MMA warp
-              umma::fence_before_sync();
-              __syncwarp();
-              if (lane == 0) mbar_arrive(smem_u32(&bar_acc_empty[slot]));
-            }
-            const uint32_t m = c == 0 ? ends[0] : (c == 1 ? ends[1] : (c == 2 ? ends[2] : ends[3]));
+          const uint32_t t_addr = tmem + lane_base + slot * kTileTok;
+
+          // reduce one 32-column chunk held in registers; 8 columns at a time (most groups of 8 hold no document end)
+          auto reduce_chunk = [&](const uint32_t (&v)[32], uint32_t m) {
 #pragma unroll
-            for (int s8 = 0; s8 < 4; ++s8) {   // 8 columns at a time: most groups of 8 hold no document end
+            for (int s8 = 0; s8 < 4; ++s8) {
               const uint32_t m8 = (m >> (8 * s8)) & 0xffu;
               if (m8 == 0u) {
                 const float x0 = fmaxf(fmaxf(__uint_as_float(v[8 * s8]), __uint_as_float(v[8 * s8 + 1])), __uint_as_float(v[8 * s8 + 2]));
@@ -347,7 +347,27 @@ maxsim_exhaustive_kernel(const __grid_constant__ ExhMaps maps, const uint32_t* _
               }
             }
             len_a += 32;
-          }
+          };
+
+          // TMEM loads are double-buffered in registers: chunk c+1 is in flight while chunk c is reduced
+          uint32_t va[32], vb[32];
+          umma::tmem_ld_32x32(t_addr, va);
+          umma::tmem_ld_wait();
+          umma::tmem_ld_32x32(t_addr + 32, vb);
+          reduce_chunk(va, ends[0]);
+          umma::tmem_ld_wait();
+          umma::tmem_ld_32x32(t_addr + 64, va);
+          reduce_chunk(vb, ends[1]);
+          umma::tmem_ld_wait();
+          umma::tmem_ld_32x32(t_addr + 96, vb);
+          reduce_chunk(va, ends[2]);
+          umma::tmem_ld_wait();
+          // all columns of the slot are in registers: hand it back to the MMA warp
+          umma::fence_before_sync();
+          __syncwarp();
+          if (lane == 0) mbar_arrive(smem_u32(&bar_acc_empty[slot]));
+          reduce_chunk(vb, ends[3]);
+
           if (a == 0) run0 = r; else if (a == 1) run1 = r; else if (a == 2) run2 = r; else run3 = r;
           doc_next = doc_a;
           len_next = len_a;
