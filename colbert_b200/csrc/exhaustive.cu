@@ -23,6 +23,7 @@
 // so the query is split into bf16 hi + lo parts and each tile is multiplied twice into the same
 // accumulator (K = 256); fp16 stores need one pass over K.
 #include <algorithm>
+#include <cstdlib>
 
 #include "umma.cuh"
 
@@ -31,7 +32,9 @@ namespace cbk {
 namespace {
 
 constexpr int kTileTok = 128;
-constexpr int kBStages = 3;
+constexpr int kSmemTiles = 6;              // 32 KB tiles in shared memory: A blocks + B stages
+constexpr int kMaxBStages = 5;
+constexpr int kPend = 8;                  // per-warp staging of finished documents before a transposed sum
 constexpr int kABlocks = 4;               // 32 KB A slots in shared memory
 constexpr int kAccSlots = 4;              // × 128 TMEM columns
 constexpr int kTileBytes = kTileTok * 256;
@@ -93,22 +96,48 @@ __global__ void pack_queries_kernel(const float* __restrict__ Q, int n_queries, 
   }
 }
 
-__device__ __forceinline__ float warp_sum(float v) {
+// Per-warp staging of finished documents: at a document end every lane (= query row) parks its row
+// maximum in pend.v[slot][lane] (and the document length in pend.len[slot]) — a handful of instructions at
+// each of the 32 unrolled column positions, which keeps the epilogue inside the instruction cache.  When
+// kPend documents are parked, lane d applies the reference's zero floor (doclen ∉ strides, SURVEY.md §8
+// a12') and adds up the 32 rows of document d (a transposed sum: no shuffle chain per document), and the
+// warp stores kPend consecutive scores at once.
+struct __align__(16) PendBuf {
+  float v[kPend][33];
+  int len[kPend];
+  int n_strides;
+  int strides[CBK_MAX_STRIDES];
+};
+
+__device__ __noinline__ void flush_pending(PendBuf* pb, int n, float* __restrict__ dst_first, bool write) {
+  __syncwarp();
+  const int lane = threadIdx.x & 31;
+  if (lane < n) {
+    const int doclen = pb->len[lane];
+    const int n_strides = pb->n_strides;
+    float floor_v = n_strides > 0 ? 0.f : -INFINITY;
+    for (int i = 0; i < n_strides; ++i)
+      if (pb->strides[i] == doclen) floor_v = -INFINITY;
+    const float* row = pb->v[lane];
+    float s0 = 0.f, s1 = 0.f, s2 = 0.f, s3 = 0.f;
 #pragma unroll
-  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
-  return v;
+    for (int i = 0; i < 32; i += 4) {
+      s0 += fmaxf(row[i], floor_v);
+      s1 += fmaxf(row[i + 1], floor_v);
+      s2 += fmaxf(row[i + 2], floor_v);
+      s3 += fmaxf(row[i + 3], floor_v);
+    }
+    if (write) dst_first[lane] = (s0 + s1) + (s2 + s3);
+  }
+  __syncwarp();
 }
 
-// End of a document reached by a whole warp (lane = query row): apply the reference's zero floor
-// (doclen ∉ strides, SURVEY.md §8 a12'), sum the 32 rows, store one score.  Deliberately NOT inlined:
-// it is reached from 32 unrolled column positions and the epilogue must stay inside the instruction cache.
-__device__ __noinline__ void finish_document(float row_max, int doclen, const int* s_strides, int n_strides,
-                                             float* __restrict__ dst, bool write) {
-  bool do_floor = n_strides > 0;
-  for (int i = 0; i < n_strides; ++i)
-    if (s_strides[i] == doclen) do_floor = false;
-  const float total = warp_sum(do_floor ? fmaxf(row_max, 0.f) : row_max);
-  if (write && (threadIdx.x & 31) == 0) *dst = total;
+// max of 8 consecutive accumulator columns and the running value
+__device__ __forceinline__ float max8(const uint32_t* v, float r) {
+  const float x0 = fmaxf(fmaxf(__uint_as_float(v[0]), __uint_as_float(v[1])), __uint_as_float(v[2]));
+  const float x1 = fmaxf(fmaxf(__uint_as_float(v[3]), __uint_as_float(v[4])), __uint_as_float(v[5]));
+  const float x2 = fmaxf(fmaxf(__uint_as_float(v[6]), __uint_as_float(v[7])), r);
+  return fmaxf(fmaxf(x0, x1), x2);
 }
 
 // =====================================================================================================
@@ -119,25 +148,29 @@ maxsim_exhaustive_kernel(const __grid_constant__ ExhMaps maps, const uint32_t* _
                          float* __restrict__ scores) {
   extern __shared__ uint8_t smem_raw[];
   __shared__ __align__(8) uint64_t bar_a_full, bar_pass_done;
-  __shared__ __align__(8) uint64_t bar_b_full[kBStages], bar_b_empty[kBStages];
+  __shared__ __align__(8) uint64_t bar_b_full[kMaxBStages], bar_b_empty[kMaxBStages];
   // acc_full is per (consuming epilogue group, slot): an mbarrier wait only tells phases apart by parity, so a
   // barrier must never have two waiters that are a whole phase apart (two groups sharing one slot would be)
   __shared__ __align__(8) uint64_t bar_acc_full[kEpiGroups * kAccSlots], bar_acc_empty[kAccSlots];
   __shared__ uint32_t tmem_base_smem;
-  __shared__ int s_strides[CBK_MAX_STRIDES];
-  __shared__ int s_n_strides;
+  __shared__ PendBuf s_pend[kEpiGroups * 4];
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-  if (tid < CBK_MAX_STRIDES) s_strides[tid] = strides.v[tid];
-  if (tid == 0) s_n_strides = strides.n;
+  if (warp >= 2 && lane <= CBK_MAX_STRIDES) {
+    if (lane == 0) s_pend[warp - 2].n_strides = strides.n;
+    else s_pend[warp - 2].strides[lane - 1] = strides.v[lane - 1];
+  }
   const uint32_t raw = smem_u32(smem_raw);
   const uint32_t a_addr = (raw + 1023u) & ~1023u;              // kABlocks × 32 KB
-  const uint32_t b_addr = a_addr + kABlocks * kTileBytes;      // kBStages × 32 KB
+  // the A region holds as many 32 KB blocks as the largest pass needs; the rest of the tiles are B stages
+  const int a_tiles = min(kABlocks, n_qblocks * parts);
+  const uint32_t b_addr = a_addr + a_tiles * kTileBytes;
+  const uint32_t kBStages = min(kMaxBStages, kSmemTiles - a_tiles);
 
   if (tid == 0) {
     mbar_init(smem_u32(&bar_a_full), 1);
     mbar_init(smem_u32(&bar_pass_done), 1);
-    for (int s = 0; s < kBStages; ++s) {
+    for (int s = 0; s < kMaxBStages; ++s) {
       mbar_init(smem_u32(&bar_b_full[s]), 1);
       mbar_init(smem_u32(&bar_b_empty[s]), 1);
     }
@@ -154,21 +187,38 @@ maxsim_exhaustive_kernel(const __grid_constant__ ExhMaps maps, const uint32_t* _
   umma::fence_after_sync();
   const uint32_t tmem = tmem_base_smem;
 
-  // four document-aligned sub-ranges per CTA; item (t, g) = tile t of sub-range g, visited t-major
-  int64_t sub_d0[kEpiGroups], sub_tok0[kEpiGroups], sub_tok1[kEpiGroups];
-  int sub_nt[kEpiGroups];
-  int max_nt = 0;
+  // A CTA owns 4 consecutive document-aligned token ranges.  In a pass with qb query blocks they are merged
+  // into n_sub = 4 / qb_eff sub-ranges (qb_eff = qb rounded up to 1, 2 or 4) whose tiles are interleaved;
+  // item (t, s) = tile t of sub-range s carries qb accumulators, and epilogue group g = s*qb_eff + a drains
+  // accumulator a of sub-range s — so every group follows ONE query block over ONE contiguous run of documents.
+  int64_t rng_d[kEpiGroups + 1], rng_tok[kEpiGroups + 1];
 #pragma unroll
-  for (int g = 0; g < kEpiGroups; ++g) {
-    sub_d0[g] = cta_doc_start[blockIdx.x * kEpiGroups + g];
-    const int64_t dend = cta_doc_start[blockIdx.x * kEpiGroups + g + 1];
-    sub_tok0[g] = pfxsum[sub_d0[g]];
-    sub_tok1[g] = pfxsum[dend];
-    sub_nt[g] = static_cast<int>((sub_tok1[g] - sub_tok0[g] + kTileTok - 1) / kTileTok);
-    max_nt = max(max_nt, sub_nt[g]);
+  for (int g = 0; g <= kEpiGroups; ++g) {
+    rng_d[g] = cta_doc_start[blockIdx.x * kEpiGroups + g];
+    rng_tok[g] = pfxsum[rng_d[g]];
   }
   const int qb_max = kABlocks / parts;                          // query blocks per pass
   const int n_passes = (n_qblocks + qb_max - 1) / qb_max;
+
+  // tiles of sub-range s when the 4 ranges are merged into n_sub sub-ranges
+  auto sub_tiles = [&](int n_sub, int s) -> int {
+    const int w = kEpiGroups / n_sub;
+    int64_t t0 = 0, t1 = 0;
+#pragma unroll
+    for (int g = 0; g <= kEpiGroups; ++g) {
+      if (g == s * w) t0 = rng_tok[g];
+      if (g == (s + 1) * w) t1 = rng_tok[g];
+    }
+    return static_cast<int>((t1 - t0 + kTileTok - 1) / kTileTok);
+  };
+  auto sub_tok0 = [&](int n_sub, int s) -> int64_t {
+    const int w = kEpiGroups / n_sub;
+    int64_t t0 = 0;
+#pragma unroll
+    for (int g = 0; g <= kEpiGroups; ++g)
+      if (g == s * w) t0 = rng_tok[g];
+    return t0;
+  };
 
   if (warp == 0) {
     // ===================================== TMA producer =============================================
@@ -179,6 +229,7 @@ maxsim_exhaustive_kernel(const __grid_constant__ ExhMaps maps, const uint32_t* _
       for (int p = 0; p < n_passes; ++p) {
         if (p > 0) mbar_wait(smem_u32(&bar_pass_done), (p - 1) & 1);   // every MMA that read the old A blocks is done
         const int qb = min(qb_max, n_qblocks - p * qb_max);
+        const int n_sub = qb == 1 ? 4 : (qb == 2 ? 2 : 1);
         const uint32_t afull = smem_u32(&bar_a_full);
         mbar_arrive_expect_tx(afull, static_cast<uint32_t>(qb * parts) * kTileBytes);
         for (int a = 0; a < qb; ++a)
@@ -188,15 +239,24 @@ maxsim_exhaustive_kernel(const __grid_constant__ ExhMaps maps, const uint32_t* _
             tma_load_2d(dst, &maps.q, 0, row, afull, kEvictLast);
             tma_load_2d(dst + kTileBytes / 2, &maps.q, 64, row, afull, kEvictLast);
           }
+        int nt[kEpiGroups];
+        int64_t t0[kEpiGroups];
+        int max_nt = 0;
+#pragma unroll
+        for (int s2 = 0; s2 < kEpiGroups; ++s2) {
+          nt[s2] = s2 < n_sub ? sub_tiles(n_sub, s2) : 0;
+          t0[s2] = s2 < n_sub ? sub_tok0(n_sub, s2) : 0;
+          max_nt = max(max_nt, nt[s2]);
+        }
         for (int t = 0; t < max_nt; ++t)
 #pragma unroll
-          for (int g = 0; g < kEpiGroups; ++g) {
-            if (t >= sub_nt[g]) continue;
+          for (int s2 = 0; s2 < kEpiGroups; ++s2) {
+            if (t >= nt[s2]) continue;
             const uint32_t st = it % kBStages;
             mbar_wait(smem_u32(&bar_b_empty[st]), ((it / kBStages) & 1u) ^ 1u);
             const uint32_t full = smem_u32(&bar_b_full[st]);
             const uint32_t dst = b_addr + st * kTileBytes;
-            const int row = static_cast<int>(sub_tok0[g]) + t * kTileTok;
+            const int row = static_cast<int>(t0[s2]) + t * kTileTok;
             mbar_arrive_expect_tx(full, kTileBytes);
             tma_load_2d(dst, &maps.store, 0, row, full, kEvictFirst);
             tma_load_2d(dst + kTileBytes / 2, &maps.store, 64, row, full, kEvictFirst);
@@ -210,12 +270,21 @@ maxsim_exhaustive_kernel(const __grid_constant__ ExhMaps maps, const uint32_t* _
       uint32_t it = 0, acc_it = 0;
       for (int p = 0; p < n_passes; ++p) {
         const int qb = min(qb_max, n_qblocks - p * qb_max);
+        const int n_sub = qb == 1 ? 4 : (qb == 2 ? 2 : 1);
+        const int qb_eff = kEpiGroups / n_sub;
+        int nt[kEpiGroups];
+        int max_nt = 0;
+#pragma unroll
+        for (int s2 = 0; s2 < kEpiGroups; ++s2) {
+          nt[s2] = s2 < n_sub ? sub_tiles(n_sub, s2) : 0;
+          max_nt = max(max_nt, nt[s2]);
+        }
         mbar_wait(smem_u32(&bar_a_full), p & 1);
         umma::fence_after_sync();
         for (int t = 0; t < max_nt; ++t)
 #pragma unroll
-          for (int g = 0; g < kEpiGroups; ++g) {
-            if (t >= sub_nt[g]) continue;
+          for (int s2 = 0; s2 < kEpiGroups; ++s2) {
+            if (t >= nt[s2]) continue;
             const uint32_t st = it % kBStages;
             mbar_wait(smem_u32(&bar_b_full[st]), (it / kBStages) & 1u);
             umma::fence_after_sync();
@@ -237,7 +306,7 @@ maxsim_exhaustive_kernel(const __grid_constant__ ExhMaps maps, const uint32_t* _
                     acc = 1;
                   }
               }
-              umma::commit(smem_u32(&bar_acc_full[g * kAccSlots + slot]));
+              umma::commit(smem_u32(&bar_acc_full[(s2 * qb_eff + a) * kAccSlots + slot]));
             }
             umma::commit(smem_u32(&bar_b_empty[st]));
             ++it;
@@ -247,135 +316,129 @@ maxsim_exhaustive_kernel(const __grid_constant__ ExhMaps maps, const uint32_t* _
     }
   } else {
     // ===================================== epilogue (warps 2..17) ===================================
-    // Code-size discipline: the loops over query blocks (a) and 32-column chunks (c) are real loops;
-    // only the columns of a chunk are unrolled (register array), and the per-document tail is a call.
-    const int grp = (warp - 2) >> 2;                 // sub-range this warp group drains
+    const int grp = (warp - 2) >> 2;                 // epilogue group
     const int quad = warp & 3;                       // TMEM lane quadrant this warp may read = query within the block
     const uint32_t lane_base = static_cast<uint32_t>(quad * 32) << 16;
-    int64_t my_d0 = 0, my_tok0 = 0, my_tok1 = 0;
-#pragma unroll
-    for (int g = 0; g < kEpiGroups; ++g)
-      if (g == grp) {
-        my_d0 = sub_d0[g];
-        my_tok0 = sub_tok0[g];
-        my_tok1 = sub_tok1[g];
-      }
+    PendBuf* const pb = &s_pend[warp - 2];
     uint32_t acc_it = 0;
     uint32_t full_parity = 0;                        // bit s = parity of this group's next wait on its barrier of slot s
     for (int p = 0; p < n_passes; ++p) {
       const int qb = min(qb_max, n_qblocks - p * qb_max);
-      int64_t doc = my_d0;
-      int cur_len = 0;
-      float run0 = -INFINITY, run1 = -INFINITY, run2 = -INFINITY, run3 = -INFINITY;
-
-      // document-end bits of a tile: 5 words starting at the tile's first row (prefetched one tile ahead)
-      uint32_t wraw[5];
-      auto load_end_bits = [&](int t) {
-        const int64_t w0 = (my_tok0 + static_cast<int64_t>(t) * kTileTok) >> 5;
+      const int n_sub = qb == 1 ? 4 : (qb == 2 ? 2 : 1);
+      const int qb_eff = kEpiGroups / n_sub;
+      const int my_s = grp / qb_eff, my_a = grp % qb_eff;
+      const bool active = my_a < qb;
+      int nt[kEpiGroups];
+      int max_nt = 0;
 #pragma unroll
-        for (int i = 0; i < 5; ++i) wraw[i] = doc_end_bits[w0 + i];
-      };
-      load_end_bits(0);
+      for (int s2 = 0; s2 < kEpiGroups; ++s2) {
+        nt[s2] = s2 < n_sub ? sub_tiles(n_sub, s2) : 0;
+        max_nt = max(max_nt, nt[s2]);
+      }
+      // my contiguous run of documents / rows
+      const int wdt = kEpiGroups / n_sub;
+      int64_t my_d0 = 0, my_tok0 = 0, my_tok1 = 0;
+#pragma unroll
+      for (int g = 0; g <= kEpiGroups; ++g) {
+        if (g == my_s * wdt) {
+          my_d0 = rng_d[g];
+          my_tok0 = rng_tok[g];
+        }
+        if (g == (my_s + 1) * wdt) my_tok1 = rng_tok[g];
+      }
+      const int q = (p * qb_max + my_a) * 4 + quad;
+      const bool write = active && q < n_queries;
+      float* const dst_row = scores + static_cast<int64_t>(write ? q : 0) * n_docs;
+
+      int64_t doc = my_d0;       // next document to finish
+      int64_t pend_first = my_d0;
+      int n_pend = 0;
+      int cur_len = 0;
+      float r = -INFINITY;
 
       for (int t = 0; t < max_nt; ++t) {
-        // accumulator slots are handed out in item order: skip over the other groups' items of this round
+        // accumulator slots are handed out in item order; find mine in this round
+        uint32_t my_acc = 0;
         bool mine = false;
+        uint32_t round_total = 0;
 #pragma unroll
-        for (int g = 0; g < kEpiGroups; ++g) {
-          if (t >= sub_nt[g]) continue;
-          if (g < grp) acc_it += qb;
-          if (g == grp) mine = true;
+        for (int s2 = 0; s2 < kEpiGroups; ++s2) {
+          if (t >= nt[s2]) continue;
+          if (s2 == my_s) {
+            mine = active;
+            my_acc = acc_it + round_total + my_a;
+          }
+          round_total += qb;
         }
-        uint32_t after = 0;
-#pragma unroll
-        for (int g = 0; g < kEpiGroups; ++g)
-          if (t < sub_nt[g] && g > grp) after += qb;
-        if (!mine) {
-          acc_it += after;
-          continue;
-        }
-        // shift so that bit j of word c is column 32c + j; drop the rows past this sub-range
+        acc_it += round_total;
+        if (!mine) continue;
+
+        // 128 document-end bits of this tile, shifted so that bit j of word c is column 32c + j
         const int64_t tbase = my_tok0 + static_cast<int64_t>(t) * kTileTok;
+        const int64_t w0 = tbase >> 5;
         const int sh = static_cast<int>(tbase & 31);
+        uint32_t wraw[5];
+#pragma unroll
+        for (int i = 0; i < 5; ++i) wraw[i] = doc_end_bits[w0 + i];
         uint32_t ends[4];
 #pragma unroll
         for (int c = 0; c < 4; ++c) {
           ends[c] = __funnelshift_r(wraw[c], wraw[c + 1], sh);
-          const int64_t left = my_tok1 - (tbase + 32 * c);
+          const int64_t left = my_tok1 - (tbase + 32 * c);       // rows of my sub-range left in the chunk
           if (left <= 0) ends[c] = 0u;
           else if (left < 32) ends[c] &= (1u << left) - 1u;
         }
-        load_end_bits(t + 1);   // in flight while this tile is reduced (the bitmap is padded past the store)
 
-        int64_t doc_next = doc;
-        int len_next = cur_len;
+        const uint32_t slot = my_acc % kAccSlots;
+        mbar_wait(smem_u32(&bar_acc_full[grp * kAccSlots + slot]), (full_parity >> slot) & 1u);
+        full_parity ^= 1u << slot;
+        umma::fence_after_sync();
+        const uint32_t t_addr = tmem + lane_base + slot * kTileTok;
 #pragma unroll 1
-        for (int a = 0; a < qb; ++a) {
-          const uint32_t slot = acc_it % kAccSlots;
-          mbar_wait(smem_u32(&bar_acc_full[grp * kAccSlots + slot]), (full_parity >> slot) & 1u);
-          full_parity ^= 1u << slot;
-          umma::fence_after_sync();
-          ++acc_it;
-          const int q = (p * qb_max + a) * 4 + quad;
-          float* const dst_row = scores + static_cast<int64_t>(q < n_queries ? q : 0) * n_docs;
-          int64_t doc_a = doc;
-          int len_a = cur_len;
-          float r = a == 0 ? run0 : (a == 1 ? run1 : (a == 2 ? run2 : run3));
-          const uint32_t t_addr = tmem + lane_base + slot * kTileTok;
-
-          // reduce one 32-column chunk held in registers; 8 columns at a time (most groups of 8 hold no document end)
-          auto reduce_chunk = [&](const uint32_t (&v)[32], uint32_t m) {
+        for (int c = 0; c < 4; ++c) {
+          uint32_t v[32];
+          umma::tmem_ld_32x32(t_addr + c * 32, v);
+          umma::tmem_ld_wait();
+          if (c == 3) {   // all columns of the slot are in registers: hand it back to the MMA warp
+            umma::fence_before_sync();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(smem_u32(&bar_acc_empty[slot]));
+          }
+          const uint32_t m = c == 0 ? ends[0] : (c == 1 ? ends[1] : (c == 2 ? ends[2] : ends[3]));
+          if (m == 0u) {   // no document ends inside these 32 columns (the common case): one max tree
+            const float y0 = max8(v, r), y1 = max8(v + 8, -INFINITY), y2 = max8(v + 16, -INFINITY), y3 = max8(v + 24, -INFINITY);
+            r = fmaxf(fmaxf(y0, y1), fmaxf(y2, y3));
+          } else {
 #pragma unroll
-            for (int s8 = 0; s8 < 4; ++s8) {
+            for (int s8 = 0; s8 < 4; ++s8) {   // 8 columns at a time: most groups of 8 still hold no document end
               const uint32_t m8 = (m >> (8 * s8)) & 0xffu;
               if (m8 == 0u) {
-                const float x0 = fmaxf(fmaxf(__uint_as_float(v[8 * s8]), __uint_as_float(v[8 * s8 + 1])), __uint_as_float(v[8 * s8 + 2]));
-                const float x1 = fmaxf(fmaxf(__uint_as_float(v[8 * s8 + 3]), __uint_as_float(v[8 * s8 + 4])), __uint_as_float(v[8 * s8 + 5]));
-                const float x2 = fmaxf(fmaxf(__uint_as_float(v[8 * s8 + 6]), __uint_as_float(v[8 * s8 + 7])), r);
-                r = fmaxf(fmaxf(x0, x1), x2);
+                r = max8(v + 8 * s8, r);
               } else {
+                if (n_pend + __popc(m8) > kPend) {   // make room for every document that ends in this group
+                  flush_pending(pb, n_pend, dst_row + pend_first, write);
+                  pend_first = doc;
+                  n_pend = 0;
+                }
 #pragma unroll
                 for (int j = 0; j < 8; ++j) {
                   r = fmaxf(r, __uint_as_float(v[8 * s8 + j]));
-                  if ((m8 >> j) & 1u) {   // this column is the last token of document doc_a (warp-uniform)
-                    finish_document(r, len_a + 8 * s8 + j + 1, s_strides, s_n_strides, dst_row + doc_a, q < n_queries);
-                    ++doc_a;
-                    len_a = -(8 * s8 + j + 1);
+                  if ((m8 >> j) & 1u) {   // this column is the last token of document `doc` (warp-uniform)
+                    pb->v[n_pend][lane] = r;
+                    if (lane == 0) pb->len[n_pend] = cur_len + 8 * s8 + j + 1;
+                    ++n_pend;
+                    ++doc;
+                    cur_len = -(8 * s8 + j + 1);
                     r = -INFINITY;
                   }
                 }
               }
             }
-            len_a += 32;
-          };
-
-          // TMEM loads are double-buffered in registers: chunk c+1 is in flight while chunk c is reduced
-          uint32_t va[32], vb[32];
-          umma::tmem_ld_32x32(t_addr, va);
-          umma::tmem_ld_wait();
-          umma::tmem_ld_32x32(t_addr + 32, vb);
-          reduce_chunk(va, ends[0]);
-          umma::tmem_ld_wait();
-          umma::tmem_ld_32x32(t_addr + 64, va);
-          reduce_chunk(vb, ends[1]);
-          umma::tmem_ld_wait();
-          umma::tmem_ld_32x32(t_addr + 96, vb);
-          reduce_chunk(va, ends[2]);
-          umma::tmem_ld_wait();
-          // all columns of the slot are in registers: hand it back to the MMA warp
-          umma::fence_before_sync();
-          __syncwarp();
-          if (lane == 0) mbar_arrive(smem_u32(&bar_acc_empty[slot]));
-          reduce_chunk(vb, ends[3]);
-
-          if (a == 0) run0 = r; else if (a == 1) run1 = r; else if (a == 2) run2 = r; else run3 = r;
-          doc_next = doc_a;
-          len_next = len_a;
+          }
+          cur_len += 32;
         }
-        doc = doc_next;
-        cur_len = len_next;
-        acc_it += after;
       }
+      if (n_pend > 0) flush_pending(pb, n_pend, dst_row + pend_first, write);
     }
   }
 
@@ -439,7 +502,7 @@ int exhaustive_dispatch(const void* d_store, int store_dtype, int64_t n_store_ro
   for (int i = 0; i < CBK_MAX_STRIDES; ++i) ss.v[i] = i < n_strides ? strides[i] : -1;
   const uint32_t fmt = bf16 ? umma::kFmtBF16 : umma::kFmtF16;
   const uint32_t idesc = umma::make_idesc(128, kTileTok, fmt, fmt);
-  const size_t smem = 1024 + static_cast<size_t>(kABlocks + kBStages) * kTileBytes;
+  const size_t smem = 1024 + static_cast<size_t>(kSmemTiles) * kTileBytes;
   CBK_CUDA(cudaFuncSetAttribute(maxsim_exhaustive_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
   maxsim_exhaustive_kernel<<<n_ctas, kExhThreads, smem, stream>>>(maps, d_doc_end_bits, d_pfxsum, d_ranges, ss,
                                                                 static_cast<int>(n_queries), n_qblocks, parts, n_docs, idesc,
