@@ -401,3 +401,29 @@ def test_retriever_search_matches_oracle(dev):
         fp, fs = O.topk_desc(ref, np.asarray(cands, dtype=np.int64), None)
         check_topk(pids, scores, rp, rs, SCORE_RTOL, fp, fs)
         assert batch_pids[b].tolist() == pids
+
+
+def test_rerank_pipeline_matches_direct_call(dev):
+    """The pipelined serving entry returns, step after step, what rank_forward_batch returns."""
+    from colbert_b200 import synthetic
+    from colbert_b200.ranking.pipeline import RerankPipeline
+    index = synthetic.make_index(81, 3000, dim=128, lo=1, hi=100)
+    ranker = make_ranker(index, dev)
+    B, n = 16, 200
+    pipe = RerankPipeline(ranker, B, 32, n, depth=10)
+    batches = []
+    for i in range(5):
+        Q = torch.from_numpy(synthetic.make_queries(90 + i, B, 32, 128)).pin_memory()
+        cand = torch.from_numpy(synthetic.make_candidates(190 + i, B, index.num_docs, n)).pin_memory()
+        batches.append((Q, cand))
+    handles, outs = [], []
+    for Q, cand in batches:
+        handles.append(pipe.submit(Q, cand))
+        if len(handles) >= 2:                                   # read the step before the one just queued
+            p, s = pipe.result(handles[-2])
+            outs.append((p.clone(), s.clone()))
+    p, s = pipe.result(handles[-1])
+    outs.append((p.clone(), s.clone()))
+    for (Q, cand), (p, s) in zip(batches, outs):
+        rp, rs = ranker.rank_forward_batch(Q, cand, depth=10)
+        assert torch.equal(p, rp.cpu()) and torch.equal(s, rs.cpu())
