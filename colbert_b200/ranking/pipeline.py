@@ -31,9 +31,10 @@ class RerankPipeline:
         local = getattr(ranker, "local", ranker)
         self.device = local.device
         self.dim = local.dim
-        self.world = getattr(ranker, "world", 1)
-        self.rank = getattr(ranker, "rank", 0)
-        self.group = getattr(ranker, "group", None)
+        sharded = hasattr(ranker, "local")                      # ShardedColbertRanker (ColbertRanker.rank is a method)
+        self.world = ranker.world if sharded else 1
+        self.rank = ranker.rank if sharded else 0
+        self.group = ranker.group if sharded else None
         self.n_queries, self.q_len, self.n_cand = n_queries, q_len, n_cand
         self.k = min(int(depth), n_cand)
         self.depth = depth
