@@ -50,6 +50,9 @@ class RerankPipeline:
         self.ev_in = [torch.cuda.Event() for _ in range(slots)]
         self.ev_done = [torch.cuda.Event() for _ in range(slots)]
         self._i = 0
+        # the input all-gather runs on the copy stream, concurrently with the key all-gather of the previous step on
+        # the compute stream: it needs its own communicator (collective call: every rank builds its pipeline)
+        self.in_group = dist.new_group(ranks=list(range(self.world))) if self.world > 1 else None
         self.h2d_bytes_per_step = (self.slice * q_len * self.dim * 4 + self.slice * n_cand * 8) * self.world
         self.d2h_bytes_per_step = n_queries * self.k * 12 * self.world
 
@@ -65,13 +68,13 @@ class RerankPipeline:
             self.copy_stream.wait_event(self.ev_done[s])            # the slot's previous step no longer reads the buffers
             self.Q_dev[s][lo:hi].copy_(Q_host[lo:hi], non_blocking=True)
             self.C_dev[s][lo:hi].copy_(cand_host[lo:hi], non_blocking=True)
+            if self.world > 1:                                      # slices → full replicated batch over NVLink
+                dist.all_gather_into_tensor(self.Q_dev[s].view(self.n_queries * self.q_len, self.dim),
+                                            self.Q_dev[s][lo:hi].reshape(self.slice * self.q_len, self.dim).clone(),
+                                            group=self.in_group)
+                dist.all_gather_into_tensor(self.C_dev[s], self.C_dev[s][lo:hi].clone(), group=self.in_group)
             self.ev_in[s].record(self.copy_stream)
         compute.wait_event(self.ev_in[s])
-        if self.world > 1:                                          # slices → full replicated batch over NVLink
-            dist.all_gather_into_tensor(self.Q_dev[s].view(self.n_queries * self.q_len, self.dim),
-                                        self.Q_dev[s][lo:hi].reshape(self.slice * self.q_len, self.dim).clone(),
-                                        group=self.group)
-            dist.all_gather_into_tensor(self.C_dev[s], self.C_dev[s][lo:hi].clone(), group=self.group)
         pids, scores = self.ranker.rank_forward_batch(self.Q_dev[s], self.C_dev[s], depth=self.depth)
         self.out_pids[s].copy_(pids, non_blocking=True)
         self.out_scores[s].copy_(scores, non_blocking=True)
