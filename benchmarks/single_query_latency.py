@@ -1,0 +1,71 @@
+#!/usr/bin/env python
+"""Latency of the reference-shaped call: ONE query, 1000 candidates, `ColbertRanker.rank_forward(Q, pids, depth=10)`
+(reference colbert_ranker.py:75-137), Python lists in and out, against the CPU port of the reference (configs[0] shape).
+
+    python benchmarks/single_query_latency.py [--docs 200000] [--iters 200]
+"""
+import argparse
+import json
+import os
+import sys
+import time
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--docs", type=int, default=200_000)
+    ap.add_argument("--cands", type=int, default=1000)
+    ap.add_argument("--iters", type=int, default=200)
+    args = ap.parse_args()
+    import numpy as np
+    import torch
+    from colbert_b200 import synthetic
+    from colbert_b200.ranking import ColbertRanker
+    from oracle.ref_port_torch import CpuRankerPort
+    index = synthetic.make_index(3, args.docs, dim=128, lo=1, hi=180)
+    ranker = ColbertRanker.from_tensors(torch.from_numpy(index.emb), index.doclens.tolist(), device="cuda:0")
+    Q = synthetic.make_queries(4, 64, 32, 128)
+    cand = synthetic.make_candidates(5, 64, index.num_docs, args.cands)
+    Qs = [torch.from_numpy(Q[i]).unsqueeze(0).permute(0, 2, 1) for i in range(64)]
+    cl = [c.tolist() for c in cand]
+    for i in range(10):
+        ranker.rank_forward(Qs[i], cl[i], depth=10)
+    torch.cuda.synchronize()
+    t0 = time.perf_counter()
+    for i in range(args.iters):
+        ranker.rank_forward(Qs[i % 64], cl[i % 64], depth=10)          # returns Python lists ⇒ synchronises
+    gpu_ms = (time.perf_counter() - t0) / args.iters * 1e3
+    # kernel-only time of the same work (device tensors prepared once)
+    dev = ranker.device
+    Qd = torch.from_numpy(Q[0:1]).to(dev)
+    cd = torch.from_numpy(cand[0]).to(dev)
+    rp = torch.tensor([0, args.cands], dtype=torch.int64, device=dev)
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    for _ in range(5):
+        ranker.score_candidates(Qd, cd, rp)
+    e0.record()
+    for _ in range(args.iters):
+        ranker.score_candidates(Qd, cd, rp)
+    e1.record()
+    torch.cuda.synchronize()
+    kern_ms = e0.elapsed_time(e1) / args.iters
+    torch.set_num_threads(os.cpu_count() or 1)
+    store = torch.zeros(index.num_tokens + 512, 128, dtype=torch.float16)
+    store[: index.num_tokens] = torch.from_numpy(index.emb)
+    port = CpuRankerPort(store, index.doclens.tolist(), max_candidates=args.cands)
+    port.rank_forward(Qs[0], cl[0], depth=10)
+    t0 = time.perf_counter()
+    n_cpu = min(32, args.iters)
+    for i in range(n_cpu):
+        port.rank_forward(Qs[i], cl[i], depth=10)
+    cpu_ms = (time.perf_counter() - t0) / n_cpu * 1e3
+    print(json.dumps({"call": "rank_forward(Q[1,128,32], 1000 pids, depth=10)", "gpu_ms_per_call": round(gpu_ms, 4),
+                      "gpu_maxsim_kernel_ms": round(kern_ms, 4), "cpu_port_ms_per_call": round(cpu_ms, 3),
+                      "cpu_threads": os.cpu_count(), "speedup": round(cpu_ms / gpu_ms, 1)}))
+
+
+if __name__ == "__main__":
+    main()

@@ -72,7 +72,8 @@ maxsim_rerank_kernel(const __grid_constant__ TmapSet tmaps, const int64_t* __res
                      StrideSet strides,
                      const float* __restrict__ Q, int q_len, int64_t n_queries,
                      const int64_t* __restrict__ cand_pids, const int64_t* __restrict__ rowptr,
-                     int64_t n_cand_bound, float* __restrict__ out, unsigned int* __restrict__ seg_counter) {
+                     int64_t n_cand_bound, int seg_cands, float* __restrict__ out,
+                     unsigned int* __restrict__ seg_counter) {
   extern __shared__ uint8_t smem_raw[];
   const int lane = threadIdx.x & 31;
   const int warp = threadIdx.x >> 5;
@@ -93,7 +94,7 @@ maxsim_rerank_kernel(const __grid_constant__ TmapSet tmaps, const int64_t* __res
   // passes an upper bound that sizes the grid
   const int64_t n_cand = min(rowptr[n_queries], n_cand_bound);
   const int n_mt = q_len > 16 ? 2 : 1;
-  const int64_t n_segs = (n_cand + kSegCands - 1) / kSegCands;
+  const int64_t n_segs = (n_cand + seg_cands - 1) / seg_cands;
   uint32_t issued = 0;    // tiles handed to the TMA so far   → stage = issued % kStages
   uint32_t consumed = 0;  // tiles multiplied so far          → stage / parity of the next wait
   int64_t cur_q = -1;
@@ -108,8 +109,8 @@ maxsim_rerank_kernel(const __grid_constant__ TmapSet tmaps, const int64_t* __res
     if (lane == 0) seg = atomicAdd(seg_counter, 1u);
     seg = __shfl_sync(0xffffffffu, seg, 0);
     if (static_cast<int64_t>(seg) >= n_segs) break;
-    const int64_t c0 = static_cast<int64_t>(seg) * kSegCands;
-    const int nc = static_cast<int>(min(static_cast<int64_t>(kSegCands), n_cand - c0));
+    const int64_t c0 = static_cast<int64_t>(seg) * seg_cands;
+    const int nc = static_cast<int>(min(static_cast<int64_t>(seg_cands), n_cand - c0));
 
     // ---- segment prologue: pid → (first row, doclen)   [colbert_ranker.py:88] --------------------
     // Candidates that need no scoring are answered here (empty document → 0; pid outside this
@@ -317,11 +318,15 @@ int launch(const TmapSet& tmaps, const int64_t* pfxsum, const int32_t* doclens, 
   const size_t smem = kWarps * sizeof(WarpSmem) + 1024;
   CBK_CUDA(cudaFuncSetAttribute(maxsim_rerank_kernel<T, kCvtBf16>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                 static_cast<int>(smem)));
-  const int64_t n_segs = (n_cand + kSegCands - 1) / kSegCands;
+  // work unit = segment of consecutive candidates claimed by one warp: 64 for big batches (amortises the claim and
+  // the metadata fetch), down to 4 for a single query so that its ~1000 candidates still spread over every SM
+  const int64_t warps_total = static_cast<int64_t>(sm_count()) * kCtasPerSm * kWarps;
+  const int seg_cands = static_cast<int>(std::max<int64_t>(4, std::min<int64_t>(kSegCands, n_cand / (2 * warps_total))));
+  const int64_t n_segs = (n_cand + seg_cands - 1) / seg_cands;
   const int64_t want = (n_segs + kWarps - 1) / kWarps;
   const int grid = static_cast<int>(std::max<int64_t>(1, std::min<int64_t>(want, static_cast<int64_t>(sm_count()) * kCtasPerSm)));
   maxsim_rerank_kernel<T, kCvtBf16><<<grid, kWarps * 32, smem, stream>>>(tmaps, pfxsum, doclens, n_docs, pid_base, skip_foreign, strides, Q, q_len,
-                                                              n_queries, cand_pids, rowptr, n_cand, out, counter);
+                                                              n_queries, cand_pids, rowptr, n_cand, seg_cands, out, counter);
   CBK_CUDA(cudaGetLastError());
   count_launch();
   return CBK_OK;
