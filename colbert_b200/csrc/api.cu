@@ -31,6 +31,8 @@ size_t topk_dense_workspace_bytes(int64_t, int64_t, int);
 int topk_dense_dispatch(const float*, int64_t, int64_t, int, int64_t, int, float*, int64_t*, void*, cudaStream_t);
 int emb2pid_dispatch(const int64_t*, int64_t, int32_t*, cudaStream_t);
 int unique_pids_dispatch(const int64_t*, int64_t, int, const int32_t*, int64_t, int64_t*, int64_t*, void*, cudaStream_t);
+int rerank_generic_dispatch(const void*, int, int64_t, int, const int64_t*, const int32_t*, int64_t, int64_t, const int32_t*, int,
+                            const float*, int, int64_t, const int64_t*, const int64_t*, float*, int, cudaStream_t);
 int umma_probe_dispatch(const void*, const void*, int, int, int, float*, cudaStream_t);
 int mask_cast_dispatch(const void*, int, int64_t, int, const void*, int, void*, int, cudaStream_t);
 
@@ -147,12 +149,13 @@ int cbk_maxsim_rerank(const void* d_store, int store_dtype, int64_t n_store_rows
                 (long long)n_store_rows, (long long)n_docs, (long long)n_queries, (long long)n_cand_total);
   CBK_CHECK_ARG(n_strides >= 0 && n_strides <= CBK_MAX_STRIDES && (n_strides == 0 || strides),
                 "cbk_maxsim_rerank: n_strides %d outside [0, %d] or strides is NULL", n_strides, CBK_MAX_STRIDES);
-  CBK_CHECK_SUPPORTED(dim == 128, "cbk_maxsim_rerank: dim %d not supported (128 only)", dim);
+  CBK_CHECK_SUPPORTED(dim >= 1 && dim <= 1536, "cbk_maxsim_rerank: dim %d outside [1, 1536]", dim);
   CBK_CHECK_SUPPORTED(q_len >= 1 && q_len <= CBK_MAX_QLEN, "cbk_maxsim_rerank: q_len %d outside [1, %d]", q_len,
                       CBK_MAX_QLEN);
   CBK_CHECK_SUPPORTED(n_store_rows < (1ll << 31), "cbk_maxsim_rerank: store of %lld rows exceeds 2^31-1",
                       (long long)n_store_rows);
-  CBK_CHECK_ARG((reinterpret_cast<uintptr_t>(d_store) & 0xff) == 0, "cbk_maxsim_rerank: store base must be 256-byte aligned");
+  CBK_CHECK_ARG(dim != 128 || (reinterpret_cast<uintptr_t>(d_store) & 0xff) == 0,
+                "cbk_maxsim_rerank: store base must be 256-byte aligned");
   if (!d_workspace || workspace_bytes < cbk_maxsim_rerank_workspace_bytes()) {
     set_error("cbk_maxsim_rerank: workspace of %zu bytes, need %zu", workspace_bytes, cbk_maxsim_rerank_workspace_bytes());
     return CBK_ERR_WORKSPACE;
@@ -160,6 +163,10 @@ int cbk_maxsim_rerank(const void* d_store, int store_dtype, int64_t n_store_rows
   int rc = check_device();
   if (rc != CBK_OK) return rc;
   if (n_cand_total == 0) return CBK_OK;
+  if (dim != 128)   // generic-width path (CUDA cores); the tensor-core kernel is specialised for dim = 128
+    return rerank_generic_dispatch(d_store, store_dtype, n_store_rows, dim, d_pfxsum, d_doclens, n_docs, pid_base, strides,
+                                   n_strides, d_Q, q_len, n_queries, d_cand_pids, d_cand_rowptr, d_out_scores, flags,
+                                   static_cast<cudaStream_t>(stream));
   return rerank_dispatch(d_store, store_dtype, n_store_rows, dim, d_pfxsum, d_doclens, n_docs, pid_base, strides, n_strides, d_Q,
                          q_len, n_queries, d_cand_pids, d_cand_rowptr, n_cand_total, d_out_scores, d_workspace, flags,
                          static_cast<cudaStream_t>(stream));

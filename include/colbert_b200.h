@@ -111,7 +111,8 @@ uint64_t cbk_launch_count(void);
  *                  bf16 values are multiplied directly with the query rounded to bf16 (8 bits; 1.2e-3,
  *                  outside the 1e-3 parity tolerance but safe for stores beyond fp16's range).
  *
- * Supported: dim == 128, 1 ≤ q_len ≤ CBK_MAX_QLEN, n_store_rows < 2^31.  pids are range-checked on
+ * Supported: 1 ≤ q_len ≤ CBK_MAX_QLEN, n_store_rows < 2^31; dim == 128 runs the TMA + tensor-core kernel, any
+ * other dim in [1, 1536] a generic CUDA-core kernel with the same results contract (fp32 arithmetic).  pids are range-checked on
  * the device; an out-of-range pid yields NaN at its position.
  * ------------------------------------------------------------------------------------------------ */
 size_t cbk_maxsim_rerank_workspace_bytes(void);

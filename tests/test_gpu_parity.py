@@ -427,3 +427,43 @@ def test_rerank_pipeline_matches_direct_call(dev):
     for (Q, cand), (p, s) in zip(batches, outs):
         rp, rs = ranker.rank_forward_batch(Q, cand, depth=10)
         assert torch.equal(p, rp.cpu()) and torch.equal(s, rs.cpu())
+
+
+# ------------------------------------------------------------------------------------------------
+# generic embedding width (dim != 128): CUDA-core kernel, same contract
+# ------------------------------------------------------------------------------------------------
+def test_score_known_answer_vector_native_shape(dev, golden_dir):
+    """BaseModel.test_score exactly as the reference runs it (h = 3): [[21., 41.]]."""
+    from colbert_b200.modeling.BaseModel import BaseModel
+    sc = np.load(os.path.join(golden_dir, "score_cases.npz"))
+    out = BaseModel.score(torch.from_numpy(sc["kat_Q"]).to(dev), torch.from_numpy(sc["kat_D"]).to(dev),
+                          torch.ones(1, 2, device=dev), torch.ones(2, 2, device=dev))
+    assert out.cpu().tolist() == [[21.0, 41.0]]
+
+
+def test_score_allpairs_golden_small_dim(dev, golden_dir):
+    from colbert_b200.modeling.BaseModel import BaseModel
+    sc = np.load(os.path.join(golden_dir, "score_cases.npz"))
+    name = "ap_small"                                        # h = 16
+    out = BaseModel.score(torch.from_numpy(sc[name + "_Q"].astype(np.float32)).to(dev),
+                          torch.from_numpy(sc[name + "_D"].astype(np.float32)).to(dev),
+                          torch.from_numpy(sc[name + "_qmask"]).to(dev), torch.from_numpy(sc[name + "_dmask"]).to(dev))
+    ref = sc[name + "_score"]
+    assert np.abs(out.cpu().numpy() - ref).max() <= 1e-5 * max(1.0, np.abs(ref).max())
+
+
+@pytest.mark.parametrize("dim", [64, 96, 768])
+def test_rank_forward_other_dims(dev, dim):
+    from colbert_b200 import synthetic
+    index = synthetic.make_index(300 + dim, 400, dim=dim, lo=1, hi=40)
+    ranker = make_ranker(index, dev)
+    Q = synthetic.make_queries(301, 2, 32, dim)
+    cand = synthetic.make_candidates(302, 2, index.num_docs, 150)
+    store, pf = O.pad_store(index.emb), O.doclens_pfxsum(index.doclens)
+    for b in range(2):
+        Qt = torch.from_numpy(Q[b]).unsqueeze(0).permute(0, 2, 1)
+        p, s = ranker.rank_forward(Qt, cand[b].tolist(), depth=10)
+        ref = O.maxsim_exact(store, index.doclens, pf, ranker.strides, Q[b], cand[b])
+        rp, rs = O.topk_desc(ref, cand[b], 10)
+        fp, fs = O.topk_desc(ref, cand[b], None)
+        check_topk(p, s, rp, rs, 1e-5, fp, fs)               # fp32 arithmetic on exact fp16 values: tight
