@@ -257,7 +257,6 @@ int cbk_mask_cast_rows(const void* d_src, int src_dtype, int64_t n_rows, int dim
   CBK_CHECK_ARG(d_src && d_out, "cbk_mask_cast_rows: null pointer argument");
   CBK_CHECK_ARG(n_rows > 0 && dim > 0, "cbk_mask_cast_rows: sizes must be positive");
   CBK_CHECK_ARG(mask_dtype == CBK_MASK_NONE || d_mask, "cbk_mask_cast_rows: mask dtype %d given but mask is NULL", mask_dtype);
-  CBK_CHECK_SUPPORTED(dim % 4 == 0, "cbk_mask_cast_rows: dim %d must be a multiple of 4", dim);
   int rc = check_device();
   if (rc != CBK_OK) return rc;
   return mask_cast_dispatch(d_src, src_dtype, n_rows, dim, mask_dtype == CBK_MASK_NONE ? nullptr : d_mask, mask_dtype,

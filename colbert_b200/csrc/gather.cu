@@ -52,13 +52,7 @@ mask_cast_rows_kernel(const TIn* __restrict__ src, int64_t n_rows, int dim, cons
   for (int64_t r = static_cast<int64_t>(blockIdx.x) * (blockDim.x >> 5) + (threadIdx.x >> 5); r < n_rows;
        r += warps_total) {
     const float m = mask ? static_cast<float>(mask[r]) : 1.f;
-    for (int c = lane * 4; c < dim; c += 128) {
-      float v[4];
-#pragma unroll
-      for (int j = 0; j < 4; ++j) v[j] = static_cast<float>(src[r * dim + c + j]) * m;
-#pragma unroll
-      for (int j = 0; j < 4; ++j) out[r * dim + c + j] = static_cast<TOut>(v[j]);
-    }
+    for (int c = lane; c < dim; c += 32) out[r * dim + c] = static_cast<TOut>(static_cast<float>(src[r * dim + c]) * m);
   }
 }
 

@@ -207,7 +207,7 @@ int cbk_embedding_ids_to_pids(const int64_t* d_emb_ids, int64_t n_queries, int n
  * Q * q_mask[...,None]) fused with the cast to the tensor-core input type:
  *     out[r, :] = (out_dtype)( (float)src[r, :] * (float)mask[r] )          mask == NULL ⇒ plain cast
  *   d_src [n_rows, dim] of src_dtype (CBK_F16 | CBK_BF16 | CBK_F32), d_mask [n_rows] of mask_dtype,
- *   d_out [n_rows, dim] of out_dtype.  dim must be a multiple of 4.
+ *   d_out [n_rows, dim] of out_dtype.
  * ------------------------------------------------------------------------------------------------ */
 int cbk_mask_cast_rows(const void* d_src, int src_dtype, int64_t n_rows, int dim, const void* d_mask, int mask_dtype,
                        void* d_out, int out_dtype, void* stream);
