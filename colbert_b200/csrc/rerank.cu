@@ -224,7 +224,6 @@ maxsim_rerank_kernel(const __grid_constant__ TmapSet tmaps, const int64_t* __res
         mbar_wait(full_addr + 8 * st, (consumed / kStages) & 1u);
         const uint32_t sbase = tiles_addr + st * kTileBytes;
 
-        const int n_sub = (len - t * kTileRows > 8) ? 2 : 1;   // a short tail tile has one 8-token sub-tile
         float acc[2][2][4];  // [sub-tile of 8 tokens][m-tile][reg]
 #pragma unroll
         for (int s = 0; s < 2; ++s)
@@ -233,15 +232,23 @@ maxsim_rerank_kernel(const __grid_constant__ TmapSet tmaps, const int64_t* __res
 #pragma unroll
             for (int r = 0; r < 4; ++r) acc[s][mt][r] = 0.f;
 
-#pragma unroll
-        for (int p = 0; p < 4; ++p) {  // 32 columns (two k-steps) per ldmatrix.x4
+        // B fragments: ldmatrix.x4 of 32 columns (two k-steps) × 8 tokens; the loads of step p+1 are issued
+        // before the conversions / MMAs of step p so that the shared-memory latency is covered
+        uint32_t bq[2][2][4];   // [buffer][sub-tile][reg]
+        auto load_b = [&](int p, uint32_t (&dst)[2][4]) {
           const int chunk = (p & 1) * 4 + lmat;
           const uint32_t coff = (p >> 1) * kHalfBytes + (((chunk ^ lrow) & 7) << 4);
 #pragma unroll
+          for (int s = 0; s < 2; ++s)
+            ldmatrix_x4(sbase + coff + (s * 8 + lrow) * 128, dst[s][0], dst[s][1], dst[s][2], dst[s][3]);
+        };
+        load_b(0, bq[0]);
+#pragma unroll
+        for (int p = 0; p < 4; ++p) {
+          if (p < 3) load_b(p + 1, bq[(p + 1) & 1]);
+#pragma unroll
           for (int s = 0; s < 2; ++s) {
-            if (s >= n_sub) break;
-            uint32_t b0, b1, b2, b3;
-            ldmatrix_x4(sbase + coff + (s * 8 + lrow) * 128, b0, b1, b2, b3);
+            uint32_t b0 = bq[p & 1][s][0], b1 = bq[p & 1][s][1], b2 = bq[p & 1][s][2], b3 = bq[p & 1][s][3];
             if (kCvtBf16) {
               b0 = bf16x2_to_f16x2(b0);
               b1 = bf16x2_to_f16x2(b1);
@@ -270,7 +277,6 @@ maxsim_rerank_kernel(const __grid_constant__ TmapSet tmaps, const int64_t* __res
         } else {
 #pragma unroll
           for (int s = 0; s < 2; ++s) {
-            if (s >= n_sub) break;
             const bool v0 = tok0 + s * 8 < len;
             const bool v1 = tok0 + s * 8 + 1 < len;
 #pragma unroll
