@@ -33,6 +33,8 @@ int emb2pid_dispatch(const int64_t*, int64_t, int32_t*, cudaStream_t);
 int unique_pids_dispatch(const int64_t*, int64_t, int, const int32_t*, int64_t, int64_t*, int64_t*, void*, cudaStream_t);
 int rerank_generic_dispatch(const void*, int, int64_t, int, const int64_t*, const int32_t*, int64_t, int64_t, const int32_t*, int,
                             const float*, int, int64_t, const int64_t*, const int64_t*, float*, int, cudaStream_t);
+int rerank_umma_dispatch(const void*, int, int64_t, int, const int64_t*, const int32_t*, int64_t, int64_t, const int32_t*, int,
+                         const float*, int, int64_t, const int64_t*, const int64_t*, int64_t, float*, void*, int, cudaStream_t);
 int umma_probe_dispatch(const void*, const void*, int, int, int, float*, cudaStream_t);
 int mask_cast_dispatch(const void*, int, int64_t, int, const void*, int, void*, int, cudaStream_t);
 
@@ -167,6 +169,10 @@ int cbk_maxsim_rerank(const void* d_store, int store_dtype, int64_t n_store_rows
     return rerank_generic_dispatch(d_store, store_dtype, n_store_rows, dim, d_pfxsum, d_doclens, n_docs, pid_base, strides,
                                    n_strides, d_Q, q_len, n_queries, d_cand_pids, d_cand_rowptr, d_out_scores, flags,
                                    static_cast<cudaStream_t>(stream));
+  if (flags & CBK_FLAG_RERANK_TCGEN05)
+    return rerank_umma_dispatch(d_store, store_dtype, n_store_rows, dim, d_pfxsum, d_doclens, n_docs, pid_base, strides,
+                                n_strides, d_Q, q_len, n_queries, d_cand_pids, d_cand_rowptr, n_cand_total, d_out_scores,
+                                d_workspace, flags, static_cast<cudaStream_t>(stream));
   return rerank_dispatch(d_store, store_dtype, n_store_rows, dim, d_pfxsum, d_doclens, n_docs, pid_base, strides, n_strides, d_Q,
                          q_len, n_queries, d_cand_pids, d_cand_rowptr, n_cand_total, d_out_scores, d_workspace, flags,
                          static_cast<cudaStream_t>(stream));

@@ -1,0 +1,464 @@
+// MaxSim rerank on tcgen05 / TMEM (sm_100a) — second-generation kernel for the same contract as
+// maxsim_rerank_kernel (rerank.cu): lookup + exact-length gather by TMA + MaxSim + zero floor, one fp32 per
+// candidate written at the candidate's own position.  Replaces reference colbert_ranker.py:88-118 and
+// BaseModel.py:41-45.
+//
+// Orientation: S[tokens, query rows] = Dtile[≤128 tokens, 128] · Q[N, 128]^T  — the document tile is the A
+// operand (M = 128 TMEM lanes = tokens), the query is the B operand (N = 32 columns for fp16 stores; for bf16
+// stores N = 64: columns 0-31 multiply the bf16 "hi" part of the fp32 query and columns 32-63 its "lo"
+// residual — both operands of a tcgen05 MMA must share a format — and the epilogue adds the two halves, which
+// keeps 16 significant bits of the query).  Neither operand passes through registers: TMA writes the swizzled
+// tile, the tensor core reads it from shared memory, and only the 128 × N accumulator comes back (tcgen05.ld).
+//
+// One CTA = one autonomous streaming unit (two per SM):
+//   warp 8  producer: claims segments of candidates, resolves pid → (row, doclen), writes the query into one
+//           of two shared-memory buffers when it changes, carves variable-size tiles out of a shared-memory
+//           ring and issues the TMA loads (exact row count per tile: one tensor map per box height 1..128);
+//   warp 9  MMA issuer (one thread): 8 × tcgen05.mma (K = 128) per tile into a ring of TMEM accumulator slots;
+//   warps 0-3 / 4-7  two epilogue groups (one warp per TMEM lane quadrant): tcgen05.ld, mask rows ≥ tile rows,
+//           transposed butterfly max over the 32 lanes (lane j ends up with the max of query row j), combine the
+//           four quadrants through shared memory, running max over the chunks of a long document, zero floor,
+//           sum over the query rows, store.  Documents alternate between the groups.
+// Completion flows back through two progress counters (items fully reduced, per group) that the producer and
+// the MMA issuer poll to recycle ring space, item slots and TMEM slots.
+#include <algorithm>
+
+#include "umma.cuh"
+
+namespace cbk {
+
+namespace {
+
+constexpr int kDim = 128;
+constexpr int kTileMax = 128;            // rows per tile (MMA M)
+constexpr int kItems = 16;               // item descriptor / full-barrier ring
+constexpr int kSegCands = 64;
+constexpr int kGroups = 2;
+constexpr int kThreads = 320;            // 8 epilogue warps + producer + MMA issuer
+constexpr int kTmemCols = 256;           // per CTA (two CTAs per SM)
+constexpr int kQBufBytes = 64 * 256;     // one query buffer: up to 64 rows × 256 B
+
+struct StrideSet {
+  int n;
+  int v[CBK_MAX_STRIDES];
+};
+
+struct TileMaps {
+  CUtensorMap m[kTileMax];               // m[r-1]: box {64 columns, r rows}
+};
+
+struct __align__(16) Item {
+  uint32_t smem_off;                     // tile offset inside the ring
+  uint16_t rows;                         // valid rows (1..128)
+  uint8_t group;                         // epilogue group that owns the document
+  uint8_t flags;                         // bit0 first chunk, bit1 last chunk, bit2 zero floor, bit3 write 0 rows
+  uint8_t qbuf;                          // query buffer
+  uint8_t pad[3];
+  uint32_t qseq;                         // query sequence number (MMA waits for this buffer fill)
+  int64_t out_idx;                       // candidate position
+};
+
+struct __align__(8) Shared {
+  uint64_t full[kItems];                 // TMA → MMA / epilogue
+  uint64_t accf[16];                     // MMA commit → epilogue, per TMEM slot
+  uint64_t qfull[2];                     // producer query fill → MMA
+  Item items[kItems];
+  int2 meta[kSegCands];                  // compacted (row, doclen)
+  uint8_t cidx[kSegCands];
+  float partial[kGroups][2][4][32];      // [group][item parity][quadrant][query row]
+  volatile int progress[kGroups * 4];    // per epilogue warp: items (by index) it has looked at and finished with
+  uint32_t tmem_base;
+};
+
+// every item with index < the returned value has been completely reduced (its ring space, item slot and TMEM
+// slot may be reused)
+__device__ __forceinline__ int ld_progress_min(const Shared* sh) {
+  int m = sh->progress[0];
+#pragma unroll
+  for (int i = 1; i < kGroups * 4; ++i) m = min(m, sh->progress[i]);
+  return m;
+}
+
+__device__ __forceinline__ void spin_until_progress(const Shared* sh, int upto) {
+  while (ld_progress_min(sh) < upto) __nanosleep(32);
+}
+
+template <typename T, int kN>
+__global__ void __launch_bounds__(kThreads, 2)
+maxsim_rerank_umma_kernel(const __grid_constant__ TileMaps maps, const int64_t* __restrict__ pfxsum,
+                          const int32_t* __restrict__ doclens, int64_t n_docs, int64_t pid_base, int skip_foreign,
+                          StrideSet strides, const float* __restrict__ Q, int q_len, int64_t n_queries,
+                          const int64_t* __restrict__ cand_pids, const int64_t* __restrict__ rowptr,
+                          int64_t n_cand_bound, int seg_cands, int ring_bytes, uint32_t idesc, float* __restrict__ out,
+                          unsigned int* __restrict__ seg_counter) {
+  extern __shared__ uint8_t smem_raw[];
+  __shared__ Shared sh;
+  constexpr int kSlots = kTmemCols / kN;
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const uint32_t raw = smem_u32(smem_raw);
+  const uint32_t ring_addr = (raw + 1023u) & ~1023u;                 // tile ring, then the two query buffers
+  const uint32_t q_addr = ring_addr + static_cast<uint32_t>(ring_bytes);
+  uint8_t* const q_ptr = smem_raw + (q_addr - raw);
+
+  if (tid == 0) {
+    for (int i = 0; i < kItems; ++i) mbar_init(smem_u32(&sh.full[i]), 1);
+    for (int i = 0; i < 16; ++i) mbar_init(smem_u32(&sh.accf[i]), 1);
+    mbar_init(smem_u32(&sh.qfull[0]), 1);
+    mbar_init(smem_u32(&sh.qfull[1]), 1);
+    for (int i = 0; i < kGroups * 4; ++i) sh.progress[i] = 0;
+    fence_mbar_init();
+  }
+  if (warp == 9) {
+    umma::tmem_alloc(smem_u32(&sh.tmem_base), kTmemCols);
+    umma::tmem_relinquish();
+  }
+  umma::fence_before_sync();
+  __syncthreads();
+  umma::fence_after_sync();
+  const uint32_t tmem = sh.tmem_base;
+  const int64_t n_cand = min(rowptr[n_queries], n_cand_bound);
+  const int64_t n_segs = (n_cand + seg_cands - 1) / seg_cands;
+
+  // The item stream ends with a sentinel item (rows == 0) that every consumer recognises.
+  if (warp == 8) {
+    // ======================================= producer ===============================================
+    if (lane < 32) {
+      for (int r = lane; r < kTileMax; r += 32) tma_prefetch_desc(&maps.m[r]);
+    }
+    int n_items = 0;             // items published so far
+    int head = 0;                // ring allocation cursor
+    int live_lo = 0;             // oldest item whose ring space is still accounted (index)
+    // per live item: ring start, kept in registers of lane (item % 32) — only lane 0's copy of head/tail logic matters
+    int tail = 0;                // ring offset of the oldest live item
+    int my_start = 0, my_end = 0;  // lane i holds [start,end) of item with index ≡ i (mod 32)
+    int64_t cur_q = -1;
+    uint32_t qseq = 0;
+    int qbuf = 1;
+    int last_item_of_buf[2] = {-1, -1};
+    int doc_parity = 0;
+
+    auto wait_items_done = [&](int upto) {   // until every item with index < upto is finished
+      if (lane == 0) spin_until_progress(&sh, upto);
+      __syncwarp();
+    };
+
+    while (true) {
+      unsigned int seg = 0;
+      if (lane == 0) seg = atomicAdd(seg_counter, 1u);
+      seg = __shfl_sync(0xffffffffu, seg, 0);
+      if (static_cast<int64_t>(seg) >= n_segs) break;
+      const int64_t c0 = static_cast<int64_t>(seg) * seg_cands;
+      const int nc = static_cast<int>(min(static_cast<int64_t>(seg_cands), n_cand - c0));
+      // ---- pid → (row, doclen); trivial candidates answered here, the rest compacted in order ----------
+      __syncwarp();
+      int nv = 0;
+      for (int i0 = 0; i0 < nc; i0 += 32) {
+        const int i = i0 + lane;
+        int row = 0, len = -1;
+        if (i < nc) {
+          const int64_t pid = cand_pids[c0 + i] - pid_base;
+          if (pid >= 0 && pid < n_docs) {
+            row = static_cast<int>(pfxsum[pid]);
+            len = doclens[pid];
+          }
+          if (len <= 0) out[c0 + i] = len == 0 ? 0.f : (skip_foreign ? -INFINITY : __int_as_float(0x7fc00000));
+        }
+        const unsigned int live = __ballot_sync(0xffffffffu, len > 0);
+        if (len > 0) {
+          const int slot = nv + __popc(live & ((1u << lane) - 1u));
+          sh.meta[slot] = make_int2(row, len);
+          sh.cidx[slot] = static_cast<uint8_t>(i);
+        }
+        nv += __popc(live);
+      }
+      __syncwarp();
+      if (nv == 0) continue;
+      // ---- query of the first scorable candidate -------------------------------------------------------
+      const int64_t cfirst = c0 + sh.cidx[0];
+      int64_t q = static_cast<int64_t>((static_cast<double>(cfirst) * n_queries) / static_cast<double>(n_cand));
+      q = max(static_cast<int64_t>(0), min(q, n_queries - 1));
+      if (!(rowptr[q] <= cfirst && cfirst < rowptr[q + 1])) {
+        int64_t lo = 0, hi = n_queries - 1;
+        while (lo < hi) {
+          const int64_t mid = (lo + hi + 1) >> 1;
+          if (rowptr[mid] <= cfirst) lo = mid; else hi = mid - 1;
+        }
+        q = lo;
+      }
+      int64_t q_end = rowptr[q + 1];
+
+      for (int ci = 0; ci < nv; ++ci) {
+        const int64_t c = c0 + sh.cidx[ci];
+        while (c >= q_end) {
+          ++q;
+          q_end = rowptr[q + 1];
+        }
+        if (q != cur_q) {
+          // ---- new query → the other buffer, once no unfinished item still multiplies with it ----------
+          cur_q = q;
+          qbuf ^= 1;
+          ++qseq;
+          wait_items_done(last_item_of_buf[qbuf] + 1);
+          const float* Qq = Q + q * static_cast<int64_t>(q_len) * kDim;
+          uint8_t* dstb = q_ptr + qbuf * kQBufBytes;
+          // element (row r, column k) → half h = k / 64, 16-byte chunk (k % 64) / 8 XOR (r & 7) (SWIZZLE_128B)
+          for (int e = lane; e < kN * (kDim / 8); e += 32) {     // one 16-byte chunk (8 columns) per iteration
+            const int r = e / (kDim / 8), ch = e % (kDim / 8);
+            const int h = ch >> 3, cc = ch & 7;
+            const int qr = r & 31;                               // rows 32-63 (bf16 store): lo part of row r-32
+            float v[8];
+#pragma unroll
+            for (int j = 0; j < 8; ++j) v[j] = qr < q_len ? Qq[qr * kDim + ch * 8 + j] : 0.f;
+            uint32_t w[4];
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+              float a = v[2 * j], b = v[2 * j + 1];
+              if (kN == 64 && r >= 32) {                         // residual after rounding to T
+                a -= to_float<T>(static_cast<T>(a));
+                b -= to_float<T>(static_cast<T>(b));
+              }
+              w[j] = pack2<T>(a, b);
+            }
+            *reinterpret_cast<uint4*>(dstb + h * (kN * 128) + r * 128 + ((cc ^ (r & 7)) << 4)) =
+                make_uint4(w[0], w[1], w[2], w[3]);
+          }
+          fence_proxy_async();
+          __syncwarp();
+          if (lane == 0) mbar_arrive(smem_u32(&sh.qfull[qbuf]));
+        }
+
+        const int2 m = sh.meta[ci];
+        const int len = m.y;
+        bool do_floor = strides.n > 0;
+#pragma unroll
+        for (int i = 0; i < CBK_MAX_STRIDES; ++i)
+          if (i < strides.n && strides.v[i] == len) do_floor = false;
+        const int group = doc_parity;
+        doc_parity ^= 1;
+        const int n_chunks = (len + kTileMax - 1) / kTileMax;
+        for (int ch = 0; ch < n_chunks; ++ch) {
+          const int rows = min(kTileMax, len - ch * kTileMax);
+          const int bytes = ((rows + 7) & ~7) * 256;
+          // ---- item slot + ring space ----------------------------------------------------------------------
+          const int idx = n_items;
+          wait_items_done(idx - kItems + 1);                     // slot idx % kItems is free again
+          int off = -1;
+          while (true) {
+            // retire finished items from the ring accounting
+            const int done = __shfl_sync(0xffffffffu, ld_progress_min(&sh), 0);   // warp-uniform snapshot
+            while (live_lo < done && live_lo < idx) {
+              ++live_lo;
+              tail = live_lo < idx ? __shfl_sync(0xffffffffu, my_start, live_lo & 31) : head;
+            }
+            if (live_lo == idx) {                                // ring empty
+              head = tail = 0;
+              off = 0;
+              break;
+            }
+            if (head >= tail) {
+              if (head + bytes <= ring_bytes) { off = head; break; }
+              if (bytes <= tail) { off = 0; break; }
+            } else if (head + bytes <= tail) {
+              off = head;
+              break;
+            }
+          }
+          head = off + bytes;
+          if (lane == (idx & 31)) my_start = off;
+          (void)my_end;
+          if (lane == 0) {
+            Item it;
+            it.smem_off = static_cast<uint32_t>(off);
+            it.rows = static_cast<uint16_t>(rows);
+            it.group = static_cast<uint8_t>(group);
+            it.flags = static_cast<uint8_t>((ch == 0 ? 1 : 0) | (ch == n_chunks - 1 ? 2 : 0) | (do_floor ? 4 : 0));
+            it.qbuf = static_cast<uint8_t>(qbuf);
+            it.qseq = qseq;
+            it.out_idx = c;
+            sh.items[idx % kItems] = it;
+            const uint32_t bar = smem_u32(&sh.full[idx % kItems]);
+            const uint32_t dst = ring_addr + off;
+            const int row = m.x + ch * kTileMax;
+            const CUtensorMap* tm = &maps.m[rows - 1];
+            mbar_arrive_expect_tx(bar, rows * 256);
+            tma_load_2d(dst, tm, 0, row, bar, kEvictFirst);
+            tma_load_2d(dst + ((rows + 7) & ~7) * 128, tm, 64, row, bar, kEvictFirst);
+          }
+          last_item_of_buf[qbuf] = idx;
+          ++n_items;
+        }
+      }
+    }
+    // sentinel: tells the MMA issuer and both epilogue groups that the stream is over
+    wait_items_done(n_items - kItems + 1);
+    if (lane == 0) {
+      Item it;
+      it.smem_off = 0; it.rows = 0; it.group = 0; it.flags = 0; it.qbuf = 0; it.qseq = 0; it.out_idx = 0;
+      sh.items[n_items % kItems] = it;
+      mbar_arrive(smem_u32(&sh.full[n_items % kItems]));
+    }
+  } else if (warp == 9) {
+    // ======================================= MMA issuer =============================================
+    if (lane == 0) {
+      uint32_t seen_qseq = 0;
+      uint32_t qparity[2] = {0, 0};
+      for (int idx = 0;; ++idx) {
+        mbar_wait(smem_u32(&sh.full[idx % kItems]), (idx / kItems) & 1);
+        const Item it = sh.items[idx % kItems];
+        if (it.rows == 0) break;
+        if (it.qseq != seen_qseq) {                              // first item of a newly written query buffer
+          mbar_wait(smem_u32(&sh.qfull[it.qbuf]), qparity[it.qbuf]);
+          qparity[it.qbuf] ^= 1u;
+          seen_qseq = it.qseq;
+        }
+        spin_until_progress(&sh, idx - kSlots + 1);              // TMEM slot idx % kSlots has been drained
+        umma::fence_after_sync();
+        const uint32_t a_base = ring_addr + it.smem_off;
+        const uint32_t a_half = ((it.rows + 7) & ~7) * 128;
+        const uint32_t b_base = q_addr + it.qbuf * kQBufBytes;
+        const uint32_t d_tmem = tmem + (idx % kSlots) * kN;
+#pragma unroll
+        for (int h = 0; h < 2; ++h)
+#pragma unroll
+          for (int k = 0; k < 4; ++k)
+            umma::mma_f16_ss(d_tmem, umma::make_smem_desc_sw128(a_base + h * a_half + k * 32),
+                             umma::make_smem_desc_sw128(b_base + h * (kN * 128) + k * 32), idesc, (h | k) ? 1u : 0u);
+        umma::commit(smem_u32(&sh.accf[idx % kSlots]));
+      }
+    }
+  } else {
+    // ======================================= epilogue groups ========================================
+    const int grp = warp >> 2, quad = warp & 3;
+    const uint32_t lane_base = static_cast<uint32_t>(quad * 32) << 16;
+    float run = -INFINITY;
+    int par = 0;
+    for (int idx = 0;; ++idx) {
+      mbar_wait(smem_u32(&sh.full[idx % kItems]), (idx / kItems) & 1);
+      const Item it = sh.items[idx % kItems];
+      if (it.rows == 0) break;
+      if (it.group != grp) {                                     // the other group's document
+        __syncwarp();
+        if (lane == 0) sh.progress[warp] = idx + 1;
+        continue;
+      }
+      // the accumulator barrier of a slot is reused every kSlots items, possibly by the other group: wait for
+      // the previous use to be completely finished before a parity wait can be unambiguous
+      spin_until_progress(&sh, idx - kSlots + 1);
+      mbar_wait(smem_u32(&sh.accf[idx % kSlots]), (idx / kSlots) & 1);
+      umma::fence_after_sync();
+      const int nvalid = min(32, max(0, static_cast<int>(it.rows) - 32 * quad));
+      if (nvalid > 0) {
+        uint32_t raw0[32];
+        umma::tmem_ld_32x32(tmem + lane_base + (idx % kSlots) * kN, raw0);
+        float v[32];
+        if (kN == 64) {   // hi + lo halves of the split query
+          uint32_t raw1[32];
+          umma::tmem_ld_32x32(tmem + lane_base + (idx % kSlots) * kN + 32, raw1);
+          umma::tmem_ld_wait();
+#pragma unroll
+          for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(raw0[j]) + __uint_as_float(raw1[j]);
+        } else {
+          umma::tmem_ld_wait();
+#pragma unroll
+          for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(raw0[j]);
+        }
+        if (lane >= nvalid) {
+#pragma unroll
+          for (int j = 0; j < 32; ++j) v[j] = -INFINITY;
+        }
+        // transposed butterfly: after the 5 steps lane j holds max over the 32 lanes (tokens) of column j
+#pragma unroll
+        for (int step = 16; step >= 1; step >>= 1) {
+          const bool up = (lane & step) != 0;
+#pragma unroll
+          for (int i = 0; i < step; ++i) {
+            const float send = up ? v[i] : v[i + step];
+            const float keep = up ? v[i + step] : v[i];
+            v[i] = fmaxf(keep, __shfl_xor_sync(0xffffffffu, send, step));
+          }
+        }
+        sh.partial[grp][par][quad][lane] = v[0];
+      }
+      umma::fence_before_sync();
+      asm volatile("bar.sync %0, 128;" ::"r"(1 + grp) : "memory");
+      if (quad == 0) {
+        const int nq = (it.rows + 31) >> 5;
+        float mx = sh.partial[grp][par][0][lane];
+        if (nq > 1) mx = fmaxf(mx, sh.partial[grp][par][1][lane]);
+        if (nq > 2) mx = fmaxf(mx, sh.partial[grp][par][2][lane]);
+        if (nq > 3) mx = fmaxf(mx, sh.partial[grp][par][3][lane]);
+        run = (it.flags & 1) ? mx : fmaxf(run, mx);
+        if (it.flags & 2) {
+          float t = (it.flags & 4) ? fmaxf(run, 0.f) : run;
+          if (lane >= q_len) t = 0.f;
+#pragma unroll
+          for (int o = 16; o > 0; o >>= 1) t += __shfl_xor_sync(0xffffffffu, t, o);
+          if (lane == 0) out[it.out_idx] = t;
+        }
+      }
+      __syncwarp();
+      if (lane == 0) {
+        __threadfence_block();
+        sh.progress[warp] = idx + 1;
+      }
+      par ^= 1;
+    }
+  }
+
+  umma::fence_before_sync();
+  __syncthreads();
+  if (warp == 9) umma::tmem_dealloc(tmem, kTmemCols);
+}
+
+}  // namespace
+
+int rerank_umma_dispatch(const void* d_store, int store_dtype, int64_t n_store_rows, int dim, const int64_t* d_pfxsum,
+                         const int32_t* d_doclens, int64_t n_docs, int64_t pid_base, const int32_t* strides, int n_strides,
+                         const float* d_Q, int q_len, int64_t n_queries, const int64_t* d_cand_pids,
+                         const int64_t* d_cand_rowptr, int64_t n_cand_total, float* d_out_scores, void* d_workspace,
+                         int flags, cudaStream_t stream) {
+  static thread_local TileMaps maps;
+  static thread_local const void* cached_base = nullptr;
+  static thread_local int64_t cached_rows = -1;
+  if (cached_base != d_store || cached_rows != n_store_rows) {
+    cached_base = nullptr;
+    for (int r = 1; r <= kTileMax; ++r) {
+      int rc = make_store_tensor_map(&maps.m[r - 1], d_store, n_store_rows, dim, 64, r);
+      if (rc != CBK_OK) return rc;
+    }
+    cached_base = d_store;
+    cached_rows = n_store_rows;
+  }
+  StrideSet ss;
+  ss.n = n_strides;
+  for (int i = 0; i < CBK_MAX_STRIDES; ++i) ss.v[i] = i < n_strides ? strides[i] : -1;
+  const int skip = (flags & CBK_FLAG_SKIP_FOREIGN_PIDS) ? 1 : 0;
+  unsigned int* counter = static_cast<unsigned int*>(d_workspace);
+  CBK_CUDA(cudaMemsetAsync(counter, 0, sizeof(unsigned int), stream));
+  const bool bf16 = store_dtype == CBK_BF16;
+  // per CTA: 1 KB alignment + ring + two query buffers; two CTAs per SM
+  const int ring_bytes = 76 * 1024;
+  const size_t smem = 1024 + static_cast<size_t>(ring_bytes) + 2 * kQBufBytes;
+  const int64_t ctas_total = static_cast<int64_t>(sm_count()) * 2;
+  const int seg_cands = static_cast<int>(std::max<int64_t>(4, std::min<int64_t>(kSegCands, n_cand_total / (2 * ctas_total))));
+  const int64_t n_segs = (n_cand_total + seg_cands - 1) / seg_cands;
+  const int grid = static_cast<int>(std::max<int64_t>(1, std::min<int64_t>(n_segs, ctas_total)));
+  if (bf16) {
+    auto kern = maxsim_rerank_umma_kernel<__nv_bfloat16, 64>;
+    CBK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
+    kern<<<grid, kThreads, smem, stream>>>(maps, d_pfxsum, d_doclens, n_docs, pid_base, skip, ss, d_Q, q_len, n_queries,
+                                           d_cand_pids, d_cand_rowptr, n_cand_total, seg_cands, ring_bytes,
+                                           umma::make_idesc(128, 64, umma::kFmtBF16, umma::kFmtBF16), d_out_scores, counter);
+  } else {
+    auto kern = maxsim_rerank_umma_kernel<__half, 32>;
+    CBK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
+    kern<<<grid, kThreads, smem, stream>>>(maps, d_pfxsum, d_doclens, n_docs, pid_base, skip, ss, d_Q, q_len, n_queries,
+                                           d_cand_pids, d_cand_rowptr, n_cand_total, seg_cands, ring_bytes,
+                                           umma::make_idesc(128, 32, umma::kFmtF16, umma::kFmtF16), d_out_scores, counter);
+  }
+  CBK_CUDA(cudaGetLastError());
+  count_launch();
+  return CBK_OK;
+}
+
+}  // namespace cbk

@@ -42,6 +42,7 @@ extern "C" {
 #define CBK_MAX_STRIDES 8      /* the reference produces at most 4 (percentiles 25/50/75 + max) */
 #define CBK_MAX_QLEN 32        /* query rows per launch; longer queries are split by the caller  */
 #define CBK_FLAG_BF16_NATIVE_MMA 1
+#define CBK_FLAG_RERANK_TCGEN05 4       /* score with the tcgen05 / TMEM kernel instead of the mma.sync one */
 #define CBK_FLAG_SKIP_FOREIGN_PIDS 2   /* sharded stores: a pid outside this shard scores -inf, not NaN */
 #define CBK_TOPK_NEG_INF_IS_PADDING 1  /* top-k: candidates scored -inf are dropped (sharded rerank) */
 
