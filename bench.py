@@ -49,6 +49,8 @@ def parse_args():
     ap.add_argument("--doclen-fixed", type=int, default=0,
                     help="every document has exactly this many rows (configs[2], multi-view: 8); 0 = U[1,180]")
     ap.add_argument("--q-len", type=int, default=32, help="query rows (multi-view: q_view)")
+    ap.add_argument("--kernel", default="auto", choices=["auto", "mma", "tcgen05"],
+                    help="rerank kernel: mma.sync (rerank.cu) or tcgen05/TMEM (rerank_umma.cu)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--cpu-queries", type=int, default=128, help="bounded CPU-baseline sample (queries)")
     return ap.parse_args()
@@ -225,6 +227,10 @@ def run_ours(args, rank, world, local_rank):
     # GPU scores ~queries*cands candidates per step.  All ranks see the same (replicated) queries and lists.
     store, doclens = build_store(torch, dev, args.docs, dim, dtype, seed=1234 + rank, doclen_fixed=args.doclen_fixed)
     ranker = ColbertRanker.from_store(store, doclens)
+    if args.kernel == "tcgen05":
+        ranker.kernel_flags |= _lib.CBK_FLAG_RERANK_TCGEN05
+    elif args.kernel == "mma":
+        ranker.kernel_flags &= ~_lib.CBK_FLAG_RERANK_TCGEN05
     n_queries = args.queries * world
     Q_host, cand_host = build_queries(torch, n_queries, q_len, dim, args.docs * world, args.cands, seed=4321)
     Q_pin, cand_pin = Q_host.pin_memory(), cand_host.pin_memory()

@@ -255,10 +255,11 @@ maxsim_rerank_umma_kernel(const __grid_constant__ TileMaps maps, const int64_t* 
               off = 0;
               break;
             }
-            if (head >= tail) {
+            // head == tail must only ever mean "empty", hence the strict comparisons against tail
+            if (head > tail) {
               if (head + bytes <= ring_bytes) { off = head; break; }
-              if (bytes <= tail) { off = 0; break; }
-            } else if (head + bytes <= tail) {
+              if (bytes < tail) { off = 0; break; }
+            } else if (head + bytes < tail) {
               off = head;
               break;
             }
