@@ -67,6 +67,7 @@ struct __align__(8) Shared {
   uint8_t cidx[kSegCands];
   float partial[kGroups][2][4][32];      // [group][item parity][quadrant][query row]
   volatile int progress[kGroups * 4];    // per epilogue warp: items (by index) it has looked at and finished with
+  int mma_done;                          // items whose MMAs have completed (their ring space may be overwritten)
   uint32_t tmem_base;
 };
 
@@ -106,6 +107,7 @@ maxsim_rerank_umma_kernel(const __grid_constant__ TileMaps maps, const int64_t* 
     mbar_init(smem_u32(&sh.qfull[0]), 1);
     mbar_init(smem_u32(&sh.qfull[1]), 1);
     for (int i = 0; i < kGroups * 4; ++i) sh.progress[i] = 0;
+    sh.mma_done = 0;
     fence_mbar_init();
   }
   if (warp == 9) {
@@ -245,7 +247,8 @@ maxsim_rerank_umma_kernel(const __grid_constant__ TileMaps maps, const int64_t* 
           int off = -1;
           while (true) {
             // retire finished items from the ring accounting
-            const int done = __shfl_sync(0xffffffffu, ld_progress_min(&sh), 0);   // warp-uniform snapshot
+            // ring space is released as soon as the tile's MMAs have completed (the epilogue may still be reducing)
+            const int done = __shfl_sync(0xffffffffu, *reinterpret_cast<volatile int*>(&sh.mma_done), 0);
             while (live_lo < done && live_lo < idx) {
               ++live_lo;
               tail = live_lo < idx ? __shfl_sync(0xffffffffu, my_start, live_lo & 31) : head;
@@ -347,6 +350,7 @@ maxsim_rerank_umma_kernel(const __grid_constant__ TileMaps maps, const int64_t* 
       spin_until_progress(&sh, idx - kSlots + 1);
       mbar_wait(smem_u32(&sh.accf[idx % kSlots]), (idx / kSlots) & 1);
       umma::fence_after_sync();
+      if (quad == 0 && lane == 0) atomicMax(&sh.mma_done, idx + 1);   // MMAs complete in order
       const int nvalid = min(32, max(0, static_cast<int>(it.rows) - 32 * quad));
       if (nvalid > 0) {
         uint32_t raw0[32];
@@ -367,16 +371,19 @@ maxsim_rerank_umma_kernel(const __grid_constant__ TileMaps maps, const int64_t* 
 #pragma unroll
           for (int j = 0; j < 32; ++j) v[j] = -INFINITY;
         }
-        // transposed butterfly: after the 5 steps lane j holds max over the 32 lanes (tokens) of column j
+        // max over the 32 lanes (tokens) of every column: one warp-wide CREDUX per column (redux.sync.max.f32,
+        // sm_100a), then a 5-level select so that lane j keeps the maximum of column j (= query row j)
 #pragma unroll
-        for (int step = 16; step >= 1; step >>= 1) {
-          const bool up = (lane & step) != 0;
+        for (int j = 0; j < 32; ++j) {
+          float r;
+          asm volatile("redux.sync.max.f32 %0, %1, 0xffffffff;" : "=f"(r) : "f"(v[j]));
+          v[j] = r;
+        }
 #pragma unroll
-          for (int i = 0; i < step; ++i) {
-            const float send = up ? v[i] : v[i + step];
-            const float keep = up ? v[i + step] : v[i];
-            v[i] = fmaxf(keep, __shfl_xor_sync(0xffffffffu, send, step));
-          }
+        for (int w = 16; w >= 1; w >>= 1) {
+          const bool up = (lane & w) != 0;
+#pragma unroll
+          for (int i = 0; i < w; ++i) v[i] = up ? v[i + w] : v[i];
         }
         sh.partial[grp][par][quad][lane] = v[0];
       }
