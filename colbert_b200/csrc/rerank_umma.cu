@@ -10,17 +10,24 @@
 // keeps 16 significant bits of the query).  Neither operand passes through registers: TMA writes the swizzled
 // tile, the tensor core reads it from shared memory, and only the 128 × N accumulator comes back (tcgen05.ld).
 //
-// One CTA = one autonomous streaming unit (two per SM):
-//   warp 8  producer: claims segments of candidates, resolves pid → (row, doclen), writes the query into one
-//           of two shared-memory buffers when it changes, carves variable-size tiles out of a shared-memory
-//           ring and issues the TMA loads (exact row count per tile: one tensor map per box height 1..128);
-//   warp 9  MMA issuer (one thread): 8 × tcgen05.mma (K = 128) per tile into a ring of TMEM accumulator slots;
-//   warps 0-3 / 4-7  two epilogue groups (one warp per TMEM lane quadrant): tcgen05.ld, mask rows ≥ tile rows,
-//           transposed butterfly max over the 32 lanes (lane j ends up with the max of query row j), combine the
-//           four quadrants through shared memory, running max over the chunks of a long document, zero floor,
-//           sum over the query rows, store.  Documents alternate between the groups.
-// Completion flows back through two progress counters (items fully reduced, per group) that the producer and
-// the MMA issuer poll to recycle ring space, item slots and TMEM slots.
+// One CTA = one autonomous streaming unit (4 per SM for fp16 stores, 3 for bf16):
+//   warp 4  producer: claims segments of candidates (the next segment's pid / pfxsum / doclens loads are in
+//           flight while the current one is issued), writes the query into one of two shared-memory buffers
+//           when it changes, carves variable-size tiles out of a shared-memory ring and issues the TMA loads
+//           (exact row count per tile: one tensor map per box height 1..128);
+//   warp 5  MMA issuer (one thread): 8 × tcgen05.mma (K = 128) per tile into a ring of TMEM accumulator slots;
+//   warps 0-3  epilogue (one warp per TMEM lane quadrant): tcgen05.ld, rows ≥ tile rows masked, max over the 32
+//           lanes of every column with one CREDUX (redux.sync.max.f32) per column, the four quadrants combined
+//           through shared memory, running max over the chunks of a long document, zero floor, sum over the
+//           query rows, store.
+// Completion flows back through progress counters (items fully reduced, per epilogue warp; items whose MMAs have
+// completed) that the producer and the MMA issuer poll to recycle ring space, item slots and TMEM slots.
+//
+// Status (round 1): bit-for-bit parity with the mma.sync kernel on fp16 stores and 2e-6 relative error on bf16
+// stores, but 16.5 ms (fp16) / 19.6 ms (bf16) on configs[1] against 14.4 / 15.4 ms for the mma.sync kernel, which
+// therefore stays the default; CBK_FLAG_RERANK_TCGEN05 selects this one.  ncu shows the epilogue warps starved
+// (waiting on the tile-landed barrier): with one document per 128-row MMA tile the per-tile bookkeeping of a
+// single producer / issuer pair per CTA limits the number of tiles in flight.
 #include <algorithm>
 
 #include "umma.cuh"
@@ -33,10 +40,11 @@ constexpr int kDim = 128;
 constexpr int kTileMax = 128;            // rows per tile (MMA M)
 constexpr int kItems = 16;               // item descriptor / full-barrier ring
 constexpr int kSegCands = 64;
-constexpr int kGroups = 2;
-constexpr int kThreads = 320;            // 8 epilogue warps + producer + MMA issuer
-constexpr int kTmemCols = 256;           // per CTA (two CTAs per SM)
-constexpr int kQBufBytes = 64 * 256;     // one query buffer: up to 64 rows × 256 B
+constexpr int kGroups = 1;               // epilogue groups per CTA (4 warps each)
+constexpr int kProducerWarp = kGroups * 4;
+constexpr int kMmaWarp = kGroups * 4 + 1;
+constexpr int kThreads = (kGroups * 4 + 2) * 32;   // epilogue warps + producer + MMA issuer
+constexpr int kTmemCols = 128;           // per CTA (up to four CTAs per SM)
 
 struct StrideSet {
   int n;
@@ -47,18 +55,24 @@ struct TileMaps {
   CUtensorMap m[kTileMax];               // m[r-1]: box {64 columns, r rows}
 };
 
-struct __align__(16) Item {
+struct __align__(16) Item {             // 16 bytes: written with one st.shared.v4, read with one ld.shared.v4
   uint32_t smem_off;                     // tile offset inside the ring
-  uint16_t rows;                         // valid rows (1..128)
-  uint8_t group;                         // epilogue group that owns the document
-  uint8_t flags;                         // bit0 first chunk, bit1 last chunk, bit2 zero floor, bit3 write 0 rows
-  uint8_t qbuf;                          // query buffer
-  uint8_t pad[3];
-  uint32_t qseq;                         // query sequence number (MMA waits for this buffer fill)
-  int64_t out_idx;                       // candidate position
+  uint16_t rows;                         // valid rows (1..128); 0 = end of stream
+  uint8_t flags;                         // bit0 first chunk, bit1 last chunk, bit2 zero floor, bit3 query buffer, bit4 group
+  uint8_t pad;
+  uint32_t qseq;                         // query sequence number (the MMA issuer waits for this buffer fill)
+  uint32_t out_idx;                      // candidate position
 };
+static_assert(sizeof(Item) == 16, "Item must stay one 16-byte word");
 
-struct __align__(8) Shared {
+__device__ __forceinline__ Item load_item(const Item* p) {
+  const uint4 w = *reinterpret_cast<const uint4*>(p);
+  Item it;
+  *reinterpret_cast<uint4*>(&it) = w;
+  return it;
+}
+
+struct __align__(16) Shared {
   uint64_t full[kItems];                 // TMA → MMA / epilogue
   uint64_t accf[16];                     // MMA commit → epilogue, per TMEM slot
   uint64_t qfull[2];                     // producer query fill → MMA
@@ -80,12 +94,8 @@ __device__ __forceinline__ int ld_progress_min(const Shared* sh) {
   return m;
 }
 
-__device__ __forceinline__ void spin_until_progress(const Shared* sh, int upto) {
-  while (ld_progress_min(sh) < upto) __nanosleep(32);
-}
-
 template <typename T, int kN>
-__global__ void __launch_bounds__(kThreads, 2)
+__global__ void __launch_bounds__(kThreads, kN == 32 ? 4 : 3)
 maxsim_rerank_umma_kernel(const __grid_constant__ TileMaps maps, const int64_t* __restrict__ pfxsum,
                           const int32_t* __restrict__ doclens, int64_t n_docs, int64_t pid_base, int skip_foreign,
                           StrideSet strides, const float* __restrict__ Q, int q_len, int64_t n_queries,
@@ -95,6 +105,7 @@ maxsim_rerank_umma_kernel(const __grid_constant__ TileMaps maps, const int64_t* 
   extern __shared__ uint8_t smem_raw[];
   __shared__ Shared sh;
   constexpr int kSlots = kTmemCols / kN;
+  constexpr int kQBufBytes = kN * 256;                               // one query buffer: kN rows × 256 B
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const uint32_t raw = smem_u32(smem_raw);
   const uint32_t ring_addr = (raw + 1023u) & ~1023u;                 // tile ring, then the two query buffers
@@ -110,7 +121,7 @@ maxsim_rerank_umma_kernel(const __grid_constant__ TileMaps maps, const int64_t* 
     sh.mma_done = 0;
     fence_mbar_init();
   }
-  if (warp == 9) {
+  if (warp == kMmaWarp) {
     umma::tmem_alloc(smem_u32(&sh.tmem_base), kTmemCols);
     umma::tmem_relinquish();
   }
@@ -122,7 +133,7 @@ maxsim_rerank_umma_kernel(const __grid_constant__ TileMaps maps, const int64_t* 
   const int64_t n_segs = (n_cand + seg_cands - 1) / seg_cands;
 
   // The item stream ends with a sentinel item (rows == 0) that every consumer recognises.
-  if (warp == 8) {
+  if (warp == kProducerWarp) {
     // ======================================= producer ===============================================
     if (lane < 32) {
       for (int r = lane; r < kTileMax; r += 32) tma_prefetch_desc(&maps.m[r]);
@@ -139,42 +150,73 @@ maxsim_rerank_umma_kernel(const __grid_constant__ TileMaps maps, const int64_t* 
     int last_item_of_buf[2] = {-1, -1};
     int doc_parity = 0;
 
+    int known_prog = 0;          // cached lower bounds of the two completion counters (both only grow)
+    int known_mma = 0;
     auto wait_items_done = [&](int upto) {   // until every item with index < upto is finished
-      if (lane == 0) spin_until_progress(&sh, upto);
-      __syncwarp();
+      if (known_prog >= upto) return;
+      int p = 0;
+      if (lane == 0) {
+        while ((p = ld_progress_min(&sh)) < upto) __nanosleep(32);
+      }
+      known_prog = __shfl_sync(0xffffffffu, p, 0);
     };
 
-    while (true) {
-      unsigned int seg = 0;
-      if (lane == 0) seg = atomicAdd(seg_counter, 1u);
-      seg = __shfl_sync(0xffffffffu, seg, 0);
-      if (static_cast<int64_t>(seg) >= n_segs) break;
-      const int64_t c0 = static_cast<int64_t>(seg) * seg_cands;
+    // The next segment's metadata is fetched while the current one is being issued: the claim (atomic) and the
+    // pid loads right after the current segment has been compacted, the dependent pfxsum / doclens loads a few
+    // documents later, so that neither round trip to HBM stalls the TMA stream.
+    unsigned int nseg = 0;
+    int64_t npid[2] = {-1, -1};
+    int nrow[2] = {0, 0}, nlen[2] = {-1, -1};
+    auto claim_next = [&]() {
+      if (lane == 0) nseg = atomicAdd(seg_counter, 1u);
+      nseg = __shfl_sync(0xffffffffu, nseg, 0);
+      if (static_cast<int64_t>(nseg) < n_segs) {
+        const int64_t b = static_cast<int64_t>(nseg) * seg_cands;
+        const int n = static_cast<int>(min(static_cast<int64_t>(seg_cands), n_cand - b));
+#pragma unroll
+        for (int k = 0; k < 2; ++k) npid[k] = lane + 32 * k < n ? cand_pids[b + lane + 32 * k] - pid_base : -1;
+      }
+    };
+    auto load_next_rows = [&]() {
+#pragma unroll
+      for (int k = 0; k < 2; ++k) {
+        nrow[k] = 0;
+        nlen[k] = -1;
+        if (npid[k] >= 0 && npid[k] < n_docs) {
+          nrow[k] = static_cast<int>(pfxsum[npid[k]]);
+          nlen[k] = doclens[npid[k]];
+        }
+      }
+    };
+    claim_next();
+    load_next_rows();
+
+    while (static_cast<int64_t>(nseg) < n_segs) {
+      const int64_t c0 = static_cast<int64_t>(nseg) * seg_cands;
       const int nc = static_cast<int>(min(static_cast<int64_t>(seg_cands), n_cand - c0));
-      // ---- pid → (row, doclen); trivial candidates answered here, the rest compacted in order ----------
+      // ---- trivial candidates are answered here, the rest compacted in order ---------------------------
       __syncwarp();
       int nv = 0;
-      for (int i0 = 0; i0 < nc; i0 += 32) {
-        const int i = i0 + lane;
-        int row = 0, len = -1;
-        if (i < nc) {
-          const int64_t pid = cand_pids[c0 + i] - pid_base;
-          if (pid >= 0 && pid < n_docs) {
-            row = static_cast<int>(pfxsum[pid]);
-            len = doclens[pid];
-          }
-          if (len <= 0) out[c0 + i] = len == 0 ? 0.f : (skip_foreign ? -INFINITY : __int_as_float(0x7fc00000));
-        }
+#pragma unroll
+      for (int k = 0; k < 2; ++k) {
+        const int i = lane + 32 * k;
+        const int len = i < nc ? nlen[k] : -1;
+        if (i < nc && len <= 0) out[c0 + i] = len == 0 ? 0.f : (skip_foreign ? -INFINITY : __int_as_float(0x7fc00000));
         const unsigned int live = __ballot_sync(0xffffffffu, len > 0);
         if (len > 0) {
           const int slot = nv + __popc(live & ((1u << lane) - 1u));
-          sh.meta[slot] = make_int2(row, len);
+          sh.meta[slot] = make_int2(nrow[k], len);
           sh.cidx[slot] = static_cast<uint8_t>(i);
         }
         nv += __popc(live);
       }
-      __syncwarp();
-      if (nv == 0) continue;
+      __syncwarp();                                              // the compacted list is visible to every lane
+      claim_next();
+      const int load_at = min(6, nv - 1);
+      if (nv == 0) {
+        load_next_rows();
+        continue;
+      }
       // ---- query of the first scorable candidate -------------------------------------------------------
       const int64_t cfirst = c0 + sh.cidx[0];
       int64_t q = static_cast<int64_t>((static_cast<double>(cfirst) * n_queries) / static_cast<double>(n_cand));
@@ -190,6 +232,7 @@ maxsim_rerank_umma_kernel(const __grid_constant__ TileMaps maps, const int64_t* 
       int64_t q_end = rowptr[q + 1];
 
       for (int ci = 0; ci < nv; ++ci) {
+        if (ci == load_at) load_next_rows();
         const int64_t c = c0 + sh.cidx[ci];
         while (c >= q_end) {
           ++q;
@@ -203,26 +246,43 @@ maxsim_rerank_umma_kernel(const __grid_constant__ TileMaps maps, const int64_t* 
           wait_items_done(last_item_of_buf[qbuf] + 1);
           const float* Qq = Q + q * static_cast<int64_t>(q_len) * kDim;
           uint8_t* dstb = q_ptr + qbuf * kQBufBytes;
-          // element (row r, column k) → half h = k / 64, 16-byte chunk (k % 64) / 8 XOR (r & 7) (SWIZZLE_128B)
-          for (int e = lane; e < kN * (kDim / 8); e += 32) {     // one 16-byte chunk (8 columns) per iteration
-            const int r = e / (kDim / 8), ch = e % (kDim / 8);
-            const int h = ch >> 3, cc = ch & 7;
-            const int qr = r & 31;                               // rows 32-63 (bf16 store): lo part of row r-32
-            float v[8];
+          // element (row r, column k) → half h = k / 64, 16-byte chunk (k % 64) / 8 XOR (r & 7) (SWIZZLE_128B);
+          // 4 chunks (8 float4 loads) per lane are in flight at a time
+          constexpr int kChunks = kN * (kDim / 8);
+#pragma unroll 1
+          for (int e0 = 0; e0 < kChunks; e0 += 128) {
+            float4 f[4][2];
 #pragma unroll
-            for (int j = 0; j < 8; ++j) v[j] = qr < q_len ? Qq[qr * kDim + ch * 8 + j] : 0.f;
-            uint32_t w[4];
-#pragma unroll
-            for (int j = 0; j < 4; ++j) {
-              float a = v[2 * j], b = v[2 * j + 1];
-              if (kN == 64 && r >= 32) {                         // residual after rounding to T
-                a -= to_float<T>(static_cast<T>(a));
-                b -= to_float<T>(static_cast<T>(b));
+            for (int u = 0; u < 4; ++u) {
+              const int e = e0 + u * 32 + lane;
+              const int r = e / (kDim / 8), ch = e % (kDim / 8);
+              const int qr = r & 31;                             // rows 32-63 (bf16 store): lo part of row r-32
+              f[u][0] = f[u][1] = make_float4(0.f, 0.f, 0.f, 0.f);
+              if (qr < q_len) {
+                const float4* src = reinterpret_cast<const float4*>(Qq + qr * kDim + ch * 8);
+                f[u][0] = src[0];
+                f[u][1] = src[1];
               }
-              w[j] = pack2<T>(a, b);
             }
-            *reinterpret_cast<uint4*>(dstb + h * (kN * 128) + r * 128 + ((cc ^ (r & 7)) << 4)) =
-                make_uint4(w[0], w[1], w[2], w[3]);
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+              const int e = e0 + u * 32 + lane;
+              const int r = e / (kDim / 8), ch = e % (kDim / 8);
+              const int h = ch >> 3, cc = ch & 7;
+              float v[8] = {f[u][0].x, f[u][0].y, f[u][0].z, f[u][0].w, f[u][1].x, f[u][1].y, f[u][1].z, f[u][1].w};
+              uint32_t w[4];
+#pragma unroll
+              for (int j = 0; j < 4; ++j) {
+                float a = v[2 * j], b = v[2 * j + 1];
+                if (kN == 64 && r >= 32) {                       // residual after rounding to T
+                  a -= to_float<T>(static_cast<T>(a));
+                  b -= to_float<T>(static_cast<T>(b));
+                }
+                w[j] = pack2<T>(a, b);
+              }
+              *reinterpret_cast<uint4*>(dstb + h * (kN * 128) + r * 128 + ((cc ^ (r & 7)) << 4)) =
+                  make_uint4(w[0], w[1], w[2], w[3]);
+            }
           }
           fence_proxy_async();
           __syncwarp();
@@ -236,7 +296,7 @@ maxsim_rerank_umma_kernel(const __grid_constant__ TileMaps maps, const int64_t* 
         for (int i = 0; i < CBK_MAX_STRIDES; ++i)
           if (i < strides.n && strides.v[i] == len) do_floor = false;
         const int group = doc_parity;
-        doc_parity ^= 1;
+        doc_parity = (doc_parity + 1) % kGroups;
         const int n_chunks = (len + kTileMax - 1) / kTileMax;
         for (int ch = 0; ch < n_chunks; ++ch) {
           const int rows = min(kTileMax, len - ch * kTileMax);
@@ -245,10 +305,11 @@ maxsim_rerank_umma_kernel(const __grid_constant__ TileMaps maps, const int64_t* 
           const int idx = n_items;
           wait_items_done(idx - kItems + 1);                     // slot idx % kItems is free again
           int off = -1;
+          bool refreshed = false;
           while (true) {
-            // retire finished items from the ring accounting
-            // ring space is released as soon as the tile's MMAs have completed (the epilogue may still be reducing)
-            const int done = __shfl_sync(0xffffffffu, *reinterpret_cast<volatile int*>(&sh.mma_done), 0);
+            // retire finished items from the ring accounting: ring space is released as soon as the tile's MMAs
+            // have completed (the epilogue may still be reducing); the counter is re-read only when needed
+            const int done = known_mma;
             while (live_lo < done && live_lo < idx) {
               ++live_lo;
               tail = live_lo < idx ? __shfl_sync(0xffffffffu, my_start, live_lo & 31) : head;
@@ -266,6 +327,9 @@ maxsim_rerank_umma_kernel(const __grid_constant__ TileMaps maps, const int64_t* 
               off = head;
               break;
             }
+            if (refreshed) __nanosleep(32);
+            known_mma = __shfl_sync(0xffffffffu, *reinterpret_cast<volatile int*>(&sh.mma_done), 0);
+            refreshed = true;
           }
           head = off + bytes;
           if (lane == (idx & 31)) my_start = off;
@@ -274,12 +338,12 @@ maxsim_rerank_umma_kernel(const __grid_constant__ TileMaps maps, const int64_t* 
             Item it;
             it.smem_off = static_cast<uint32_t>(off);
             it.rows = static_cast<uint16_t>(rows);
-            it.group = static_cast<uint8_t>(group);
-            it.flags = static_cast<uint8_t>((ch == 0 ? 1 : 0) | (ch == n_chunks - 1 ? 2 : 0) | (do_floor ? 4 : 0));
-            it.qbuf = static_cast<uint8_t>(qbuf);
+            it.flags = static_cast<uint8_t>((ch == 0 ? 1 : 0) | (ch == n_chunks - 1 ? 2 : 0) | (do_floor ? 4 : 0) |
+                                            (qbuf << 3) | (group << 4));
+            it.pad = 0;
             it.qseq = qseq;
-            it.out_idx = c;
-            sh.items[idx % kItems] = it;
+            it.out_idx = static_cast<uint32_t>(c);
+            *reinterpret_cast<uint4*>(&sh.items[idx % kItems]) = *reinterpret_cast<const uint4*>(&it);
             const uint32_t bar = smem_u32(&sh.full[idx % kItems]);
             const uint32_t dst = ring_addr + off;
             const int row = m.x + ch * kTileMax;
@@ -296,30 +360,33 @@ maxsim_rerank_umma_kernel(const __grid_constant__ TileMaps maps, const int64_t* 
     // sentinel: tells the MMA issuer and both epilogue groups that the stream is over
     wait_items_done(n_items - kItems + 1);
     if (lane == 0) {
-      Item it;
-      it.smem_off = 0; it.rows = 0; it.group = 0; it.flags = 0; it.qbuf = 0; it.qseq = 0; it.out_idx = 0;
-      sh.items[n_items % kItems] = it;
+      *reinterpret_cast<uint4*>(&sh.items[n_items % kItems]) = make_uint4(0u, 0u, 0u, 0u);
       mbar_arrive(smem_u32(&sh.full[n_items % kItems]));
     }
-  } else if (warp == 9) {
+  } else if (warp == kMmaWarp) {
     // ======================================= MMA issuer =============================================
     if (lane == 0) {
       uint32_t seen_qseq = 0;
-      uint32_t qparity[2] = {0, 0};
+      uint32_t qparity = 0;                                      // bit b = parity of the next wait on qfull[b]
+      int known_prog = 0;
       for (int idx = 0;; ++idx) {
         mbar_wait(smem_u32(&sh.full[idx % kItems]), (idx / kItems) & 1);
-        const Item it = sh.items[idx % kItems];
+        const Item it = load_item(&sh.items[idx % kItems]);
         if (it.rows == 0) break;
+        const uint32_t qb = (it.flags >> 3) & 1u;
         if (it.qseq != seen_qseq) {                              // first item of a newly written query buffer
-          mbar_wait(smem_u32(&sh.qfull[it.qbuf]), qparity[it.qbuf]);
-          qparity[it.qbuf] ^= 1u;
+          mbar_wait(smem_u32(&sh.qfull[qb]), (qparity >> qb) & 1u);
+          qparity ^= 1u << qb;
           seen_qseq = it.qseq;
         }
-        spin_until_progress(&sh, idx - kSlots + 1);              // TMEM slot idx % kSlots has been drained
+        while (known_prog < idx - kSlots + 1) {                  // TMEM slot idx % kSlots has been drained
+          known_prog = ld_progress_min(&sh);
+          if (known_prog < idx - kSlots + 1) __nanosleep(32);
+        }
         umma::fence_after_sync();
         const uint32_t a_base = ring_addr + it.smem_off;
         const uint32_t a_half = ((it.rows + 7) & ~7) * 128;
-        const uint32_t b_base = q_addr + it.qbuf * kQBufBytes;
+        const uint32_t b_base = q_addr + qb * kQBufBytes;
         const uint32_t d_tmem = tmem + (idx % kSlots) * kN;
 #pragma unroll
         for (int h = 0; h < 2; ++h)
@@ -336,18 +403,22 @@ maxsim_rerank_umma_kernel(const __grid_constant__ TileMaps maps, const int64_t* 
     const uint32_t lane_base = static_cast<uint32_t>(quad * 32) << 16;
     float run = -INFINITY;
     int par = 0;
+    int known_prog = 0;
     for (int idx = 0;; ++idx) {
       mbar_wait(smem_u32(&sh.full[idx % kItems]), (idx / kItems) & 1);
-      const Item it = sh.items[idx % kItems];
+      const Item it = load_item(&sh.items[idx % kItems]);
       if (it.rows == 0) break;
-      if (it.group != grp) {                                     // the other group's document
+      if (((it.flags >> 4) & 1) != grp) {                        // the other group's document
         __syncwarp();
         if (lane == 0) sh.progress[warp] = idx + 1;
         continue;
       }
       // the accumulator barrier of a slot is reused every kSlots items, possibly by the other group: wait for
       // the previous use to be completely finished before a parity wait can be unambiguous
-      spin_until_progress(&sh, idx - kSlots + 1);
+      while (known_prog < idx - kSlots + 1) {
+        known_prog = ld_progress_min(&sh);
+        if (known_prog < idx - kSlots + 1) __nanosleep(32);
+      }
       mbar_wait(smem_u32(&sh.accf[idx % kSlots]), (idx / kSlots) & 1);
       umma::fence_after_sync();
       if (quad == 0 && lane == 0) atomicMax(&sh.mma_done, idx + 1);   // MMAs complete in order
@@ -415,7 +486,7 @@ maxsim_rerank_umma_kernel(const __grid_constant__ TileMaps maps, const int64_t* 
 
   umma::fence_before_sync();
   __syncthreads();
-  if (warp == 9) umma::tmem_dealloc(tmem, kTmemCols);
+  if (warp == kMmaWarp) umma::tmem_dealloc(tmem, kTmemCols);
 }
 
 }  // namespace
@@ -437,6 +508,7 @@ int rerank_umma_dispatch(const void* d_store, int store_dtype, int64_t n_store_r
     cached_base = d_store;
     cached_rows = n_store_rows;
   }
+  CBK_CHECK_SUPPORTED(n_cand_total < (1ll << 32), "cbk_maxsim_rerank (tcgen05): more than 2^32 candidates in one launch");
   StrideSet ss;
   ss.n = n_strides;
   for (int i = 0; i < CBK_MAX_STRIDES; ++i) ss.v[i] = i < n_strides ? strides[i] : -1;
@@ -444,10 +516,11 @@ int rerank_umma_dispatch(const void* d_store, int store_dtype, int64_t n_store_r
   unsigned int* counter = static_cast<unsigned int*>(d_workspace);
   CBK_CUDA(cudaMemsetAsync(counter, 0, sizeof(unsigned int), stream));
   const bool bf16 = store_dtype == CBK_BF16;
-  // per CTA: 1 KB alignment + ring + two query buffers; two CTAs per SM
-  const int ring_bytes = 76 * 1024;
-  const size_t smem = 1024 + static_cast<size_t>(ring_bytes) + 2 * kQBufBytes;
-  const int64_t ctas_total = static_cast<int64_t>(sm_count()) * 2;
+  // per CTA: 1 KB alignment + tile ring + two query buffers; 4 CTAs per SM for fp16 stores (N = 32), 3 for bf16 (N = 64)
+  const int ctas_per_sm = bf16 ? 3 : 4;
+  const int ring_bytes = bf16 ? 38 * 1024 : 34 * 1024;
+  const size_t smem = 1024 + static_cast<size_t>(ring_bytes) + 2 * (bf16 ? 64 : 32) * 256;
+  const int64_t ctas_total = static_cast<int64_t>(sm_count()) * ctas_per_sm;
   const int seg_cands = static_cast<int>(std::max<int64_t>(4, std::min<int64_t>(kSegCands, n_cand_total / (2 * ctas_total))));
   const int64_t n_segs = (n_cand_total + seg_cands - 1) / seg_cands;
   const int grid = static_cast<int>(std::max<int64_t>(1, std::min<int64_t>(n_segs, ctas_total)));
