@@ -467,3 +467,26 @@ def test_rank_forward_other_dims(dev, dim):
         rp, rs = O.topk_desc(ref, cand[b], 10)
         fp, fs = O.topk_desc(ref, cand[b], None)
         check_topk(p, s, rp, rs, 1e-5, fp, fs)               # fp32 arithmetic on exact fp16 values: tight
+
+
+def test_rank_forward_bsize_candidates_and_depth_clamp(dev):
+    """The reference's BSIZE (16384 candidates in one call), duplicate pids, depth larger than the list."""
+    from colbert_b200 import synthetic
+    index = synthetic.make_index(404, 20_000, dim=128, lo=1, hi=60)
+    ranker = make_ranker(index, dev)
+    Q = synthetic.make_queries(405, 1, 32, 128)[0]
+    Qt = torch.from_numpy(Q).unsqueeze(0).permute(0, 2, 1)
+    rng = np.random.default_rng(406)
+    pids = rng.integers(0, index.num_docs, size=16384).astype(np.int64)          # duplicates certain
+    p, s = ranker.rank_forward(Qt, pids.tolist(), depth=100)
+    store, pf = O.pad_store(index.emb), O.doclens_pfxsum(index.doclens)
+    ref = O.maxsim_exact(store, index.doclens, pf, ranker.strides, Q, pids)
+    rp, rs = O.topk_desc(ref, pids, 100)
+    fp, fs = O.topk_desc(ref, pids, None)
+    check_topk(p, s, rp, rs, SCORE_RTOL, fp, fs)
+    with pytest.raises(ValueError):
+        ranker.rank_forward(Qt, pids.tolist() + [0], depth=10)                   # one more than BSIZE
+    p, s = ranker.rank_forward(Qt, [5, 9, 5], depth=10)                          # depth > n: everything, sorted
+    assert len(p) == 3 and s[0] >= s[1] >= s[2] and sorted(p) == [5, 5, 9]
+    p, s = ranker.rank_forward(Qt, [7], depth=None)
+    assert p == [7] and abs(s[0] - O.maxsim_exact(store, index.doclens, pf, ranker.strides, Q, [7])[0]) < 1e-3 * max(1, abs(s[0]))
