@@ -129,8 +129,8 @@ def build_store(torch, dev, n_docs, dim, dtype, seed, doclen_fixed=0):
 def build_queries(torch, n_q, q_len, dim, n_docs, n_cand, seed):
     g = torch.Generator(device="cpu"); g.manual_seed(seed)
     Q = torch.nn.functional.normalize(torch.randn(n_q, q_len, dim, generator=g), p=2, dim=2)
-    # distinct pids per query, uniform over the corpus: random start + random odd stride modulo a prime-free trick
-    # would be biased; use rejection-free sampling through sorting random keys on a window instead
+    # distinct pids per query, uniform over the corpus: draw a few extra, de-duplicate, shuffle back (the reference
+    # receives list(set(...)), i.e. an arbitrary order)
     cand = torch.empty(n_q, n_cand, dtype=torch.int64)
     for b in range(0, n_q, 256):
         e = min(n_q, b + 256)
@@ -352,6 +352,8 @@ def run_ours(args, rank, world, local_rank):
                 "store_bytes_per_gpu": int(store.numel() * 2),
                 "l2_policy": "inputs larger than L2: each step gathers "
                              f"{algo_bytes / 1e9:.1f} GB of distinct document rows from a {store.numel() * 2 / 1e9:.1f} GB store",
+                "compute": ("16-bit store rows multiplied on tensor cores (m16n8k16, fp32 accumulate); a bf16 store is "
+                            "converted to fp16 in registers so the query keeps 11 significant bits"),
                 "parallelism": (f"store sharded by pid range over {world} GPUs, queries replicated, one NCCL all-gather "
                                 f"of packed top-{k} keys per step + replicated merge") if world > 1 else "single GPU",
             },

@@ -135,15 +135,12 @@ maxsim_rerank_umma_kernel(const __grid_constant__ TileMaps maps, const int64_t* 
   // The item stream ends with a sentinel item (rows == 0) that every consumer recognises.
   if (warp == kProducerWarp) {
     // ======================================= producer ===============================================
-    if (lane < 32) {
-      for (int r = lane; r < kTileMax; r += 32) tma_prefetch_desc(&maps.m[r]);
-    }
+    for (int r = lane; r < kTileMax; r += 32) tma_prefetch_desc(&maps.m[r]);
     int n_items = 0;             // items published so far
     int head = 0;                // ring allocation cursor
     int live_lo = 0;             // oldest item whose ring space is still accounted (index)
-    // per live item: ring start, kept in registers of lane (item % 32) — only lane 0's copy of head/tail logic matters
     int tail = 0;                // ring offset of the oldest live item
-    int my_start = 0, my_end = 0;  // lane i holds [start,end) of item with index ≡ i (mod 32)
+    int my_start = 0;            // lane i remembers the ring offset of the live item with index ≡ i (mod 32)
     int64_t cur_q = -1;
     uint32_t qseq = 0;
     int qbuf = 1;
@@ -333,7 +330,6 @@ maxsim_rerank_umma_kernel(const __grid_constant__ TileMaps maps, const int64_t* 
           }
           head = off + bytes;
           if (lane == (idx & 31)) my_start = off;
-          (void)my_end;
           if (lane == 0) {
             Item it;
             it.smem_off = static_cast<uint32_t>(off);

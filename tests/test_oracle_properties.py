@@ -1,0 +1,48 @@
+"""Property tests of the oracle (CPU, hypothesis): the faithful op-sequence restatement of rank_forward and the
+exact-doclen + zero-floor formulation the CUDA kernels implement agree on arbitrary small indexes; sharding plans
+partition the corpus; packed keys round-trip and order like (score desc, pid asc)."""
+import numpy as np
+import torch
+from hypothesis import given, settings, strategies as st
+
+from colbert_b200.sharding import plan_shards
+from oracle import maxsim_oracle as O
+
+
+@settings(max_examples=25, deadline=None)
+@given(st.integers(0, 2**31 - 1), st.integers(4, 40), st.integers(1, 24), st.integers(1, 8))
+def test_faithful_and_exact_formulations_agree(seed, n_docs, max_len, q_len):
+    rng = np.random.default_rng(seed)
+    doclens = rng.integers(1, max_len + 1, size=n_docs).astype(np.int64)
+    emb = rng.standard_normal((int(doclens.sum()), 16)).astype(np.float16)       # signs vary: the floor matters
+    store, pf = O.pad_store(emb), O.doclens_pfxsum(doclens)
+    strides = O.compute_strides(doclens)
+    Q = rng.standard_normal((q_len, 16)).astype(np.float32)
+    pids = rng.permutation(n_docs)[: max(1, n_docs // 2)]
+    _, _, all_scores = O.rank_forward(store, doclens, pf, strides, np.transpose(Q[None], (0, 2, 1)), pids, depth=None,
+                                      return_all_scores=True)
+    exact = O.maxsim_exact(store, doclens, pf, strides, Q, pids)
+    np.testing.assert_allclose(exact, all_scores, rtol=1e-5, atol=1e-5)
+
+
+@settings(max_examples=50, deadline=None)
+@given(st.integers(0, 2**31 - 1), st.integers(1, 300), st.integers(1, 9))
+def test_plan_shards_partitions_the_corpus(seed, n_docs, world):
+    rng = np.random.default_rng(seed)
+    dl = torch.from_numpy(rng.integers(1, 50, size=n_docs))
+    pf = torch.cat([torch.zeros(1, dtype=torch.int64), torch.cumsum(dl, 0)])
+    b = plan_shards(pf, world)
+    assert len(b) == world + 1 and b[0] == 0 and b[-1] == n_docs and all(b[i] <= b[i + 1] for i in range(world))
+
+
+@settings(max_examples=50, deadline=None)
+@given(st.lists(st.tuples(st.floats(-100, 100, width=32), st.integers(0, 2**32 - 2)), min_size=1, max_size=60, unique_by=lambda t: t[1]))
+def test_packed_keys_order_and_roundtrip(pairs):
+    scores = np.array([p[0] for p in pairs], dtype=np.float32)
+    pids = np.array([p[1] for p in pairs], dtype=np.int64)
+    keys = O.pack_keys(scores, pids)
+    s2, p2 = O.unpack_keys(keys)
+    assert np.array_equal(p2, pids) and np.array_equal(s2, scores + np.float32(0.0))
+    order = np.argsort(keys)[::-1]
+    ref_p, ref_s = O.topk_desc(scores, pids, None)
+    assert np.array_equal(pids[order], ref_p)
