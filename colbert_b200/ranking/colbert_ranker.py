@@ -103,6 +103,21 @@ class ColbertRanker:
         assert int(self.doclens_pfxsum[-1]) == self.num_embeddings, "doclens do not add up to the store size"
         return self
 
+    @classmethod
+    def from_flat(cls, flat_path: str, device=None, pid_lo: int = 0, pid_hi: Optional[int] = None,
+                  model=None) -> "ColbertRanker":
+        """Load (a pid range of) an index converted with ``indexing.flat_store.convert_index``: raw mmap → HBM.
+        For a shard, pass its pid range and use the result as the ``local`` ranker of ``ShardedColbertRanker``
+        (which sets ``pid_base`` and the corpus-wide strides)."""
+        from ..indexing.flat_store import load_flat
+        dev = torch.device(device if device is not None else DEVICE)
+        if dev.type != "cuda":
+            raise RuntimeError("colbert_b200.ColbertRanker needs a CUDA device (sm_100a); there is no CPU path")
+        store, doclens, lo, _ = load_flat(flat_path, dev, pid_lo, pid_hi)
+        self = cls.from_store(store, doclens, model=model)
+        self.pid_base = int(lo)
+        return self
+
     # -- reference colbert_ranker.py:61-73 ---------------------------------------------------------
     def _load_parts(self, dim, verbose=None):
         store = torch.zeros(self.num_embeddings + TAIL_PAD_ROWS, dim, dtype=self.store_dtype, device=self.device)

@@ -490,3 +490,24 @@ def test_rank_forward_bsize_candidates_and_depth_clamp(dev):
     assert len(p) == 3 and s[0] >= s[1] >= s[2] and sorted(p) == [5, 5, 9]
     p, s = ranker.rank_forward(Qt, [7], depth=None)
     assert p == [7] and abs(s[0] - O.maxsim_exact(store, index.doclens, pf, ranker.strides, Q, [7])[0]) < 1e-3 * max(1, abs(s[0]))
+
+
+def test_ranker_from_flat_store(dev, tmp_path):
+    """Flat .bin store: whole index and a pid-range shard rank like the reference-layout loader."""
+    from colbert_b200 import synthetic
+    from colbert_b200.indexing.flat_store import convert_index
+    from colbert_b200.ranking import ColbertRanker
+    index, queries, cands = build_case(CASES[0])
+    synthetic.write_index(index, str(tmp_path / "ref"))
+    convert_index(str(tmp_path / "ref"), str(tmp_path / "flat"))
+    a = ColbertRanker(str(tmp_path / "ref"), dim=128, device=dev)
+    b = ColbertRanker.from_flat(str(tmp_path / "flat"), device=dev)
+    assert torch.equal(a.tensor, b.tensor) and a.strides == b.strides
+    Qt = torch.from_numpy(queries[0]).unsqueeze(0).permute(0, 2, 1)
+    assert a.rank_forward(Qt, cands[0].tolist(), depth=10) == b.rank_forward(Qt, cands[0].tolist(), depth=10)
+    shard = ColbertRanker.from_flat(str(tmp_path / "flat"), device=dev, pid_lo=100, pid_hi=300)
+    shard.strides = a.strides                                        # corpus-wide strides, as ShardedColbertRanker sets them
+    mine = [int(p) for p in cands[0] if 100 <= p < 300]
+    pa, sa = a.rank_forward(Qt, mine, depth=None)
+    pb, sb = shard.rank_forward(Qt, mine, depth=None)               # global pids, pid_base = 100
+    assert pa == pb and sa == sb

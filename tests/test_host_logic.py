@@ -61,3 +61,23 @@ def test_product_never_imports_the_oracle():
                 elif isinstance(node, ast.ImportFrom):
                     names = [node.module or ""]
                 assert not any(n.split(".")[0] == "oracle" for n in names), (f, names)
+
+
+def test_flat_store_roundtrip(tmp_path):
+    """convert_index: reference layout → store.bin + doclens.i32 + meta.json; load_flat reads any pid range back
+    bit-exactly in the reference's in-memory layout (512 zero tail rows)."""
+    from colbert_b200.indexing.flat_store import convert_index, load_flat, read_meta
+    idx = synthetic.make_index(12, 90, dim=128, lo=1, hi=30, num_parts=4)
+    src, dst = tmp_path / "ref", tmp_path / "flat"
+    synthetic.write_index(idx, str(src))
+    meta = convert_index(str(src), str(dst))
+    assert meta == {"dim": 128, "dtype": "float16", "num_docs": 90, "num_embeddings": idx.num_tokens, "parts": 4}
+    m2, dl = read_meta(str(dst))
+    assert m2 == meta and np.array_equal(dl, idx.doclens)
+    assert os.path.getsize(dst / "store.bin") == idx.num_tokens * 256
+    store, doclens, lo, _ = load_flat(str(dst), "cpu")
+    assert np.array_equal(store.numpy(), O.pad_store(idx.emb)) and np.array_equal(doclens.numpy(), idx.doclens)
+    pf = O.doclens_pfxsum(idx.doclens)
+    store, doclens, lo, _ = load_flat(str(dst), "cpu", 17, 53)
+    assert lo == 17 and np.array_equal(doclens.numpy(), idx.doclens[17:53])
+    assert np.array_equal(store.numpy()[:-512], idx.emb[pf[17]: pf[53]]) and not store.numpy()[-512:].any()
