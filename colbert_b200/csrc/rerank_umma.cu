@@ -380,16 +380,17 @@ maxsim_rerank_umma_kernel(const __grid_constant__ TileMaps maps, const int64_t* 
           if (known_prog < idx - kSlots + 1) __nanosleep(32);
         }
         umma::fence_after_sync();
+        // descriptors differ only in their 14-bit start-address field: +2 (32 bytes >> 4) per k-step
         const uint32_t a_base = ring_addr + it.smem_off;
         const uint32_t a_half = ((it.rows + 7) & ~7) * 128;
         const uint32_t b_base = q_addr + qb * kQBufBytes;
+        const uint64_t a0 = umma::make_smem_desc_sw128(a_base), a1 = umma::make_smem_desc_sw128(a_base + a_half);
+        const uint64_t b0 = umma::make_smem_desc_sw128(b_base), b1 = umma::make_smem_desc_sw128(b_base + kN * 128);
         const uint32_t d_tmem = tmem + (idx % kSlots) * kN;
 #pragma unroll
-        for (int h = 0; h < 2; ++h)
+        for (int k = 0; k < 4; ++k) umma::mma_f16_ss(d_tmem, a0 + 2 * k, b0 + 2 * k, idesc, k ? 1u : 0u);
 #pragma unroll
-          for (int k = 0; k < 4; ++k)
-            umma::mma_f16_ss(d_tmem, umma::make_smem_desc_sw128(a_base + h * a_half + k * 32),
-                             umma::make_smem_desc_sw128(b_base + h * (kN * 128) + k * 32), idesc, (h | k) ? 1u : 0u);
+        for (int k = 0; k < 4; ++k) umma::mma_f16_ss(d_tmem, a1 + 2 * k, b1 + 2 * k, idesc, 1u);
         umma::commit(smem_u32(&sh.accf[idx % kSlots]));
       }
     }
