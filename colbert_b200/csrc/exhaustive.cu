@@ -420,16 +420,36 @@ maxsim_exhaustive_kernel(const __grid_constant__ ExhMaps maps, const uint32_t* _
                   pend_first = doc;
                   n_pend = 0;
                 }
+                if ((m8 & (m8 - 1u)) == 0u) {
+                  // exactly one document ends in this group (the usual case), at column e: branch-free split into
+                  // the maximum up to e (closes the document) and the maximum after e (opens the next one)
+                  const int e = __ffs(m8) - 1;
+                  float head = r, tail = -INFINITY;
 #pragma unroll
-                for (int j = 0; j < 8; ++j) {
-                  r = fmaxf(r, __uint_as_float(v[8 * s8 + j]));
-                  if ((m8 >> j) & 1u) {   // this column is the last token of document `doc` (warp-uniform)
-                    pb->v[n_pend][lane] = r;
-                    if (lane == 0) pb->len[n_pend] = cur_len + 8 * s8 + j + 1;
-                    ++n_pend;
-                    ++doc;
-                    cur_len = -(8 * s8 + j + 1);
-                    r = -INFINITY;
+                  for (int j = 0; j < 8; ++j) {
+                    const float x = __uint_as_float(v[8 * s8 + j]);
+                    const bool in_head = j <= e;
+                    head = in_head ? fmaxf(head, x) : head;
+                    tail = in_head ? tail : fmaxf(tail, x);
+                  }
+                  pb->v[n_pend][lane] = head;
+                  if (lane == 0) pb->len[n_pend] = cur_len + 8 * s8 + e + 1;
+                  ++n_pend;
+                  ++doc;
+                  cur_len = -(8 * s8 + e + 1);
+                  r = tail;
+                } else {
+#pragma unroll
+                  for (int j = 0; j < 8; ++j) {
+                    r = fmaxf(r, __uint_as_float(v[8 * s8 + j]));
+                    if ((m8 >> j) & 1u) {   // this column is the last token of document `doc` (warp-uniform)
+                      pb->v[n_pend][lane] = r;
+                      if (lane == 0) pb->len[n_pend] = cur_len + 8 * s8 + j + 1;
+                      ++n_pend;
+                      ++doc;
+                      cur_len = -(8 * s8 + j + 1);
+                      r = -INFINITY;
+                    }
                   }
                 }
               }
