@@ -31,6 +31,10 @@ constexpr int kStages = 4;
 constexpr int kWarps = 4;
 constexpr int kCtasPerSm = 3;
 constexpr int kSegCands = 64;
+// Tiles prefetched into L2 (cp.async.bulk.prefetch.tensor) ahead of the shared-memory ring.  Measured on B200,
+// configs[1]: 0 → 14.2 / 13.4 ms (bf16 / fp16 store), 4..16 → 15.7-16.0 / 14.5-14.8 ms: the extra L2 traffic costs
+// more than the shorter ring turnaround gains, so it is off.
+constexpr int kL2Ahead = 0;
 constexpr int kTileBytes = kTileRows * kDim * 2;  // 4096
 constexpr int kHalfBytes = kTileRows * 128;       // one 64-column half of a tile
 
@@ -176,6 +180,24 @@ maxsim_rerank_kernel(const __grid_constant__ TmapSet tmaps, const int64_t* __res
         ++pc;
       }
     };
+    // L2 prefetch cursor: runs kL2Ahead tiles ahead of the ring, so that the ring's own loads mostly hit L2 and
+    // a stage turns over in an L2 round trip instead of a loaded-HBM one (the ring is what bounds bytes in flight)
+    int fc = 0, ft = 0;
+    auto prefetch_tile = [&]() {
+      if (kL2Ahead == 0 || fc >= nv) return;
+      const int2 m = ws->meta[fc];
+      if (lane == 0) {
+        const int rows = min(kTileRows, m.y - ft * kTileRows);
+        tma_prefetch_l2_2d(&tmaps.m[rows - 1], 0, m.x + ft * kTileRows);   // 256-B L2 promotion brings whole rows
+      }
+      ++ft;
+      if (ft * kTileRows >= m.y) {
+        ft = 0;
+        ++fc;
+      }
+    };
+#pragma unroll 1
+    for (int s = 0; s < kL2Ahead + kStages - 1; ++s) prefetch_tile();
 #pragma unroll
     for (int s = 0; s < kStages - 1; ++s) issue_tile();
 
@@ -219,6 +241,7 @@ maxsim_rerank_kernel(const __grid_constant__ TmapSet tmaps, const int64_t* __res
       float rmax[2][2] = {{-INFINITY, -INFINITY}, {-INFINITY, -INFINITY}};
 
       for (int t = 0; t < ntiles; ++t) {
+        prefetch_tile();
         issue_tile();
         const uint32_t st = consumed % kStages;
         mbar_wait(full_addr + 8 * st, (consumed / kStages) & 1u);
