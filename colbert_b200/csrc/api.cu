@@ -104,6 +104,30 @@ int make_store_tensor_map(CUtensorMap* out, const void* base, int64_t rows, int 
   return CBK_OK;
 }
 
+// One TMA op for a whole [rows, 128] tile in the layout the kernels use ([half][row][64 columns], 128-B swizzle):
+// the store is described as 3-D {64 columns, rows, 2 halves} with byte strides {256 (row), 128 (half)} — the third
+// dimension has the SMALLER stride — and a box of {64, box_rows, 2}.
+int make_store_tensor_map_3d(CUtensorMap* out, const void* base, int64_t rows, int box_rows) {
+  EncodeTiledFn fn = encode_tiled_fn();
+  if (!fn) {
+    set_error("cuTensorMapEncodeTiled is not available from the installed driver");
+    return CBK_ERR_CUDA;
+  }
+  const cuuint64_t gdim[3] = {64, static_cast<cuuint64_t>(rows), 2};
+  const cuuint64_t gstride[2] = {256, 128};
+  const cuuint32_t box[3] = {64, static_cast<cuuint32_t>(box_rows), 2};
+  const cuuint32_t estride[3] = {1, 1, 1};
+  CUresult r = fn(out, CU_TENSOR_MAP_DATA_TYPE_UINT16, 3, const_cast<void*>(base), gdim, gstride, box, estride,
+                  CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                  CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) {
+    set_error("cuTensorMapEncodeTiled (3-D) failed with CUresult %d (rows %lld box_rows %d)", static_cast<int>(r),
+              static_cast<long long>(rows), box_rows);
+    return CBK_ERR_CUDA;
+  }
+  return CBK_OK;
+}
+
 static int check_device() {
   int dev = 0;
   CBK_CUDA(cudaGetDevice(&dev));

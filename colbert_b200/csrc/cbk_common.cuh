@@ -48,6 +48,8 @@ int sm_count();
 // {box_cols, box_rows} box and 128-byte swizzle.  Returns a cbk_status.
 int make_store_tensor_map(CUtensorMap* out, const void* base, int64_t rows, int dim, int box_cols,
                           int box_rows);
+// 3-D variant for dim = 128: one op loads both 64-column halves of a [box_rows, 128] tile (see api.cu)
+int make_store_tensor_map_3d(CUtensorMap* out, const void* base, int64_t rows, int box_rows);
 
 // ---------------------------------------------------------------------------------------------
 // device: shared-memory address, mbarrier, TMA
@@ -108,11 +110,14 @@ __device__ __forceinline__ void tma_load_2d(uint32_t smem_dst, const CUtensorMap
       : "memory");
 }
 
-// TMA prefetch of a box into L2 only (no shared-memory destination, no completion to wait for)
-__device__ __forceinline__ void tma_prefetch_l2_2d(const CUtensorMap* map, int x, int y) {
-  asm volatile("cp.async.bulk.prefetch.tensor.2d.L2.global.tile [%0, {%1, %2}];"
-               ::"l"(reinterpret_cast<uint64_t>(map)), "r"(x), "r"(y)
-               : "memory");
+// 3-D tiled TMA load (x = column, y = row, z = 64-column half), completion on an mbarrier
+__device__ __forceinline__ void tma_load_3d(uint32_t smem_dst, const CUtensorMap* map, int x, int y, int z,
+                                            uint32_t bar, uint64_t policy) {
+  asm volatile(
+      "cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint"
+      " [%0], [%1, {%2, %3, %4}], [%5], %6;"
+      ::"r"(smem_dst), "l"(reinterpret_cast<uint64_t>(map)), "r"(x), "r"(y), "r"(z), "r"(bar), "l"(policy)
+      : "memory");
 }
 
 __device__ __forceinline__ void tma_prefetch_desc(const CUtensorMap* map) {

@@ -6,10 +6,10 @@
 //
 // Design (DESIGN.md §"rerank kernel"):
 //   * every warp is an autonomous streaming unit: it owns a 4-stage ring of 16-row × 256-B document
-//     tiles in shared memory, issues its own TMA loads (2-D tensor maps over the flat store, row
-//     coordinate = pfxsum[pid] + 16·tile, 128-byte swizzle; one map per box height 1..16 so a
-//     document's tail tile reads exactly its remaining rows) and waits on its own mbarriers — there
-//     is no block-wide barrier anywhere in the main loop;
+//     tiles in shared memory, issues its own TMA loads (one op per tile: the store is described as a
+//     3-D tensor {64 columns, rows, 2 halves}, row coordinate = pfxsum[pid] + 16·tile, 128-byte swizzle;
+//     one map per box height 1..16 so a document's tail tile reads exactly its remaining rows) and
+//     waits on its own mbarriers — there is no block-wide barrier anywhere in the main loop;
 //   * the query matrix (≤ 32 × 128) lives in REGISTERS as mma.sync A-fragments (64 regs) for as long
 //     as the warp keeps scoring candidates of the same query;
 //   * document tiles are read with conflict-free ldmatrix.x4 straight out of the swizzled layout the
@@ -31,12 +31,10 @@ constexpr int kStages = 4;
 constexpr int kWarps = 4;
 constexpr int kCtasPerSm = 3;
 constexpr int kSegCands = 64;
-// Tiles prefetched into L2 (cp.async.bulk.prefetch.tensor) ahead of the shared-memory ring.  Measured on B200,
-// configs[1]: 0 → 14.2 / 13.4 ms (bf16 / fp16 store), 4..16 → 15.7-16.0 / 14.5-14.8 ms: the extra L2 traffic costs
-// more than the shorter ring turnaround gains, so it is off.
-constexpr int kL2Ahead = 0;
+// Tried and dropped: prefetching tiles into L2 (cp.async.bulk.prefetch.tensor) 4-16 tiles ahead of the ring
+// so that a stage turns over in an L2 round trip.  Measured on B200, configs[1]: 14.2 / 13.4 ms (bf16 / fp16 store)
+// without, 15.7-16.0 / 14.5-14.8 ms with: the extra L2 traffic costs more than the shorter turnaround gains.
 constexpr int kTileBytes = kTileRows * kDim * 2;  // 4096
-constexpr int kHalfBytes = kTileRows * 128;       // one 64-column half of a tile
 
 struct StrideSet {
   int n;
@@ -170,8 +168,7 @@ maxsim_rerank_kernel(const __grid_constant__ TmapSet tmaps, const int64_t* __res
         const int rows = min(kTileRows, m.y - pt * kTileRows);   // exact: the tail tile is shorter
         const CUtensorMap* tm = &tmaps.m[rows - 1];
         mbar_arrive_expect_tx(bar, rows * kDim * 2);
-        tma_load_2d(dst, tm, 0, row, bar, kEvictFirst);
-        tma_load_2d(dst + kHalfBytes, tm, 64, row, bar, kEvictFirst);
+        tma_load_3d(dst, tm, 0, row, 0, bar, kEvictFirst);   // both 64-column halves in one op: [half][row][64]
       }
       ++issued;
       ++pt;
@@ -180,24 +177,6 @@ maxsim_rerank_kernel(const __grid_constant__ TmapSet tmaps, const int64_t* __res
         ++pc;
       }
     };
-    // L2 prefetch cursor: runs kL2Ahead tiles ahead of the ring, so that the ring's own loads mostly hit L2 and
-    // a stage turns over in an L2 round trip instead of a loaded-HBM one (the ring is what bounds bytes in flight)
-    int fc = 0, ft = 0;
-    auto prefetch_tile = [&]() {
-      if (kL2Ahead == 0 || fc >= nv) return;
-      const int2 m = ws->meta[fc];
-      if (lane == 0) {
-        const int rows = min(kTileRows, m.y - ft * kTileRows);
-        tma_prefetch_l2_2d(&tmaps.m[rows - 1], 0, m.x + ft * kTileRows);   // 256-B L2 promotion brings whole rows
-      }
-      ++ft;
-      if (ft * kTileRows >= m.y) {
-        ft = 0;
-        ++fc;
-      }
-    };
-#pragma unroll 1
-    for (int s = 0; s < kL2Ahead + kStages - 1; ++s) prefetch_tile();
 #pragma unroll
     for (int s = 0; s < kStages - 1; ++s) issue_tile();
 
@@ -241,7 +220,6 @@ maxsim_rerank_kernel(const __grid_constant__ TmapSet tmaps, const int64_t* __res
       float rmax[2][2] = {{-INFINITY, -INFINITY}, {-INFINITY, -INFINITY}};
 
       for (int t = 0; t < ntiles; ++t) {
-        prefetch_tile();
         issue_tile();
         const uint32_t st = consumed % kStages;
         mbar_wait(full_addr + 8 * st, (consumed / kStages) & 1u);
@@ -257,13 +235,18 @@ maxsim_rerank_kernel(const __grid_constant__ TmapSet tmaps, const int64_t* __res
 
         // B fragments: ldmatrix.x4 of 32 columns (two k-steps) × 8 tokens; the loads of step p+1 are issued
         // before the conversions / MMAs of step p so that the shared-memory latency is covered
+        const int tile_rows = min(kTileRows, len - t * kTileRows);
         uint32_t bq[2][2][4];   // [buffer][sub-tile][reg]
         auto load_b = [&](int p, uint32_t (&dst)[2][4]) {
+          // the second half starts right after the rows this tile really holds, so its rows sit at physical row
+          // tile_rows + j and the 128-B swizzle (a function of the address) XORs the chunk with that row's low bits
           const int chunk = (p & 1) * 4 + lmat;
-          const uint32_t coff = (p >> 1) * kHalfBytes + (((chunk ^ lrow) & 7) << 4);
+          const int prow0 = (p >> 1) * tile_rows + lrow;
 #pragma unroll
-          for (int s = 0; s < 2; ++s)
-            ldmatrix_x4(sbase + coff + (s * 8 + lrow) * 128, dst[s][0], dst[s][1], dst[s][2], dst[s][3]);
+          for (int s = 0; s < 2; ++s) {
+            const int prow = prow0 + s * 8;
+            ldmatrix_x4(sbase + prow * 128 + (((chunk ^ prow) & 7) << 4), dst[s][0], dst[s][1], dst[s][2], dst[s][3]);
+          }
         };
         load_b(0, bq[0]);
 #pragma unroll
@@ -375,7 +358,7 @@ int rerank_dispatch(const void* d_store, int store_dtype, int64_t n_store_rows, 
   if (cached_base != d_store || cached_rows != n_store_rows) {
     cached_base = nullptr;
     for (int r = 1; r <= kTileRows; ++r) {
-      int rc = make_store_tensor_map(&tmaps.m[r - 1], d_store, n_store_rows, dim, 64, r);
+      int rc = make_store_tensor_map_3d(&tmaps.m[r - 1], d_store, n_store_rows, r);
       if (rc != CBK_OK) return rc;
     }
     cached_base = d_store;

@@ -13,7 +13,7 @@ struct ProbeMaps {
 };
 
 __global__ void __launch_bounds__(128, 1)
-umma_probe_kernel(const __grid_constant__ ProbeMaps maps, int N, uint32_t idesc, float* __restrict__ C) {
+umma_probe_kernel(const __grid_constant__ ProbeMaps maps, int N, uint32_t idesc, float* __restrict__ C, int use_3d) {
   extern __shared__ uint8_t smem_raw[];
   __shared__ __align__(8) uint64_t bar_full, bar_mma;
   __shared__ uint32_t tmem_base_smem;
@@ -43,10 +43,15 @@ umma_probe_kernel(const __grid_constant__ ProbeMaps maps, int N, uint32_t idesc,
   if (tid == 0) {
     const uint32_t full = smem_u32(&bar_full);
     mbar_arrive_expect_tx(full, 32768u + 2u * b_half);
-    tma_load_2d(a_addr, &maps.a, 0, 0, full, kEvictNormal);
-    tma_load_2d(a_addr + 16384, &maps.a, 64, 0, full, kEvictNormal);
-    tma_load_2d(b_addr, &maps.b, 0, 0, full, kEvictNormal);
-    tma_load_2d(b_addr + b_half, &maps.b, 64, 0, full, kEvictNormal);
+    if (use_3d) {   // one op per operand: {64 columns, rows, 2 halves} box
+      tma_load_3d(a_addr, &maps.a, 0, 0, 0, full, kEvictNormal);
+      tma_load_3d(b_addr, &maps.b, 0, 0, 0, full, kEvictNormal);
+    } else {
+      tma_load_2d(a_addr, &maps.a, 0, 0, full, kEvictNormal);
+      tma_load_2d(a_addr + 16384, &maps.a, 64, 0, full, kEvictNormal);
+      tma_load_2d(b_addr, &maps.b, 0, 0, full, kEvictNormal);
+      tma_load_2d(b_addr + b_half, &maps.b, 64, 0, full, kEvictNormal);
+    }
     mbar_wait(full, 0);
     umma::fence_after_sync();
 #pragma unroll
@@ -80,15 +85,18 @@ umma_probe_kernel(const __grid_constant__ ProbeMaps maps, int N, uint32_t idesc,
 
 int umma_probe_dispatch(const void* d_A, const void* d_B, int N, int a_bf16, int b_bf16, float* d_C, cudaStream_t stream) {
   ProbeMaps maps;
-  int rc = make_store_tensor_map(&maps.a, d_A, 128, 128, 64, 128);
+  const int use_3d = (a_bf16 | b_bf16) & 2 ? 1 : 0;   // bit 1 of either format flag: load each operand with one 3-D TMA op
+  a_bf16 &= 1;
+  b_bf16 &= 1;
+  int rc = use_3d ? make_store_tensor_map_3d(&maps.a, d_A, 128, 128) : make_store_tensor_map(&maps.a, d_A, 128, 128, 64, 128);
   if (rc != CBK_OK) return rc;
-  rc = make_store_tensor_map(&maps.b, d_B, N, 128, 64, N);
+  rc = use_3d ? make_store_tensor_map_3d(&maps.b, d_B, N, N) : make_store_tensor_map(&maps.b, d_B, N, 128, 64, N);
   if (rc != CBK_OK) return rc;
   const uint32_t idesc = umma::make_idesc(128, static_cast<uint32_t>(N), a_bf16 ? umma::kFmtBF16 : umma::kFmtF16,
                                           b_bf16 ? umma::kFmtBF16 : umma::kFmtF16);
   const size_t smem = 32768 + static_cast<size_t>(N) * 256 + 1024;
   CBK_CUDA(cudaFuncSetAttribute(umma_probe_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
-  umma_probe_kernel<<<1, 128, smem, stream>>>(maps, N, idesc, d_C);
+  umma_probe_kernel<<<1, 128, smem, stream>>>(maps, N, idesc, d_C, use_3d);
   CBK_CUDA(cudaGetLastError());
   count_launch();
   return CBK_OK;

@@ -185,8 +185,9 @@ def partition_candidates(cand_pids: torch.Tensor, cand_rowptr: torch.Tensor, pid
     return out_p, out_r
 
 
-def selftest_umma_gemm(A: torch.Tensor, B: torch.Tensor) -> torch.Tensor:
-    """C[128, N] = A[128,128] · B[N,128]^T through TMA → tcgen05.mma → TMEM → tcgen05.ld (one CTA)."""
+def selftest_umma_gemm(A: torch.Tensor, B: torch.Tensor, tma_3d: bool = False) -> torch.Tensor:
+    """C[128, N] = A[128,128] · B[N,128]^T through TMA → tcgen05.mma → TMEM → tcgen05.ld (one CTA).
+    ``tma_3d``: load each operand with ONE 3-D TMA op instead of one op per 64-column half."""
     lib = _lib.load()
     dev = A.device
     _need(A, "A", A.dtype, dev)
@@ -195,7 +196,8 @@ def selftest_umma_gemm(A: torch.Tensor, B: torch.Tensor) -> torch.Tensor:
     N = B.size(0)
     Cout = torch.empty((128, N), dtype=torch.float32, device=dev)
     with torch.cuda.device(dev):
-        rc = lib.cbk_selftest_umma_gemm(_ptr(A), _ptr(B), N, int(A.dtype == torch.bfloat16), int(B.dtype == torch.bfloat16),
+        rc = lib.cbk_selftest_umma_gemm(_ptr(A), _ptr(B), N, int(A.dtype == torch.bfloat16) | (2 if tma_3d else 0),
+                                        int(B.dtype == torch.bfloat16),
                                         _ptr(Cout), C.c_void_p(_lib.current_stream_ptr(dev)))
     _lib.check("cbk_selftest_umma_gemm", rc)
     return Cout

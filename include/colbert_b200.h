@@ -247,7 +247,8 @@ int cbk_topk_dense(const float* d_scores, int64_t n_queries, int64_t n_docs, int
 /* ------------------------------------------------------------------------------------------------
  * Self-test of the tcgen05 / TMEM / TMA building blocks the query-batched kernels are made of:
  *     C[128, N] = A[128, 128] · B[N, 128]^T      16-bit inputs (a_bf16 / b_bf16: 0 = fp16, 1 = bf16), fp32 out
- * N a multiple of 16 in [16, 256]; one CTA.  Not part of the scoring path.
+ * N a multiple of 16 in [16, 256]; one CTA.  Bit 1 of a_bf16 selects the 3-D tensor-map variant (one TMA op
+ * per operand instead of one per 64-column half).  Not part of the scoring path.
  * ------------------------------------------------------------------------------------------------ */
 int cbk_selftest_umma_gemm(const void* d_A, const void* d_B, int N, int a_bf16, int b_bf16, float* d_C, void* stream);
 

@@ -22,3 +22,17 @@ def test_umma_gemm_matches_float64(N, dt):
     err = (C - ref).abs().max().item()
     print(f"N={N} {dt}: max abs err {err:.3e} (ref max {ref.abs().max().item():.1f})")
     assert err < 2e-3
+
+
+@pytest.mark.parametrize("N", [16, 96, 256])
+def test_umma_gemm_with_3d_tensor_map(N):
+    """One TMA op per [rows, 128] tile: the store described as {64 columns, rows, 2 halves} with the half
+    dimension having the smaller stride.  Same result as the two-op form."""
+    from colbert_b200 import kernels
+    dev = torch.device("cuda", 0)
+    g = torch.Generator().manual_seed(100 + N)
+    A = torch.randn(128, 128, generator=g).to(torch.float16)
+    B = torch.randn(N, 128, generator=g).to(torch.float16)
+    C3 = kernels.selftest_umma_gemm(A.to(dev), B.to(dev), tma_3d=True).cpu().double()
+    ref = A.double() @ B.double().T
+    assert (C3 - ref).abs().max().item() < 2e-3
