@@ -105,3 +105,18 @@ def test_sharded_exhaustive_matches_single_store(world):
         keys.append(kernels.topk_dense(shard.score_all(Q), k, pid_base=lo, as_keys=True))
     scores, pids = kernels.merge_topk_keys(torch.stack(keys).contiguous(), k)
     assert torch.equal(pids, ref_pids) and torch.equal(scores, ref_scores)
+
+
+@pytest.mark.parametrize("n_docs", [4, 5, 7, 149])   # < 4 documents: the reference's kthvalue(k=0) raises, so does ours
+def test_exhaustive_tiny_corpora(n_docs):
+    """Fewer documents than CTA sub-ranges; k larger than the corpus."""
+    from colbert_b200 import synthetic
+    from colbert_b200.ranking import ColbertRanker
+    index = synthetic.make_index(600 + n_docs, n_docs, dim=128, lo=1, hi=200)
+    ranker = ColbertRanker.from_tensors(torch.from_numpy(index.emb), index.doclens.tolist(), device=DEV)
+    Q = synthetic.make_queries(601, 3, 32, 128)
+    got = ranker.score_all(torch.from_numpy(Q).to(DEV)).cpu().numpy()
+    ref = _oracle_scores(index, ranker.strides, Q, index.emb)
+    assert np.abs(got - ref).max() <= SCORE_RTOL * max(1.0, np.abs(ref).max())
+    pids, scores = ranker.rank_exhaustive(torch.from_numpy(Q), k=1000)
+    assert pids.shape == (3, n_docs) and sorted(pids[0].tolist()) == list(range(n_docs))
