@@ -23,11 +23,14 @@
 // Completion flows back through progress counters (items fully reduced, per epilogue warp; items whose MMAs have
 // completed) that the producer and the MMA issuer poll to recycle ring space, item slots and TMEM slots.
 //
-// Status (round 1): bit-for-bit parity with the mma.sync kernel on fp16 stores and 2e-6 relative error on bf16
-// stores, but 16.5 ms (fp16) / 19.6 ms (bf16) on configs[1] against 14.4 / 15.4 ms for the mma.sync kernel, which
-// therefore stays the default; CBK_FLAG_RERANK_TCGEN05 selects this one.  ncu shows the epilogue warps starved
-// (waiting on the tile-landed barrier): with one document per 128-row MMA tile the per-tile bookkeeping of a
-// single producer / issuer pair per CTA limits the number of tiles in flight.
+// Status (round 1): parity with the mma.sync kernel to 1e-6 on fp16 stores and 2e-6 relative error against the
+// oracle on bf16 stores, but 15.5 ms (fp16) / 18.8 ms (bf16) on configs[1] against 14.4 / 15.4 ms for the mma.sync
+// kernel, which therefore stays the default; CBK_FLAG_RERANK_TCGEN05 selects this one.  Measured trade-off: the
+// gather is bound by (bytes in flight) / (loaded HBM latency, ≈ 3 µs) and bytes in flight by shared memory.  With
+// 4 small CTAs per SM the tile rings total 136 KB (two query buffers and a 128-row-capable ring per CTA eat the
+// rest), less than the 192 KB of stages the mma.sync kernel keeps; with 2 big CTAs (176 KB of rings) the single
+// producer warp of each CTA cannot issue tiles fast enough (17.3 ms).  Disabling the epilogue's reduction changes
+// the time by 3 % only: the tensor-core side is not what limits this kernel.
 #include <algorithm>
 
 #include "umma.cuh"
@@ -76,12 +79,12 @@ struct __align__(16) Shared {
   uint64_t full[kItems];                 // TMA → MMA / epilogue
   uint64_t accf[16];                     // MMA commit → epilogue, per TMEM slot
   uint64_t qfull[2];                     // producer query fill → MMA
+  uint64_t ring_free[kItems];            // MMA commit → producer: the tile's shared memory may be overwritten
   Item items[kItems];
   int2 meta[kSegCands];                  // compacted (row, doclen)
   uint8_t cidx[kSegCands];
   float partial[kGroups][2][4][32];      // [group][item parity][quadrant][query row]
   volatile int progress[kGroups * 4];    // per epilogue warp: items (by index) it has looked at and finished with
-  int mma_done;                          // items whose MMAs have completed (their ring space may be overwritten)
   uint32_t tmem_base;
 };
 
@@ -115,10 +118,10 @@ maxsim_rerank_umma_kernel(const __grid_constant__ TileMaps maps, const int64_t* 
   if (tid == 0) {
     for (int i = 0; i < kItems; ++i) mbar_init(smem_u32(&sh.full[i]), 1);
     for (int i = 0; i < 16; ++i) mbar_init(smem_u32(&sh.accf[i]), 1);
+    for (int i = 0; i < kItems; ++i) mbar_init(smem_u32(&sh.ring_free[i]), 1);
     mbar_init(smem_u32(&sh.qfull[0]), 1);
     mbar_init(smem_u32(&sh.qfull[1]), 1);
     for (int i = 0; i < kGroups * 4; ++i) sh.progress[i] = 0;
-    sh.mma_done = 0;
     fence_mbar_init();
   }
   if (warp == kMmaWarp) {
@@ -148,7 +151,6 @@ maxsim_rerank_umma_kernel(const __grid_constant__ TileMaps maps, const int64_t* 
     int doc_parity = 0;
 
     int known_prog = 0;          // cached lower bounds of the two completion counters (both only grow)
-    int known_mma = 0;
     auto wait_items_done = [&](int upto) {   // until every item with index < upto is finished
       if (known_prog >= upto) return;
       int p = 0;
@@ -301,16 +303,14 @@ maxsim_rerank_umma_kernel(const __grid_constant__ TileMaps maps, const int64_t* 
           // ---- item slot + ring space ----------------------------------------------------------------------
           const int idx = n_items;
           wait_items_done(idx - kItems + 1);                     // slot idx % kItems is free again
+          // retire everything the epilogue has finished (keeps live_lo within kItems of idx, so a ring_free
+          // barrier is never waited on a whole phase late)
+          while (live_lo < known_prog && live_lo < idx) {
+            ++live_lo;
+            tail = live_lo < idx ? __shfl_sync(0xffffffffu, my_start, live_lo & 31) : head;
+          }
           int off = -1;
-          bool refreshed = false;
           while (true) {
-            // retire finished items from the ring accounting: ring space is released as soon as the tile's MMAs
-            // have completed (the epilogue may still be reducing); the counter is re-read only when needed
-            const int done = known_mma;
-            while (live_lo < done && live_lo < idx) {
-              ++live_lo;
-              tail = live_lo < idx ? __shfl_sync(0xffffffffu, my_start, live_lo & 31) : head;
-            }
             if (live_lo == idx) {                                // ring empty
               head = tail = 0;
               off = 0;
@@ -324,9 +324,11 @@ maxsim_rerank_umma_kernel(const __grid_constant__ TileMaps maps, const int64_t* 
               off = head;
               break;
             }
-            if (refreshed) __nanosleep(32);
-            known_mma = __shfl_sync(0xffffffffu, *reinterpret_cast<volatile int*>(&sh.mma_done), 0);
-            refreshed = true;
+            // no room: wait until the MMAs of the oldest live tile have completed (tcgen05.commit on its
+            // ring_free barrier — independent of the epilogue), then retire it
+            mbar_wait(smem_u32(&sh.ring_free[live_lo % kItems]), (live_lo / kItems) & 1);
+            ++live_lo;
+            tail = live_lo < idx ? __shfl_sync(0xffffffffu, my_start, live_lo & 31) : head;
           }
           head = off + bytes;
           if (lane == (idx & 31)) my_start = off;
@@ -392,6 +394,7 @@ maxsim_rerank_umma_kernel(const __grid_constant__ TileMaps maps, const int64_t* 
 #pragma unroll
         for (int k = 0; k < 4; ++k) umma::mma_f16_ss(d_tmem, a1 + 2 * k, b1 + 2 * k, idesc, 1u);
         umma::commit(smem_u32(&sh.accf[idx % kSlots]));
+        umma::commit(smem_u32(&sh.ring_free[idx % kItems]));
       }
     }
   } else {
@@ -418,7 +421,6 @@ maxsim_rerank_umma_kernel(const __grid_constant__ TileMaps maps, const int64_t* 
       }
       mbar_wait(smem_u32(&sh.accf[idx % kSlots]), (idx / kSlots) & 1);
       umma::fence_after_sync();
-      if (quad == 0 && lane == 0) atomicMax(&sh.mma_done, idx + 1);   // MMAs complete in order
       const int nvalid = min(32, max(0, static_cast<int>(it.rows) - 32 * quad));
       if (nvalid > 0) {
         uint32_t raw0[32];
