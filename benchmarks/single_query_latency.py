@@ -38,6 +38,20 @@ def main():
     for i in range(args.iters):
         ranker.rank_forward(Qs[i % 64], cl[i % 64], depth=10)          # returns Python lists ⇒ synchronises
     gpu_ms = (time.perf_counter() - t0) / args.iters * 1e3
+    # same call, query in the reference's own dim-major layout (transposed while staging)
+    Qc = [q.contiguous() for q in Qs]
+    t0 = time.perf_counter()
+    for i in range(args.iters):
+        ranker.rank_forward(Qc[i % 64], cl[i % 64], depth=10)
+    gpu_dm_ms = (time.perf_counter() - t0) / args.iters * 1e3
+    # the general path (device tensors, separate torch copies + two library calls), for comparison
+    Qg = [q.to(ranker.device) for q in Qs]
+    for i in range(5):
+        ranker.rank_forward(Qg[i], cl[i], depth=10)
+    t0 = time.perf_counter()
+    for i in range(args.iters):
+        ranker.rank_forward(Qg[i % 64], cl[i % 64], depth=10)
+    gpu_general_ms = (time.perf_counter() - t0) / args.iters * 1e3
     # kernel-only time of the same work (device tensors prepared once)
     dev = ranker.device
     Qd = torch.from_numpy(Q[0:1]).to(dev)
@@ -63,6 +77,7 @@ def main():
         port.rank_forward(Qs[i], cl[i], depth=10)
     cpu_ms = (time.perf_counter() - t0) / n_cpu * 1e3
     print(json.dumps({"call": "rank_forward(Q[1,128,32], 1000 pids, depth=10)", "gpu_ms_per_call": round(gpu_ms, 4),
+                      "gpu_ms_per_call_dim_major_q": round(gpu_dm_ms, 4), "gpu_ms_per_call_general_path": round(gpu_general_ms, 4),
                       "gpu_maxsim_kernel_ms": round(kern_ms, 4), "cpu_port_ms_per_call": round(cpu_ms, 3),
                       "cpu_threads": os.cpu_count(), "speedup": round(cpu_ms / gpu_ms, 1)}))
 

@@ -35,6 +35,9 @@ SIGNATURES = {
                                     _vp, _vp, _i64, _vp, _vp, _sz, _i32, _vp]),
     "cbk_topk_max_candidates": (_i64, []),
     "cbk_topk_per_query": (C.c_int, [_vp, _vp, _vp, _i64, _i64, _i32, _i32, _vp, _vp, _vp]),
+    "cbk_rank_forward_scratch_bytes": (_sz, [_i64, _i32, _i32, _i32]),
+    "cbk_rank_forward_host": (C.c_int, [_vp, _i32, _i64, _i32, _vp, _vp, _i64, _i64, _vp, _i32, _vp, _i32, _i32, _vp, _i64,
+                                        _i32, _vp, _vp, _vp, _vp, _sz, _i32, _vp]),
     "cbk_topk_per_query_keys": (C.c_int, [_vp, _vp, _vp, _i64, _i64, _i32, _i32, _vp, _vp]),
     "cbk_merge_topk_keys": (C.c_int, [_vp, _i32, _i64, _i32, _i32, _vp, _vp, _vp]),
     "cbk_gather_rows": (C.c_int, [_vp, _i32, _i64, _i32, _vp, _vp, _i64, _vp, _i64, _i32, _vp, _vp, _vp]),

@@ -236,6 +236,84 @@ int cbk_topk_per_query_keys(const float* d_scores, const int64_t* d_cand_pids, c
                      flags, nullptr, nullptr, d_out_keys, stream);
 }
 
+// scratch layout shared by the device and the page-locked copy (offsets in bytes):
+//   [0, 256) rerank workspace | rowptr 2 x i64 | Q q_len*dim f32 | pids n x i64 | out_pids k x i64 | out_scores k x f32 |
+//   scores n x f32 (device only)
+namespace {
+struct RankForwardLayout {
+  size_t rowptr, q, pids, out_pids, out_scores, scores, total;
+};
+RankForwardLayout rank_forward_layout(int64_t n, int q_len, int dim, int k) {
+  auto up = [](size_t v) { return (v + 255) & ~static_cast<size_t>(255); };
+  RankForwardLayout L;
+  L.rowptr = 256;
+  L.q = L.rowptr + 16;
+  L.pids = up(L.q + sizeof(float) * q_len * dim);
+  L.out_pids = up(L.pids + sizeof(int64_t) * n);
+  L.out_scores = L.out_pids + sizeof(int64_t) * k;
+  L.scores = up(L.out_scores + sizeof(float) * k);
+  L.total = up(L.scores + sizeof(float) * n);
+  return L;
+}
+}  // namespace
+
+size_t cbk_rank_forward_scratch_bytes(int64_t n, int q_len, int dim, int k) {
+  if (n < 1 || q_len < 1 || dim < 1 || k < 1) return 0;
+  return rank_forward_layout(n, q_len, dim, k).total;
+}
+
+int cbk_rank_forward_host(const void* d_store, int store_dtype, int64_t n_store_rows, int dim, const int64_t* d_pfxsum,
+                          const int32_t* d_doclens, int64_t n_docs, int64_t pid_base, const int32_t* strides, int n_strides,
+                          const float* h_Q, int q_len, int q_dim_major, const int64_t* h_pids, int64_t n, int k,
+                          int64_t* h_out_pids, float* h_out_scores, void* d_scratch, void* h_pinned, size_t scratch_bytes,
+                          int flags, void* stream) {
+  CBK_CHECK_ARG(h_Q && h_pids && h_out_pids && h_out_scores && d_scratch && h_pinned,
+                "cbk_rank_forward_host: null pointer argument");
+  CBK_CHECK_ARG(n >= 1 && k >= 1 && k <= n, "cbk_rank_forward_host: need 1 <= k <= n (n %lld, k %d)", (long long)n, k);
+  CBK_CHECK_SUPPORTED(q_len >= 1 && q_len <= CBK_MAX_QLEN && dim >= 1 && dim <= 1536,
+                      "cbk_rank_forward_host: q_len %d outside [1, %d] or dim %d outside [1, 1536]", q_len, CBK_MAX_QLEN, dim);
+  CBK_CHECK_SUPPORTED(n <= topk_max_candidates(), "cbk_rank_forward_host: %lld candidates exceed the limit of %lld",
+                      (long long)n, (long long)topk_max_candidates());
+  const RankForwardLayout L = rank_forward_layout(n, q_len, dim, k);
+  if (scratch_bytes < L.total) {
+    set_error("cbk_rank_forward_host: scratch of %zu bytes, need %zu", scratch_bytes, L.total);
+    return CBK_ERR_WORKSPACE;
+  }
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  char* hp = static_cast<char*>(h_pinned);
+  char* dp = static_cast<char*>(d_scratch);
+  // stage: rowptr, query (transposed to [q_len, dim] when it arrives dim-major), pids
+  int64_t* h_rowptr = reinterpret_cast<int64_t*>(hp + L.rowptr);
+  h_rowptr[0] = 0;
+  h_rowptr[1] = n;
+  float* hq = reinterpret_cast<float*>(hp + L.q);
+  if (q_dim_major) {
+    for (int d = 0; d < dim; ++d)
+      for (int m = 0; m < q_len; ++m) hq[static_cast<size_t>(m) * dim + d] = h_Q[static_cast<size_t>(d) * q_len + m];
+  } else {
+    memcpy(hq, h_Q, sizeof(float) * q_len * dim);
+  }
+  memcpy(hp + L.pids, h_pids, sizeof(int64_t) * n);
+  const size_t in_bytes = L.pids + sizeof(int64_t) * n - L.rowptr;
+  CBK_CUDA(cudaMemcpyAsync(dp + L.rowptr, hp + L.rowptr, in_bytes, cudaMemcpyHostToDevice, st));
+  const int64_t* d_rowptr = reinterpret_cast<const int64_t*>(dp + L.rowptr);
+  const int64_t* d_pids = reinterpret_cast<const int64_t*>(dp + L.pids);
+  float* d_scores = reinterpret_cast<float*>(dp + L.scores);
+  int rc = cbk_maxsim_rerank(d_store, store_dtype, n_store_rows, dim, d_pfxsum, d_doclens, n_docs, pid_base, strides, n_strides,
+                             reinterpret_cast<const float*>(dp + L.q), q_len, 1, d_pids, d_rowptr, n, d_scores, dp, 256,
+                             flags, stream);
+  if (rc != CBK_OK) return rc;
+  rc = cbk_topk_per_query(d_scores, d_pids, d_rowptr, 1, n, k, 0, reinterpret_cast<float*>(dp + L.out_scores),
+                          reinterpret_cast<int64_t*>(dp + L.out_pids), stream);
+  if (rc != CBK_OK) return rc;
+  const size_t out_bytes = sizeof(int64_t) * k + sizeof(float) * k;
+  CBK_CUDA(cudaMemcpyAsync(hp + L.out_pids, dp + L.out_pids, out_bytes, cudaMemcpyDeviceToHost, st));
+  CBK_CUDA(cudaStreamSynchronize(st));
+  memcpy(h_out_pids, hp + L.out_pids, sizeof(int64_t) * k);
+  memcpy(h_out_scores, hp + L.out_scores, sizeof(float) * k);
+  return CBK_OK;
+}
+
 int cbk_merge_topk_keys(const uint64_t* d_keys, int world, int64_t n_queries, int k_in, int k, float* d_out_scores,
                         int64_t* d_out_pids, void* stream) {
   CBK_CHECK_ARG(d_keys && d_out_scores && d_out_pids, "cbk_merge_topk_keys: null pointer argument");

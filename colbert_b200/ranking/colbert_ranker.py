@@ -18,8 +18,11 @@ What changed relative to the reference and why:
 """
 from __future__ import annotations
 
+import ctypes as C
+from array import array
 from typing import List, Optional, Sequence, Tuple, Union
 
+import numpy as np
 import torch
 
 from .. import kernels
@@ -143,6 +146,8 @@ class ColbertRanker:
             print(f"#> Using strides {self.strides}..", flush=True)
         self._views = None
         self.buffers = {}
+        self._strides_c = (C.c_int32 * max(1, len(self.strides)))(*[int(s) for s in self.strides])
+        self._host_scratch = None       # (device bytes, pinned bytes) of the single-call path, grown on demand
         # device-side copies the kernels index by pid
         self._doclens_dev = self.doclens.to(torch.int32).to(self.device)
         self._pfxsum_dev = self.doclens_pfxsum.to(self.device)
@@ -236,6 +241,9 @@ class ColbertRanker:
             raise ValueError("rank_forward expects Q of shape [1, dim, q_len]")
         if len(pids) > BSIZE:
             raise ValueError(f"{len(pids)} candidates exceed BSIZE={BSIZE} (reference colbert_ranker.py:11)")
+        if (not output_D_embedding and Q.device.type == "cpu" and Q.size(2) <= kernels._lib.CBK_MAX_QLEN
+                and not (isinstance(pids, torch.Tensor) and pids.device.type != "cpu")):
+            return self._rank_forward_host(Q, pids, depth)
         Qb = Q.to(self.device, dtype=self.maxsim_dtype).permute(0, 2, 1).contiguous()   # [1, q_len, dim]
         pids_t = torch.as_tensor(pids, dtype=torch.int64).to(self.device)
         n = pids_t.numel()
@@ -255,6 +263,56 @@ class ColbertRanker:
         stride = self.strides[int(buckets[0])]
         D, mask = kernels.gather_rows(self.tensor, self._pfxsum_dev, self._doclens_dev, top_pids[0].contiguous(), stride)
         return top_pids[0].tolist(), D, mask
+
+    def _rank_forward_host(self, Q: torch.Tensor, pids, depth):
+        """Host query + host pids → Python lists through ONE library call (cbk_rank_forward_host): a staged
+        host→device copy, the MaxSim launch, the top-k launch and one device→host copy of the winners."""
+        lib = kernels._lib.load()
+        dim, q_len = Q.size(1), Q.size(2)
+        q0 = Q[0]
+        if q0.dtype != torch.float32:
+            q0 = q0.float()
+        if q0.t().is_contiguous():
+            dim_major = 0                                   # a permuted view of a [q_len, dim] matrix
+        else:
+            q0, dim_major = q0.contiguous(), 1              # the reference's own layout
+        if isinstance(pids, torch.Tensor):
+            keep = pids.to(torch.int64).contiguous()
+            pid_ptr, n = keep.data_ptr(), keep.numel()
+        elif isinstance(pids, np.ndarray):
+            keep = np.ascontiguousarray(pids, dtype=np.int64)
+            pid_ptr, n = keep.ctypes.data, keep.size
+        else:
+            keep = array("q", pids)
+            pid_ptr, n = keep.buffer_info()
+        k = n if depth is None else min(int(depth), n)
+        need = lib.cbk_rank_forward_scratch_bytes(n, q_len, dim, k)
+        if self._host_scratch is None or self._host_scratch[0].numel() < need:
+            cap = max(need, 1 << 20)
+            self._host_scratch = (torch.zeros(cap, dtype=torch.uint8, device=self.device),
+                                  torch.zeros(cap, dtype=torch.uint8).pin_memory())
+        d_scr, h_scr = self._host_scratch
+        out_pids = (C.c_int64 * k)()
+        out_scores = (C.c_float * k)()
+        store = self.tensor
+        switch = torch.cuda.current_device() != self.device.index
+        if switch:
+            prev = torch.cuda.current_device()
+            torch.cuda.set_device(self.device)
+        try:
+            rc = lib.cbk_rank_forward_host(store.data_ptr(), kernels._lib.dtype_code(store.dtype), store.size(0), dim,
+                                           self._pfxsum_dev.data_ptr(), self._doclens_dev.data_ptr(),
+                                           self._doclens_dev.numel(), int(self.pid_base),
+                                           C.cast(self._strides_c, C.c_void_p), len(self.strides), q0.data_ptr(), q_len,
+                                           dim_major, pid_ptr, n, k, C.cast(out_pids, C.c_void_p),
+                                           C.cast(out_scores, C.c_void_p), d_scr.data_ptr(), h_scr.data_ptr(),
+                                           d_scr.numel(), int(self.kernel_flags),
+                                           C.c_void_p(kernels._lib.current_stream_ptr(self.device)))
+        finally:
+            if switch:
+                torch.cuda.set_device(prev)
+        kernels._lib.check("cbk_rank_forward_host", rc)
+        return list(out_pids), list(out_scores)
 
     # upstream ColBERT name for the same call (IndexRanker.rank)
     def rank(self, Q, pids, views=None, depth=10):

@@ -141,6 +141,30 @@ int cbk_topk_per_query(const float* d_scores, const int64_t* d_cand_pids, const 
                        int64_t n_queries, int64_t max_cand_per_query, int k, int flags,
                        float* d_out_scores, int64_t* d_out_pids, void* stream);
 
+/* ------------------------------------------------------------------------------------------------
+ * One reference-shaped call with HOST buffers — the whole of ColbertRanker.rank_forward
+ * (colbert_ranker.py:75-137) for one query: stage query + candidate pids through page-locked memory,
+ * one host→device copy, cbk_maxsim_rerank, cbk_topk_per_query, one device→host copy of the k winners,
+ * and a synchronise of `stream`; the function returns with h_out_* filled.
+ *
+ *   h_Q          fp32 query: [q_len, dim] row-major, or — q_dim_major != 0 — [dim, q_len], the layout
+ *                the reference passes (Q[0] of its [1, dim, q_len] tensor, colbert_ranker.py:78)
+ *   h_pids       [n] int64 candidates, 1 ≤ n ≤ cbk_topk_max_candidates(); k ≤ n
+ *   h_out_pids   [k] int64, h_out_scores [k] fp32, score-descending (order of cbk_topk_per_query)
+ *   d_scratch    device scratch and h_pinned page-locked host scratch, each of at least
+ *                cbk_rank_forward_scratch_bytes(n, q_len, dim, k) bytes; owned by the caller, reusable
+ *                across calls, not shared between concurrent calls
+ *   store / metadata / strides / pid_base / flags as for cbk_maxsim_rerank
+ * ------------------------------------------------------------------------------------------------ */
+size_t cbk_rank_forward_scratch_bytes(int64_t n, int q_len, int dim, int k);
+
+int cbk_rank_forward_host(const void* d_store, int store_dtype, int64_t n_store_rows, int dim,
+                          const int64_t* d_pfxsum, const int32_t* d_doclens, int64_t n_docs, int64_t pid_base,
+                          const int32_t* strides, int n_strides,
+                          const float* h_Q, int q_len, int q_dim_major, const int64_t* h_pids, int64_t n, int k,
+                          int64_t* h_out_pids, float* h_out_scores,
+                          void* d_scratch, void* h_pinned, size_t scratch_bytes, int flags, void* stream);
+
 /* Same selection, but the k winners of each query are returned as packed 64-bit keys
  * [ordered(score) : 32 | ~pid : 32] (0 = padding) — the unit the shards exchange: one all-gather of
  * [n_queries, k] uint64 per rank instead of separate score and pid buffers.  d_out_keys [n_queries, k]. */

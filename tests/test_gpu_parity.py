@@ -511,3 +511,40 @@ def test_ranker_from_flat_store(dev, tmp_path):
     pa, sa = a.rank_forward(Qt, mine, depth=None)
     pb, sb = shard.rank_forward(Qt, mine, depth=None)               # global pids, pid_base = 100
     assert pa == pb and sa == sb
+
+
+def test_rank_forward_host_call_matches_device_path(dev):
+    """cbk_rank_forward_host (host query + host pids, one library call) returns what the general device path does,
+    for every accepted form of the arguments: dim-major query (the reference's layout) or a permuted view, pids
+    as list / numpy / tensor, depth None, growing scratch."""
+    from colbert_b200 import synthetic
+    index = synthetic.make_index(41, 3000, dim=128, lo=1, hi=90)
+    ranker = make_ranker(index, dev)
+    Q = synthetic.make_queries(42, 3, 32, 128)
+    cands = synthetic.make_candidates(43, 3, index.num_docs, 700)
+    store, pf = O.pad_store(index.emb), O.doclens_pfxsum(index.doclens)
+    for qi in range(3):
+        view = torch.from_numpy(Q[qi]).unsqueeze(0).permute(0, 2, 1)           # non-contiguous [1, dim, q_len]
+        dim_major = view.contiguous()                                          # the layout the reference passes
+        pl = [int(x) for x in cands[qi]]
+        ref_p, ref_s = ranker.rank_forward(view.to(dev), pl, depth=25)         # device query ⇒ general path
+        for Qin in (view, dim_major, dim_major.double()):
+            for pin in (pl, np.asarray(pl), torch.tensor(pl), np.asarray(pl, dtype=np.int32)):
+                p, s = ranker.rank_forward(Qin, pin, depth=25)
+                assert p == ref_p and s == ref_s
+        p, s = ranker.rank_forward(dim_major, pl, depth=None)
+        fp, fs = ranker.rank_forward(view.to(dev), pl, depth=None)
+        assert p == fp and s == fs and len(p) == 700
+        ref = O.maxsim_exact(store, index.doclens, pf, ranker.strides, Q[qi], cands[qi])
+        rp, rs = O.topk_desc(ref, cands[qi], 25)
+        check_topk(p[:25], s[:25], rp, rs, SCORE_RTOL, *O.topk_desc(ref, cands[qi], None))
+    # a bigger call than the scratch was sized for
+    big = synthetic.make_candidates(44, 1, index.num_docs, 2900)[0].tolist()
+    p, s = ranker.rank_forward(torch.from_numpy(Q[0]).unsqueeze(0).permute(0, 2, 1).contiguous(), big, depth=10)
+    rp, rs = ranker.rank_forward(torch.from_numpy(Q[0]).unsqueeze(0).permute(0, 2, 1).to(dev), big, depth=10)
+    assert p == rp and s == rs
+    # q_len of 1 and a short query
+    for q_len in (1, 5):
+        Qs = synthetic.make_queries(45, 1, q_len, 128)[0]
+        Qt = torch.from_numpy(Qs).unsqueeze(0).permute(0, 2, 1).contiguous()
+        assert ranker.rank_forward(Qt, pl, depth=7) == ranker.rank_forward(Qt.to(dev), pl, depth=7)
