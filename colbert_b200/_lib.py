@@ -54,6 +54,7 @@ SIGNATURES = {
     "cbk_topk_dense_workspace_bytes": (_sz, [_i64, _i64, _i32]),
     "cbk_topk_dense": (C.c_int, [_vp, _i64, _i64, _i32, _i64, _i32, _vp, _vp, _vp, _sz, _vp]),
     "cbk_selftest_umma_gemm": (C.c_int, [_vp, _vp, _i32, _i32, _i32, _vp, _vp]),
+    "cbk_selftest_umma_rate": (C.c_int, [_i32, _i32, _i32, _i32, _i32, _vp, _vp]),
     "cbk_mask_cast_rows": (C.c_int, [_vp, _i32, _i64, _i32, _vp, _i32, _vp, _i32, _vp]),
 }
 

@@ -222,23 +222,29 @@ maxsim_exhaustive_kernel(const __grid_constant__ ExhMaps maps, const uint32_t* _
 
   if (warp == 0) {
     // ===================================== TMA producer =============================================
-    if (lane == 0) {
-      tma_prefetch_desc(&maps.store);
-      tma_prefetch_desc(&maps.q);
+    // (whole warp, uniform control flow; one elected lane issues — see elect_one in cbk_common.cuh)
+    {
+      if (lane == 0) {
+        tma_prefetch_desc(&maps.store);
+        tma_prefetch_desc(&maps.q);
+      }
       uint32_t it = 0;
       for (int p = 0; p < n_passes; ++p) {
         if (p > 0) mbar_wait(smem_u32(&bar_pass_done), (p - 1) & 1);   // every MMA that read the old A blocks is done
         const int qb = min(qb_max, n_qblocks - p * qb_max);
         const int n_sub = qb == 1 ? 4 : (qb == 2 ? 2 : 1);
         const uint32_t afull = smem_u32(&bar_a_full);
-        mbar_arrive_expect_tx(afull, static_cast<uint32_t>(qb * parts) * kTileBytes);
-        for (int a = 0; a < qb; ++a)
-          for (int part = 0; part < parts; ++part) {
-            const int row = (part * n_qblocks + p * qb_max + a) * 128;
-            const uint32_t dst = a_addr + (a * parts + part) * kTileBytes;
-            tma_load_2d(dst, &maps.q, 0, row, afull, kEvictLast);
-            tma_load_2d(dst + kTileBytes / 2, &maps.q, 64, row, afull, kEvictLast);
-          }
+        if (elect_one()) {
+          mbar_arrive_expect_tx(afull, static_cast<uint32_t>(qb * parts) * kTileBytes);
+          for (int a = 0; a < qb; ++a)
+            for (int part = 0; part < parts; ++part) {
+              const int row = (part * n_qblocks + p * qb_max + a) * 128;
+              const uint32_t dst = a_addr + (a * parts + part) * kTileBytes;
+              tma_load_2d(dst, &maps.q, 0, row, afull, kEvictLast);
+              tma_load_2d(dst + kTileBytes / 2, &maps.q, 64, row, afull, kEvictLast);
+            }
+        }
+        __syncwarp();
         int nt[kEpiGroups];
         int64_t t0[kEpiGroups];
         int max_nt = 0;
@@ -257,16 +263,20 @@ maxsim_exhaustive_kernel(const __grid_constant__ ExhMaps maps, const uint32_t* _
             const uint32_t full = smem_u32(&bar_b_full[st]);
             const uint32_t dst = b_addr + st * kTileBytes;
             const int row = static_cast<int>(t0[s2]) + t * kTileTok;
-            mbar_arrive_expect_tx(full, kTileBytes);
-            tma_load_2d(dst, &maps.store, 0, row, full, kEvictFirst);
-            tma_load_2d(dst + kTileBytes / 2, &maps.store, 64, row, full, kEvictFirst);
+            if (elect_one()) {
+              mbar_arrive_expect_tx(full, kTileBytes);
+              tma_load_2d(dst, &maps.store, 0, row, full, kEvictFirst);
+              tma_load_2d(dst + kTileBytes / 2, &maps.store, 64, row, full, kEvictFirst);
+            }
+            __syncwarp();
             ++it;
           }
       }
     }
   } else if (warp == 1) {
     // ===================================== MMA issuer ===============================================
-    if (lane == 0) {
+    // (whole warp, uniform control flow; one elected lane issues — see elect_one in cbk_common.cuh)
+    {
       uint32_t it = 0, acc_it = 0;
       for (int p = 0; p < n_passes; ++p) {
         const int qb = min(qb_max, n_qblocks - p * qb_max);
@@ -294,24 +304,29 @@ maxsim_exhaustive_kernel(const __grid_constant__ ExhMaps maps, const uint32_t* _
               mbar_wait(smem_u32(&bar_acc_empty[slot]), ((acc_it / kAccSlots) & 1u) ^ 1u);
               umma::fence_after_sync();
               const uint32_t d_tmem = tmem + slot * kTileTok;
-              uint32_t acc = 0;
-              for (int part = 0; part < parts; ++part) {
-                const uint32_t at = a_addr + (a * parts + part) * kTileBytes;
+              if (elect_one()) {
+                uint32_t acc = 0;
+                for (int part = 0; part < parts; ++part) {
+                  const uint32_t at = a_addr + (a * parts + part) * kTileBytes;
 #pragma unroll
-                for (int h = 0; h < 2; ++h)
+                  for (int h = 0; h < 2; ++h)
 #pragma unroll
-                  for (int k = 0; k < 4; ++k) {
-                    umma::mma_f16_ss(d_tmem, umma::make_smem_desc_sw128(at + h * (kTileBytes / 2) + k * 32),
-                                     umma::make_smem_desc_sw128(bt + h * (kTileBytes / 2) + k * 32), idesc, acc);
-                    acc = 1;
-                  }
+                    for (int k = 0; k < 4; ++k) {
+                      umma::mma_f16_ss(d_tmem, umma::make_smem_desc_sw128(at + h * (kTileBytes / 2) + k * 32),
+                                       umma::make_smem_desc_sw128(bt + h * (kTileBytes / 2) + k * 32), idesc, acc);
+                      acc = 1;
+                    }
+                }
+                umma::commit(smem_u32(&bar_acc_full[(s2 * qb_eff + a) * kAccSlots + slot]));
               }
-              umma::commit(smem_u32(&bar_acc_full[(s2 * qb_eff + a) * kAccSlots + slot]));
+              __syncwarp();
             }
-            umma::commit(smem_u32(&bar_b_empty[st]));
+            if (elect_one()) umma::commit(smem_u32(&bar_b_empty[st]));
+            __syncwarp();
             ++it;
           }
-        umma::commit(smem_u32(&bar_pass_done));
+        if (elect_one()) umma::commit(smem_u32(&bar_pass_done));
+        __syncwarp();
       }
     }
   } else {

@@ -160,7 +160,7 @@ maxsim_rerank_kernel(const __grid_constant__ TmapSet tmaps, const int64_t* __res
     auto issue_tile = [&]() {
       if (pc >= nv) return;
       const int2 m = ws->meta[pc];
-      if (lane == 0) {
+      if (elect_one()) {                                        // not `lane == 0`: see elect_one in cbk_common.cuh
         const uint32_t st = issued % kStages;
         const uint32_t bar = full_addr + 8 * st;
         const uint32_t dst = tiles_addr + st * kTileBytes;

@@ -332,7 +332,7 @@ maxsim_rerank_umma_kernel(const __grid_constant__ TileMaps maps, const int64_t* 
           }
           head = off + bytes;
           if (lane == (idx & 31)) my_start = off;
-          if (lane == 0) {
+          if (elect_one()) {
             Item it;
             it.smem_off = static_cast<uint32_t>(off);
             it.rows = static_cast<uint16_t>(rows);
@@ -363,32 +363,36 @@ maxsim_rerank_umma_kernel(const __grid_constant__ TileMaps maps, const int64_t* 
     }
   } else if (warp == kMmaWarp) {
     // ======================================= MMA issuer =============================================
-    if (lane == 0) {
-      uint32_t seen_qseq = 0;
-      uint32_t qparity = 0;                                      // bit b = parity of the next wait on qfull[b]
-      int known_prog = 0;
-      for (int idx = 0;; ++idx) {
-        mbar_wait(smem_u32(&sh.full[idx % kItems]), (idx / kItems) & 1);
-        const Item it = load_item(&sh.items[idx % kItems]);
-        if (it.rows == 0) break;
-        const uint32_t qb = (it.flags >> 3) & 1u;
-        if (it.qseq != seen_qseq) {                              // first item of a newly written query buffer
-          mbar_wait(smem_u32(&sh.qfull[qb]), (qparity >> qb) & 1u);
-          qparity ^= 1u << qb;
-          seen_qseq = it.qseq;
-        }
-        while (known_prog < idx - kSlots + 1) {                  // TMEM slot idx % kSlots has been drained
-          known_prog = ld_progress_min(&sh);
-          if (known_prog < idx - kSlots + 1) __nanosleep(32);
-        }
-        umma::fence_after_sync();
-        // descriptors differ only in their 14-bit start-address field: +2 (32 bytes >> 4) per k-step
-        const uint32_t a_base = ring_addr + it.smem_off;
-        const uint32_t a_half = ((it.rows + 7) & ~7) * 128;
-        const uint32_t b_base = q_addr + qb * kQBufBytes;
-        const uint64_t a0 = umma::make_smem_desc_sw128(a_base), a1 = umma::make_smem_desc_sw128(a_base + a_half);
-        const uint64_t b0 = umma::make_smem_desc_sw128(b_base), b1 = umma::make_smem_desc_sw128(b_base + kN * 128);
-        const uint32_t d_tmem = tmem + (idx % kSlots) * kN;
+    // The whole warp walks the item stream with uniform control flow and one elected lane issues: from a
+    // `lane == 0` branch ptxas wraps every tcgen05.mma in an ELECT / R2UR / branch loop (see umma::elect_one).
+    uint32_t seen_qseq = 0;
+    uint32_t qparity = 0;                                      // bit b = parity of the next wait on qfull[b]
+    int known_prog = 0;
+    for (int idx = 0;; ++idx) {
+      mbar_wait(smem_u32(&sh.full[idx % kItems]), (idx / kItems) & 1);
+      const Item it = load_item(&sh.items[idx % kItems]);
+      if (it.rows == 0) break;
+      const uint32_t qb = (it.flags >> 3) & 1u;
+      if (it.qseq != seen_qseq) {                              // first item of a newly written query buffer
+        mbar_wait(smem_u32(&sh.qfull[qb]), (qparity >> qb) & 1u);
+        qparity ^= 1u << qb;
+        seen_qseq = it.qseq;
+      }
+      while (known_prog < idx - kSlots + 1) {                  // TMEM slot idx % kSlots has been drained
+        int p = 0;
+        if (lane == 0) p = ld_progress_min(&sh);
+        known_prog = __shfl_sync(0xffffffffu, p, 0);
+        if (known_prog < idx - kSlots + 1) __nanosleep(32);
+      }
+      umma::fence_after_sync();
+      // descriptors differ only in their 14-bit start-address field: +2 (32 bytes >> 4) per k-step
+      const uint32_t a_base = ring_addr + it.smem_off;
+      const uint32_t a_half = ((it.rows + 7) & ~7) * 128;
+      const uint32_t b_base = q_addr + qb * kQBufBytes;
+      const uint64_t a0 = umma::make_smem_desc_sw128(a_base), a1 = umma::make_smem_desc_sw128(a_base + a_half);
+      const uint64_t b0 = umma::make_smem_desc_sw128(b_base), b1 = umma::make_smem_desc_sw128(b_base + kN * 128);
+      const uint32_t d_tmem = tmem + (idx % kSlots) * kN;
+      if (umma::elect_one()) {
 #pragma unroll
         for (int k = 0; k < 4; ++k) umma::mma_f16_ss(d_tmem, a0 + 2 * k, b0 + 2 * k, idesc, k ? 1u : 0u);
 #pragma unroll
@@ -396,6 +400,7 @@ maxsim_rerank_umma_kernel(const __grid_constant__ TileMaps maps, const int64_t* 
         umma::commit(smem_u32(&sh.accf[idx % kSlots]));
         umma::commit(smem_u32(&sh.ring_free[idx % kItems]));
       }
+      __syncwarp();
     }
   } else {
     // ======================================= epilogue groups ========================================

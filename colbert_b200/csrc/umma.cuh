@@ -45,6 +45,8 @@ __host__ __device__ constexpr uint32_t make_idesc(uint32_t M, uint32_t N, uint32
   return (1u << 4) | (a_fmt << 7) | (b_fmt << 10) | ((N >> 3) << 17) | ((M >> 4) << 24);
 }
 
+using ::cbk::elect_one;   // tcgen05.mma must be issued through it, see cbk_common.cuh
+
 // ---- MMA issue / completion (one thread) ------------------------------------------------------------
 // D[tmem] (+)= A[smem] · B[smem]^T, shape M × N × 16
 __device__ __forceinline__ void mma_f16_ss(uint32_t tmem_d, uint64_t a_desc, uint64_t b_desc, uint32_t idesc,
@@ -54,6 +56,17 @@ __device__ __forceinline__ void mma_f16_ss(uint32_t tmem_d, uint64_t a_desc, uin
       "setp.ne.b32 p, %4, 0;\n\t"
       "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
       ::"r"(tmem_d), "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+
+// same with the A operand read from TMEM (128 lanes × 8 columns of packed 16-bit pairs per K = 16)
+__device__ __forceinline__ void mma_f16_ts(uint32_t tmem_d, uint32_t tmem_a, uint64_t b_desc, uint32_t idesc,
+                                           uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], [%1], %2, %3, p;\n\t}"
+      ::"r"(tmem_d), "r"(tmem_a), "l"(b_desc), "r"(idesc), "r"(accumulate)
       : "memory");
 }
 

@@ -81,7 +81,140 @@ umma_probe_kernel(const __grid_constant__ ProbeMaps maps, int N, uint32_t idesc,
   if (warp == 1) umma::tmem_dealloc(tmem, ncols);
 }
 
+// Issue-rate probe: every CTA multiplies resident (zero-filled) shared-memory operands `iters` times,
+// K = 128 per tile (8 MMAs), rotating over n_acc TMEM accumulators; cycles per CTA are written out.
+// mode 0: A and B from shared memory (SS); mode 1: A from TMEM (TS), B from shared memory.
+__global__ void __launch_bounds__(128)
+umma_rate_kernel(int N, uint32_t idesc, int mode, int iters, int n_acc, uint32_t ncols, long long* __restrict__ out_cycles) {
+  extern __shared__ uint8_t smem_raw[];
+  __shared__ __align__(8) uint64_t bars[8];
+  __shared__ uint32_t tmem_base_smem;
+  const int tid = threadIdx.x, warp = tid >> 5;
+  const uint32_t raw = smem_u32(smem_raw);
+  const uint32_t base = (raw + 1023u) & ~1023u;
+  const uint32_t a_addr = base, b_addr = base + 32768;
+  const uint32_t b_half = static_cast<uint32_t>(N) * 128u;
+  uint4* z = reinterpret_cast<uint4*>(smem_raw + (base - raw));
+  for (uint32_t i = tid; i < (32768u + 2u * b_half) / 16u; i += 128) z[i] = make_uint4(0, 0, 0, 0);
+  if (tid == 0) {
+    for (int i = 0; i < 8; ++i) mbar_init(smem_u32(&bars[i]), 1);
+    fence_mbar_init();
+  }
+  fence_proxy_async();
+  if (warp == 1) {
+    umma::tmem_alloc(smem_u32(&tmem_base_smem), ncols);
+    umma::tmem_relinquish();
+  }
+  umma::fence_before_sync();
+  __syncthreads();
+  umma::fence_after_sync();
+  const uint32_t tmem = tmem_base_smem;
+  if (warp == 0 && (mode & 4)) {
+    // converged-warp issue: the whole warp walks the loop, one elected lane issues
+    const long long t0 = clock64();
+    for (int i = 0; i < iters; ++i) {
+      const int slot = i % n_acc;
+      if (i >= n_acc) mbar_wait(smem_u32(&bars[slot]), ((i / n_acc) - 1) & 1);
+      umma::fence_after_sync();
+      const uint32_t d = tmem + static_cast<uint32_t>(slot * N);
+      if (umma::elect_one()) {
+#pragma unroll
+        for (int h = 0; h < 2; ++h)
+#pragma unroll
+          for (int k = 0; k < 4; ++k) {
+            const uint64_t bd = umma::make_smem_desc_sw128(b_addr + h * b_half + k * 32);
+            const uint64_t ad = umma::make_smem_desc_sw128(a_addr + h * 16384 + k * 32);
+            umma::mma_f16_ss(d, ad, bd, idesc, (h | k) ? 1u : 0u);
+          }
+        umma::commit(smem_u32(&bars[slot]));
+      }
+      __syncwarp();
+    }
+    for (int slot = 0; slot < n_acc && slot < iters; ++slot) {
+      const int uses = (iters - slot + n_acc - 1) / n_acc;
+      mbar_wait(smem_u32(&bars[slot]), (uses - 1) & 1);
+    }
+    if (tid == 0) out_cycles[blockIdx.x] = clock64() - t0;
+  } else if (tid == 0 && !(mode & 4)) {
+    const uint32_t a_tmem = tmem + ncols - 64;     // TS mode: 128 lanes × 64 columns hold A[128, 128] 16-bit
+    const long long t0 = clock64();
+    if (false) {
+      // interleaved issue: consecutive MMAs go to different accumulators (k-step outer, accumulator inner);
+      // `iters` counts tiles, so one round covers n_acc of them
+      const int rounds = iters / n_acc;
+      for (int r = 0; r < rounds; ++r) {
+        if (r >= 2) mbar_wait(smem_u32(&bars[r & 1]), ((r >> 1) - 1) & 1);
+        umma::fence_after_sync();
+#pragma unroll
+        for (int h = 0; h < 2; ++h)
+#pragma unroll
+          for (int k = 0; k < 4; ++k) {
+            const uint64_t bd = umma::make_smem_desc_sw128(b_addr + h * b_half + k * 32);
+            const uint64_t ad = umma::make_smem_desc_sw128(a_addr + h * 16384 + k * 32);
+            for (int slot = 0; slot < n_acc; ++slot) {
+              const uint32_t d = tmem + static_cast<uint32_t>(slot * N);
+              if (mode & 1) umma::mma_f16_ts(d, a_tmem + (h * 4 + k) * 8, bd, idesc, (h | k) ? 1u : 0u);
+              else umma::mma_f16_ss(d, ad, bd, idesc, (h | k) ? 1u : 0u);
+            }
+          }
+        umma::commit(smem_u32(&bars[r & 1]));
+      }
+      for (int b = 0; b < 2 && b < rounds; ++b) {
+        const int uses = (rounds - b + 1) / 2;
+        mbar_wait(smem_u32(&bars[b]), (uses - 1) & 1);
+      }
+      out_cycles[blockIdx.x] = clock64() - t0;
+    } else {
+    for (int i = 0; i < iters; ++i) {
+      const int slot = i % n_acc;
+      if (i >= n_acc) mbar_wait(smem_u32(&bars[slot]), ((i / n_acc) - 1) & 1);
+      umma::fence_after_sync();
+      const uint32_t d = tmem + static_cast<uint32_t>(slot * N);
+#pragma unroll
+      for (int h = 0; h < 2; ++h)
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+          const uint64_t bd = umma::make_smem_desc_sw128(b_addr + h * b_half + k * 32);
+          if (mode & 1) {
+            umma::mma_f16_ts(d, a_tmem + (h * 4 + k) * 8, bd, idesc, (h | k) ? 1u : 0u);
+          } else {
+            const uint64_t ad = umma::make_smem_desc_sw128(a_addr + h * 16384 + k * 32);
+            umma::mma_f16_ss(d, ad, bd, idesc, (h | k) ? 1u : 0u);
+          }
+        }
+      umma::commit(smem_u32(&bars[slot]));
+    }
+    for (int slot = 0; slot < n_acc && slot < iters; ++slot) {
+      const int uses = (iters - slot + n_acc - 1) / n_acc;
+      mbar_wait(smem_u32(&bars[slot]), (uses - 1) & 1);
+    }
+    out_cycles[blockIdx.x] = clock64() - t0;
+    }
+  }
+  umma::fence_before_sync();
+  __syncthreads();
+  if (warp == 1) umma::tmem_dealloc(tmem, ncols);
+}
+
 }  // namespace
+
+int umma_rate_dispatch(int N, int mode, int iters, int n_acc, int ctas_per_sm, long long* d_cycles, cudaStream_t stream) {
+  CBK_CHECK_ARG(N >= 16 && N <= 256 && N % 16 == 0 && iters >= 1 && n_acc >= 1 && n_acc <= 8 && mode >= 0 && mode <= 7 &&
+                    ctas_per_sm >= 1 && ctas_per_sm <= 4 && d_cycles,
+                "cbk_selftest_umma_rate: bad arguments");
+  const int need = n_acc * N + ((mode & 1) ? 64 : 0);
+  uint32_t ncols = 32;
+  while (ncols < static_cast<uint32_t>(need)) ncols <<= 1;
+  CBK_CHECK_ARG(ncols * ctas_per_sm <= 512, "cbk_selftest_umma_rate: %d TMEM columns x %d CTAs exceed 512", ncols, ctas_per_sm);
+  const uint32_t idesc = umma::make_idesc(128, static_cast<uint32_t>(N), umma::kFmtF16, umma::kFmtF16);
+  const size_t smem = 32768 + static_cast<size_t>(N) * 256 + 1024;
+  CBK_CHECK_ARG(smem * ctas_per_sm <= 220 * 1024, "cbk_selftest_umma_rate: shared memory");
+  CBK_CUDA(cudaFuncSetAttribute(umma_rate_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
+  umma_rate_kernel<<<sm_count() * ctas_per_sm, 128, smem, stream>>>(N, idesc, mode, iters, n_acc, ncols, d_cycles);
+  CBK_CUDA(cudaGetLastError());
+  count_launch();
+  return CBK_OK;
+}
 
 int umma_probe_dispatch(const void* d_A, const void* d_B, int N, int a_bf16, int b_bf16, float* d_C, cudaStream_t stream) {
   ProbeMaps maps;

@@ -203,6 +203,20 @@ def selftest_umma_gemm(A: torch.Tensor, B: torch.Tensor, tma_3d: bool = False) -
     return Cout
 
 
+def selftest_umma_rate(N: int, mode: int, iters: int, n_acc: int, ctas_per_sm: int = 1, device=None) -> torch.Tensor:
+    """Cycles each CTA took to issue and retire ``iters`` tiles of [128, N] += A[128,128] · B[N,128]^T
+    (cbk_selftest_umma_rate; mode 0 = both operands from shared memory, 1 = A from TMEM)."""
+    lib = _lib.load()
+    dev = torch.device(device if device is not None else "cuda:0")
+    n_sm = torch.cuda.get_device_properties(dev).multi_processor_count
+    out = torch.zeros(n_sm * ctas_per_sm, dtype=torch.int64, device=dev)
+    with torch.cuda.device(dev):
+        rc = lib.cbk_selftest_umma_rate(int(N), int(mode), int(iters), int(n_acc), int(ctas_per_sm), _ptr(out),
+                                        C.c_void_p(_lib.current_stream_ptr(dev)))
+    _lib.check("cbk_selftest_umma_rate", rc)
+    return out
+
+
 def build_doc_end_bits(pfxsum: torch.Tensor, n_store_rows: int) -> torch.Tensor:
     """Index-time metadata for the exhaustive kernel: one bit per store row, set on the last row of each
     document (int32 words).  See cbk_build_doc_end_bits."""

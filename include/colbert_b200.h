@@ -276,6 +276,13 @@ int cbk_topk_dense(const float* d_scores, int64_t n_queries, int64_t n_docs, int
  * ------------------------------------------------------------------------------------------------ */
 int cbk_selftest_umma_gemm(const void* d_A, const void* d_B, int N, int a_bf16, int b_bf16, float* d_C, void* stream);
 
+/* Issue-rate probe for the same building block: ctas_per_sm CTAs per SM each run `iters` tiles of
+ * [128, N] += A[128, 128] · B[N, 128]^T over resident shared-memory operands, rotating over n_acc TMEM
+ * accumulators (mode 0: A from shared memory; mode 1: A from TMEM).  d_cycles [n_SMs * ctas_per_sm] int64
+ * receives the clock cycles each CTA took.  Used to place the tensor-bound kernels against what the MMA
+ * shape itself can sustain (benchmarks/umma_rate.py).  Not part of the scoring path. */
+int cbk_selftest_umma_rate(int N, int mode, int iters, int n_acc, int ctas_per_sm, int64_t* d_cycles, void* stream);
+
 #ifdef __cplusplus
 }
 #endif
