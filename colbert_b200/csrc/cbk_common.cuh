@@ -58,6 +58,13 @@ __device__ __forceinline__ uint32_t smem_u32(const void* p) {
   return static_cast<uint32_t>(__cvta_generic_to_shared(p));
 }
 
+// Pins a value in a register: the compiler may not rematerialise it at every use (shared-window addresses of
+// barriers otherwise get re-derived from SR_CgaCtaId inside the issue loops).
+__device__ __forceinline__ uint32_t hold(uint32_t x) {
+  asm volatile("" : "+r"(x));
+  return x;
+}
+
 __device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
   asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");
 }

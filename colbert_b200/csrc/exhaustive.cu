@@ -132,6 +132,39 @@ __device__ __noinline__ void flush_pending(PendBuf* pb, int n, float* __restrict
   __syncwarp();
 }
 
+// Epilogue state of one warp: st.r is each lane's running maximum over the open document's rows seen so far;
+// doc_start (row index, relative to the warp's sub-range, of the open document's first row) and docs_done
+// (documents closed so far in this pass; docs_done % kPend of them are parked in the PendBuf) are warp-uniform.
+struct EpiState {
+  float r;
+  int doc_start;
+  int docs_done;
+};
+
+// The 8 accumulator columns x0..x7 (rows col..col+7 of the sub-range) hold at least one document end (m8: bit j
+// set = column j is the last row of a document).  One out-of-line copy serves every call site, which keeps the
+// epilogue loop itself small enough to stay in the instruction cache.
+__device__ __noinline__ EpiState close_docs_in_group(PendBuf* pb, EpiState st, float x0, float x1, float x2, float x3, float x4,
+                                                     float x5, float x6, float x7, uint32_t m8, int col, float* dst_row,
+                                                     int write) {
+  const int lane = threadIdx.x & 31;
+  const float x[8] = {x0, x1, x2, x3, x4, x5, x6, x7};
+#pragma unroll
+  for (int j = 0; j < 8; ++j) {
+    st.r = fmaxf(st.r, x[j]);
+    if ((m8 >> j) & 1u) {   // warp-uniform
+      const int slot = st.docs_done & (kPend - 1);
+      pb->v[slot][lane] = st.r;
+      if (lane == 0) pb->len[slot] = col + j + 1 - st.doc_start;
+      st.doc_start = col + j + 1;
+      ++st.docs_done;
+      st.r = -INFINITY;
+      if ((st.docs_done & (kPend - 1)) == 0) flush_pending(pb, kPend, dst_row + (st.docs_done - kPend), write != 0);
+    }
+  }
+  return st;
+}
+
 // max of 8 consecutive accumulator columns and the running value
 __device__ __forceinline__ float max8(const uint32_t* v, float r) {
   const float x0 = fmaxf(fmaxf(__uint_as_float(v[0]), __uint_as_float(v[1])), __uint_as_float(v[2]));
@@ -275,59 +308,67 @@ maxsim_exhaustive_kernel(const __grid_constant__ ExhMaps maps, const uint32_t* _
     }
   } else if (warp == 1) {
     // ===================================== MMA issuer ===============================================
-    // (whole warp, uniform control flow; one elected lane issues — see elect_one in cbk_common.cuh)
-    {
-      uint32_t it = 0, acc_it = 0;
-      for (int p = 0; p < n_passes; ++p) {
-        const int qb = min(qb_max, n_qblocks - p * qb_max);
-        const int n_sub = qb == 1 ? 4 : (qb == 2 ? 2 : 1);
-        const int qb_eff = kEpiGroups / n_sub;
-        int nt[kEpiGroups];
-        int max_nt = 0;
-#pragma unroll
-        for (int s2 = 0; s2 < kEpiGroups; ++s2) {
-          nt[s2] = s2 < n_sub ? sub_tiles(n_sub, s2) : 0;
-          max_nt = max(max_nt, nt[s2]);
-        }
-        mbar_wait(smem_u32(&bar_a_full), p & 1);
-        umma::fence_after_sync();
-        for (int t = 0; t < max_nt; ++t)
-#pragma unroll
-          for (int s2 = 0; s2 < kEpiGroups; ++s2) {
-            if (t >= nt[s2]) continue;
-            const uint32_t st = it % kBStages;
-            mbar_wait(smem_u32(&bar_b_full[st]), (it / kBStages) & 1u);
+    // Whole warp, uniform control flow; one elected lane issues (see elect_one in cbk_common.cuh).  This warp is the
+    // pacemaker of the kernel, so its loop is kept short: barrier addresses and descriptor words are formed once,
+    // ring positions advance by increments, and there is ONE copy of the issue code.
+    const uint32_t bfull0 = hold(smem_u32(&bar_b_full[0])), bempty0 = hold(smem_u32(&bar_b_empty[0]));
+    const uint32_t accfull0 = hold(smem_u32(&bar_acc_full[0])), accempty0 = hold(smem_u32(&bar_acc_empty[0]));
+    const uint32_t a_lo0 = hold(umma::desc_lo_sw128(a_addr)), b_lo0 = hold(umma::desc_lo_sw128(b_addr));
+    constexpr uint32_t kTileDesc = kTileBytes >> 4, kHalfDesc = (kTileBytes / 2) >> 4;
+    uint32_t st = 0, st_parity = 0;                       // B stage ring position / parity of its next full phase
+    uint32_t acc_it = 0;
+    for (int p = 0; p < n_passes; ++p) {
+      const int qb = min(qb_max, n_qblocks - p * qb_max);
+      const int n_sub = qb == 1 ? 4 : (qb == 2 ? 2 : 1);
+      const int qb_eff = kEpiGroups / n_sub;
+      const int nt0 = sub_tiles(n_sub, 0), nt1 = n_sub > 1 ? sub_tiles(n_sub, 1) : 0;
+      const int nt2 = n_sub > 2 ? sub_tiles(n_sub, 2) : 0, nt3 = n_sub > 3 ? sub_tiles(n_sub, 3) : 0;
+      const int max_nt = max(max(nt0, nt1), max(nt2, nt3));
+      mbar_wait(smem_u32(&bar_a_full), p & 1);
+      umma::fence_after_sync();
+      for (int t = 0; t < max_nt; ++t) {
+#pragma unroll 1
+        for (int s2 = 0; s2 < n_sub; ++s2) {
+          const int nts = s2 == 0 ? nt0 : (s2 == 1 ? nt1 : (s2 == 2 ? nt2 : nt3));
+          if (t >= nts) continue;
+          mbar_wait(bfull0 + 8 * st, st_parity);
+          umma::fence_after_sync();
+          const uint32_t b_lo = b_lo0 + st * kTileDesc;
+#pragma unroll 1
+          for (int a = 0; a < qb; ++a, ++acc_it) {
+            const uint32_t slot = acc_it % kAccSlots;
+            mbar_wait(accempty0 + 8 * slot, ((acc_it / kAccSlots) & 1u) ^ 1u);
             umma::fence_after_sync();
-            const uint32_t bt = b_addr + st * kTileBytes;
-            for (int a = 0; a < qb; ++a, ++acc_it) {
-              const uint32_t slot = acc_it % kAccSlots;
-              mbar_wait(smem_u32(&bar_acc_empty[slot]), ((acc_it / kAccSlots) & 1u) ^ 1u);
-              umma::fence_after_sync();
-              const uint32_t d_tmem = tmem + slot * kTileTok;
-              if (elect_one()) {
-                uint32_t acc = 0;
-                for (int part = 0; part < parts; ++part) {
-                  const uint32_t at = a_addr + (a * parts + part) * kTileBytes;
+            const uint32_t d_tmem = tmem + slot * kTileTok;
+            const uint32_t a_lo = a_lo0 + static_cast<uint32_t>(a * parts) * kTileDesc;
+            const uint32_t full_bar = accfull0 + 8 * ((s2 * qb_eff + a) * kAccSlots + slot);
+            if (elect_one()) {
 #pragma unroll
-                  for (int h = 0; h < 2; ++h)
+              for (int h = 0; h < 2; ++h)
 #pragma unroll
-                    for (int k = 0; k < 4; ++k) {
-                      umma::mma_f16_ss(d_tmem, umma::make_smem_desc_sw128(at + h * (kTileBytes / 2) + k * 32),
-                                       umma::make_smem_desc_sw128(bt + h * (kTileBytes / 2) + k * 32), idesc, acc);
-                      acc = 1;
-                    }
-                }
-                umma::commit(smem_u32(&bar_acc_full[(s2 * qb_eff + a) * kAccSlots + slot]));
+                for (int k = 0; k < 4; ++k)
+                  umma::mma_f16_ss_lo(d_tmem, a_lo + h * kHalfDesc + 2 * k, b_lo + h * kHalfDesc + 2 * k, idesc, (h | k) ? 1u : 0u);
+              if (parts > 1) {   // bf16 store: the lo part of the query, same accumulator
+#pragma unroll
+                for (int h = 0; h < 2; ++h)
+#pragma unroll
+                  for (int k = 0; k < 4; ++k)
+                    umma::mma_f16_ss_lo(d_tmem, a_lo + kTileDesc + h * kHalfDesc + 2 * k, b_lo + h * kHalfDesc + 2 * k, idesc, 1u);
               }
-              __syncwarp();
+              umma::commit(full_bar);
             }
-            if (elect_one()) umma::commit(smem_u32(&bar_b_empty[st]));
             __syncwarp();
-            ++it;
           }
-        if (elect_one()) umma::commit(smem_u32(&bar_pass_done));
-        __syncwarp();
+          if (elect_one()) umma::commit(bempty0 + 8 * st);
+          __syncwarp();
+          if (++st == kBStages) {
+            st = 0;
+            st_parity ^= 1u;
+          }
+        }
       }
+      if (elect_one()) umma::commit(smem_u32(&bar_pass_done));
+      __syncwarp();
     }
   } else {
     // ===================================== epilogue (warps 2..17) ===================================
@@ -362,46 +403,51 @@ maxsim_exhaustive_kernel(const __grid_constant__ ExhMaps maps, const uint32_t* _
         if (g == (my_s + 1) * wdt) my_tok1 = rng_tok[g];
       }
       const int q = (p * qb_max + my_a) * 4 + quad;
-      const bool write = active && q < n_queries;
-      float* const dst_row = scores + static_cast<int64_t>(write ? q : 0) * n_docs;
+      const int write = active && q < n_queries;
+      float* const dst_row = scores + static_cast<int64_t>(write ? q : 0) * n_docs + my_d0;   // score of my first document
+      // document-end bits of my rows: bit (my_tok0 & 31) of word wp[0] is my first row; everything below is
+      // 32-bit arithmetic relative to the start of the sub-range
+      const uint32_t* const wp = doc_end_bits + (my_tok0 >> 5);
+      const int sh = static_cast<int>(my_tok0 & 31);
+      const int my_rows = static_cast<int>(my_tok1 - my_tok0);
+      int my_nt = 0;
+#pragma unroll
+      for (int s2 = 0; s2 < kEpiGroups; ++s2)
+        if (s2 == my_s) my_nt = nt[s2];
 
-      int64_t doc = my_d0;       // next document to finish
-      int64_t pend_first = my_d0;
-      int n_pend = 0;
-      int cur_len = 0;
-      float r = -INFINITY;
+      EpiState st;
+      st.r = -INFINITY;
+      st.doc_start = 0;
+      st.docs_done = 0;
 
       for (int t = 0; t < max_nt; ++t) {
         // accumulator slots are handed out in item order; find mine in this round
-        uint32_t my_acc = 0;
-        bool mine = false;
-        uint32_t round_total = 0;
+        uint32_t before_me = 0, round_total = 0;
 #pragma unroll
         for (int s2 = 0; s2 < kEpiGroups; ++s2) {
           if (t >= nt[s2]) continue;
-          if (s2 == my_s) {
-            mine = active;
-            my_acc = acc_it + round_total + my_a;
-          }
+          if (s2 < my_s) before_me += qb;
           round_total += qb;
         }
+        const uint32_t my_acc = acc_it + before_me + my_a;
         acc_it += round_total;
-        if (!mine) continue;
+        if (!active || t >= my_nt) continue;
 
         // 128 document-end bits of this tile, shifted so that bit j of word c is column 32c + j
-        const int64_t tbase = my_tok0 + static_cast<int64_t>(t) * kTileTok;
-        const int64_t w0 = tbase >> 5;
-        const int sh = static_cast<int>(tbase & 31);
         uint32_t wraw[5];
 #pragma unroll
-        for (int i = 0; i < 5; ++i) wraw[i] = doc_end_bits[w0 + i];
+        for (int i = 0; i < 5; ++i) wraw[i] = wp[4 * t + i];
         uint32_t ends[4];
 #pragma unroll
-        for (int c = 0; c < 4; ++c) {
-          ends[c] = __funnelshift_r(wraw[c], wraw[c + 1], sh);
-          const int64_t left = my_tok1 - (tbase + 32 * c);       // rows of my sub-range left in the chunk
-          if (left <= 0) ends[c] = 0u;
-          else if (left < 32) ends[c] &= (1u << left) - 1u;
+        for (int c = 0; c < 4; ++c) ends[c] = __funnelshift_r(wraw[c], wraw[c + 1], sh);
+        const int left = my_rows - t * kTileTok;                   // rows of my sub-range in this tile and after
+        if (left < kTileTok) {                                     // last tile: drop the ends that belong to my neighbour
+#pragma unroll
+          for (int c = 0; c < 4; ++c) {
+            const int l = left - 32 * c;
+            if (l <= 0) ends[c] = 0u;
+            else if (l < 32) ends[c] &= (1u << l) - 1u;
+          }
         }
 
         const uint32_t slot = my_acc % kAccSlots;
@@ -409,6 +455,7 @@ maxsim_exhaustive_kernel(const __grid_constant__ ExhMaps maps, const uint32_t* _
         full_parity ^= 1u << slot;
         umma::fence_after_sync();
         const uint32_t t_addr = tmem + lane_base + slot * kTileTok;
+        uint32_t m = ends[0], m1 = ends[1], m2 = ends[2], m3 = ends[3];
 #pragma unroll 1
         for (int c = 0; c < 4; ++c) {
           uint32_t v[32];
@@ -419,61 +466,31 @@ maxsim_exhaustive_kernel(const __grid_constant__ ExhMaps maps, const uint32_t* _
             __syncwarp();
             if (lane == 0) mbar_arrive(smem_u32(&bar_acc_empty[slot]));
           }
-          const uint32_t m = c == 0 ? ends[0] : (c == 1 ? ends[1] : (c == 2 ? ends[2] : ends[3]));
           if (m == 0u) {   // no document ends inside these 32 columns (the common case): one max tree
-            const float y0 = max8(v, r), y1 = max8(v + 8, -INFINITY), y2 = max8(v + 16, -INFINITY), y3 = max8(v + 24, -INFINITY);
-            r = fmaxf(fmaxf(y0, y1), fmaxf(y2, y3));
+            const float y0 = max8(v, st.r), y1 = max8(v + 8, -INFINITY), y2 = max8(v + 16, -INFINITY), y3 = max8(v + 24, -INFINITY);
+            st.r = fmaxf(fmaxf(y0, y1), fmaxf(y2, y3));
           } else {
+            const int col = t * kTileTok + c * 32;
 #pragma unroll
             for (int s8 = 0; s8 < 4; ++s8) {   // 8 columns at a time: most groups of 8 still hold no document end
               const uint32_t m8 = (m >> (8 * s8)) & 0xffu;
               if (m8 == 0u) {
-                r = max8(v + 8 * s8, r);
+                st.r = max8(v + 8 * s8, st.r);
               } else {
-                if (n_pend + __popc(m8) > kPend) {   // make room for every document that ends in this group
-                  flush_pending(pb, n_pend, dst_row + pend_first, write);
-                  pend_first = doc;
-                  n_pend = 0;
-                }
-                if ((m8 & (m8 - 1u)) == 0u) {
-                  // exactly one document ends in this group (the usual case), at column e: branch-free split into
-                  // the maximum up to e (closes the document) and the maximum after e (opens the next one)
-                  const int e = __ffs(m8) - 1;
-                  float head = r, tail = -INFINITY;
-#pragma unroll
-                  for (int j = 0; j < 8; ++j) {
-                    const float x = __uint_as_float(v[8 * s8 + j]);
-                    const bool in_head = j <= e;
-                    head = in_head ? fmaxf(head, x) : head;
-                    tail = in_head ? tail : fmaxf(tail, x);
-                  }
-                  pb->v[n_pend][lane] = head;
-                  if (lane == 0) pb->len[n_pend] = cur_len + 8 * s8 + e + 1;
-                  ++n_pend;
-                  ++doc;
-                  cur_len = -(8 * s8 + e + 1);
-                  r = tail;
-                } else {
-#pragma unroll
-                  for (int j = 0; j < 8; ++j) {
-                    r = fmaxf(r, __uint_as_float(v[8 * s8 + j]));
-                    if ((m8 >> j) & 1u) {   // this column is the last token of document `doc` (warp-uniform)
-                      pb->v[n_pend][lane] = r;
-                      if (lane == 0) pb->len[n_pend] = cur_len + 8 * s8 + j + 1;
-                      ++n_pend;
-                      ++doc;
-                      cur_len = -(8 * s8 + j + 1);
-                      r = -INFINITY;
-                    }
-                  }
-                }
+                const uint32_t* x = v + 8 * s8;
+                st = close_docs_in_group(pb, st, __uint_as_float(x[0]), __uint_as_float(x[1]), __uint_as_float(x[2]),
+                                         __uint_as_float(x[3]), __uint_as_float(x[4]), __uint_as_float(x[5]),
+                                         __uint_as_float(x[6]), __uint_as_float(x[7]), m8, col + 8 * s8, dst_row, write);
               }
             }
           }
-          cur_len += 32;
+          m = m1;
+          m1 = m2;
+          m2 = m3;
         }
       }
-      if (n_pend > 0) flush_pending(pb, n_pend, dst_row + pend_first, write);
+      const int n_pend = st.docs_done & (kPend - 1);
+      if (n_pend > 0) flush_pending(pb, n_pend, dst_row + (st.docs_done - n_pend), write != 0);
     }
   }
 

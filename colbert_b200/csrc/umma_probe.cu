@@ -84,7 +84,7 @@ umma_probe_kernel(const __grid_constant__ ProbeMaps maps, int N, uint32_t idesc,
 // Issue-rate probe: every CTA multiplies resident (zero-filled) shared-memory operands `iters` times,
 // K = 128 per tile (8 MMAs), rotating over n_acc TMEM accumulators; cycles per CTA are written out.
 // mode 0: A and B from shared memory (SS); mode 1: A from TMEM (TS), B from shared memory.
-__global__ void __launch_bounds__(128)
+__global__ void __launch_bounds__(640)
 umma_rate_kernel(int N, uint32_t idesc, int mode, int iters, int n_acc, uint32_t ncols, long long* __restrict__ out_cycles) {
   extern __shared__ uint8_t smem_raw[];
   __shared__ __align__(8) uint64_t bars[8];
@@ -95,7 +95,7 @@ umma_rate_kernel(int N, uint32_t idesc, int mode, int iters, int n_acc, uint32_t
   const uint32_t a_addr = base, b_addr = base + 32768;
   const uint32_t b_half = static_cast<uint32_t>(N) * 128u;
   uint4* z = reinterpret_cast<uint4*>(smem_raw + (base - raw));
-  for (uint32_t i = tid; i < (32768u + 2u * b_half) / 16u; i += 128) z[i] = make_uint4(0, 0, 0, 0);
+  for (uint32_t i = tid; i < (32768u + 2u * b_half) / 16u; i += blockDim.x) z[i] = make_uint4(0, 0, 0, 0);
   if (tid == 0) {
     for (int i = 0; i < 8; ++i) mbar_init(smem_u32(&bars[i]), 1);
     fence_mbar_init();
@@ -109,7 +109,24 @@ umma_rate_kernel(int N, uint32_t idesc, int mode, int iters, int n_acc, uint32_t
   __syncthreads();
   umma::fence_after_sync();
   const uint32_t tmem = tmem_base_smem;
-  if (warp == 0 && (mode & 4)) {
+  __shared__ volatile int s_done;
+  if (tid == 0) s_done = 0;
+  __syncthreads();
+  if (warp >= 4) {
+    // mode bit 16: sixteen more warps read the accumulators back (tcgen05.ld + max tree) for as long as the MMA
+    // stream runs — the interference an epilogue causes
+    float acc = 0.f;
+    const uint32_t base = tmem + (static_cast<uint32_t>((warp & 3) * 32) << 16);
+    int i = 0;
+    while (!s_done) {
+      uint32_t v[32];
+      umma::tmem_ld_32x32(base + ((i++ * 32) & (ncols - 1)), v);
+      umma::tmem_ld_wait();
+#pragma unroll
+      for (int j = 0; j < 32; j += 2) acc = fmaxf(acc, fmaxf(__uint_as_float(v[j]), __uint_as_float(v[j + 1])));
+    }
+    if (acc == 12345.678f) out_cycles[blockIdx.x] = 0;
+  } else if (warp == 0 && (mode & 4)) {
     // converged-warp issue: the whole warp walks the loop, one elected lane issues
     const long long t0 = clock64();
     for (int i = 0; i < iters; ++i) {
@@ -135,6 +152,7 @@ umma_rate_kernel(int N, uint32_t idesc, int mode, int iters, int n_acc, uint32_t
       mbar_wait(smem_u32(&bars[slot]), (uses - 1) & 1);
     }
     if (tid == 0) out_cycles[blockIdx.x] = clock64() - t0;
+    s_done = 1;
   } else if (tid == 0 && !(mode & 4)) {
     const uint32_t a_tmem = tmem + ncols - 64;     // TS mode: 128 lanes × 64 columns hold A[128, 128] 16-bit
     const long long t0 = clock64();
@@ -190,16 +208,64 @@ umma_rate_kernel(int N, uint32_t idesc, int mode, int iters, int n_acc, uint32_t
     }
     out_cycles[blockIdx.x] = clock64() - t0;
     }
+    s_done = 1;
   }
   umma::fence_before_sync();
   __syncthreads();
   if (warp == 1) umma::tmem_dealloc(tmem, ncols);
 }
 
+// TMEM read-rate probe: `blockDim.x / 32` warps (warp w reads lane quadrant w % 4) each issue `iters` tcgen05.ld
+// of 32 lanes x 32 columns (4 KB), `depth` loads between waits; cycles of warp 0 are written out.
+__global__ void __launch_bounds__(512)
+tmem_ld_rate_kernel(int iters, int depth, long long* __restrict__ out_cycles) {
+  __shared__ uint32_t tmem_base_smem;
+  const int warp = threadIdx.x >> 5;
+  if (warp == 0) {
+    umma::tmem_alloc(smem_u32(&tmem_base_smem), 512);
+    umma::tmem_relinquish();
+  }
+  umma::fence_before_sync();
+  __syncthreads();
+  umma::fence_after_sync();
+  const uint32_t tmem = tmem_base_smem;
+  const uint32_t base = tmem + (static_cast<uint32_t>((warp & 3) * 32) << 16) + static_cast<uint32_t>((warp >> 2) * 128);
+  float acc = 0.f;
+  __syncthreads();
+  const long long t0 = clock64();
+  for (int i = 0; i < iters; i += depth) {
+    uint32_t v[2][32];
+    umma::tmem_ld_32x32(base + (i & 3) * 32, v[0]);
+    if (depth > 1) umma::tmem_ld_32x32(base + ((i + 1) & 3) * 32, v[1]);
+    umma::tmem_ld_wait();
+#pragma unroll
+    for (int j = 0; j < 32; j += 2) acc = fmaxf(acc, fmaxf(__uint_as_float(v[0][j]), __uint_as_float(v[0][j + 1])));
+    if (depth > 1) {
+#pragma unroll
+      for (int j = 0; j < 32; j += 2) acc = fmaxf(acc, fmaxf(__uint_as_float(v[1][j]), __uint_as_float(v[1][j + 1])));
+    }
+  }
+  __syncthreads();
+  const long long t1 = clock64();
+  if (threadIdx.x == 0) out_cycles[blockIdx.x] = t1 - t0;
+  if (acc == 12345.678f) out_cycles[blockIdx.x] = 0;   // keep the loads alive
+  umma::fence_before_sync();
+  __syncthreads();
+  if (warp == 0) umma::tmem_dealloc(tmem, 512);
+}
+
 }  // namespace
 
 int umma_rate_dispatch(int N, int mode, int iters, int n_acc, int ctas_per_sm, long long* d_cycles, cudaStream_t stream) {
-  CBK_CHECK_ARG(N >= 16 && N <= 256 && N % 16 == 0 && iters >= 1 && n_acc >= 1 && n_acc <= 8 && mode >= 0 && mode <= 7 &&
+  if (mode == 8) {   // TMEM read rate: N = warps per CTA (4, 8, 12, 16), n_acc = loads between waits (1 or 2)
+    CBK_CHECK_ARG((N == 4 || N == 8 || N == 12 || N == 16) && (n_acc == 1 || n_acc == 2) && iters >= 2 && d_cycles,
+                  "cbk_selftest_umma_rate: bad TMEM-read arguments");
+    tmem_ld_rate_kernel<<<sm_count(), N * 32, 0, stream>>>(iters, n_acc, d_cycles);
+    CBK_CUDA(cudaGetLastError());
+    count_launch();
+    return CBK_OK;
+  }
+  CBK_CHECK_ARG(N >= 16 && N <= 256 && N % 16 == 0 && iters >= 1 && n_acc >= 1 && n_acc <= 8 && mode >= 0 && mode <= 23 &&
                     ctas_per_sm >= 1 && ctas_per_sm <= 4 && d_cycles,
                 "cbk_selftest_umma_rate: bad arguments");
   const int need = n_acc * N + ((mode & 1) ? 64 : 0);
@@ -210,7 +276,7 @@ int umma_rate_dispatch(int N, int mode, int iters, int n_acc, int ctas_per_sm, l
   const size_t smem = 32768 + static_cast<size_t>(N) * 256 + 1024;
   CBK_CHECK_ARG(smem * ctas_per_sm <= 220 * 1024, "cbk_selftest_umma_rate: shared memory");
   CBK_CUDA(cudaFuncSetAttribute(umma_rate_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
-  umma_rate_kernel<<<sm_count() * ctas_per_sm, 128, smem, stream>>>(N, idesc, mode, iters, n_acc, ncols, d_cycles);
+  umma_rate_kernel<<<sm_count() * ctas_per_sm, (mode & 16) ? 640 : 128, smem, stream>>>(N, idesc, mode & 7, iters, n_acc, ncols, d_cycles);
   CBK_CUDA(cudaGetLastError());
   count_launch();
   return CBK_OK;
