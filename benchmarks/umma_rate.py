@@ -25,7 +25,7 @@ def main():
     rows = []
     for (N, mode, n_acc, cps) in [(128, 0, 1, 1), (128, 0, 4, 1), (256, 0, 2, 1), (64, 0, 4, 1), (128, 1, 2, 1), (256, 1, 1, 1),
                                   (128, 0, 2, 2), (64, 0, 2, 4),
-                                  (128, 4, 1, 1), (128, 4, 4, 1), (64, 4, 4, 1), (256, 4, 2, 1), (128, 4, 2, 2), (128, 20, 4, 1), (256, 20, 2, 1)]:
+                                  (128, 4, 1, 1), (128, 4, 4, 1), (64, 4, 4, 1), (256, 4, 2, 1), (128, 4, 2, 2), (128, 20, 4, 1), (256, 20, 2, 1), (128, 6, 4, 1), (128, 22, 4, 1), (64, 6, 4, 1)]:
         kernels.selftest_umma_rate(N, mode, 200, n_acc, cps, dev)
         torch.cuda.synchronize()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
@@ -36,7 +36,7 @@ def main():
         ms = e0.elapsed_time(e1)
         flop = 2.0 * 128 * N * 128 * args.iters * n_sm * cps
         c = cyc.float()
-        rows.append({"N": N, "A": "tmem" if mode & 1 else "smem", "issue": "elect_one in a converged warp" if mode & 4 else "thread 0 in a divergent branch",
+        rows.append({"N": N, "A": "tmem" if mode & 1 else "smem", "issue": ("two warps, elect_one each" if mode & 2 else "elect_one in a converged warp") if mode & 4 else "thread 0 in a divergent branch",
                      "concurrent_tmem_readers": 16 if mode & 16 else 0, "accumulators": n_acc, "ctas_per_sm": cps,
                      "cycles_per_tile_per_cta": round(float(c.mean()) / args.iters, 1),
                      "cycles_per_tile_per_sm": round(float(c.mean()) / args.iters / cps, 1),

@@ -39,7 +39,9 @@ constexpr int kABlocks = 4;               // 32 KB A slots in shared memory
 constexpr int kAccSlots = 4;              // × 128 TMEM columns
 constexpr int kTileBytes = kTileTok * 256;
 constexpr int kEpiGroups = 4;             // epilogue warp groups (4 warps each, one per TMEM lane quadrant)
-constexpr int kExhThreads = 64 + kEpiGroups * 128;
+constexpr int kIssuers = 2;               // MMA-issuing warps: one warp sustains one 128x128x16 MMA per ~90 cycles, two reach the 64-cycle floor
+constexpr int kIssuer1Warp = 2 + kEpiGroups * 4;   // warp 1 issues for groups 0-1, this warp for groups 2-3
+constexpr int kExhThreads = 64 + kEpiGroups * 128 + 32;
 
 struct StrideSet {
   int n;
@@ -184,12 +186,12 @@ maxsim_exhaustive_kernel(const __grid_constant__ ExhMaps maps, const uint32_t* _
   __shared__ __align__(8) uint64_t bar_b_full[kMaxBStages], bar_b_empty[kMaxBStages];
   // acc_full is per (consuming epilogue group, slot): an mbarrier wait only tells phases apart by parity, so a
   // barrier must never have two waiters that are a whole phase apart (two groups sharing one slot would be)
-  __shared__ __align__(8) uint64_t bar_acc_full[kEpiGroups * kAccSlots], bar_acc_empty[kAccSlots];
+  __shared__ __align__(8) uint64_t bar_acc_full[kEpiGroups], bar_acc_empty[kEpiGroups];   // group g owns TMEM slot g
   __shared__ uint32_t tmem_base_smem;
   __shared__ PendBuf s_pend[kEpiGroups * 4];
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-  if (warp >= 2 && lane <= CBK_MAX_STRIDES) {
+  if (warp >= 2 && warp < kIssuer1Warp && lane <= CBK_MAX_STRIDES) {
     if (lane == 0) s_pend[warp - 2].n_strides = strides.n;
     else s_pend[warp - 2].strides[lane - 1] = strides.v[lane - 1];
   }
@@ -202,13 +204,15 @@ maxsim_exhaustive_kernel(const __grid_constant__ ExhMaps maps, const uint32_t* _
 
   if (tid == 0) {
     mbar_init(smem_u32(&bar_a_full), 1);
-    mbar_init(smem_u32(&bar_pass_done), 1);
+    mbar_init(smem_u32(&bar_pass_done), kIssuers);   // every issuer commits once per pass
     for (int s = 0; s < kMaxBStages; ++s) {
       mbar_init(smem_u32(&bar_b_full[s]), 1);
-      mbar_init(smem_u32(&bar_b_empty[s]), 1);
+      mbar_init(smem_u32(&bar_b_empty[s]), kIssuers);   // every issuer commits once per tile
     }
-    for (int s = 0; s < kEpiGroups * kAccSlots; ++s) mbar_init(smem_u32(&bar_acc_full[s]), 1);
-    for (int s = 0; s < kAccSlots; ++s) mbar_init(smem_u32(&bar_acc_empty[s]), 4);   // one arrival per epilogue warp
+    for (int s = 0; s < kEpiGroups; ++s) {
+      mbar_init(smem_u32(&bar_acc_full[s]), 1);
+      mbar_init(smem_u32(&bar_acc_empty[s]), 4);   // one arrival per epilogue warp
+    }
     fence_mbar_init();
   }
   if (warp == 1) {
@@ -306,17 +310,21 @@ maxsim_exhaustive_kernel(const __grid_constant__ ExhMaps maps, const uint32_t* _
           }
       }
     }
-  } else if (warp == 1) {
-    // ===================================== MMA issuer ===============================================
-    // Whole warp, uniform control flow; one elected lane issues (see elect_one in cbk_common.cuh).  This warp is the
-    // pacemaker of the kernel, so its loop is kept short: barrier addresses and descriptor words are formed once,
-    // ring positions advance by increments, and there is ONE copy of the issue code.
+  } else if (warp == 1 || warp == kIssuer1Warp) {
+    // ===================================== MMA issuers ==============================================
+    // Two warps, each with uniform control flow and one elected lane issuing (see elect_one in cbk_common.cuh):
+    // issuer w feeds epilogue groups 2w and 2w+1.  A single issuing warp sustains one 128x128x16 MMA per ~90
+    // cycles, two reach the tensor pipe's 64-cycle floor (benchmarks/umma_rate.py).  These warps pace the kernel,
+    // so their loop is kept short: barrier addresses and descriptor words are formed once, ring positions advance
+    // by increments, and there is one copy of the issue code.  Both issuers walk every tile (wait for it, commit
+    // its release) even when it carries no accumulator of theirs, which keeps the stage barriers' counts fixed.
+    const int w = warp == 1 ? 0 : 1;
     const uint32_t bfull0 = hold(smem_u32(&bar_b_full[0])), bempty0 = hold(smem_u32(&bar_b_empty[0]));
     const uint32_t accfull0 = hold(smem_u32(&bar_acc_full[0])), accempty0 = hold(smem_u32(&bar_acc_empty[0]));
     const uint32_t a_lo0 = hold(umma::desc_lo_sw128(a_addr)), b_lo0 = hold(umma::desc_lo_sw128(b_addr));
     constexpr uint32_t kTileDesc = kTileBytes >> 4, kHalfDesc = (kTileBytes / 2) >> 4;
     uint32_t st = 0, st_parity = 0;                       // B stage ring position / parity of its next full phase
-    uint32_t acc_it = 0;
+    uint32_t empty_parity = 0;                            // bit g = parity of the next wait on bar_acc_empty[g]
     for (int p = 0; p < n_passes; ++p) {
       const int qb = min(qb_max, n_qblocks - p * qb_max);
       const int n_sub = qb == 1 ? 4 : (qb == 2 ? 2 : 1);
@@ -335,13 +343,14 @@ maxsim_exhaustive_kernel(const __grid_constant__ ExhMaps maps, const uint32_t* _
           umma::fence_after_sync();
           const uint32_t b_lo = b_lo0 + st * kTileDesc;
 #pragma unroll 1
-          for (int a = 0; a < qb; ++a, ++acc_it) {
-            const uint32_t slot = acc_it % kAccSlots;
-            mbar_wait(accempty0 + 8 * slot, ((acc_it / kAccSlots) & 1u) ^ 1u);
+          for (int a = 0; a < qb; ++a) {
+            const uint32_t g = static_cast<uint32_t>(s2 * qb_eff + a);     // epilogue group = TMEM slot
+            if (static_cast<int>(g >> 1) != w) continue;
+            mbar_wait(accempty0 + 8 * g, ((empty_parity >> g) & 1u) ^ 1u);
+            empty_parity ^= 1u << g;
             umma::fence_after_sync();
-            const uint32_t d_tmem = tmem + slot * kTileTok;
+            const uint32_t d_tmem = tmem + g * kTileTok;
             const uint32_t a_lo = a_lo0 + static_cast<uint32_t>(a * parts) * kTileDesc;
-            const uint32_t full_bar = accfull0 + 8 * ((s2 * qb_eff + a) * kAccSlots + slot);
             if (elect_one()) {
 #pragma unroll
               for (int h = 0; h < 2; ++h)
@@ -355,7 +364,7 @@ maxsim_exhaustive_kernel(const __grid_constant__ ExhMaps maps, const uint32_t* _
                   for (int k = 0; k < 4; ++k)
                     umma::mma_f16_ss_lo(d_tmem, a_lo + kTileDesc + h * kHalfDesc + 2 * k, b_lo + h * kHalfDesc + 2 * k, idesc, 1u);
               }
-              umma::commit(full_bar);
+              umma::commit(accfull0 + 8 * g);
             }
             __syncwarp();
           }
@@ -376,8 +385,7 @@ maxsim_exhaustive_kernel(const __grid_constant__ ExhMaps maps, const uint32_t* _
     const int quad = warp & 3;                       // TMEM lane quadrant this warp may read = query within the block
     const uint32_t lane_base = static_cast<uint32_t>(quad * 32) << 16;
     PendBuf* const pb = &s_pend[warp - 2];
-    uint32_t acc_it = 0;
-    uint32_t full_parity = 0;                        // bit s = parity of this group's next wait on its barrier of slot s
+    uint32_t full_parity = 0;                        // parity of this group's next wait on its accumulator-full barrier
     for (int p = 0; p < n_passes; ++p) {
       const int qb = min(qb_max, n_qblocks - p * qb_max);
       const int n_sub = qb == 1 ? 4 : (qb == 2 ? 2 : 1);
@@ -421,16 +429,6 @@ maxsim_exhaustive_kernel(const __grid_constant__ ExhMaps maps, const uint32_t* _
       st.docs_done = 0;
 
       for (int t = 0; t < max_nt; ++t) {
-        // accumulator slots are handed out in item order; find mine in this round
-        uint32_t before_me = 0, round_total = 0;
-#pragma unroll
-        for (int s2 = 0; s2 < kEpiGroups; ++s2) {
-          if (t >= nt[s2]) continue;
-          if (s2 < my_s) before_me += qb;
-          round_total += qb;
-        }
-        const uint32_t my_acc = acc_it + before_me + my_a;
-        acc_it += round_total;
         if (!active || t >= my_nt) continue;
 
         // 128 document-end bits of this tile, shifted so that bit j of word c is column 32c + j
@@ -450,11 +448,10 @@ maxsim_exhaustive_kernel(const __grid_constant__ ExhMaps maps, const uint32_t* _
           }
         }
 
-        const uint32_t slot = my_acc % kAccSlots;
-        mbar_wait(smem_u32(&bar_acc_full[grp * kAccSlots + slot]), (full_parity >> slot) & 1u);
-        full_parity ^= 1u << slot;
+        mbar_wait(smem_u32(&bar_acc_full[grp]), full_parity);      // group g owns TMEM slot g
+        full_parity ^= 1u;
         umma::fence_after_sync();
-        const uint32_t t_addr = tmem + lane_base + slot * kTileTok;
+        const uint32_t t_addr = tmem + lane_base + grp * kTileTok;
         uint32_t m = ends[0], m1 = ends[1], m2 = ends[2], m3 = ends[3];
 #pragma unroll 1
         for (int c = 0; c < 4; ++c) {
@@ -464,7 +461,7 @@ maxsim_exhaustive_kernel(const __grid_constant__ ExhMaps maps, const uint32_t* _
           if (c == 3) {   // all columns of the slot are in registers: hand it back to the MMA warp
             umma::fence_before_sync();
             __syncwarp();
-            if (lane == 0) mbar_arrive(smem_u32(&bar_acc_empty[slot]));
+            if (lane == 0) mbar_arrive(smem_u32(&bar_acc_empty[grp]));
           }
           if (m == 0u) {   // no document ends inside these 32 columns (the common case): one max tree
             const float y0 = max8(v, st.r), y1 = max8(v + 8, -INFINITY), y2 = max8(v + 16, -INFINITY), y3 = max8(v + 24, -INFINITY);

@@ -126,7 +126,35 @@ umma_rate_kernel(int N, uint32_t idesc, int mode, int iters, int n_acc, uint32_t
       for (int j = 0; j < 32; j += 2) acc = fmaxf(acc, fmaxf(__uint_as_float(v[j]), __uint_as_float(v[j + 1])));
     }
     if (acc == 12345.678f) out_cycles[blockIdx.x] = 0;
-  } else if (warp == 0 && (mode & 4)) {
+  } else if ((mode & 6) == 6 && warp < 2) {
+    // two issuing warps in one CTA, each with its own half of the accumulators and iters / 2 tiles
+    const int my_acc = n_acc / 2, my_iters = iters / 2;
+    const long long t0 = clock64();
+    for (int i = 0; i < my_iters; ++i) {
+      const int slot = warp * my_acc + i % my_acc;
+      if (i >= my_acc) mbar_wait(smem_u32(&bars[slot]), ((i / my_acc) - 1) & 1);
+      umma::fence_after_sync();
+      const uint32_t d = tmem + static_cast<uint32_t>(slot * N);
+      if (umma::elect_one()) {
+#pragma unroll
+        for (int h = 0; h < 2; ++h)
+#pragma unroll
+          for (int k = 0; k < 4; ++k) {
+            const uint64_t bd = umma::make_smem_desc_sw128(b_addr + h * b_half + k * 32);
+            const uint64_t ad = umma::make_smem_desc_sw128(a_addr + h * 16384 + k * 32);
+            umma::mma_f16_ss(d, ad, bd, idesc, (h | k) ? 1u : 0u);
+          }
+        umma::commit(smem_u32(&bars[slot]));
+      }
+      __syncwarp();
+    }
+    for (int j = 0; j < my_acc && j < my_iters; ++j) {
+      const int uses = (my_iters - j + my_acc - 1) / my_acc;
+      mbar_wait(smem_u32(&bars[warp * my_acc + j]), (uses - 1) & 1);
+    }
+    if (tid == 0) out_cycles[blockIdx.x] = clock64() - t0;
+    if (warp == 0) s_done = 1;
+  } else if (warp == 0 && (mode & 6) == 4) {
     // converged-warp issue: the whole warp walks the loop, one elected lane issues
     const long long t0 = clock64();
     for (int i = 0; i < iters; ++i) {
@@ -153,7 +181,7 @@ umma_rate_kernel(int N, uint32_t idesc, int mode, int iters, int n_acc, uint32_t
     }
     if (tid == 0) out_cycles[blockIdx.x] = clock64() - t0;
     s_done = 1;
-  } else if (tid == 0 && !(mode & 4)) {
+  } else if (tid == 0 && !(mode & 4) && warp == 0) {
     const uint32_t a_tmem = tmem + ncols - 64;     // TS mode: 128 lanes × 64 columns hold A[128, 128] 16-bit
     const long long t0 = clock64();
     if (false) {
