@@ -14,8 +14,8 @@
 //     32 rows is one warp reduction per (query, document);
 //   * document boundaries come from a bitmap with one bit per store row (set on the last row of each
 //     document), so the epilogue never chases pfxsum;
-//   * warp roles: warp 0 TMA producer, warp 1 MMA issuer (one thread), warps 2-17 epilogue: four groups of
-//     four warps (one TMEM lane quadrant = one query each).  A CTA owns four document-aligned token
+//   * warp roles: warp 0 TMA producer, warps 1 and 18 MMA issuers (one elected lane each), warps 2-17 epilogue: four
+//     groups of four warps (one TMEM lane quadrant = one query each).  A CTA owns four document-aligned token
 //     sub-ranges and interleaves their tiles; group g drains the accumulators of sub-range g, so four
 //     accumulators are being reduced while the next ones are being multiplied.  3-stage smem ring for
 //     document tiles, 4 TMEM accumulator slots of 128 columns.
