@@ -81,14 +81,19 @@ umma_probe_kernel(const __grid_constant__ ProbeMaps maps, int N, uint32_t idesc,
   if (warp == 1) umma::tmem_dealloc(tmem, ncols);
 }
 
-// Issue-rate probe: every CTA multiplies resident (zero-filled) shared-memory operands `iters` times,
-// K = 128 per tile (8 MMAs), rotating over n_acc TMEM accumulators; cycles per CTA are written out.
-// mode 0: A and B from shared memory (SS); mode 1: A from TMEM (TS), B from shared memory.
+// Issue-rate probe: every CTA multiplies resident (zero-filled) shared-memory operands `iters` times, K = 128 per
+// tile (8 MMAs), rotating over n_acc TMEM accumulators; the cycles the CTA took are written out.  mode bits:
+//   1  A operand from TMEM (TS) instead of shared memory (legacy issue path only)
+//   4  issue through elect.sync on a converged warp (otherwise: thread 0 inside a divergent branch — the slow way,
+//      kept so that the difference stays measurable)
+//   2  (with 4) two issuing warps, each with half of the accumulators and half of the tiles
+//   16 sixteen more warps read the accumulators back with tcgen05.ld while the MMA stream runs
 __global__ void __launch_bounds__(640)
 umma_rate_kernel(int N, uint32_t idesc, int mode, int iters, int n_acc, uint32_t ncols, long long* __restrict__ out_cycles) {
   extern __shared__ uint8_t smem_raw[];
   __shared__ __align__(8) uint64_t bars[8];
   __shared__ uint32_t tmem_base_smem;
+  __shared__ volatile int s_done;
   const int tid = threadIdx.x, warp = tid >> 5;
   const uint32_t raw = smem_u32(smem_raw);
   const uint32_t base = (raw + 1023u) & ~1023u;
@@ -99,6 +104,7 @@ umma_rate_kernel(int N, uint32_t idesc, int mode, int iters, int n_acc, uint32_t
   if (tid == 0) {
     for (int i = 0; i < 8; ++i) mbar_init(smem_u32(&bars[i]), 1);
     fence_mbar_init();
+    s_done = 0;
   }
   fence_proxy_async();
   if (warp == 1) {
@@ -109,108 +115,53 @@ umma_rate_kernel(int N, uint32_t idesc, int mode, int iters, int n_acc, uint32_t
   __syncthreads();
   umma::fence_after_sync();
   const uint32_t tmem = tmem_base_smem;
-  __shared__ volatile int s_done;
-  if (tid == 0) s_done = 0;
-  __syncthreads();
+  const int n_issuers = (mode & 6) == 6 ? 2 : 1;
+
   if (warp >= 4) {
-    // mode bit 16: sixteen more warps read the accumulators back (tcgen05.ld + max tree) for as long as the MMA
-    // stream runs — the interference an epilogue causes
+    // the interference an epilogue causes: tcgen05.ld + max tree for as long as the MMA stream runs
     float acc = 0.f;
-    const uint32_t base = tmem + (static_cast<uint32_t>((warp & 3) * 32) << 16);
+    const uint32_t rd = tmem + (static_cast<uint32_t>((warp & 3) * 32) << 16);
     int i = 0;
     while (!s_done) {
       uint32_t v[32];
-      umma::tmem_ld_32x32(base + ((i++ * 32) & (ncols - 1)), v);
+      umma::tmem_ld_32x32(rd + ((i++ * 32) & (ncols - 1)), v);
       umma::tmem_ld_wait();
 #pragma unroll
       for (int j = 0; j < 32; j += 2) acc = fmaxf(acc, fmaxf(__uint_as_float(v[j]), __uint_as_float(v[j + 1])));
     }
-    if (acc == 12345.678f) out_cycles[blockIdx.x] = 0;
-  } else if ((mode & 6) == 6 && warp < 2) {
-    // two issuing warps in one CTA, each with its own half of the accumulators and iters / 2 tiles
-    const int my_acc = n_acc / 2, my_iters = iters / 2;
+    if (acc == 12345.678f) out_cycles[blockIdx.x] = 0;   // keeps the loads alive
+  } else if ((mode & 4) && warp < n_issuers) {
+    // converged-warp issue: the whole warp walks the loop, one elected lane issues
+    const int my_acc = n_acc / n_issuers, my_iters = iters / n_issuers;
     const long long t0 = clock64();
     for (int i = 0; i < my_iters; ++i) {
       const int slot = warp * my_acc + i % my_acc;
       if (i >= my_acc) mbar_wait(smem_u32(&bars[slot]), ((i / my_acc) - 1) & 1);
       umma::fence_after_sync();
       const uint32_t d = tmem + static_cast<uint32_t>(slot * N);
-      if (umma::elect_one()) {
+      if (elect_one()) {
 #pragma unroll
         for (int h = 0; h < 2; ++h)
 #pragma unroll
-          for (int k = 0; k < 4; ++k) {
-            const uint64_t bd = umma::make_smem_desc_sw128(b_addr + h * b_half + k * 32);
-            const uint64_t ad = umma::make_smem_desc_sw128(a_addr + h * 16384 + k * 32);
-            umma::mma_f16_ss(d, ad, bd, idesc, (h | k) ? 1u : 0u);
-          }
+          for (int k = 0; k < 4; ++k)
+            umma::mma_f16_ss(d, umma::make_smem_desc_sw128(a_addr + h * 16384 + k * 32),
+                             umma::make_smem_desc_sw128(b_addr + h * b_half + k * 32), idesc, (h | k) ? 1u : 0u);
         umma::commit(smem_u32(&bars[slot]));
       }
       __syncwarp();
     }
-    for (int j = 0; j < my_acc && j < my_iters; ++j) {
+    for (int j = 0; j < my_acc && j < my_iters; ++j) {   // last use of each of my accumulators
       const int uses = (my_iters - j + my_acc - 1) / my_acc;
       mbar_wait(smem_u32(&bars[warp * my_acc + j]), (uses - 1) & 1);
     }
-    if (tid == 0) out_cycles[blockIdx.x] = clock64() - t0;
-    if (warp == 0) s_done = 1;
-  } else if (warp == 0 && (mode & 6) == 4) {
-    // converged-warp issue: the whole warp walks the loop, one elected lane issues
-    const long long t0 = clock64();
-    for (int i = 0; i < iters; ++i) {
-      const int slot = i % n_acc;
-      if (i >= n_acc) mbar_wait(smem_u32(&bars[slot]), ((i / n_acc) - 1) & 1);
-      umma::fence_after_sync();
-      const uint32_t d = tmem + static_cast<uint32_t>(slot * N);
-      if (umma::elect_one()) {
-#pragma unroll
-        for (int h = 0; h < 2; ++h)
-#pragma unroll
-          for (int k = 0; k < 4; ++k) {
-            const uint64_t bd = umma::make_smem_desc_sw128(b_addr + h * b_half + k * 32);
-            const uint64_t ad = umma::make_smem_desc_sw128(a_addr + h * 16384 + k * 32);
-            umma::mma_f16_ss(d, ad, bd, idesc, (h | k) ? 1u : 0u);
-          }
-        umma::commit(smem_u32(&bars[slot]));
-      }
-      __syncwarp();
+    if (tid == 0) {
+      out_cycles[blockIdx.x] = clock64() - t0;
+      s_done = 1;
     }
-    for (int slot = 0; slot < n_acc && slot < iters; ++slot) {
-      const int uses = (iters - slot + n_acc - 1) / n_acc;
-      mbar_wait(smem_u32(&bars[slot]), (uses - 1) & 1);
-    }
-    if (tid == 0) out_cycles[blockIdx.x] = clock64() - t0;
-    s_done = 1;
-  } else if (tid == 0 && !(mode & 4) && warp == 0) {
+  } else if (!(mode & 4) && tid == 0) {
+    // legacy issue path: one thread inside a divergent branch (ptxas wraps every MMA in an ELECT / R2UR loop)
     const uint32_t a_tmem = tmem + ncols - 64;     // TS mode: 128 lanes × 64 columns hold A[128, 128] 16-bit
     const long long t0 = clock64();
-    if (false) {
-      // interleaved issue: consecutive MMAs go to different accumulators (k-step outer, accumulator inner);
-      // `iters` counts tiles, so one round covers n_acc of them
-      const int rounds = iters / n_acc;
-      for (int r = 0; r < rounds; ++r) {
-        if (r >= 2) mbar_wait(smem_u32(&bars[r & 1]), ((r >> 1) - 1) & 1);
-        umma::fence_after_sync();
-#pragma unroll
-        for (int h = 0; h < 2; ++h)
-#pragma unroll
-          for (int k = 0; k < 4; ++k) {
-            const uint64_t bd = umma::make_smem_desc_sw128(b_addr + h * b_half + k * 32);
-            const uint64_t ad = umma::make_smem_desc_sw128(a_addr + h * 16384 + k * 32);
-            for (int slot = 0; slot < n_acc; ++slot) {
-              const uint32_t d = tmem + static_cast<uint32_t>(slot * N);
-              if (mode & 1) umma::mma_f16_ts(d, a_tmem + (h * 4 + k) * 8, bd, idesc, (h | k) ? 1u : 0u);
-              else umma::mma_f16_ss(d, ad, bd, idesc, (h | k) ? 1u : 0u);
-            }
-          }
-        umma::commit(smem_u32(&bars[r & 1]));
-      }
-      for (int b = 0; b < 2 && b < rounds; ++b) {
-        const int uses = (rounds - b + 1) / 2;
-        mbar_wait(smem_u32(&bars[b]), (uses - 1) & 1);
-      }
-      out_cycles[blockIdx.x] = clock64() - t0;
-    } else {
     for (int i = 0; i < iters; ++i) {
       const int slot = i % n_acc;
       if (i >= n_acc) mbar_wait(smem_u32(&bars[slot]), ((i / n_acc) - 1) & 1);
@@ -224,8 +175,7 @@ umma_rate_kernel(int N, uint32_t idesc, int mode, int iters, int n_acc, uint32_t
           if (mode & 1) {
             umma::mma_f16_ts(d, a_tmem + (h * 4 + k) * 8, bd, idesc, (h | k) ? 1u : 0u);
           } else {
-            const uint64_t ad = umma::make_smem_desc_sw128(a_addr + h * 16384 + k * 32);
-            umma::mma_f16_ss(d, ad, bd, idesc, (h | k) ? 1u : 0u);
+            umma::mma_f16_ss(d, umma::make_smem_desc_sw128(a_addr + h * 16384 + k * 32), bd, idesc, (h | k) ? 1u : 0u);
           }
         }
       umma::commit(smem_u32(&bars[slot]));
@@ -235,7 +185,6 @@ umma_rate_kernel(int N, uint32_t idesc, int mode, int iters, int n_acc, uint32_t
       mbar_wait(smem_u32(&bars[slot]), (uses - 1) & 1);
     }
     out_cycles[blockIdx.x] = clock64() - t0;
-    }
     s_done = 1;
   }
   umma::fence_before_sync();
@@ -293,9 +242,12 @@ int umma_rate_dispatch(int N, int mode, int iters, int n_acc, int ctas_per_sm, l
     count_launch();
     return CBK_OK;
   }
-  CBK_CHECK_ARG(N >= 16 && N <= 256 && N % 16 == 0 && iters >= 1 && n_acc >= 1 && n_acc <= 8 && mode >= 0 && mode <= 23 &&
+  CBK_CHECK_ARG(N >= 16 && N <= 256 && N % 16 == 0 && iters >= 2 && n_acc >= 1 && n_acc <= 8 && mode >= 0 && mode <= 23 &&
                     ctas_per_sm >= 1 && ctas_per_sm <= 4 && d_cycles,
                 "cbk_selftest_umma_rate: bad arguments");
+  CBK_CHECK_ARG((mode & 6) != 2 && ((mode & 6) != 6 || (n_acc % 2 == 0 && iters % 2 == 0)) && (!(mode & 1) || !(mode & 4)),
+                "cbk_selftest_umma_rate: mode %d: two issuers need the elect path and even n_acc / iters; TS needs the legacy path",
+                mode);
   const int need = n_acc * N + ((mode & 1) ? 64 : 0);
   uint32_t ncols = 32;
   while (ncols < static_cast<uint32_t>(need)) ncols <<= 1;

@@ -278,9 +278,12 @@ int cbk_selftest_umma_gemm(const void* d_A, const void* d_B, int N, int a_bf16, 
 
 /* Issue-rate probe for the same building block: ctas_per_sm CTAs per SM each run `iters` tiles of
  * [128, N] += A[128, 128] · B[N, 128]^T over resident shared-memory operands, rotating over n_acc TMEM
- * accumulators (mode 0: A from shared memory; mode 1: A from TMEM).  d_cycles [n_SMs * ctas_per_sm] int64
- * receives the clock cycles each CTA took.  Used to place the tensor-bound kernels against what the MMA
- * shape itself can sustain (benchmarks/umma_rate.py).  Not part of the scoring path. */
+ * accumulators; d_cycles [n_SMs * ctas_per_sm] int64 receives the clock cycles each CTA took.  mode bits:
+ * 1 = A operand from TMEM, 4 = issue through elect.sync on a converged warp (otherwise thread 0 in a divergent
+ * branch), 2 = (with 4) two issuing warps, 16 = sixteen more warps read the accumulators back meanwhile.
+ * mode 8: TMEM read rate instead — N = warps per CTA (4/8/12/16), n_acc = loads between waits (1/2).
+ * Used to place the tensor-bound kernels against what the MMA shape itself can sustain
+ * (benchmarks/umma_rate.py).  Not part of the scoring path. */
 int cbk_selftest_umma_rate(int N, int mode, int iters, int n_acc, int ctas_per_sm, int64_t* d_cycles, void* stream);
 
 #ifdef __cplusplus

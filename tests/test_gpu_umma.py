@@ -36,3 +36,20 @@ def test_umma_gemm_with_3d_tensor_map(N):
     C3 = kernels.selftest_umma_gemm(A.to(dev), B.to(dev), tma_3d=True).cpu().double()
     ref = A.double() @ B.double().T
     assert (C3 - ref).abs().max().item() < 2e-3
+
+
+def test_umma_rate_probe_runs_and_elect_issue_is_faster():
+    """cbk_selftest_umma_rate: the measurement behind the issue-path choices of the tcgen05 kernels."""
+    import torch
+    from colbert_b200 import kernels
+    dev = torch.device("cuda", 0)
+    it = 2000
+    legacy = kernels.selftest_umma_rate(128, 0, it, 4, 1, dev).float().mean().item() / it
+    elect = kernels.selftest_umma_rate(128, 4, it, 4, 1, dev).float().mean().item() / it
+    two = kernels.selftest_umma_rate(128, 6, it, 4, 1, dev).float().mean().item() / it
+    torch.cuda.synchronize()
+    assert 400 < two <= elect < legacy < 3000, (legacy, elect, two)     # cycles per 128x128x128 tile; floor 512
+    rd = kernels.selftest_umma_rate(16, 8, 256, 2, 1, dev)
+    assert int(rd.min()) > 0
+    with pytest.raises(Exception):
+        kernels.selftest_umma_rate(128, 2, it, 4, 1, dev)               # two issuers without the elect path
