@@ -230,7 +230,7 @@ def maxsim_exact(store: np.ndarray, doclens: np.ndarray, pfxsum: np.ndarray, str
     out = np.empty(len(pids_a), dtype=np.float32)
     for i in range(len(pids_a)):
         D = store[offs[i]:offs[i] + dl[i]].astype(np.float32)   # [doclen, dim]
-        mx = (Qf @ D.T).max(-1)                                  # [q_len]
+        mx = (Qf @ D.T).max(-1, initial=-np.inf)                 # [q_len]; an empty document has no rows: -inf
         if fl[i]:
             mx = np.maximum(mx, np.float32(0.0))
         out[i] = mx.sum(dtype=np.float32)

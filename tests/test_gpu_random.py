@@ -59,3 +59,34 @@ def test_random_problems_all_kernels(seed):
     full = np.stack([O.maxsim_exact(store, index.doclens, pf, ranker.strides, Q[b], np.arange(index.num_docs)) for b in range(Q.shape[0])])
     rel = np.abs(dense - full) / np.maximum(np.abs(full), 1.0)
     assert rel.max() <= SCORE_RTOL, (seed, "exhaustive", rel.max())
+
+
+@pytest.mark.parametrize("dim", [128, 64])
+def test_empty_documents_score_zero(dim):
+    """Documents of length 0 among the candidates (the reference scores them 0, see tests/test_oracle_properties.py):
+    every rerank kernel — mma.sync, tcgen05, generic width — and the full rank_forward call."""
+    from colbert_b200 import _lib, synthetic
+    from colbert_b200.ranking import ColbertRanker
+    index = synthetic.make_index(977 + dim, 400, dim=dim, lo=0, hi=14)
+    n_empty = int((index.doclens == 0).sum())
+    assert 0 < n_empty < 90
+    ranker = ColbertRanker.from_tensors(torch.from_numpy(index.emb), index.doclens.tolist(), device=DEV)
+    assert 0 not in ranker.strides
+    store, pf = O.pad_store(index.emb), O.doclens_pfxsum(index.doclens)
+    Q = synthetic.make_queries(978, 2, 32, dim)
+    pids = np.arange(400, dtype=np.int64)
+    flat = np.concatenate([pids, pids[::-1]])
+    rowptr = np.array([0, 400, 800], dtype=np.int64)
+    ref = np.concatenate([O.maxsim_exact(store, index.doclens, pf, ranker.strides, Q[0], pids),
+                          O.maxsim_exact(store, index.doclens, pf, ranker.strides, Q[1], pids[::-1])])
+    for flags in ((0, _lib.CBK_FLAG_RERANK_TCGEN05) if dim == 128 else (0,)):
+        ranker.kernel_flags = flags
+        got = ranker.score_candidates(torch.from_numpy(Q).to(DEV), torch.from_numpy(flat).to(DEV),
+                                      torch.from_numpy(rowptr).to(DEV)).cpu().numpy()
+        assert np.all(got[np.concatenate([index.doclens, index.doclens[::-1]]) == 0] == 0.0)
+        rel = np.abs(got - ref) / np.maximum(np.abs(ref), 1.0)
+        assert rel.max() <= SCORE_RTOL, (dim, flags, rel.max())
+    ranker.kernel_flags = 0
+    p, s = ranker.rank_forward(torch.from_numpy(Q[0]).unsqueeze(0).permute(0, 2, 1), pids.tolist(), depth=None)
+    assert sorted(p) == pids.tolist() and all(a >= b for a, b in zip(s, s[1:]))
+    assert all(sc == 0.0 for pid, sc in zip(p, s) if index.doclens[pid] == 0)

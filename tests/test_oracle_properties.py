@@ -46,3 +46,21 @@ def test_packed_keys_order_and_roundtrip(pairs):
     order = np.argsort(keys)[::-1]
     ref_p, ref_s = O.topk_desc(scores, pids, None)
     assert np.array_equal(pids[order], ref_p)
+
+
+def test_empty_documents_score_zero_in_both_formulations():
+    """A document of length 0: the reference gathers the NEXT document's rows under an all-false mask, so every
+    query token's maximum is 0 and the score is 0 (colbert_ranker.py:105-109, BaseModel.py:41-46); the exact-length
+    formulation reaches the same value through the zero floor (0 is not a stride)."""
+    from colbert_b200 import synthetic
+    index = synthetic.make_index(77, 300, dim=32, lo=0, hi=12)
+    assert 0 < int((index.doclens == 0).sum()) < 70
+    strides = O.compute_strides(index.doclens)
+    assert 0 not in strides
+    store, pf = O.pad_store(index.emb), O.doclens_pfxsum(index.doclens)
+    Q = synthetic.make_queries(78, 1, 8, 32)[0]
+    pids = np.arange(300)
+    exact = O.maxsim_exact(store, index.doclens, pf, strides, Q, pids)
+    assert np.all(exact[index.doclens == 0] == 0.0)
+    _, _, ref = O.rank_forward(store, index.doclens, pf, strides, Q.T[None], pids, depth=None, return_all_scores=True)
+    np.testing.assert_allclose(exact, ref, rtol=1e-5, atol=1e-5)
