@@ -213,12 +213,27 @@ class ColbertRanker:
 
     def score_all(self, Q: torch.Tensor) -> torch.Tensor:
         """fp32 ``[B, n_docs]``: every document of this store against every query (``Q`` ``[B, q_len ≤ 32, dim]``
-        fp32 on the device) — the query-batched tcgen05 kernel."""
+        fp32 on the device) — the query-batched tcgen05 kernel.  The kernel walks the
+        store row by row, so documents without rows are taken out first and get the score the reference gives
+        them (0, see tests/test_oracle_properties.py)."""
+        if int(self.doclens.max()) == 0:
+            return torch.zeros((Q.size(0), self.doclens.numel()), dtype=torch.float32, device=self.device)
         if getattr(self, "_doc_end_bits", None) is None:
-            assert int(self.doclens.min()) >= 1, "exhaustive scoring needs every document to have at least one row"
-            self._doc_end_bits = kernels.build_doc_end_bits(self._pfxsum_dev, self.tensor.size(0))
-        return kernels.maxsim_exhaustive(self.tensor, self._pfxsum_dev, self._doc_end_bits, self.strides, Q,
-                                         flags=self.kernel_flags & kernels._lib.CBK_FLAG_BF16_NATIVE_MMA)
+            nonempty = self.doclens > 0
+            if bool(nonempty.all()):
+                self._exh_cols, self._exh_pfxsum = None, self._pfxsum_dev
+            else:
+                idx = torch.nonzero(nonempty).flatten()
+                self._exh_cols = idx.to(self.device)
+                self._exh_pfxsum = torch.cat([self.doclens_pfxsum[idx], self.doclens_pfxsum[-1:]]).to(self.device)
+            self._doc_end_bits = kernels.build_doc_end_bits(self._exh_pfxsum, self.tensor.size(0))
+        dense = kernels.maxsim_exhaustive(self.tensor, self._exh_pfxsum, self._doc_end_bits, self.strides, Q,
+                                          flags=self.kernel_flags & kernels._lib.CBK_FLAG_BF16_NATIVE_MMA)
+        if self._exh_cols is None:
+            return dense
+        full = torch.zeros((Q.size(0), self.doclens.numel()), dtype=torch.float32, device=self.device)
+        full[:, self._exh_cols] = dense
+        return full
 
     def rank_exhaustive(self, Q: torch.Tensor, k: int = 1000) -> Tuple[torch.Tensor, torch.Tensor]:
         """No candidate generation: score the whole store and keep the top ``k`` per query.

@@ -87,6 +87,14 @@ def test_empty_documents_score_zero(dim):
         rel = np.abs(got - ref) / np.maximum(np.abs(ref), 1.0)
         assert rel.max() <= SCORE_RTOL, (dim, flags, rel.max())
     ranker.kernel_flags = 0
+    if dim == 128:   # the exhaustive kernel takes the empty documents out and scatters zeros back
+        dense = ranker.score_all(torch.from_numpy(Q).to(DEV)).cpu().numpy()
+        full = np.stack([O.maxsim_exact(store, index.doclens, pf, ranker.strides, Q[b], pids) for b in range(2)])
+        assert np.all(dense[:, index.doclens == 0] == 0.0)
+        assert (np.abs(dense - full) / np.maximum(np.abs(full), 1.0)).max() <= SCORE_RTOL
+        tp, ts = ranker.rank_exhaustive(torch.from_numpy(Q), k=25)
+        want_p, want_s = O.topk_desc(full[0], pids, 25)
+        assert np.abs(ts[0].cpu().numpy() - want_s).max() <= SCORE_RTOL * np.maximum(np.abs(want_s), 1.0).max()
     p, s = ranker.rank_forward(torch.from_numpy(Q[0]).unsqueeze(0).permute(0, 2, 1), pids.tolist(), depth=None)
     assert sorted(p) == pids.tolist() and all(a >= b for a, b in zip(s, s[1:]))
     assert all(sc == 0.0 for pid, sc in zip(p, s) if index.doclens[pid] == 0)
