@@ -29,10 +29,10 @@ METRIC = "candidates MaxSim-scored/sec (k=1000 rerank)"
 UNIT = "candidates/s"
 
 # dram__bytes_read.sum + dram__bytes_write.sum of ONE maxsim_rerank_kernel launch of the default workload, from the
-# `ncu --set full` capture summarised in profiles/r01_final_rerank_ncu_full_summary.csv (94.984 GB read + 0.017 GB
-# written; algorithmic 94.869 GB — the difference is candidate/query metadata).  Only valid for the default
-# arguments (same seeds → same candidate lists).
-NCU_TRAFFIC_DEFAULT_BYTES = 95_000_589_496
+# `ncu --set full` capture summarised in profiles/r01_end_rerank_ncu_full_summary.csv (95.067 GB read + 0.016 GB
+# written; algorithmic 94.869 GB — the difference is candidate/query metadata and DRAM sector granularity).  Only
+# valid for the default arguments (same seeds → same candidate lists).
+NCU_TRAFFIC_DEFAULT_BYTES = 95_083_146_640
 
 
 def parse_args():
