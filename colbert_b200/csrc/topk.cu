@@ -72,6 +72,171 @@ __device__ __forceinline__ void emit(uint64_t key, int64_t pos, float* out_score
   }
 }
 
+// ---- radix select over dense score rows --------------------------------------------------------------
+// Top-k of a long row (exhaustive scoring: up to millions of documents per query) without sorting it: three
+// histogram levels over the 32-bit ordered score (12 + 12 + 8 bits) locate the k-th largest score; everything above
+// it plus the bin that holds it is compacted (≤ kTopkMaxCand keys, normally ≈ k) and only that is sorted.  A level is
+// skipped as soon as the survivors fit.  The score matrix is read three times instead of being bitonic-sorted in
+// 16384-wide chunks (2.0 → 0.2 ms for 16 × 1.1 M scores, k = 1000).
+constexpr int kSelChunk = 16384;          // scores per CTA
+constexpr int kSelThreads = 256;
+constexpr int kSelBins = 4096;
+
+struct SelState {            // per query, zero-initialised per call
+  uint32_t prefix;           // resolved high bits of the k-th largest ordered score
+  uint32_t bits;             // how many bits are resolved (0, 12, 24, 32)
+  uint32_t k_rem;            // how many of the top k lie inside the current bin
+  uint32_t done;             // survivors (above + inside the bin) fit into kTopkMaxCand: no further level
+  uint32_t n_cand;           // compaction cursor
+  uint32_t overflow;         // more than kTopkMaxCand scores tie with the k-th: this query takes the chunk-sort path
+  uint32_t pad[2];
+};
+
+__device__ __forceinline__ uint32_t sel_key(float x) { return float_to_ordered(x + 0.0f); }   // -0.0 ≡ +0.0
+
+// level L histogram of the scores whose resolved prefix matches; hist [n_queries][kSelBins]
+template <int kLevel>
+__global__ void __launch_bounds__(kSelThreads)
+radix_hist_kernel(const float* __restrict__ scores, int64_t n_docs, const SelState* __restrict__ state,
+                  uint32_t* __restrict__ hist) {
+  __shared__ uint32_t sh[kSelBins];
+  const int64_t q = blockIdx.y;
+  const SelState stq = state[q];
+  if (kLevel > 0 && stq.done) return;
+  constexpr int kShift = kLevel == 0 ? 20 : (kLevel == 1 ? 8 : 0);
+  constexpr uint32_t kMask = kLevel == 2 ? 0xffu : 0xfffu;
+  constexpr int kPrevShift = kLevel == 1 ? 20 : 8;       // (unused at level 0: nothing is resolved yet)
+  for (int i = threadIdx.x; i < kSelBins; i += kSelThreads) sh[i] = 0;
+  __syncthreads();
+  const int64_t first = static_cast<int64_t>(blockIdx.x) * kSelChunk;
+  const int n = static_cast<int>(min(static_cast<int64_t>(kSelChunk), n_docs - first));
+  const float* row = scores + q * n_docs + first;
+  for (int i0 = 0; i0 < n; i0 += kSelThreads) {
+    const int i = i0 + threadIdx.x;
+    bool take = i < n;
+    uint32_t key = 0;
+    if (take) {
+      key = sel_key(row[i]);
+      if (kLevel > 0) take = (key >> kPrevShift) == stq.prefix;
+    }
+    const uint32_t bin = (key >> kShift) & kMask;
+    // scores cluster in a few bins (one binade = 8 level-0 bins): aggregate equal bins inside the warp first
+    const uint32_t act = __ballot_sync(0xffffffffu, take);
+    if (take) {
+      const uint32_t peers = __match_any_sync(act, bin);
+      if ((threadIdx.x & 31) == __ffs(peers) - 1) atomicAdd(&sh[bin], __popc(peers));
+    }
+  }
+  __syncthreads();
+  uint32_t* hq = hist + q * kSelBins;
+  for (int i = threadIdx.x; i < kSelBins; i += kSelThreads)
+    if (sh[i]) atomicAdd(&hq[i], sh[i]);
+}
+
+// one CTA per query: walk the level histogram from the top until k_rem scores are covered
+template <int kLevel>
+__global__ void __launch_bounds__(kSelThreads)
+radix_select_kernel(uint32_t* __restrict__ hist, SelState* __restrict__ state, int k) {
+  __shared__ uint32_t part[kSelThreads];
+  __shared__ uint32_t s_bin, s_above;
+  const int64_t q = blockIdx.x;
+  SelState stq = state[q];
+  if (kLevel > 0 && stq.done) return;
+  if (kLevel == 0) stq.k_rem = static_cast<uint32_t>(k);
+  constexpr int kBins = kLevel == 2 ? 256 : kSelBins;
+  constexpr int kPer = kBins / kSelThreads;              // bins per thread (16 or 1)
+  uint32_t* hq = hist + q * kSelBins;
+  // thread t owns bins [hi - kPer + 1, hi] counted from the top: t = 0 holds the largest bins
+  const int top = kBins - 1 - threadIdx.x * kPer;
+  uint32_t mine = 0;
+#pragma unroll
+  for (int j = 0; j < kPer; ++j) mine += hq[top - j];
+  part[threadIdx.x] = mine;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    uint32_t cum = 0;
+    int t = 0;
+    for (; t < kSelThreads; ++t) {
+      if (cum + part[t] >= stq.k_rem) break;
+      cum += part[t];
+    }
+    // (k_rem ≤ the number of scores that reached this level, so t < kSelThreads)
+    int b = kBins - 1 - t * kPer;
+    for (int j = 0; j < kPer; ++j, --b) {
+      if (cum + hq[b] >= stq.k_rem) break;
+      cum += hq[b];
+    }
+    s_bin = static_cast<uint32_t>(b);
+    s_above = cum;
+  }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    constexpr int kBitsHere = kLevel == 2 ? 8 : 12;
+    const uint32_t in_bin = hq[s_bin];
+    stq.prefix = (stq.prefix << kBitsHere) | s_bin;
+    stq.bits += kBitsHere;
+    stq.k_rem -= s_above;
+    const uint32_t n_above_total = static_cast<uint32_t>(k) - stq.k_rem;      // strictly above the bin, all levels
+    if (n_above_total + in_bin <= static_cast<uint32_t>(kTopkMaxCand)) stq.done = 1;
+    else if (kLevel == 2) stq.overflow = 1;                                    // > kTopkMaxCand exact ties with the k-th
+    state[q] = stq;
+  }
+}
+
+// every score at or above the located bin becomes a packed key in cand[q][0 .. n_cand)
+__global__ void __launch_bounds__(kSelThreads)
+radix_compact_kernel(const float* __restrict__ scores, int64_t n_docs, int64_t pid_base, SelState* __restrict__ state,
+                     uint64_t* __restrict__ cand) {
+  const int64_t q = blockIdx.y;
+  const SelState stq = state[q];
+  if (stq.overflow) return;
+  const int shift = 32 - static_cast<int>(stq.bits);
+  const int64_t first = static_cast<int64_t>(blockIdx.x) * kSelChunk;
+  const int n = static_cast<int>(min(static_cast<int64_t>(kSelChunk), n_docs - first));
+  const float* row = scores + q * n_docs + first;
+  uint64_t* cq = cand + q * kTopkMaxCand;
+  for (int i0 = 0; i0 < n; i0 += kSelThreads) {
+    const int i = i0 + threadIdx.x;
+    uint32_t key = 0;
+    bool take = false;
+    if (i < n) {
+      key = sel_key(row[i]);
+      take = shift >= 32 ? true : (key >> shift) >= stq.prefix;
+    }
+    const uint32_t act = __ballot_sync(0xffffffffu, take);
+    if (act) {
+      uint32_t base = 0;
+      const int lane = threadIdx.x & 31;
+      if (lane == __ffs(act) - 1) base = atomicAdd(&state[q].n_cand, __popc(act));
+      base = __shfl_sync(0xffffffffu, base, __ffs(act) - 1);
+      if (take) {
+        const uint32_t pos = base + __popc(act & ((1u << lane) - 1u));
+        if (pos < static_cast<uint32_t>(kTopkMaxCand))
+          cq[pos] = (static_cast<uint64_t>(key) << 32) | ~static_cast<uint32_t>(pid_base + first + i);
+      }
+    }
+  }
+}
+
+// one CTA per query: sort the survivors, emit the top k
+__global__ void __launch_bounds__(1024)
+radix_final_kernel(const uint64_t* __restrict__ cand, const SelState* __restrict__ state, int k, float* __restrict__ out_scores,
+                   int64_t* __restrict__ out_pids, uint64_t* __restrict__ out_keys) {
+  extern __shared__ uint64_t keys[];
+  const int64_t q = blockIdx.x;
+  const SelState stq = state[q];
+  if (stq.overflow) return;                       // the chunk-sort path writes this query's row
+  const int n = static_cast<int>(min(stq.n_cand, static_cast<uint32_t>(kTopkMaxCand)));
+  const int tid = threadIdx.x;
+  int P = 32;
+  while (P < n) P <<= 1;
+  const uint64_t* cq = cand + q * kTopkMaxCand;
+  for (int i = tid; i < P; i += blockDim.x) keys[i] = i < n ? cq[i] : 0ull;
+  __syncthreads();
+  bitonic_sort_desc(keys, P, tid);
+  for (int i = tid; i < k; i += blockDim.x) emit(i < n ? keys[i] : 0ull, q * k + i, out_scores, out_pids, out_keys);
+}
+
 // One CTA per query: candidates (scores + pids, CSR) → top-k as (scores, pids) or as packed keys.
 __global__ void __launch_bounds__(kTopkThreads)
 topk_per_query_kernel(const float* __restrict__ scores, const int64_t* __restrict__ cand_pids,
@@ -110,10 +275,11 @@ topk_per_query_kernel(const float* __restrict__ scores, const int64_t* __restric
 __global__ void __launch_bounds__(1024)
 merge_topk_keys_kernel(const uint64_t* __restrict__ in_keys, int n_lists, int G, int64_t sw, int64_t sq, int k_in, int Pmax,
                        int k, float* __restrict__ out_scores, int64_t* __restrict__ out_pids,
-                       uint64_t* __restrict__ out_keys) {
+                       uint64_t* __restrict__ out_keys, const SelState* __restrict__ gate) {
   extern __shared__ uint64_t keys[];
   const int g = blockIdx.x;
   const int64_t q = blockIdx.y;
+  if (gate && !gate[q].overflow) return;   // fallback of the radix-select path: only for the queries that need it
   const int first = g * G;
   const int cnt = min(G, n_lists - first);
   const int n = cnt * k_in;
@@ -138,10 +304,11 @@ merge_topk_keys_kernel(const uint64_t* __restrict__ in_keys, int n_lists, int G,
 // (pid = pid_base + column) and emits its top-k keys at out_keys[(q*gridDim.x + c)*k ..].
 __global__ void __launch_bounds__(1024)
 topk_dense_chunks_kernel(const float* __restrict__ scores, int64_t n_docs, int chunk, int64_t pid_base, int k,
-                         uint64_t* __restrict__ out_keys) {
+                         uint64_t* __restrict__ out_keys, const SelState* __restrict__ gate) {
   extern __shared__ uint64_t keys[];
   const int c = blockIdx.x;
   const int64_t q = blockIdx.y;
+  if (gate && !gate[q].overflow) return;
   const int64_t first = static_cast<int64_t>(c) * chunk;
   const int n = static_cast<int>(min(static_cast<int64_t>(chunk), n_docs - first));
   const int tid = threadIdx.x;
@@ -188,7 +355,8 @@ int topk_dispatch(const float* d_scores, const int64_t* d_cand_pids, const int64
 }
 
 static int launch_merge(const uint64_t* in, int n_lists, int G, int64_t sw, int64_t sq, int k_in, int64_t n_queries, int k,
-                        float* out_scores, int64_t* out_pids, uint64_t* out_keys, cudaStream_t stream) {
+                        float* out_scores, int64_t* out_pids, uint64_t* out_keys, cudaStream_t stream,
+                        const SelState* gate = nullptr) {
   const int n_groups = (n_lists + G - 1) / G;
   const int P = padded_pow2(static_cast<int64_t>(std::min(G, n_lists)) * k_in);
   const size_t smem = static_cast<size_t>(P) * sizeof(uint64_t);
@@ -196,7 +364,7 @@ static int launch_merge(const uint64_t* in, int n_lists, int G, int64_t sw, int6
   CBK_CUDA(cudaFuncSetAttribute(merge_topk_keys_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                 static_cast<int>(smem)));
   merge_topk_keys_kernel<<<dim3(n_groups, static_cast<unsigned int>(n_queries)), threads, smem, stream>>>(
-      in, n_lists, G, sw, sq, k_in, P, k, out_scores, out_pids, out_keys);
+      in, n_lists, G, sw, sq, k_in, P, k, out_scores, out_pids, out_keys, gate);
   CBK_CUDA(cudaGetLastError());
   count_launch();
   return CBK_OK;
@@ -210,8 +378,9 @@ int merge_dispatch(const uint64_t* d_keys, int world, int64_t n_queries, int k_i
 
 // ---- top-k over dense score rows [n_queries, n_docs] (exhaustive scoring) ----------------------------
 constexpr int kDenseChunk = 16384;
+constexpr int64_t kRadixMinDocs = 2 * kDenseChunk;      // shorter rows: one or two chunk sorts are cheaper
 
-size_t topk_dense_workspace_bytes(int64_t n_queries, int64_t n_docs, int k) {
+static size_t chunk_sort_workspace_bytes(int64_t n_queries, int64_t n_docs, int k) {
   const int64_t nch = (n_docs + kDenseChunk - 1) / kDenseChunk;
   const int64_t k1 = std::min<int64_t>(k, kDenseChunk);
   const int64_t G = std::max<int64_t>(2, kTopkMaxCand / k1);
@@ -219,8 +388,25 @@ size_t topk_dense_workspace_bytes(int64_t n_queries, int64_t n_docs, int k) {
   return static_cast<size_t>(n_queries * (nch + lvl2) * k1) * sizeof(uint64_t) + 256;
 }
 
-int topk_dense_dispatch(const float* d_scores, int64_t n_queries, int64_t n_docs, int k, int64_t pid_base, int as_keys,
-                        float* d_out_scores, int64_t* d_out_pids, void* d_workspace, cudaStream_t stream) {
+// radix-select scratch: [SelState × B | 3 histograms × B × kSelBins | candidates B × kTopkMaxCand keys]
+static size_t radix_zeroed_bytes(int64_t n_queries) {
+  return static_cast<size_t>(n_queries) * (sizeof(SelState) + 3 * kSelBins * sizeof(uint32_t));
+}
+static size_t radix_workspace_bytes(int64_t n_queries) {
+  return ((radix_zeroed_bytes(n_queries) + 255) & ~static_cast<size_t>(255)) +
+         static_cast<size_t>(n_queries) * kTopkMaxCand * sizeof(uint64_t);
+}
+
+size_t topk_dense_workspace_bytes(int64_t n_queries, int64_t n_docs, int k) {
+  size_t b = chunk_sort_workspace_bytes(n_queries, n_docs, k);
+  if (n_docs > kRadixMinDocs) b += radix_workspace_bytes(n_queries) + 256;
+  return b;
+}
+
+// the chunk-sort path: every 16384-wide chunk is sorted, the per-chunk winners are merged level by level
+static int chunk_sort_dispatch(const float* d_scores, int64_t n_queries, int64_t n_docs, int k, int64_t pid_base, int as_keys,
+                               float* d_out_scores, int64_t* d_out_pids, void* d_workspace, const SelState* gate,
+                               cudaStream_t stream) {
   const int nch = static_cast<int>((n_docs + kDenseChunk - 1) / kDenseChunk);
   const int k1 = static_cast<int>(std::min<int64_t>(k, std::min<int64_t>(kDenseChunk, n_docs)));
   const int G = std::max(2, kTopkMaxCand / k1);
@@ -231,7 +417,7 @@ int topk_dense_dispatch(const float* d_scores, int64_t n_queries, int64_t n_docs
   CBK_CUDA(cudaFuncSetAttribute(topk_dense_chunks_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                 static_cast<int>(smem)));
   topk_dense_chunks_kernel<<<dim3(nch, static_cast<unsigned int>(n_queries)), P >= 4096 ? 1024 : kTopkThreads, smem, stream>>>(
-      d_scores, n_docs, kDenseChunk, pid_base, k1, bufA);
+      d_scores, n_docs, kDenseChunk, pid_base, k1, bufA, gate);
   CBK_CUDA(cudaGetLastError());
   count_launch();
   int n_lists = nch;
@@ -242,13 +428,46 @@ int topk_dense_dispatch(const float* d_scores, int64_t n_queries, int64_t n_docs
     const bool last = n_groups == 1;
     int rc = launch_merge(in, n_lists, G, k1, static_cast<int64_t>(n_lists) * k1, k1, n_queries, last ? k : k1,
                           (last && !as_keys) ? d_out_scores : nullptr, (last && !as_keys) ? d_out_pids : nullptr,
-                          last ? (as_keys ? reinterpret_cast<uint64_t*>(d_out_pids) : nullptr) : out, stream);
+                          last ? (as_keys ? reinterpret_cast<uint64_t*>(d_out_pids) : nullptr) : out, stream, gate);
     if (rc != CBK_OK) return rc;
     if (last) break;
     n_lists = n_groups;
     std::swap(in, out);
   }
   return CBK_OK;
+}
+
+int topk_dense_dispatch(const float* d_scores, int64_t n_queries, int64_t n_docs, int k, int64_t pid_base, int as_keys,
+                        float* d_out_scores, int64_t* d_out_pids, void* d_workspace, cudaStream_t stream) {
+  if (n_docs <= kRadixMinDocs)
+    return chunk_sort_dispatch(d_scores, n_queries, n_docs, k, pid_base, as_keys, d_out_scores, d_out_pids, d_workspace, nullptr,
+                               stream);
+  // radix select; the chunk-sort kernels follow, gated per query on SelState::overflow (more than kTopkMaxCand scores
+  // tied with the k-th — they exit at once otherwise), so the result is exact without a host round trip
+  char* ws = static_cast<char*>(d_workspace);
+  ws += (256 - (reinterpret_cast<uintptr_t>(ws) & 255)) & 255;
+  SelState* state = reinterpret_cast<SelState*>(ws);
+  uint32_t* hist = reinterpret_cast<uint32_t*>(ws + static_cast<size_t>(n_queries) * sizeof(SelState));
+  uint64_t* cand = reinterpret_cast<uint64_t*>(ws + ((radix_zeroed_bytes(n_queries) + 255) & ~static_cast<size_t>(255)));
+  void* chunk_ws = ws + radix_workspace_bytes(n_queries);
+  CBK_CUDA(cudaMemsetAsync(state, 0, radix_zeroed_bytes(n_queries), stream));
+  const dim3 grid(static_cast<unsigned int>((n_docs + kSelChunk - 1) / kSelChunk), static_cast<unsigned int>(n_queries));
+  const unsigned int nq = static_cast<unsigned int>(n_queries);
+  const size_t hstride = static_cast<size_t>(n_queries) * kSelBins;
+  radix_hist_kernel<0><<<grid, kSelThreads, 0, stream>>>(d_scores, n_docs, state, hist);
+  radix_select_kernel<0><<<nq, kSelThreads, 0, stream>>>(hist, state, k);
+  radix_hist_kernel<1><<<grid, kSelThreads, 0, stream>>>(d_scores, n_docs, state, hist + hstride);
+  radix_select_kernel<1><<<nq, kSelThreads, 0, stream>>>(hist + hstride, state, k);
+  radix_hist_kernel<2><<<grid, kSelThreads, 0, stream>>>(d_scores, n_docs, state, hist + 2 * hstride);
+  radix_select_kernel<2><<<nq, kSelThreads, 0, stream>>>(hist + 2 * hstride, state, k);
+  radix_compact_kernel<<<grid, kSelThreads, 0, stream>>>(d_scores, n_docs, pid_base, state, cand);
+  const size_t smem = static_cast<size_t>(kTopkMaxCand) * sizeof(uint64_t);
+  CBK_CUDA(cudaFuncSetAttribute(radix_final_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
+  radix_final_kernel<<<nq, 1024, smem, stream>>>(cand, state, k, as_keys ? nullptr : d_out_scores, as_keys ? nullptr : d_out_pids,
+                                                 as_keys ? reinterpret_cast<uint64_t*>(d_out_pids) : nullptr);
+  CBK_CUDA(cudaGetLastError());
+  count_launch(8);
+  return chunk_sort_dispatch(d_scores, n_queries, n_docs, k, pid_base, as_keys, d_out_scores, d_out_pids, chunk_ws, state, stream);
 }
 
 }  // namespace cbk

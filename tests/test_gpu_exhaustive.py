@@ -67,6 +67,42 @@ def test_topk_dense_matches_oracle(n_docs, k):
         assert np.array_equal(tp[b].cpu().numpy(), rp) and np.array_equal(ts[b].cpu().numpy(), rs)
 
 
+@pytest.mark.parametrize("case", ["normal_k8192", "just_over_threshold", "massive_ties", "two_values", "negatives_and_zeros",
+                                  "clustered"])
+def test_topk_dense_radix_select(case):
+    """Rows long enough for the radix-select path (> 32768 scores): exact top-k in the total order (score desc, pid asc)
+    including when more than 16384 scores tie with the k-th (those queries fall back to the chunk sort on the device)."""
+    from colbert_b200 import kernels
+    rng = np.random.default_rng(sum(map(ord, case)))
+    n_docs, k, B = 200_000, 1000, 3
+    if case == "normal_k8192":
+        sc, k = rng.standard_normal((B, n_docs)).astype(np.float32) * 7 + 20, 8192
+    elif case == "just_over_threshold":
+        n_docs = 32_769
+        sc = rng.standard_normal((B, n_docs)).astype(np.float32)
+    elif case == "massive_ties":
+        sc = rng.integers(0, 3, size=(B, n_docs)).astype(np.float32)             # ~66 k scores tie with the k-th
+    elif case == "two_values":
+        sc = np.zeros((B, n_docs), dtype=np.float32)
+        sc[:, ::1000] = 5.0                                                       # 200 winners, then 199 800 ties at 0
+    elif case == "negatives_and_zeros":
+        sc = -np.abs(rng.standard_normal((B, n_docs))).astype(np.float32)
+        sc[:, rng.integers(0, n_docs, 300)] = 0.0
+        sc[:, rng.integers(0, n_docs, 300)] = -0.0                                # -0.0 ties with +0.0, lower pid first
+    else:   # clustered: everything inside one binade, differences in the low mantissa bits only
+        sc = (16.0 + rng.integers(0, 4000, size=(B, n_docs)) * np.float32(2.0 ** -19)).astype(np.float32)
+    dev_sc = torch.from_numpy(sc).to(DEV)
+    ts, tp = kernels.topk_dense(dev_sc, k, pid_base=7)
+    keys = kernels.topk_dense(dev_sc, k, pid_base=7, as_keys=True)
+    pids = np.arange(n_docs, dtype=np.int64) + 7
+    for b in range(B):
+        rp, rs = O.topk_desc(sc[b] + np.float32(0.0), pids, k)
+        assert np.array_equal(tp[b].cpu().numpy(), rp), case
+        assert np.array_equal(ts[b].cpu().numpy(), rs + np.float32(0.0)), case
+        ks, kp = O.unpack_keys(keys[b].cpu().numpy())
+        assert np.array_equal(kp, rp) and np.array_equal(ks, rs + np.float32(0.0)), case
+
+
 def test_rank_exhaustive_topk():
     from colbert_b200 import synthetic
     from colbert_b200.ranking import ColbertRanker
