@@ -295,6 +295,34 @@ def run_ours(args, rank, world, local_rank):
     ms_total = t0.elapsed_time(t1)
     kern_ms = sum(a.elapsed_time(b) for a, b in zip(ev_k0, ev_k1)) / args.steps
 
+    # ---- where a sharded step spends its time (outside the timed region; reported as `phases_ms`) -------
+    phases = None
+    if sharded is not None:
+        names = ["partition", "maxsim", "topk_keys", "all_gather", "merge"]
+        acc = [0.0] * len(names)
+        n_probe = 3
+        for _ in range(n_probe):
+            ev = [torch.cuda.Event(enable_timing=True) for _ in range(len(names) + 1)]
+            ev[0].record()
+            pids_i, rowptr_i = kernels.partition_candidates(cand_dev, rowptr, rank * args.docs, (rank + 1) * args.docs)
+            ev[1].record()
+            scores = ranker.score_candidates(Q_dev, pids_i, rowptr_i)
+            ev[2].record()
+            keys = kernels.topk_per_query(scores, pids_i, rowptr_i, k, args.cands, flags=_lib.CBK_TOPK_NEG_INF_IS_PADDING,
+                                          as_keys=True)
+            ev[3].record()
+            gathered = sharded._exchange(keys)
+            ev[4].record()
+            sharded._merge(gathered, k)
+            ev[5].record()
+            torch.cuda.synchronize()
+            for j in range(len(names)):
+                acc[j] += ev[j].elapsed_time(ev[j + 1]) / n_probe
+        pt = torch.tensor(acc, dtype=torch.float64, device=dev)
+        dist.all_reduce(pt, op=dist.ReduceOp.MAX)
+        phases = {n: round(v, 4) for n, v in zip(names, pt.tolist())}
+        barrier()
+
     # ---- end to end through the public API with host buffers: `e2e` ---------------------------------
     # Public serving API: RerankPipeline.submit(pinned host inputs) / .result() → pinned host outputs.  Every step
     # copies its own inputs host→device and its results device→host inside the timed region; consecutive steps
@@ -371,6 +399,8 @@ def run_ours(args, rank, world, local_rank):
             "gpu_launches": int(launches),
             "clocks": clocks,
         }
+        if phases is not None:
+            line["phases_ms"] = phases          # max over ranks, measured on 3 extra steps after the timed region
         if world == 1 and not args.no_cpu_baseline:
             arm = CpuArm(args.cpu_queries, args.cands, args.depth)
             best = min(arm.run() for _ in range(2))
