@@ -160,9 +160,11 @@ radix_select_kernel(uint32_t* __restrict__ hist, SelState* __restrict__ state, i
       if (cum + part[t] >= stq.k_rem) break;
       cum += part[t];
     }
-    // (k_rem ≤ the number of scores that reached this level, so t < kSelThreads)
+    // k_rem ≤ the number of scores that reached this level, so the walk ends inside the histogram; the clamps only
+    // keep a violated precondition from reading out of bounds
+    t = min(t, kSelThreads - 1);
     int b = kBins - 1 - t * kPer;
-    for (int j = 0; j < kPer; ++j, --b) {
+    for (int j = 0; j < kPer - 1; ++j, --b) {
       if (cum + hq[b] >= stq.k_rem) break;
       cum += hq[b];
     }
