@@ -58,6 +58,12 @@ def test_invalid_arguments_are_reported_not_crashed(built_lib):
     assert rc == -1
     rc = lib.cbk_gather_rows(None, 0, 1, 128, None, None, 1, None, 1, 1, None, None, None)
     assert rc == -1
+    rc = lib.cbk_rank_forward_host(None, 0, 10, 128, None, None, 1, 0, None, 0, None, 32, 1, None, 5, 3, None, None, None, None, 0, 0, None)
+    assert rc == -1 and b"cbk_rank_forward_host" in lib.cbk_last_error()
+    assert lib.cbk_rank_forward_scratch_bytes(1000, 32, 128, 10) >= 1000 * 12 + 32 * 128 * 4 + 256
+    assert lib.cbk_rank_forward_scratch_bytes(0, 32, 128, 10) == 0
+    rc = lib.cbk_selftest_umma_rate(128, 2, 100, 4, 1, None, None)                 # no output buffer
+    assert rc != 0
     with pytest.raises(_lib.CbkError):
         _lib.check("cbk_gather_rows", rc)
 
