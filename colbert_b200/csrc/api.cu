@@ -304,11 +304,19 @@ int cbk_rank_forward_host(const void* d_store, int store_dtype, int64_t n_store_
                              reinterpret_cast<const float*>(dp + L.q), q_len, 1, d_pids, d_rowptr, n, d_scores, dp, 256,
                              flags, stream);
   if (rc != CBK_OK) return rc;
-  rc = cbk_topk_per_query(d_scores, d_pids, d_rowptr, 1, n, k, 0, reinterpret_cast<float*>(dp + L.out_scores),
-                          reinterpret_cast<int64_t*>(dp + L.out_pids), stream);
+  // the k winners go straight into the page-locked scratch when the device can address it (unified addressing maps
+  // every cudaHostAlloc'ed buffer): one copy engine round trip less per call
+  void* mapped = nullptr;
+  const bool zero_copy = cudaHostGetDevicePointer(&mapped, hp, 0) == cudaSuccess && mapped != nullptr;
+  if (!zero_copy) (void)cudaGetLastError();
+  char* op = zero_copy ? static_cast<char*>(mapped) : dp;
+  rc = cbk_topk_per_query(d_scores, d_pids, d_rowptr, 1, n, k, 0, reinterpret_cast<float*>(op + L.out_scores),
+                          reinterpret_cast<int64_t*>(op + L.out_pids), stream);
   if (rc != CBK_OK) return rc;
-  const size_t out_bytes = sizeof(int64_t) * k + sizeof(float) * k;
-  CBK_CUDA(cudaMemcpyAsync(hp + L.out_pids, dp + L.out_pids, out_bytes, cudaMemcpyDeviceToHost, st));
+  if (!zero_copy) {
+    const size_t out_bytes = sizeof(int64_t) * k + sizeof(float) * k;
+    CBK_CUDA(cudaMemcpyAsync(hp + L.out_pids, dp + L.out_pids, out_bytes, cudaMemcpyDeviceToHost, st));
+  }
   CBK_CUDA(cudaStreamSynchronize(st));
   memcpy(h_out_pids, hp + L.out_pids, sizeof(int64_t) * k);
   memcpy(h_out_scores, hp + L.out_scores, sizeof(float) * k);

@@ -331,9 +331,10 @@ int launch(const TmapSet& tmaps, const int64_t* pfxsum, const int32_t* doclens, 
   CBK_CUDA(cudaFuncSetAttribute(maxsim_rerank_kernel<T, kCvtBf16>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                 static_cast<int>(smem)));
   // work unit = segment of consecutive candidates claimed by one warp: 64 for big batches (amortises the claim and
-  // the metadata fetch), down to 4 for a single query so that its ~1000 candidates still spread over every SM
+  // the metadata fetch), down to 1 for a single query so that each of its ~1000 candidates gets a warp of its own
+  // (1776 resident warps): the call is latency-bound, not bandwidth-bound
   const int64_t warps_total = static_cast<int64_t>(sm_count()) * kCtasPerSm * kWarps;
-  const int seg_cands = static_cast<int>(std::max<int64_t>(4, std::min<int64_t>(kSegCands, n_cand / (2 * warps_total))));
+  const int seg_cands = static_cast<int>(std::max<int64_t>(1, std::min<int64_t>(kSegCands, n_cand / (2 * warps_total))));
   const int64_t n_segs = (n_cand + seg_cands - 1) / seg_cands;
   const int64_t want = (n_segs + kWarps - 1) / kWarps;
   const int grid = static_cast<int>(std::max<int64_t>(1, std::min<int64_t>(want, static_cast<int64_t>(sm_count()) * kCtasPerSm)));

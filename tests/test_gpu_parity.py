@@ -204,6 +204,38 @@ def test_topk_kernel_total_order_and_padding(dev):
             assert np.all(tp[b, kk:] == -1) and np.all(np.isneginf(ts[b, kk:]))
 
 
+@pytest.mark.parametrize("as_keys", [False, True])
+def test_topk_small_lists_tournament_path(dev, as_keys):
+    """Lists of at most 1024 candidates with k ≤ 32 take the in-register tournament kernel (the reference's own call:
+    1000 candidates, depth 10): same total order as the sort, including ties, -0.0, -inf padding, short lists."""
+    from colbert_b200 import _lib, kernels
+    rng = np.random.default_rng(55)
+    lens = [0, 1, 2, 31, 32, 33, 64, 65, 500, 1000, 1023, 1024]
+    sc = [np.round(rng.standard_normal(l), 1).astype(np.float32) for l in lens]   # rounding → many exact ties
+    sc[8][:7] = -np.inf
+    sc[9][::50] = -0.0
+    sc[9][1::50] = 0.0
+    ids = [rng.permutation(1_000_000)[:l].astype(np.int64) for l in lens]
+    rowptr = np.concatenate([[0], np.cumsum(lens)]).astype(np.int64)
+    flat_s, flat_i = torch.from_numpy(np.concatenate(sc)).to(dev), torch.from_numpy(np.concatenate(ids)).to(dev)
+    for k in (1, 10, 32):
+        for flags in (0, _lib.CBK_TOPK_NEG_INF_IS_PADDING):
+            got = kernels.topk_per_query(flat_s, flat_i, torch.from_numpy(rowptr).to(dev), k, 1024, flags=flags, as_keys=as_keys)
+            if as_keys:
+                ts, tp = O.unpack_keys(got.cpu().numpy())
+            else:
+                ts, tp = got[0].cpu().numpy(), got[1].cpu().numpy()
+            for b, l in enumerate(lens):
+                s_b, i_b = sc[b] + np.float32(0.0), ids[b]
+                if flags:
+                    keep = ~np.isneginf(s_b)
+                    s_b, i_b = s_b[keep], i_b[keep]
+                rp, rs = O.topk_desc(s_b, i_b, k)
+                kk = len(rp)
+                assert np.array_equal(tp[b, :kk], rp) and np.array_equal(ts[b, :kk], rs), (k, flags, l)
+                assert np.all(tp[b, kk:] == -1) and np.all(np.isneginf(ts[b, kk:]))
+
+
 def test_gather_rows_bit_exact(dev):
     from colbert_b200 import kernels, synthetic
     index = synthetic.make_index(17, 200, dim=128, lo=1, hi=50)
