@@ -21,6 +21,7 @@ CBK_MAX_QLEN = 32
 CBK_FLAG_BF16_NATIVE_MMA = 1
 CBK_FLAG_SKIP_FOREIGN_PIDS = 2
 CBK_FLAG_RERANK_TCGEN05 = 4
+CBK_FLAG_RERANK_GENERIC = 8
 CBK_TOPK_NEG_INF_IS_PADDING = 1
 
 # name → (restype, argtypes); mirrors include/colbert_b200.h one to one

@@ -33,6 +33,9 @@ int emb2pid_dispatch(const int64_t*, int64_t, int32_t*, cudaStream_t);
 int unique_pids_dispatch(const int64_t*, int64_t, int, const int32_t*, int64_t, int64_t*, int64_t*, void*, cudaStream_t);
 int rerank_generic_dispatch(const void*, int, int64_t, int, const int64_t*, const int32_t*, int64_t, int64_t, const int32_t*, int,
                             const float*, int, int64_t, const int64_t*, const int64_t*, float*, int, cudaStream_t);
+bool rerank_wide_supports(int dim);
+int rerank_wide_dispatch(const void*, int, int64_t, int, const int64_t*, const int32_t*, int64_t, int64_t, const int32_t*, int,
+                         const float*, int, int64_t, const int64_t*, const int64_t*, int64_t, float*, void*, int, cudaStream_t);
 int rerank_umma_dispatch(const void*, int, int64_t, int, const int64_t*, const int32_t*, int64_t, int64_t, const int32_t*, int,
                          const float*, int, int64_t, const int64_t*, const int64_t*, int64_t, float*, void*, int, cudaStream_t);
 int umma_probe_dispatch(const void*, const void*, int, int, int, float*, cudaStream_t);
@@ -129,6 +132,29 @@ int make_store_tensor_map_3d(CUtensorMap* out, const void* base, int64_t rows, i
   return CBK_OK;
 }
 
+// The same idea for any width that is a multiple of 64: {64 columns, rows, dim/64 slabs}, byte strides {2*dim (row),
+// 128 (slab)}, box {64, box_rows, dim/64} ⇒ shared memory [slab][row][64 columns], each slab swizzled on its own.
+int make_store_tensor_map_3d_wide(CUtensorMap* out, const void* base, int64_t rows, int dim, int box_rows) {
+  EncodeTiledFn fn = encode_tiled_fn();
+  if (!fn) {
+    set_error("cuTensorMapEncodeTiled is not available from the installed driver");
+    return CBK_ERR_CUDA;
+  }
+  const cuuint64_t gdim[3] = {64, static_cast<cuuint64_t>(rows), static_cast<cuuint64_t>(dim / 64)};
+  const cuuint64_t gstride[2] = {static_cast<cuuint64_t>(dim) * 2, 128};
+  const cuuint32_t box[3] = {64, static_cast<cuuint32_t>(box_rows), static_cast<cuuint32_t>(dim / 64)};
+  const cuuint32_t estride[3] = {1, 1, 1};
+  CUresult r = fn(out, CU_TENSOR_MAP_DATA_TYPE_UINT16, 3, const_cast<void*>(base), gdim, gstride, box, estride,
+                  CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                  CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) {
+    set_error("cuTensorMapEncodeTiled (3-D, dim %d) failed with CUresult %d (rows %lld box_rows %d)", dim, static_cast<int>(r),
+              static_cast<long long>(rows), box_rows);
+    return CBK_ERR_CUDA;
+  }
+  return CBK_OK;
+}
+
 static int check_device() {
   int dev = 0;
   CBK_CUDA(cudaGetDevice(&dev));
@@ -190,7 +216,12 @@ int cbk_maxsim_rerank(const void* d_store, int store_dtype, int64_t n_store_rows
   int rc = check_device();
   if (rc != CBK_OK) return rc;
   if (n_cand_total == 0) return CBK_OK;
-  if (dim != 128)   // generic-width path (CUDA cores); the tensor-core kernel is specialised for dim = 128
+  if (dim != 128 && !(flags & CBK_FLAG_RERANK_GENERIC) && rerank_wide_supports(dim) &&
+      (reinterpret_cast<uintptr_t>(d_store) & 0xf) == 0)
+    return rerank_wide_dispatch(d_store, store_dtype, n_store_rows, dim, d_pfxsum, d_doclens, n_docs, pid_base, strides, n_strides,
+                                d_Q, q_len, n_queries, d_cand_pids, d_cand_rowptr, n_cand_total, d_out_scores, d_workspace, flags,
+                                static_cast<cudaStream_t>(stream));   // K-split tensor-core kernel: dim = 64, 192, …, 768, 1024
+  if (dim != 128)   // any other width (CUDA cores)
     return rerank_generic_dispatch(d_store, store_dtype, n_store_rows, dim, d_pfxsum, d_doclens, n_docs, pid_base, strides,
                                    n_strides, d_Q, q_len, n_queries, d_cand_pids, d_cand_rowptr, d_out_scores, flags,
                                    static_cast<cudaStream_t>(stream));

@@ -44,6 +44,7 @@ extern "C" {
 #define CBK_FLAG_BF16_NATIVE_MMA 1
 #define CBK_FLAG_RERANK_TCGEN05 4       /* score with the tcgen05 / TMEM kernel instead of the mma.sync one */
 #define CBK_FLAG_SKIP_FOREIGN_PIDS 2   /* sharded stores: a pid outside this shard scores -inf, not NaN */
+#define CBK_FLAG_RERANK_GENERIC 8       /* dim != 128: score with the CUDA-core kernel even where the tensor-core one applies */
 #define CBK_TOPK_NEG_INF_IS_PADDING 1  /* top-k: candidates scored -inf are dropped (sharded rerank) */
 
 typedef enum cbk_status {
@@ -112,8 +113,10 @@ uint64_t cbk_launch_count(void);
  *                  bf16 values are multiplied directly with the query rounded to bf16 (8 bits; 1.2e-3,
  *                  outside the 1e-3 parity tolerance but safe for stores beyond fp16's range).
  *
- * Supported: 1 ≤ q_len ≤ CBK_MAX_QLEN, n_store_rows < 2^31; dim == 128 runs the TMA + tensor-core kernel, any
- * other dim in [1, 1536] a generic CUDA-core kernel with the same results contract (fp32 arithmetic).  pids are range-checked on
+ * Supported: 1 ≤ q_len ≤ CBK_MAX_QLEN, n_store_rows < 2^31; dim == 128 runs the TMA + tensor-core kernel the
+ * benchmarks quote, any other multiple of 64 up to 1024 (the author's configuration: 768) a K-split TMA + tensor-core
+ * kernel, any other dim in [1, 1536] a generic CUDA-core kernel with the same results contract (fp32 arithmetic;
+ * CBK_FLAG_RERANK_GENERIC forces it).  pids are range-checked on
  * the device; an out-of-range pid yields NaN at its position.
  * ------------------------------------------------------------------------------------------------ */
 size_t cbk_maxsim_rerank_workspace_bytes(void);

@@ -1,0 +1,66 @@
+"""K-split tensor-core rerank kernel for wide embeddings (dim a multiple of 64 other than 128; the author's configuration
+uses 768) against the oracle and against the generic CUDA-core kernel."""
+import numpy as np
+import pytest
+import torch
+
+from oracle import maxsim_oracle as O
+from parity_utils import SCORE_RTOL, check_topk
+
+pytestmark = [pytest.mark.gpu, pytest.mark.timeout(300)]
+DEV = torch.device("cuda", 0)
+
+
+@pytest.mark.parametrize("dim", [64, 192, 256, 384, 512, 768, 1024])
+@pytest.mark.parametrize("dt", [torch.float16, torch.bfloat16], ids=["fp16", "bf16"])
+def test_wide_rerank_matches_oracle_and_generic(dim, dt):
+    from colbert_b200 import _lib, synthetic
+    from colbert_b200.ranking import ColbertRanker
+    rng = np.random.default_rng(dim)
+    doclens = np.concatenate([rng.integers(1, 200, size=250), [0, 0, 1, 15, 16, 17, 31, 32, 33, 400]]).astype(np.int64)
+    index = synthetic.make_index(900 + dim, len(doclens), dim=dim, doclens=doclens)
+    emb = torch.from_numpy(index.emb).to(dt)
+    ranker = ColbertRanker.from_tensors(emb, index.doclens.tolist(), device=DEV, store_dtype=dt)
+    store, pf = O.pad_store(emb.float().numpy()), O.doclens_pfxsum(index.doclens)
+    for q_len in (32, 7):
+        n_q = 5
+        Q = synthetic.make_queries(901 + q_len, n_q, q_len, dim)
+        lens = [0, 1, 40, 97, 260]
+        cands = [rng.integers(0, index.num_docs, size=l).astype(np.int64) for l in lens]
+        cands[4][:10] = np.arange(250, 260)                                        # the edge-length documents
+        flat = np.concatenate(cands)
+        rowptr = np.concatenate([[0], np.cumsum(lens)]).astype(np.int64)
+        ref = np.concatenate([O.maxsim_exact(store, index.doclens, pf, ranker.strides, Q[b], cands[b]) if lens[b] else
+                              np.zeros(0, np.float32) for b in range(n_q)])
+        got = {}
+        for name, flags in (("wide", 0), ("generic", _lib.CBK_FLAG_RERANK_GENERIC)):
+            ranker.kernel_flags = flags
+            got[name] = ranker.score_candidates(torch.from_numpy(Q).to(DEV), torch.from_numpy(flat).to(DEV),
+                                                torch.from_numpy(rowptr).to(DEV)).cpu().numpy()
+            rel = np.abs(got[name] - ref) / np.maximum(np.abs(ref), 1.0)
+            assert rel.max() <= SCORE_RTOL, (dim, q_len, name, rel.max())
+        assert np.abs(got["wide"] - got["generic"]).max() <= SCORE_RTOL * max(1.0, np.abs(ref).max())
+    ranker.kernel_flags = 0
+
+
+def test_wide_rerank_foreign_pids_and_rank_forward():
+    """dim 768 end to end through rank_forward, plus out-of-range pids (NaN, or -inf on a shard)."""
+    from colbert_b200 import _lib, synthetic
+    from colbert_b200.ranking import ColbertRanker
+    dim = 768
+    index = synthetic.make_index(77, 600, dim=dim, lo=1, hi=120)
+    ranker = ColbertRanker.from_tensors(torch.from_numpy(index.emb), index.doclens.tolist(), device=DEV)
+    store, pf = O.pad_store(index.emb), O.doclens_pfxsum(index.doclens)
+    Q = synthetic.make_queries(78, 1, 32, dim)[0]
+    pids = np.random.default_rng(79).permutation(600)[:300].astype(np.int64)
+    p, s = ranker.rank_forward(torch.from_numpy(Q).unsqueeze(0).permute(0, 2, 1), pids.tolist(), depth=20)
+    ref = O.maxsim_exact(store, index.doclens, pf, ranker.strides, Q, pids)
+    rp, rs = O.topk_desc(ref, pids, 20)
+    check_topk(p, s, rp, rs, SCORE_RTOL, *O.topk_desc(ref, pids, None))
+    bad = torch.tensor([5, 600, -1, 7], dtype=torch.int64, device=DEV)
+    rp2 = torch.tensor([0, 4], dtype=torch.int64, device=DEV)
+    sc = ranker.score_candidates(torch.from_numpy(Q[None]).to(DEV), bad, rp2).cpu().numpy()
+    assert np.isnan(sc[1]) and np.isnan(sc[2]) and np.isfinite(sc[0]) and np.isfinite(sc[3])
+    ranker.kernel_flags = _lib.CBK_FLAG_SKIP_FOREIGN_PIDS
+    sc = ranker.score_candidates(torch.from_numpy(Q[None]).to(DEV), bad, rp2).cpu().numpy()
+    assert np.isneginf(sc[1]) and np.isneginf(sc[2])
