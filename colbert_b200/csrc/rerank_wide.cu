@@ -56,8 +56,10 @@ struct WideCtl {                          // static shared memory
   unsigned int seg;
 };
 
-template <typename T, bool kCvtBf16>
-__global__ void __launch_bounds__(kWThreads, 1)
+// kMaxKs: k-steps per warp this instantiation can hold (dim ≤ 128·kMaxKs); kCtas: CTAs per SM it is compiled for — narrower
+// rows need fewer query registers, and two resident CTAs overlap one's block barrier and reduction with the other's MMAs
+template <typename T, bool kCvtBf16, int kMaxKs, int kCtas>
+__global__ void __launch_bounds__(kWThreads, kCtas)
 maxsim_wide_kernel(const __grid_constant__ CUtensorMap tmap, const int64_t* __restrict__ pfxsum,
                    const int32_t* __restrict__ doclens, int64_t n_docs, int64_t pid_base, int skip_foreign, StrideSet strides,
                    const float* __restrict__ Q, int q_len, int dim, int64_t n_queries, const int64_t* __restrict__ cand_pids,
@@ -90,7 +92,7 @@ maxsim_wide_kernel(const __grid_constant__ CUtensorMap tmap, const int64_t* __re
   uint32_t p_stage = 0;                   // producer: next stage to fill
   uint32_t c_stage = 0, c_parity = 0;     // consumer: next stage to read / parity of its next full phase
   int64_t cur_q = -1;
-  uint32_t qa[2][kWMaxKs][4];             // A fragments of my slice of the current query: [m-tile][k-step][reg]
+  uint32_t qa[2][kMaxKs][4];              // A fragments of my slice of the current query: [m-tile][k-step][reg]
   int buf = 0;
 
   // ldmatrix.x4 of one k-step: matrices 0/1 = tokens 0-7, columns k..k+7 / k+8..k+15; matrices 2/3 = tokens 8-15
@@ -178,7 +180,7 @@ maxsim_wide_kernel(const __grid_constant__ CUtensorMap tmap, const int64_t* __re
           const int r0 = mt * 16 + (lane >> 2);
           const int r1 = r0 + 8;
 #pragma unroll
-          for (int j = 0; j < kWMaxKs; ++j) {
+          for (int j = 0; j < kMaxKs; ++j) {
             if (j < my_nks) {
               const int k0 = (my_ks0 + j) * 16 + 2 * (lane & 3);
               float2 v00 = make_float2(0.f, 0.f), v10 = v00, v01 = v00, v11 = v00;
@@ -214,9 +216,9 @@ maxsim_wide_kernel(const __grid_constant__ CUtensorMap tmap, const int64_t* __re
 #pragma unroll
             for (int r = 0; r < 4; ++r) acc[s][mt][r] = 0.f;
         // all of my B fragments first (their shared-memory latencies overlap), then the MMAs
-        uint32_t bf[kWMaxKs][4];
+        uint32_t bf[kMaxKs][4];
 #pragma unroll
-        for (int j = 0; j < kWMaxKs; ++j) {
+        for (int j = 0; j < kMaxKs; ++j) {
           if (j < my_nks) {
             const int ks = my_ks0 + j;
             const int chunk = ((ks & 3) << 1) + lhalf;          // 16-byte chunk inside the 128-byte slab row
@@ -225,7 +227,7 @@ maxsim_wide_kernel(const __grid_constant__ CUtensorMap tmap, const int64_t* __re
           }
         }
 #pragma unroll
-        for (int j = 0; j < kWMaxKs; ++j) {
+        for (int j = 0; j < kMaxKs; ++j) {
           if (j < my_nks) {
             uint32_t b0 = bf[j][0], b1 = bf[j][1], b2 = bf[j][2], b3 = bf[j][3];
             if (kCvtBf16) {
@@ -289,25 +291,40 @@ maxsim_wide_kernel(const __grid_constant__ CUtensorMap tmap, const int64_t* __re
   }
 }
 
+template <typename T, bool kCvtBf16, int kMaxKs, int kCtas>
+int launch_wide_as(const CUtensorMap& tmap, const int64_t* pfxsum, const int32_t* doclens, int64_t n_docs, int64_t pid_base,
+                   int skip_foreign, const StrideSet& strides, const float* Q, int q_len, int dim, int64_t n_queries,
+                   const int64_t* cand_pids, const int64_t* rowptr, int64_t n_cand, float* out, unsigned int* counter,
+                   cudaStream_t stream) {
+  const size_t tile_bytes = static_cast<size_t>(dim) * 2 * kWTileRows;
+  const size_t partial_bytes = 2 * kWWarps * kWPartialFloats * sizeof(float);
+  const size_t budget = (224 * 1024) / kCtas - 2048;
+  const int n_stages = static_cast<int>(std::max<size_t>(2, std::min<size_t>(kWMaxStages, (budget - partial_bytes) / tile_bytes)));
+  const size_t smem = n_stages * tile_bytes + partial_bytes + 1024;
+  auto kern = maxsim_wide_kernel<T, kCvtBf16, kMaxKs, kCtas>;
+  CBK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
+  const int64_t n_segs = (n_cand + kWSegCands - 1) / kWSegCands;
+  const int grid = static_cast<int>(std::max<int64_t>(1, std::min<int64_t>(n_segs, static_cast<int64_t>(sm_count()) * kCtas)));
+  kern<<<grid, kWThreads, smem, stream>>>(tmap, pfxsum, doclens, n_docs, pid_base, skip_foreign, strides, Q, q_len, dim, n_queries,
+                                         cand_pids, rowptr, n_cand, n_stages, out, counter);
+  CBK_CUDA(cudaGetLastError());
+  count_launch();
+  return CBK_OK;
+}
+
 template <typename T, bool kCvtBf16>
 int launch_wide(const CUtensorMap& tmap, const int64_t* pfxsum, const int32_t* doclens, int64_t n_docs, int64_t pid_base,
                 int skip_foreign, const StrideSet& strides, const float* Q, int q_len, int dim, int64_t n_queries,
                 const int64_t* cand_pids, const int64_t* rowptr, int64_t n_cand, float* out, unsigned int* counter,
                 cudaStream_t stream) {
-  const size_t tile_bytes = static_cast<size_t>(dim) * 2 * kWTileRows;
-  const size_t partial_bytes = 2 * kWWarps * kWPartialFloats * sizeof(float);
-  const size_t budget = 224 * 1024;
-  const int n_stages = static_cast<int>(std::max<size_t>(2, std::min<size_t>(kWMaxStages, (budget - partial_bytes) / tile_bytes)));
-  const size_t smem = n_stages * tile_bytes + partial_bytes + 1024;
-  CBK_CUDA(cudaFuncSetAttribute(maxsim_wide_kernel<T, kCvtBf16>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
-  const int64_t n_segs = (n_cand + kWSegCands - 1) / kWSegCands;
-  const int grid = static_cast<int>(std::max<int64_t>(1, std::min<int64_t>(n_segs, sm_count())));
-  maxsim_wide_kernel<T, kCvtBf16><<<grid, kWThreads, smem, stream>>>(tmap, pfxsum, doclens, n_docs, pid_base, skip_foreign, strides, Q,
-                                                                    q_len, dim, n_queries, cand_pids, rowptr, n_cand, n_stages, out,
-                                                                    counter);
-  CBK_CUDA(cudaGetLastError());
-  count_launch();
-  return CBK_OK;
+  if (dim <= 384)
+    return launch_wide_as<T, kCvtBf16, 3, 2>(tmap, pfxsum, doclens, n_docs, pid_base, skip_foreign, strides, Q, q_len, dim, n_queries,
+                                             cand_pids, rowptr, n_cand, out, counter, stream);
+  if (dim <= 768)
+    return launch_wide_as<T, kCvtBf16, 6, 2>(tmap, pfxsum, doclens, n_docs, pid_base, skip_foreign, strides, Q, q_len, dim, n_queries,
+                                             cand_pids, rowptr, n_cand, out, counter, stream);
+  return launch_wide_as<T, kCvtBf16, 8, 1>(tmap, pfxsum, doclens, n_docs, pid_base, skip_foreign, strides, Q, q_len, dim, n_queries,
+                                           cand_pids, rowptr, n_cand, out, counter, stream);
 }
 
 }  // namespace
