@@ -498,7 +498,9 @@ def test_rank_forward_other_dims(dev, dim):
         ref = O.maxsim_exact(store, index.doclens, pf, ranker.strides, Q[b], cand[b])
         rp, rs = O.topk_desc(ref, cand[b], 10)
         fp, fs = O.topk_desc(ref, cand[b], None)
-        check_topk(p, s, rp, rs, 1e-5, fp, fs)               # fp32 arithmetic on exact fp16 values: tight
+        # 96 runs the generic kernel (fp32 arithmetic on exact fp16 values: tight); 64 and 768 run the K-split
+        # tensor-core kernel, whose query is rounded to fp16 like the 128-wide one
+        check_topk(p, s, rp, rs, 1e-5 if dim % 64 else SCORE_RTOL, fp, fs)
 
 
 def test_rank_forward_bsize_candidates_and_depth_clamp(dev):
