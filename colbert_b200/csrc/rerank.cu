@@ -48,9 +48,9 @@ struct TmapSet {
 };
 
 struct __align__(1024) WarpSmem {
-  uint8_t tiles[kStages][kTileBytes];
+  uint8_t tiles[kStages * kTileBytes];   // 4 stages of 16 rows, or 8 stages of 8 rows (kShort)
   int2 meta[kSegCands];     // compacted list of scorable candidates: .x = first store row, .y = doclen (> 0)
-  uint64_t full[kStages];
+  uint64_t full[2 * kStages];
   uint8_t cidx[kSegCands];  // position of each compacted entry inside the segment
 };
 static_assert(sizeof(WarpSmem) % 1024 == 0, "per-warp smem must keep 1024-B swizzle-atom alignment");
@@ -67,7 +67,10 @@ __device__ __forceinline__ uint32_t bf16x2_to_f16x2(uint32_t v) {
 
 // T = type fed to the tensor cores.  kCvtBf16: the store holds bf16 but is multiplied as fp16
 // (converted in registers after ldmatrix) so that the query keeps 11 significant bits instead of 8.
-template <typename T, bool kCvtBf16>
+// kShort: every document has at most 8 rows (multi-view indexes: d_view rows per document) — the ring is cut into 8 stages of
+// 8 rows instead of 4 of 16, which more than doubles the bytes a warp keeps in flight, and the second 8-token sub-tile
+// is not computed.
+template <typename T, bool kCvtBf16, bool kShort>
 __global__ void __launch_bounds__(kWarps * 32, kCtasPerSm)
 maxsim_rerank_kernel(const __grid_constant__ TmapSet tmaps, const int64_t* __restrict__ pfxsum,
                      const int32_t* __restrict__ doclens, int64_t n_docs, int64_t pid_base, int skip_foreign,
@@ -77,17 +80,21 @@ maxsim_rerank_kernel(const __grid_constant__ TmapSet tmaps, const int64_t* __res
                      int64_t n_cand_bound, int seg_cands, float* __restrict__ out,
                      unsigned int* __restrict__ seg_counter) {
   extern __shared__ uint8_t smem_raw[];
+  constexpr int kTR = kShort ? 8 : kTileRows;             // rows per tile
+  constexpr int kST = kShort ? 2 * kStages : kStages;     // stages of the ring (same 16 KB either way)
+  constexpr int kTB = kTR * kDim * 2;                     // bytes per stage
+  constexpr int kSub = kShort ? 1 : 2;                    // 8-token sub-tiles per tile
   const int lane = threadIdx.x & 31;
   const int warp = threadIdx.x >> 5;
   const uint32_t raw_addr = smem_u32(smem_raw);
   const uint32_t pad = ((raw_addr + 1023u) & ~1023u) - raw_addr;
   WarpSmem* ws = reinterpret_cast<WarpSmem*>(smem_raw + pad) + warp;
-  const uint32_t tiles_addr = smem_u32(&ws->tiles[0][0]);
+  const uint32_t tiles_addr = smem_u32(&ws->tiles[0]);
   const uint32_t full_addr = smem_u32(&ws->full[0]);
 
-  if (lane < kTileRows) tma_prefetch_desc(&tmaps.m[lane]);
+  if (lane < kTR) tma_prefetch_desc(&tmaps.m[lane]);
   if (lane == 0) {
-    for (int s = 0; s < kStages; ++s) mbar_init(full_addr + 8 * s, 1);
+    for (int s = 0; s < kST; ++s) mbar_init(full_addr + 8 * s, 1);
     fence_mbar_init();
   }
   __syncwarp();
@@ -97,7 +104,7 @@ maxsim_rerank_kernel(const __grid_constant__ TmapSet tmaps, const int64_t* __res
   const int64_t n_cand = min(rowptr[n_queries], n_cand_bound);
   const int n_mt = q_len > 16 ? 2 : 1;
   const int64_t n_segs = (n_cand + seg_cands - 1) / seg_cands;
-  uint32_t issued = 0;    // tiles handed to the TMA so far   → stage = issued % kStages
+  uint32_t issued = 0;    // tiles handed to the TMA so far   → stage = issued % kST
   uint32_t consumed = 0;  // tiles multiplied so far          → stage / parity of the next wait
   int64_t cur_q = -1;
   uint32_t qa[2][8][4];   // A fragments of the current query: [m-tile][k-step][reg]
@@ -155,30 +162,30 @@ maxsim_rerank_kernel(const __grid_constant__ TmapSet tmaps, const int64_t* __res
     }
     int64_t q_end = rowptr[q + 1];
 
-    // ---- producer cursor (runs kStages-1 tiles ahead of the consumer inside the segment) ---------
+    // ---- producer cursor (runs kST-1 tiles ahead of the consumer inside the segment) ---------
     int pc = 0, pt = 0;
     auto issue_tile = [&]() {
       if (pc >= nv) return;
       const int2 m = ws->meta[pc];
       if (elect_one()) {                                        // not `lane == 0`: see elect_one in cbk_common.cuh
-        const uint32_t st = issued % kStages;
+        const uint32_t st = issued % kST;
         const uint32_t bar = full_addr + 8 * st;
-        const uint32_t dst = tiles_addr + st * kTileBytes;
-        const int row = m.x + pt * kTileRows;
-        const int rows = min(kTileRows, m.y - pt * kTileRows);   // exact: the tail tile is shorter
+        const uint32_t dst = tiles_addr + st * kTB;
+        const int row = m.x + pt * kTR;
+        const int rows = min(kTR, m.y - pt * kTR);   // exact: the tail tile is shorter
         const CUtensorMap* tm = &tmaps.m[rows - 1];
         mbar_arrive_expect_tx(bar, rows * kDim * 2);
         tma_load_3d(dst, tm, 0, row, 0, bar, kEvictFirst);   // both 64-column halves in one op: [half][row][64]
       }
       ++issued;
       ++pt;
-      if (pt * kTileRows >= m.y) {
+      if (pt * kTR >= m.y) {
         pt = 0;
         ++pc;
       }
     };
 #pragma unroll
-    for (int s = 0; s < kStages - 1; ++s) issue_tile();
+    for (int s = 0; s < kST - 1; ++s) issue_tile();
 
     for (int ci = 0; ci < nv; ++ci) {
       const int64_t c = c0 + ws->cidx[ci];
@@ -216,18 +223,18 @@ maxsim_rerank_kernel(const __grid_constant__ TmapSet tmaps, const int64_t* __res
 
       const int2 m = ws->meta[ci];
       const int len = m.y;
-      const int ntiles = (len + kTileRows - 1) / kTileRows;
+      const int ntiles = (len + kTR - 1) / kTR;
       float rmax[2][2] = {{-INFINITY, -INFINITY}, {-INFINITY, -INFINITY}};
 
       for (int t = 0; t < ntiles; ++t) {
         issue_tile();
-        const uint32_t st = consumed % kStages;
-        mbar_wait(full_addr + 8 * st, (consumed / kStages) & 1u);
-        const uint32_t sbase = tiles_addr + st * kTileBytes;
+        const uint32_t st = consumed % kST;
+        mbar_wait(full_addr + 8 * st, (consumed / kST) & 1u);
+        const uint32_t sbase = tiles_addr + st * kTB;
 
         float acc[2][2][4];  // [sub-tile of 8 tokens][m-tile][reg]
 #pragma unroll
-        for (int s = 0; s < 2; ++s)
+        for (int s = 0; s < kSub; ++s)
 #pragma unroll
           for (int mt = 0; mt < 2; ++mt)
 #pragma unroll
@@ -235,7 +242,7 @@ maxsim_rerank_kernel(const __grid_constant__ TmapSet tmaps, const int64_t* __res
 
         // B fragments: ldmatrix.x4 of 32 columns (two k-steps) × 8 tokens; the loads of step p+1 are issued
         // before the conversions / MMAs of step p so that the shared-memory latency is covered
-        const int tile_rows = min(kTileRows, len - t * kTileRows);
+        const int tile_rows = min(kTR, len - t * kTR);
         uint32_t bq[2][2][4];   // [buffer][sub-tile][reg]
         auto load_b = [&](int p, uint32_t (&dst)[2][4]) {
           // the second half starts right after the rows this tile really holds, so its rows sit at physical row
@@ -243,7 +250,7 @@ maxsim_rerank_kernel(const __grid_constant__ TmapSet tmaps, const int64_t* __res
           const int chunk = (p & 1) * 4 + lmat;
           const int prow0 = (p >> 1) * tile_rows + lrow;
 #pragma unroll
-          for (int s = 0; s < 2; ++s) {
+          for (int s = 0; s < kSub; ++s) {
             const int prow = prow0 + s * 8;
             ldmatrix_x4(sbase + prow * 128 + (((chunk ^ prow) & 7) << 4), dst[s][0], dst[s][1], dst[s][2], dst[s][3]);
           }
@@ -253,7 +260,7 @@ maxsim_rerank_kernel(const __grid_constant__ TmapSet tmaps, const int64_t* __res
         for (int p = 0; p < 4; ++p) {
           if (p < 3) load_b(p + 1, bq[(p + 1) & 1]);
 #pragma unroll
-          for (int s = 0; s < 2; ++s) {
+          for (int s = 0; s < kSub; ++s) {
             uint32_t b0 = bq[p & 1][s][0], b1 = bq[p & 1][s][1], b2 = bq[p & 1][s][2], b3 = bq[p & 1][s][3];
             if (kCvtBf16) {
               b0 = bf16x2_to_f16x2(b0);
@@ -271,10 +278,10 @@ maxsim_rerank_kernel(const __grid_constant__ TmapSet tmaps, const int64_t* __res
         }
 
         // ---- running max over this tile's tokens; tokens ≥ doclen are ignored -------------------
-        const int tok0 = t * kTileRows + 2 * (lane & 3);
-        if ((t + 1) * kTileRows <= len) {
+        const int tok0 = t * kTR + 2 * (lane & 3);
+        if ((t + 1) * kTR <= len) {
 #pragma unroll
-          for (int s = 0; s < 2; ++s)
+          for (int s = 0; s < kSub; ++s)
 #pragma unroll
             for (int mt = 0; mt < 2; ++mt) {
               rmax[mt][0] = fmaxf(rmax[mt][0], fmaxf(acc[s][mt][0], acc[s][mt][1]));
@@ -282,7 +289,7 @@ maxsim_rerank_kernel(const __grid_constant__ TmapSet tmaps, const int64_t* __res
             }
         } else {
 #pragma unroll
-          for (int s = 0; s < 2; ++s) {
+          for (int s = 0; s < kSub; ++s) {
             const bool v0 = tok0 + s * 8 < len;
             const bool v1 = tok0 + s * 8 + 1 < len;
 #pragma unroll
@@ -323,12 +330,12 @@ maxsim_rerank_kernel(const __grid_constant__ TmapSet tmaps, const int64_t* __res
   }
 }
 
-template <typename T, bool kCvtBf16>
+template <typename T, bool kCvtBf16, bool kShort>
 int launch(const TmapSet& tmaps, const int64_t* pfxsum, const int32_t* doclens, int64_t n_docs, int64_t pid_base,
            int skip_foreign, const StrideSet& strides, const float* Q, int q_len, int64_t n_queries, const int64_t* cand_pids,
            const int64_t* rowptr, int64_t n_cand, float* out, unsigned int* counter, cudaStream_t stream) {
   const size_t smem = kWarps * sizeof(WarpSmem) + 1024;
-  CBK_CUDA(cudaFuncSetAttribute(maxsim_rerank_kernel<T, kCvtBf16>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+  CBK_CUDA(cudaFuncSetAttribute(maxsim_rerank_kernel<T, kCvtBf16, kShort>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                 static_cast<int>(smem)));
   // work unit = segment of consecutive candidates claimed by one warp: 64 for big batches (amortises the claim and
   // the metadata fetch), down to 1 for a single query so that each of its ~1000 candidates gets a warp of its own
@@ -338,7 +345,7 @@ int launch(const TmapSet& tmaps, const int64_t* pfxsum, const int32_t* doclens, 
   const int64_t n_segs = (n_cand + seg_cands - 1) / seg_cands;
   const int64_t want = (n_segs + kWarps - 1) / kWarps;
   const int grid = static_cast<int>(std::max<int64_t>(1, std::min<int64_t>(want, static_cast<int64_t>(sm_count()) * kCtasPerSm)));
-  maxsim_rerank_kernel<T, kCvtBf16><<<grid, kWarps * 32, smem, stream>>>(tmaps, pfxsum, doclens, n_docs, pid_base, skip_foreign, strides, Q, q_len,
+  maxsim_rerank_kernel<T, kCvtBf16, kShort><<<grid, kWarps * 32, smem, stream>>>(tmaps, pfxsum, doclens, n_docs, pid_base, skip_foreign, strides, Q, q_len,
                                                               n_queries, cand_pids, rowptr, n_cand, seg_cands, out, counter);
   CBK_CUDA(cudaGetLastError());
   count_launch();
@@ -371,14 +378,22 @@ int rerank_dispatch(const void* d_store, int store_dtype, int64_t n_store_rows, 
   const int skip = (flags & CBK_FLAG_SKIP_FOREIGN_PIDS) ? 1 : 0;
   unsigned int* counter = static_cast<unsigned int*>(d_workspace);
   CBK_CUDA(cudaMemsetAsync(counter, 0, sizeof(unsigned int), stream));
-  if (store_dtype == CBK_F16)
-    return launch<__half, false>(tmaps, d_pfxsum, d_doclens, n_docs, pid_base, skip, ss, d_Q, q_len, n_queries, d_cand_pids,
-                                 d_cand_rowptr, n_cand_total, d_out_scores, counter, stream);
-  if (flags & CBK_FLAG_BF16_NATIVE_MMA)
-    return launch<__nv_bfloat16, false>(tmaps, d_pfxsum, d_doclens, n_docs, pid_base, skip, ss, d_Q, q_len, n_queries, d_cand_pids,
-                                        d_cand_rowptr, n_cand_total, d_out_scores, counter, stream);
-  return launch<__half, true>(tmaps, d_pfxsum, d_doclens, n_docs, pid_base, skip, ss, d_Q, q_len, n_queries, d_cand_pids,
-                              d_cand_rowptr, n_cand_total, d_out_scores, counter, stream);
+  // strides holds the longest document (its last entry, reference colbert_ranker.py:36-40): multi-view indexes with at
+  // most 8 rows per document take the 8-stage × 8-row instantiation
+  int max_len = 1 << 30;
+  if (n_strides > 0) {
+    max_len = 0;
+    for (int i = 0; i < n_strides; ++i) max_len = std::max(max_len, static_cast<int>(strides[i]));
+  }
+#define CBK_LAUNCH(T, CVT)                                                                                                  \
+  (max_len <= 8 ? launch<T, CVT, true>(tmaps, d_pfxsum, d_doclens, n_docs, pid_base, skip, ss, d_Q, q_len, n_queries,       \
+                                       d_cand_pids, d_cand_rowptr, n_cand_total, d_out_scores, counter, stream)              \
+                : launch<T, CVT, false>(tmaps, d_pfxsum, d_doclens, n_docs, pid_base, skip, ss, d_Q, q_len, n_queries,      \
+                                        d_cand_pids, d_cand_rowptr, n_cand_total, d_out_scores, counter, stream))
+  if (store_dtype == CBK_F16) return CBK_LAUNCH(__half, false);
+  if (flags & CBK_FLAG_BF16_NATIVE_MMA) return CBK_LAUNCH(__nv_bfloat16, false);
+  return CBK_LAUNCH(__half, true);
+#undef CBK_LAUNCH
 }
 
 }  // namespace cbk
