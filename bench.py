@@ -52,6 +52,8 @@ def parse_args():
     ap.add_argument("--kernel", default="auto", choices=["auto", "mma", "tcgen05"],
                     help="rerank kernel: mma.sync (rerank.cu) or tcgen05/TMEM (rerank_umma.cu)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--dim", type=int, default=128, help="embedding width (configs use 128; the author's config is 768: "
+                    "pair it with --docs 300000 so that the store fits)")
     ap.add_argument("--cpu-queries", type=int, default=128, help="bounded CPU-baseline sample (queries)")
     return ap.parse_args()
 
@@ -220,7 +222,7 @@ def run_ours(args, rank, world, local_rank):
     lib = _lib.load()
     assert lib.cbk_device_supported(local_rank) == 1, "bench.py needs an sm_100 device"
     dtype = torch.bfloat16 if args.dtype == "bf16" else torch.float16
-    dim, q_len = 128, args.q_len
+    dim, q_len = args.dim, args.q_len
 
     # Weak scaling: every GPU holds a shard of `--docs` documents (pids [rank*docs, (rank+1)*docs)); the job
     # scores `--queries * world` queries, each with `--cands` candidates drawn over the WHOLE corpus, so every
@@ -374,9 +376,9 @@ def run_ours(args, rank, world, local_rank):
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": args.dtype, "data": "synthetic",
             "config": {
                 "workload": f"rerank: {n_queries} queries x {args.cands} candidates ({args.queries}x{args.cands} per GPU), "
-                            f"q_len {q_len}, dim 128, doclen {args.doclen_fixed or 'U[1,180]'}, {args.dtype} store of "
+                            f"q_len {q_len}, dim {dim}, doclen {args.doclen_fixed or 'U[1,180]'}, {args.dtype} store of "
                             f"{args.docs} docs per GPU, top-{k} per query "
-                            f"(BASELINE.json configs[{2 if args.doclen_fixed else 1}])",
+                            + (f"(BASELINE.json configs[{2 if args.doclen_fixed else 1}])" if dim == 128 else "(configs[1] at the author's width)"),
                 "store_bytes_per_gpu": int(store.numel() * 2),
                 "l2_policy": "inputs larger than L2: each step gathers "
                              f"{algo_bytes / 1e9:.1f} GB of distinct document rows from a {store.numel() * 2 / 1e9:.1f} GB store",
@@ -388,8 +390,8 @@ def run_ours(args, rank, world, local_rank):
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                          "traffic": (NCU_TRAFFIC_DEFAULT_BYTES if (world == 1 and args.queries == 4096 and args.cands == 1000
                                                                      and args.docs == 2_000_000 and not args.doclen_fixed
-                                                                     and args.q_len == 32) else None),
-                         "kernel": "maxsim_rerank_kernel", "algorithmic_bytes_per_launch": algo_bytes,
+                                                                     and args.q_len == 32 and dim == 128) else None),
+                         "kernel": "maxsim_rerank_kernel" if dim == 128 else "maxsim_wide_kernel", "algorithmic_bytes_per_launch": algo_bytes,
                          "kernel_ms": kern_ms, "peak_source": peak_src},
             "e2e": {"value": total_cands * args.steps / (e2e_ms_total * 1e-3), "unit": UNIT,
                     "h2d_bytes_per_step": int(pipe.h2d_bytes_per_step), "d2h_bytes_per_step": int(pipe.d2h_bytes_per_step),
