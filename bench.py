@@ -29,10 +29,10 @@ METRIC = "candidates MaxSim-scored/sec (k=1000 rerank)"
 UNIT = "candidates/s"
 
 # dram__bytes_read.sum + dram__bytes_write.sum of ONE maxsim_rerank_kernel launch of the default workload, from the
-# `ncu --set full` capture summarised in profiles/r01_end_rerank_ncu_full_summary.csv (95.067 GB read + 0.016 GB
+# `ncu --set full` capture summarised in profiles/r01_end_rerank_ncu_full_summary.csv (94.950 GB read + 0.019 GB
 # written; algorithmic 94.869 GB — the difference is candidate/query metadata and DRAM sector granularity).  Only
 # valid for the default arguments (same seeds → same candidate lists).
-NCU_TRAFFIC_DEFAULT_BYTES = 95_083_146_640
+NCU_TRAFFIC_DEFAULT_BYTES = 94_968_766_096
 
 
 def parse_args():
