@@ -36,7 +36,7 @@ def convert_index(index_path: str, out_path: str) -> dict:
     dim, dtype_name, rows = None, None, 0
     with open(os.path.join(out_path, "store.bin"), "wb") as out:
         for path, dl in zip(part_files, parts_doclens):
-            part = load_index_part(path)
+            part = load_index_part(path, verbose=False)
             assert part.size(0) == sum(dl), (path, part.size(0), sum(dl))
             name = str(part.dtype).replace("torch.", "")
             assert name in _DTYPES, f"unsupported part dtype {part.dtype}"

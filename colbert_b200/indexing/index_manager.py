@@ -1,24 +1,57 @@
-"""Part-file (de)serialisation with the reference's names
-(reference colbert/indexing/index_manager.py:4-18)."""
+"""Part files of the index: one ``{i}.pt`` per part holding the per-token embeddings ``[N_i, dim]``
+(names and call signatures of reference colbert/indexing/index_manager.py:4-18).
+
+The loader is what feeds the HBM-resident store, so it checks what the kernels later rely on (2-D, floating point,
+a single width per index) instead of failing inside a launch, and can memory-map a part so that a 100 GB index is
+streamed into the device buffer without a second host copy.
+"""
 from __future__ import annotations
+
+import os
+from typing import Optional
 
 import torch
 
 
+def _as_part_tensor(obj, filename: str) -> torch.Tensor:
+    # parts written by old encoders are Python lists of per-batch tensors (the reference concatenates them too)
+    if isinstance(obj, (list, tuple)):
+        if len(obj) == 0:
+            raise ValueError(f"{filename}: empty part")
+        obj = torch.cat([torch.as_tensor(x) for x in obj])
+    if not isinstance(obj, torch.Tensor):
+        raise TypeError(f"{filename}: expected a tensor (or a list of tensors), found {type(obj).__name__}")
+    if obj.dim() != 2 or not obj.is_floating_point():
+        raise ValueError(f"{filename}: expected a floating-point [rows, dim] matrix, found {tuple(obj.shape)} {obj.dtype}")
+    return obj
+
+
+def load_index_part(filename: str, verbose: bool = True, mmap: bool = False, dim: Optional[int] = None) -> torch.Tensor:
+    """The embeddings of one part as a host tensor ``[N_i, dim]``.  ``mmap``: map the file instead of reading it
+    (zip-format checkpoints only); ``dim``: width the caller expects, checked here."""
+    kwargs = {"map_location": "cpu"}
+    if mmap:
+        kwargs["mmap"] = True
+    try:
+        obj = torch.load(filename, weights_only=True, **kwargs)
+    except Exception:                      # legacy pickles that the weights-only unpickler refuses
+        obj = torch.load(filename, weights_only=False, **kwargs)
+    part = _as_part_tensor(obj, filename)
+    if dim is not None and part.size(1) != dim:
+        raise ValueError(f"{filename}: embeddings are {part.size(1)} wide, the ranker was built for dim={dim}")
+    if verbose:
+        print(f"#> loaded {os.path.basename(filename)}: {part.size(0)} embeddings x {part.size(1)} ({part.dtype})", flush=True)
+    return part
+
+
 class IndexManager:
-    """Writer side of the ``{i}.pt`` layout: ``save(tensor, path)`` is a plain ``torch.save``."""
+    """Writer side of the same layout (the reference's encoder calls ``IndexManager(dim).save(embs, path)``)."""
 
     def __init__(self, dim=None):
         self.dim = dim
 
     def save(self, tensor: torch.Tensor, path_prefix: str) -> None:
-        torch.save(tensor, path_prefix)
-
-
-def load_index_part(filename: str, verbose: bool = True) -> torch.Tensor:
-    """One part as a ``[N_i, dim]`` tensor on the host; legacy parts saved as a list of tensors are
-    concatenated (reference index_manager.py:15-16)."""
-    part = torch.load(filename, map_location="cpu")
-    if isinstance(part, list):
-        part = torch.cat(part)
-    return part
+        part = _as_part_tensor(tensor, path_prefix)
+        if self.dim is not None and part.size(1) != self.dim:
+            raise ValueError(f"refusing to write a {part.size(1)}-wide part into a dim={self.dim} index")
+        torch.save(part.contiguous(), path_prefix)
