@@ -582,3 +582,23 @@ def test_rank_forward_host_call_matches_device_path(dev):
         Qs = synthetic.make_queries(45, 1, q_len, 128)[0]
         Qt = torch.from_numpy(Qs).unsqueeze(0).permute(0, 2, 1).contiguous()
         assert ranker.rank_forward(Qt, pl, depth=7) == ranker.rank_forward(Qt.to(dev), pl, depth=7)
+
+
+def test_colbert_score_upstream_alias(dev):
+    """``colbert_score(Q, D_padded, D_mask)`` (upstream ColBERT's name for the operator): one query against many padded
+    documents, and query i against document i — both equal the oracle's all-pairs ``score``."""
+    from colbert_b200.modeling.inference import ModelInference, colbert_score
+    rng = np.random.default_rng(31)
+    B, n, h, m = 37, 23, 128, 32
+    D = rng.standard_normal((B, n, h)).astype(np.float32)
+    D /= np.linalg.norm(D, axis=2, keepdims=True)
+    D = D.astype(np.float16).astype(np.float32)
+    dmask = (np.arange(n)[None, :] < rng.integers(1, n + 1, size=B)[:, None])
+    Q = rng.standard_normal((B, m, h)).astype(np.float32)
+    Q /= np.linalg.norm(Q, axis=2, keepdims=True)
+    ref = O.score_allpairs(Q, D, np.ones((B, m), np.int64), dmask.astype(np.int64))          # [B, B]
+    Dd, Md = torch.from_numpy(D).to(dev), torch.from_numpy(dmask).to(dev)
+    one = colbert_score(torch.from_numpy(Q[:1]).to(dev), Dd, Md).cpu().numpy()
+    assert np.abs(one - ref[0]).max() <= SCORE_RTOL * max(1.0, np.abs(ref).max())
+    pair = ModelInference.colbert_score(torch.from_numpy(Q).to(dev), Dd, Md.unsqueeze(-1)).cpu().numpy()
+    assert np.abs(pair - np.diag(ref)).max() <= SCORE_RTOL * max(1.0, np.abs(ref).max())
