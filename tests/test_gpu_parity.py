@@ -312,15 +312,16 @@ def test_baseline_scale_properties(dev):
 # sharded path, exercised on ONE GPU: W shard rankers side by side, the packed-key
 # exchange emulated by stacking, merged by the device kernel
 # ------------------------------------------------------------------------------------------------
-@pytest.mark.parametrize("world", [2, 3, 8])
-def test_sharded_path_matches_single_store(dev, world):
+@pytest.mark.parametrize("world,dim", [(2, 128), (3, 128), (8, 128), (3, 256), (2, 768)])
+def test_sharded_path_matches_single_store(dev, world, dim):
+    """dim 128: the per-warp kernel; 256 / 768: the K-split kernel (same routing, foreign-pid and device-side count rules)."""
     from colbert_b200 import _lib, kernels, synthetic
     from colbert_b200.ranking import ColbertRanker
     from colbert_b200.sharding import plan_shards
-    index = synthetic.make_index(909, 4000, dim=128, lo=1, hi=120)
+    index = synthetic.make_index(909, 4000 if dim == 128 else 1500, dim=dim, lo=1, hi=120)
     single = make_ranker(index, dev)
     B, n, k = 9, 400, 25
-    Q = torch.from_numpy(synthetic.make_queries(910, B, 32, 128)).to(dev)
+    Q = torch.from_numpy(synthetic.make_queries(910, B, 32, dim)).to(dev)
     cand = torch.from_numpy(synthetic.make_candidates(911, B, index.num_docs, n)).to(dev)
     ref_pids, ref_scores = single.rank_forward_batch(Q, cand, depth=k)
     rowptr = torch.arange(0, (B + 1) * n, n, dtype=torch.int64, device=dev)
