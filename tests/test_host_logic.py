@@ -83,3 +83,24 @@ def test_flat_store_roundtrip(tmp_path):
     store, doclens, lo, _ = load_flat(str(dst), "cpu", 17, 53)
     assert lo == 17 and np.array_equal(doclens.numpy(), idx.doclens[17:53])
     assert np.array_equal(store.numpy()[:-512], idx.emb[pf[17]: pf[53]]) and not store.numpy()[-512:].any()
+
+
+def test_index_part_loader_validates_and_maps(tmp_path):
+    """load_index_part / IndexManager: list parts, width and shape checks, memory-mapped load."""
+    from colbert_b200.indexing.index_manager import IndexManager, load_index_part
+    good = torch.randn(7, 16).half()
+    IndexManager(16).save(good, str(tmp_path / "0.pt"))
+    assert torch.equal(load_index_part(str(tmp_path / "0.pt"), verbose=False), good)
+    assert torch.equal(load_index_part(str(tmp_path / "0.pt"), verbose=False, mmap=True, dim=16), good)
+    with pytest.raises(ValueError):
+        load_index_part(str(tmp_path / "0.pt"), verbose=False, dim=32)              # the ranker was built for another width
+    with pytest.raises(ValueError):
+        IndexManager(8).save(good, str(tmp_path / "1.pt"))                          # refuses to write a foreign width
+    torch.save(torch.arange(10), str(tmp_path / "2.pt"))
+    with pytest.raises(ValueError):
+        load_index_part(str(tmp_path / "2.pt"), verbose=False)                      # not a [rows, dim] float matrix
+    torch.save({"a": 1}, str(tmp_path / "3.pt"))
+    with pytest.raises(TypeError):
+        load_index_part(str(tmp_path / "3.pt"), verbose=False)
+    torch.save([good[:3], good[3:]], str(tmp_path / "4.pt"))                        # legacy list-of-batches part
+    assert torch.equal(load_index_part(str(tmp_path / "4.pt"), verbose=False), good)
