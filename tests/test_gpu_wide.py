@@ -11,7 +11,7 @@ pytestmark = [pytest.mark.gpu, pytest.mark.timeout(300)]
 DEV = torch.device("cuda", 0)
 
 
-@pytest.mark.parametrize("dim", [64, 192, 256, 384, 512, 768, 1024])
+@pytest.mark.parametrize("dim", [64, 192, 256, 320, 384, 448, 512, 768, 832, 1024])   # 320 / 448 / 832: uneven k-step split
 @pytest.mark.parametrize("dt", [torch.float16, torch.bfloat16], ids=["fp16", "bf16"])
 def test_wide_rerank_matches_oracle_and_generic(dim, dt):
     from colbert_b200 import _lib, synthetic
