@@ -269,9 +269,13 @@ topk_per_query_kernel(const float* __restrict__ scores, const int64_t* __restric
 }
 
 // Short lists, shallow depth (n ≤ 1024, k ≤ 32 — the reference's own call: 1000 candidates, depth 10): a tournament
-// in registers instead of a full sort.  Every warp sorts its 32 keys with shuffles; then, five times, the upper half of
-// the surviving warps hand their list (reversed) to the lower half, which keeps max(a[i], b[31-i]) — the top 32 of both,
-// as a bitonic sequence — and merges it in five more shuffle steps.  Warp 0 ends with the top 32 in order.
+// in registers instead of a full sort.  The list is taken 256 keys at a time: every warp sorts its 32 keys with shuffles;
+// then, three times, the upper half of the surviving warps hand their list (reversed) to the lower half, which keeps
+// max(a[i], b[31-i]) — the top 32 of both, as a bitonic sequence — and merges it in five more shuffle steps; warp 0 folds
+// the chunk's top 32 into the running top 32 the same way.  256 threads per query: eight CTAs per SM stay resident, and a
+// routed list of ~125 candidates (8-GPU shards) costs one chunk.
+constexpr int kSmallThreads = 256;
+
 __device__ __forceinline__ uint64_t warp_merge32_desc(uint64_t v, int lane) {
 #pragma unroll
   for (int s = 16; s >= 1; s >>= 1) {
@@ -281,44 +285,52 @@ __device__ __forceinline__ uint64_t warp_merge32_desc(uint64_t v, int lane) {
   return v;
 }
 
-__global__ void __launch_bounds__(1024)
+__global__ void __launch_bounds__(kSmallThreads)
 topk_small_kernel(const float* __restrict__ scores, const int64_t* __restrict__ cand_pids, const int64_t* __restrict__ rowptr,
                   int k, int neg_inf_is_padding, float* __restrict__ out_scores, int64_t* __restrict__ out_pids,
                   uint64_t* __restrict__ out_keys) {
-  __shared__ uint64_t ex[16][32];
+  __shared__ uint64_t ex[kSmallThreads / 64][32];
   const int64_t q = blockIdx.x;
   const int64_t beg = rowptr[q];
   const int n = static_cast<int>(min(rowptr[q + 1] - beg, static_cast<int64_t>(1024)));
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-  uint64_t v = 0;
-  if (tid < n) {
-    const float sc = scores[beg + tid] + 0.0f;  // -0.0 → +0.0: they tie
-    if (!(neg_inf_is_padding && sc == -INFINITY))
-      v = (static_cast<uint64_t>(float_to_ordered(sc)) << 32) | ~static_cast<uint32_t>(cand_pids[beg + tid]);
-  }
-  // 32 keys per warp, sorted descending along the lanes
-#pragma unroll
-  for (int size = 2; size <= 32; size <<= 1)
-#pragma unroll
-    for (int s = size >> 1; s >= 1; s >>= 1) {
-      const uint64_t o = shfl_xor_u64(v, s);
-      const bool keep_max = ((lane & s) == 0) == ((lane & size) == 0);
-      v = keep_max ? (v > o ? v : o) : (v < o ? v : o);
+  uint64_t run = 0;                                   // warp 0: the top 32 so far, descending along the lanes
+  for (int base = 0; base < n || base == 0; base += kSmallThreads) {
+    const int i = base + tid;
+    uint64_t v = 0;
+    if (i < n) {
+      const float sc = scores[beg + i] + 0.0f;        // -0.0 → +0.0: they tie
+      if (!(neg_inf_is_padding && sc == -INFINITY))
+        v = (static_cast<uint64_t>(float_to_ordered(sc)) << 32) | ~static_cast<uint32_t>(cand_pids[beg + i]);
     }
-  const int n_warps = (n + 31) >> 5;              // warps beyond hold only padding
-  int active = 1;
-  while (active < n_warps) active <<= 1;
-  for (; active > 1; active >>= 1) {
-    const int half = active >> 1;
-    if (warp >= half && warp < active) ex[warp - half][31 - lane] = v;
-    __syncthreads();
-    if (warp < half) {
-      const uint64_t o = ex[warp][lane];
-      v = warp_merge32_desc(v > o ? v : o, lane);
+    // 32 keys per warp, sorted descending along the lanes
+#pragma unroll
+    for (int size = 2; size <= 32; size <<= 1)
+#pragma unroll
+      for (int s = size >> 1; s >= 1; s >>= 1) {
+        const uint64_t o = shfl_xor_u64(v, s);
+        const bool keep_max = ((lane & s) == 0) == ((lane & size) == 0);
+        v = keep_max ? (v > o ? v : o) : (v < o ? v : o);
+      }
+    const int n_warps = (min(n - base, kSmallThreads) + 31) >> 5;   // warps beyond hold only padding
+    int active = 1;
+    while (active < n_warps) active <<= 1;
+    for (; active > 1; active >>= 1) {
+      const int half = active >> 1;
+      if (warp >= half && warp < active) ex[warp - half][31 - lane] = v;
+      __syncthreads();
+      if (warp < half) {
+        const uint64_t o = ex[warp][lane];
+        v = warp_merge32_desc(v > o ? v : o, lane);
+      }
+      __syncthreads();
     }
-    __syncthreads();
+    if (warp == 0) {
+      const uint64_t rv = shfl_xor_u64(v, 31);        // the chunk's top 32, reversed
+      run = warp_merge32_desc(run > rv ? run : rv, lane);
+    }
   }
-  if (warp == 0 && lane < k) emit(v, q * k + lane, out_scores, out_pids, out_keys);
+  if (warp == 0 && lane < k) emit(run, q * k + lane, out_scores, out_pids, out_keys);
 }
 
 // Merge of sorted key lists.  CTA (g, q) merges lists g*G .. g*G+G-1 of query q; list w of query q starts at
@@ -398,7 +410,7 @@ int topk_dispatch(const float* d_scores, const int64_t* d_cand_pids, const int64
                   int64_t max_cand_per_query, int k, int flags, float* d_out_scores, int64_t* d_out_pids,
                   uint64_t* d_out_keys, cudaStream_t stream) {
   if (max_cand_per_query <= 1024 && k <= 32) {
-    topk_small_kernel<<<static_cast<unsigned int>(n_queries), 1024, 0, stream>>>(
+    topk_small_kernel<<<static_cast<unsigned int>(n_queries), kSmallThreads, 0, stream>>>(
         d_scores, d_cand_pids, d_cand_rowptr, k, (flags & CBK_TOPK_NEG_INF_IS_PADDING) ? 1 : 0, d_out_scores, d_out_pids,
         d_out_keys);
     CBK_CUDA(cudaGetLastError());
