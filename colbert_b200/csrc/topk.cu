@@ -285,24 +285,14 @@ __device__ __forceinline__ uint64_t warp_merge32_desc(uint64_t v, int lane) {
   return v;
 }
 
-__global__ void __launch_bounds__(kSmallThreads)
-topk_small_kernel(const float* __restrict__ scores, const int64_t* __restrict__ cand_pids, const int64_t* __restrict__ rowptr,
-                  int k, int neg_inf_is_padding, float* __restrict__ out_scores, int64_t* __restrict__ out_pids,
-                  uint64_t* __restrict__ out_keys) {
-  __shared__ uint64_t ex[kSmallThreads / 64][32];
-  const int64_t q = blockIdx.x;
-  const int64_t beg = rowptr[q];
-  const int n = static_cast<int>(min(rowptr[q + 1] - beg, static_cast<int64_t>(1024)));
+// the tournament itself: key_of(i) yields key i of this CTA's list (0 = padding), n ≤ 1024; warp 0 returns the top 32
+template <typename KeyOf>
+__device__ __forceinline__ uint64_t tournament_top32(KeyOf key_of, int n, uint64_t (*ex)[32]) {
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   uint64_t run = 0;                                   // warp 0: the top 32 so far, descending along the lanes
   for (int base = 0; base < n || base == 0; base += kSmallThreads) {
     const int i = base + tid;
-    uint64_t v = 0;
-    if (i < n) {
-      const float sc = scores[beg + i] + 0.0f;        // -0.0 → +0.0: they tie
-      if (!(neg_inf_is_padding && sc == -INFINITY))
-        v = (static_cast<uint64_t>(float_to_ordered(sc)) << 32) | ~static_cast<uint32_t>(cand_pids[beg + i]);
-    }
+    uint64_t v = i < n ? key_of(i) : 0ull;
     // 32 keys per warp, sorted descending along the lanes
 #pragma unroll
     for (int size = 2; size <= 32; size <<= 1)
@@ -330,7 +320,42 @@ topk_small_kernel(const float* __restrict__ scores, const int64_t* __restrict__ 
       run = warp_merge32_desc(run > rv ? run : rv, lane);
     }
   }
-  if (warp == 0 && lane < k) emit(run, q * k + lane, out_scores, out_pids, out_keys);
+  return run;
+}
+
+__global__ void __launch_bounds__(kSmallThreads)
+topk_small_kernel(const float* __restrict__ scores, const int64_t* __restrict__ cand_pids, const int64_t* __restrict__ rowptr,
+                  int k, int neg_inf_is_padding, float* __restrict__ out_scores, int64_t* __restrict__ out_pids,
+                  uint64_t* __restrict__ out_keys) {
+  __shared__ uint64_t ex[kSmallThreads / 64][32];
+  const int64_t q = blockIdx.x;
+  const int64_t beg = rowptr[q];
+  const int n = static_cast<int>(min(rowptr[q + 1] - beg, static_cast<int64_t>(1024)));
+  const uint64_t run = tournament_top32(
+      [&](int i) -> uint64_t {
+        const float sc = scores[beg + i] + 0.0f;      // -0.0 → +0.0: they tie
+        if (neg_inf_is_padding && sc == -INFINITY) return 0ull;
+        return (static_cast<uint64_t>(float_to_ordered(sc)) << 32) | ~static_cast<uint32_t>(cand_pids[beg + i]);
+      },
+      n, ex);
+  const int lane = threadIdx.x & 31;
+  if (threadIdx.x < 32 && lane < k) emit(run, q * k + lane, out_scores, out_pids, out_keys);
+}
+
+// the same tournament over already-packed keys: W short sorted lists per query (the all-gathered shard winners)
+__global__ void __launch_bounds__(kSmallThreads)
+merge_small_kernel(const uint64_t* __restrict__ in_keys, int n_lists, int64_t sw, int64_t sq, int k_in, int k,
+                   float* __restrict__ out_scores, int64_t* __restrict__ out_pids, uint64_t* __restrict__ out_keys) {
+  __shared__ uint64_t ex[kSmallThreads / 64][32];
+  const int64_t q = blockIdx.x;
+  const uint64_t run = tournament_top32(
+      [&](int i) -> uint64_t {
+        const int w = i / k_in, j = i - w * k_in;
+        return in_keys[static_cast<int64_t>(w) * sw + q * sq + j];
+      },
+      n_lists * k_in, ex);
+  const int lane = threadIdx.x & 31;
+  if (threadIdx.x < 32 && lane < k) emit(run, q * k + lane, out_scores, out_pids, out_keys);
 }
 
 // Merge of sorted key lists.  CTA (g, q) merges lists g*G .. g*G+G-1 of query q; list w of query q starts at
@@ -433,6 +458,13 @@ static int launch_merge(const uint64_t* in, int n_lists, int G, int64_t sw, int6
                         float* out_scores, int64_t* out_pids, uint64_t* out_keys, cudaStream_t stream,
                         const SelState* gate = nullptr) {
   const int n_groups = (n_lists + G - 1) / G;
+  if (n_groups == 1 && !gate && static_cast<int64_t>(n_lists) * k_in <= 1024 && k <= 32) {
+    merge_small_kernel<<<static_cast<unsigned int>(n_queries), kSmallThreads, 0, stream>>>(in, n_lists, sw, sq, k_in, k, out_scores,
+                                                                                            out_pids, out_keys);
+    CBK_CUDA(cudaGetLastError());
+    count_launch();
+    return CBK_OK;
+  }
   const int P = padded_pow2(static_cast<int64_t>(std::min(G, n_lists)) * k_in);
   const size_t smem = static_cast<size_t>(P) * sizeof(uint64_t);
   const int threads = P >= 4096 ? 1024 : kTopkThreads;
