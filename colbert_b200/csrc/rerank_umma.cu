@@ -24,7 +24,7 @@
 // completed) that the producer and the MMA issuer poll to recycle ring space, item slots and TMEM slots.
 //
 // Status (round 1): parity with the mma.sync kernel to 1e-6 on fp16 stores and 2e-6 relative error against the
-// oracle on bf16 stores, but 15.5 ms (fp16) / 18.8 ms (bf16) on configs[1] against 14.4 / 15.4 ms for the mma.sync
+// oracle on bf16 stores, but 15.3-15.5 ms (fp16) / 18.5-18.8 ms (bf16) on configs[1] against 14.4 / 15.4 ms for the mma.sync
 // kernel, which therefore stays the default; CBK_FLAG_RERANK_TCGEN05 selects this one.  Measured trade-off: the
 // gather is bound by (bytes in flight) / (loaded HBM latency, ≈ 3 µs) and bytes in flight by shared memory.  With
 // 4 small CTAs per SM the tile rings total 136 KB (two query buffers and a 128-row-capable ring per CTA eat the
