@@ -56,6 +56,16 @@ class OracleShardedRanker(ShardedColbertRanker):
                 out[b, : keys.shape[0]] = keys
         return torch.from_numpy(out.view(np.int64))
 
+    def _local_exhaustive_keys(self, Q, k):
+        Qn = Q.numpy()
+        out = np.zeros((Qn.shape[0], k), dtype=np.uint64)          # key 0 = padding: a shard smaller than k
+        pids = np.arange(self.lo, self.hi, dtype=np.int64)
+        for b in range(Qn.shape[0]):
+            s = O.maxsim_exact(self.store, self.dl, self.pf, self.strides, Qn[b], pids - self.lo)
+            keys = np.sort(O.pack_keys(s, pids))[::-1][:k]
+            out[b, : keys.shape[0]] = keys
+        return torch.from_numpy(out.view(np.int64))
+
     def _merge(self, gathered, k):
         g = gathered.numpy().view(np.uint64)                       # [W, B, k]
         W, B, kin = g.shape
@@ -108,5 +118,40 @@ def test_sharded_rank_equals_single_process(world):
     for b in range(B):
         ref = O.maxsim_exact(store, index.doclens, pf, strides, Q[b], cand[b])
         rp, rs = O.topk_desc(ref, cand[b], k)
+        assert ret[0][0][b].tolist() == rp.tolist()
+        np.testing.assert_allclose(ret[0][1][b], rs, rtol=1e-6)
+
+
+def _worker_exhaustive(rank, world, port, ret):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        index = synthetic.make_index(81, 120, dim=128, lo=1, hi=40)
+        pf = torch.from_numpy(O.doclens_pfxsum(index.doclens))
+        ranker = OracleShardedRanker(index, plan_shards(pf, world), O.compute_strides(index.doclens))
+        Q = synthetic.make_queries(82, 3, 32, 128)
+        pids, scores = ranker.rank_exhaustive(torch.from_numpy(Q), k=50)      # k larger than a shard of ~40 documents
+        ret[rank] = (pids.numpy().copy(), scores.numpy().copy())
+    finally:
+        dist.destroy_process_group()
+
+
+def test_sharded_exhaustive_equals_single_process():
+    """rank_exhaustive over 3 shards of ~40 documents with k = 50: every shard pads its list, the merged top-k equals
+    the single-process ranking of the whole corpus on every rank."""
+    world = 3
+    port = _free_port()
+    ret = mp.Manager().dict()
+    mp.spawn(_worker_exhaustive, args=(world, port, ret), nprocs=world, join=True)
+    index = synthetic.make_index(81, 120, dim=128, lo=1, hi=40)
+    store, pf = O.pad_store(index.emb), O.doclens_pfxsum(index.doclens)
+    strides = O.compute_strides(index.doclens)
+    Q = synthetic.make_queries(82, 3, 32, 128)
+    allp = np.arange(index.num_docs, dtype=np.int64)
+    for r in range(world):
+        assert np.array_equal(ret[r][0], ret[0][0]) and np.array_equal(ret[r][1], ret[0][1])
+    for b in range(3):
+        ref = O.maxsim_exact(store, index.doclens, pf, strides, Q[b], allp)
+        rp, rs = O.topk_desc(ref, allp, 50)
         assert ret[0][0][b].tolist() == rp.tolist()
         np.testing.assert_allclose(ret[0][1][b], rs, rtol=1e-6)
