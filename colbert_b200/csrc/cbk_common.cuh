@@ -202,9 +202,12 @@ __device__ __forceinline__ float to_float<__nv_bfloat16>(__nv_bfloat16 v) {
   return __bfloat162float(v);
 }
 
-// score bits → unsigned key that sorts ascending like the float
+// score bits → unsigned key that sorts ascending like the float.  NaN (the score of a pid outside the index, see
+// cbk_maxsim_rerank) maps to 1: below -inf (0x007fffff) and above the padding key 0, so an invalid candidate sorts
+// LAST instead of first; ordered_to_float(1) is again a NaN.
 __device__ __forceinline__ uint32_t float_to_ordered(float f) {
   uint32_t u = __float_as_uint(f);
+  if (f != f) return 1u;
   return (u & 0x80000000u) ? ~u : (u | 0x80000000u);
 }
 __device__ __forceinline__ float ordered_to_float(uint32_t u) {

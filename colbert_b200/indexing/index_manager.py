@@ -26,15 +26,30 @@ def _as_part_tensor(obj, filename: str) -> torch.Tensor:
     return obj
 
 
-def load_index_part(filename: str, verbose: bool = True, mmap: bool = False, dim: Optional[int] = None) -> torch.Tensor:
+ALLOW_PICKLE_ENV = "COLBERT_B200_ALLOW_PICKLE"
+
+
+def load_index_part(filename: str, verbose: bool = True, mmap: bool = False, dim: Optional[int] = None,
+                    allow_pickle: Optional[bool] = None) -> torch.Tensor:
     """The embeddings of one part as a host tensor ``[N_i, dim]``.  ``mmap``: map the file instead of reading it
-    (zip-format checkpoints only); ``dim``: width the caller expects, checked here."""
+    (zip-format checkpoints only); ``dim``: width the caller expects, checked here.
+
+    Parts are read with the weights-only unpickler (tensors and lists of tensors — both forms the reference writes —
+    load under it).  A file it refuses is NOT retried with the full pickle machinery unless the caller opts in with
+    ``allow_pickle=True`` (or ``COLBERT_B200_ALLOW_PICKLE=1`` in the environment): a part file is data, and a crafted
+    one must not get code execution just by failing the safe load."""
     kwargs = {"map_location": "cpu"}
     if mmap:
         kwargs["mmap"] = True
+    if allow_pickle is None:
+        allow_pickle = os.environ.get(ALLOW_PICKLE_ENV, "0") == "1"
     try:
         obj = torch.load(filename, weights_only=True, **kwargs)
-    except Exception:                      # legacy pickles that the weights-only unpickler refuses
+    except Exception as exc:
+        if not allow_pickle:
+            raise RuntimeError(
+                f"{filename}: the weights-only loader refused this part ({type(exc).__name__}: {exc}). If it is a "
+                f"trusted legacy pickle, pass allow_pickle=True or set {ALLOW_PICKLE_ENV}=1.") from exc
         obj = torch.load(filename, weights_only=False, **kwargs)
     part = _as_part_tensor(obj, filename)
     if dim is not None and part.size(1) != dim:

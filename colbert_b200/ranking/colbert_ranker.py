@@ -46,6 +46,16 @@ def flatten(L):
     return [x for y in L for x in y]
 
 
+def _is_builtin_scorer(model) -> bool:
+    """True when ``model`` is None or this package's own ``BaseModel`` (class or instance): scoring then is the
+    fused kernel.  Any other object with ``.score`` is an injected scorer and is called as the reference calls it."""
+    if model is None:
+        return True
+    from ..modeling.BaseModel import BaseModel
+    return model is BaseModel or isinstance(model, BaseModel) or (isinstance(model, type) and issubclass(model, BaseModel)
+                                                                  and model.score is BaseModel.score)
+
+
 class ColbertRanker:
     """Drop-in for the reference ``ColbertRanker`` (upstream ColBERT: ``IndexPart`` + ``IndexRanker``)."""
 
@@ -59,7 +69,15 @@ class ColbertRanker:
             self.device = torch.device("cuda", torch.cuda.current_device())
         self.maxsim_dtype = torch.float32
         self.store_dtype = store_dtype
-        self.model = model          # accepted for signature compatibility; scoring is the fused kernel
+        # The reference's plugin seam (colbert_ranker.py:28,111): any object with .score(Q, D, q_mask, d_mask).
+        # None or this package's BaseModel → the fused kernel; anything else is HONOURED: rank_forward then gathers
+        # the stride-bucket tensors on the GPU (cbk_gather_rows) and calls model.score on them, bucket by bucket,
+        # exactly as the reference does (see _scores_injected).  The batched / exhaustive entry points have no
+        # counterpart in the reference and always run the fused kernel.
+        self.model = model
+        self._model_is_builtin = _is_builtin_scorer(model)
+        if not self._model_is_builtin and not hasattr(model, "score"):
+            raise TypeError("model= must offer .score(Q, D, q_mask, d_mask) (reference colbert_ranker.py:111)")
         self.verbose = verbose
         self.dim = dim
         # bf16 stores are multiplied as fp16 by default (see cbk_maxsim_rerank `flags`); set to
@@ -139,19 +157,30 @@ class ColbertRanker:
         self.doclens_pfxsum = torch.zeros(self.doclens.numel() + 1, dtype=torch.int64)
         torch.cumsum(self.doclens, 0, out=self.doclens_pfxsum[1:])
         self.dim = self.tensor.size(-1)
-        self.strides = [torch_percentile(self.doclens, p) for p in [25, 50, 75]]
-        self.strides.append(self.doclens.max().item())
-        self.strides = sorted(list(set(self.strides)))
+        strides = [torch_percentile(self.doclens, p) for p in [25, 50, 75]]
+        strides.append(self.doclens.max().item())
+        self.strides = sorted(list(set(strides)))
         if self.verbose:
             print(f"#> Using strides {self.strides}..", flush=True)
-        self._views = None
         self.buffers = {}
-        self._strides_c = (C.c_int32 * max(1, len(self.strides)))(*[int(s) for s in self.strides])
         self._host_scratch = None       # (device bytes, pinned bytes) of the single-call path, grown on demand
         # device-side copies the kernels index by pid
         self._doclens_dev = self.doclens.to(torch.int32).to(self.device)
         self._pfxsum_dev = self.doclens_pfxsum.to(self.device)
         assert self.tensor.size(0) < 2 ** 31, "store exceeds 2^31-1 rows"
+
+    @property
+    def strides(self) -> List[int]:
+        return self._strides
+
+    @strides.setter
+    def strides(self, value) -> None:
+        """Everything derived from the stride list follows it: the ctypes copy the single-call path hands to the
+        library, and the stride-views.  (``ShardedColbertRanker`` replaces a shard's strides with the corpus-wide
+        list; a stale copy would apply the zero floor with the wrong list.)"""
+        self._strides = [int(s) for s in value]
+        self._strides_c = (C.c_int32 * max(1, len(self._strides)))(*self._strides)
+        self._views = None
 
     @property
     def views(self) -> List[torch.Tensor]:
@@ -256,6 +285,11 @@ class ColbertRanker:
             raise ValueError("rank_forward expects Q of shape [1, dim, q_len]")
         if len(pids) > BSIZE:
             raise ValueError(f"{len(pids)} candidates exceed BSIZE={BSIZE} (reference colbert_ranker.py:11)")
+        if not isinstance(pids, torch.Tensor):
+            pids = np.asarray(pids, dtype=np.int64)          # one conversion serves the range check and the call
+        self._check_pids(pids)
+        if not self._model_is_builtin:
+            return self._rank_forward_injected(Q, pids, depth, output_D_embedding)
         if (not output_D_embedding and Q.device.type == "cpu" and Q.size(2) <= kernels._lib.CBK_MAX_QLEN
                 and not (isinstance(pids, torch.Tensor) and pids.device.type != "cpu")):
             return self._rank_forward_host(Q, pids, depth)
@@ -270,14 +304,71 @@ class ColbertRanker:
             return top_pids[0].tolist(), top_scores[0].tolist()
         # output_D_embedding: the reference can only concatenate when every candidate fell into one
         # stride bucket (colbert_ranker.py:131-132), i.e. multi-view / fixed-length indexes
-        dl = self.doclens[pids_t.cpu()]
-        buckets = (dl.unsqueeze(1) > torch.tensor(self.strides).unsqueeze(0) + 1e-6).sum(-1)
+        local = (pids_t - self.pid_base).cpu()                       # doclens / pfxsum are indexed by LOCAL pid
+        buckets = self._buckets(self.doclens[local])
         if int(buckets.min()) != int(buckets.max()):
             raise RuntimeError("output_D_embedding needs all candidates in one stride bucket "
                                f"(got buckets {sorted(set(buckets.tolist()))}); the reference fails here too")
         stride = self.strides[int(buckets[0])]
-        D, mask = kernels.gather_rows(self.tensor, self._pfxsum_dev, self._doclens_dev, top_pids[0].contiguous(), stride)
+        D, mask = kernels.gather_rows(self.tensor, self._pfxsum_dev, self._doclens_dev,
+                                      (top_pids[0] - self.pid_base).contiguous(), stride)
         return top_pids[0].tolist(), D, mask
+
+    def _buckets(self, doclens: torch.Tensor) -> torch.Tensor:
+        """reference colbert_ranker.py:90 — bucket g = #{s in strides : s < doclen}."""
+        return (doclens.unsqueeze(1) > torch.tensor(self.strides, device=doclens.device).unsqueeze(0) + 1e-6).sum(-1)
+
+    def _check_pids(self, pids) -> None:
+        """The reference indexes ``doclens[pids]`` on the host and raises IndexError for a pid outside the index
+        (colbert_ranker.py:88).  A shard ranker (CBK_FLAG_SKIP_FOREIGN_PIDS) legitimately sees foreign pids and skips
+        the check; device-resident pid tensors are not pulled back for it (the kernel scores them NaN, which sorts
+        last)."""
+        if self.kernel_flags & kernels._lib.CBK_FLAG_SKIP_FOREIGN_PIDS:
+            return
+        if isinstance(pids, torch.Tensor):
+            if pids.device.type != "cpu" or pids.numel() == 0:
+                return
+            lo, hi = int(pids.min()), int(pids.max())
+        else:
+            lo, hi = int(pids.min()), int(pids.max())
+        n_docs = int(self._doclens_dev.numel())
+        if lo < self.pid_base or hi >= self.pid_base + n_docs:
+            raise IndexError(f"candidate pid out of range: [{lo}, {hi}] vs index pids "
+                             f"[{self.pid_base}, {self.pid_base + n_docs})")
+
+    def _rank_forward_injected(self, Q, pids, depth, output_D_embedding):
+        """The reference's own flow for an INJECTED scorer (colbert_ranker.py:88-137): bucket the candidates by
+        stride, gather each bucket's ``[n_g, stride_g, dim]`` fp32 tensor and length mask (``cbk_gather_rows``: the
+        same rows the reference's stride-view ``index_select`` reads, on the GPU), call
+        ``model.score(Q [1,q_len,dim], D, q_mask, d_mask)[0]``, un-permute, sort."""
+        dev = self.device
+        Qd = Q.to(dev, dtype=self.maxsim_dtype)
+        pids_t = torch.as_tensor(pids, dtype=torch.int64).to(dev)
+        local = pids_t - self.pid_base
+        buckets = self._buckets(self._doclens_dev[local].to(torch.int64))
+        scores = torch.empty(pids_t.numel(), dtype=torch.float32, device=dev)
+        D_all, M_all, order = [], [], []
+        q_mask = torch.ones((1, Qd.size(2)), dtype=torch.long, device=dev)
+        for g, stride in enumerate(self.strides):
+            sel = torch.nonzero(buckets == g).flatten()
+            if sel.numel() == 0:
+                continue
+            D, mask = kernels.gather_rows(self.tensor, self._pfxsum_dev, self._doclens_dev, local[sel].contiguous(), stride)
+            scores[sel] = self.model.score(Q=Qd.permute(0, 2, 1), D=D, q_mask=q_mask, d_mask=mask.to(torch.long))[0] \
+                .to(device=dev, dtype=torch.float32)
+            if output_D_embedding:
+                D_all.append(D); M_all.append(mask); order.append(sel)
+        n = pids_t.numel()
+        k = n if depth is None else min(int(depth), n)
+        rowptr = torch.tensor([0, n], dtype=torch.int64, device=dev)
+        top_scores, top_pids = kernels.topk_per_query(scores, pids_t, rowptr, k, n)
+        if not output_D_embedding:
+            return top_pids[0].tolist(), top_scores[0].tolist()
+        if len(D_all) != 1:
+            raise RuntimeError("output_D_embedding needs all candidates in one stride bucket; the reference fails here too")
+        pos = {int(p): i for i, p in enumerate(pids_t[order[0]].tolist())}
+        idx = torch.tensor([pos[int(p)] for p in top_pids[0].tolist()], device=dev)
+        return top_pids[0].tolist(), D_all[0][idx], M_all[0][idx]
 
     def _rank_forward_host(self, Q: torch.Tensor, pids, depth):
         """Host query + host pids → Python lists through ONE library call (cbk_rank_forward_host): a staged

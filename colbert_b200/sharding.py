@@ -109,13 +109,16 @@ class ShardedColbertRanker:
         """Every document of this shard against every query; local top-k as packed keys (global pids)."""
         return kernels.topk_dense(self.local.score_all(Q), k, pid_base=self.pid_base, as_keys=True)
 
+    def _local_num_docs(self) -> int:
+        return int(self.local.doclens.numel())
+
     def rank_exhaustive(self, Q: torch.Tensor, k: int = 1000):
         """Exhaustive scoring over the whole sharded corpus: every rank scans its own
         shard, one all-gather of [B, k] packed keys, replicated merge → (pids [B,k], scores [B,k]), identical on
         all ranks and equal to a single-GPU ``ColbertRanker.rank_exhaustive`` over the whole corpus."""
         dev = self.local.device if self.local is not None else Q.device
         Q = Q.to(dev, dtype=torch.float32, non_blocking=True).contiguous()
-        k_local = min(int(k), int(self.local.doclens.numel())) if self.local is not None else int(k)
+        k_local = min(int(k), self._local_num_docs())
         keys = self._local_exhaustive_keys(Q, k_local)
         if k_local < k:   # a shard smaller than k: pad its list so that every rank contributes [B, k]
             pad = torch.zeros((keys.size(0), k - k_local), dtype=keys.dtype, device=keys.device)

@@ -131,7 +131,8 @@ int cbk_maxsim_rerank(const void* d_store, int store_dtype, int64_t n_store_rows
 /* ------------------------------------------------------------------------------------------------
  * Per-query top-k — replaces colbert_ranker.py:128-130 (full sort, descending, truncate to depth).
  * Total order: score descending, then pid ascending (the reference's torch.sort is unstable, so its
- * order among exact ties is unspecified).
+ * order among exact ties is unspecified).  A NaN score (cbk_maxsim_rerank's answer for a pid outside the
+ * index) sorts LAST, below -inf, so an invalid candidate can never displace a real one.
  *
  *   d_scores, d_cand_pids, d_cand_rowptr as above; each query may hold at most
  *   cbk_topk_max_candidates() candidates; pids must be < 2^32.  flags: CBK_TOPK_NEG_INF_IS_PADDING.

@@ -34,11 +34,15 @@ def make_ranker(index, dev, store_dtype=torch.float16):
 # ------------------------------------------------------------------------------------------------
 # rank_forward against the reference's golden vectors
 # ------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("store_dtype", [torch.float16, torch.bfloat16], ids=["fp16", "bf16"])
 @pytest.mark.parametrize("case", CASES, ids=[c["name"] for c in CASES])
-def test_rank_forward_golden(dev, golden_dir, case):
+def test_rank_forward_golden(dev, golden_dir, case, store_dtype):
+    """Both store dtypes against the REFERENCE's fp32 results on its fp16 index: the bf16 store (the headline
+    configuration of bench.py) is built by rounding the reference's fp16 index to bf16, and must still be within
+    the north-star tolerance of what the unmodified reference returned."""
     g = np.load(os.path.join(golden_dir, f"rank_{case['name']}.npz"))
     index, queries, cands = build_case(case)
-    ranker = make_ranker(index, dev)
+    ranker = make_ranker(index, dev, store_dtype)
     assert ranker.strides == g["strides"].tolist()
     assert ranker.tensor.size(0) == int(g["store_rows"][0])
     assert ranker.doclens_pfxsum[-4:].tolist() == g["pfxsum_tail"].tolist()
@@ -52,17 +56,22 @@ def test_rank_forward_golden(dev, golden_dir, case):
             worst = max(worst, check_topk(p, s, g[f"q{qi}_{dname}_pids"], g[f"q{qi}_{dname}_scores"], SCORE_RTOL,
                                           full_p, full_s))
             assert all(s[i] >= s[i + 1] for i in range(len(s) - 1))
-        if case.get("output_D"):
+        if case.get("output_D") and store_dtype == torch.float16:    # bit-exact rows: only the reference's own dtype
             p, D, M = ranker.rank_forward(Qt, [int(x) for x in pids], depth=case["output_D"], output_D_embedding=True)
             assert p == g[f"q{qi}_D_pids"].tolist()
             assert D.dtype == torch.float32 and M.dtype == torch.bool
             assert np.array_equal(D.cpu().numpy().astype(np.float16), g[f"q{qi}_D_rows"])      # bit-exact rows
             assert np.array_equal(D.cpu().numpy(), g[f"q{qi}_D_rows"].astype(np.float32))
             assert np.array_equal(M.cpu().numpy(), g[f"q{qi}_D_mask"])
-    print(f"[{case['name']}] worst relative score error vs reference fp32: {worst:.3e}")
+    print(f"[{case['name']}, {store_dtype}] worst relative score error vs reference fp32: {worst:.3e}")
+    WORST_VS_REFERENCE[(case["name"], str(store_dtype))] = worst
 
 
-def test_rank_forward_from_disk_index(dev, tmp_path, golden_dir):
+WORST_VS_REFERENCE = {}
+
+
+@pytest.mark.parametrize("store_dtype", [torch.float16, torch.bfloat16], ids=["fp16", "bf16"])
+def test_rank_forward_from_disk_index(dev, tmp_path, golden_dir, store_dtype):
     """Same answers when the store is loaded from the reference's on-disk layout (3 parts)."""
     from colbert_b200 import synthetic
     from colbert_b200.ranking import ColbertRanker
@@ -70,10 +79,13 @@ def test_rank_forward_from_disk_index(dev, tmp_path, golden_dir):
     g = np.load(os.path.join(golden_dir, "rank_small.npz"))
     index, queries, cands = build_case(case)
     synthetic.write_index(index, str(tmp_path))
-    ranker = ColbertRanker(str(tmp_path), model=None, dim=128, device=dev)
+    ranker = ColbertRanker(str(tmp_path), model=None, dim=128, device=dev, store_dtype=store_dtype)
     assert ranker.strides == g["strides"].tolist()
     ref_store = O.pad_store(index.emb)
-    assert np.array_equal(ranker.tensor.cpu().numpy(), ref_store)              # bit-exact store incl. zero tail
+    if store_dtype == torch.float16:
+        assert np.array_equal(ranker.tensor.cpu().numpy(), ref_store)          # bit-exact store incl. zero tail
+    else:                                                                      # the fp16 index rounded once to bf16
+        assert torch.equal(ranker.tensor.cpu(), torch.from_numpy(ref_store).to(torch.bfloat16))
     assert np.array_equal(ranker.doclens_pfxsum.numpy(), O.doclens_pfxsum(index.doclens))
     Qt = torch.from_numpy(queries[0]).unsqueeze(0).permute(0, 2, 1)
     p, s = ranker.rank_forward(Qt, cands[0].tolist(), depth=10)
@@ -179,8 +191,27 @@ def test_out_of_range_pid_yields_nan_not_a_fault(dev):
     Q = torch.from_numpy(synthetic.make_queries(1, 1, 32, 128)).to(dev)
     cand = torch.tensor([3, 50, -1, 49], dtype=torch.int64, device=dev)
     rowptr = torch.tensor([0, 4], dtype=torch.int64, device=dev)
-    s = ranker.score_candidates(Q, cand, rowptr).cpu().numpy()
+    sc = ranker.score_candidates(Q, cand, rowptr)
+    s = sc.cpu().numpy()
     assert np.isfinite(s[0]) and np.isfinite(s[3]) and np.isnan(s[1]) and np.isnan(s[2])
+    # ... and an invalid candidate sorts LAST in the top-k (below every real score), never first
+    from colbert_b200 import kernels
+    for n_pad in (0, 2000):                         # tournament path (n <= 1024) and shared-memory sort path
+        c2 = torch.cat([cand, torch.arange(n_pad, dtype=torch.int64, device=dev) % 50])
+        s2 = torch.cat([sc, torch.full((n_pad,), -5.0, device=dev)])
+        rp2 = torch.tensor([0, 4 + n_pad], dtype=torch.int64, device=dev)
+        ts, tp = kernels.topk_per_query(s2, c2, rp2, 4 + min(n_pad, 4), 4 + n_pad)
+        assert set(tp[0, :2].tolist()) == {3, 49} and torch.isfinite(ts[0, :2]).all()
+        if n_pad == 0:
+            assert torch.isnan(ts[0, 2:]).all() and set(tp[0, 2:].tolist()) == {50, 2 ** 32 - 1}
+        else:
+            assert torch.isfinite(ts[0]).all()
+    # the reference-shaped call validates host pids like the reference's doclens[pids] does (colbert_ranker.py:88)
+    Qt = torch.from_numpy(synthetic.make_queries(1, 1, 32, 128)).permute(0, 2, 1)
+    with pytest.raises(IndexError):
+        ranker.rank_forward(Qt, [3, 50, 49])
+    with pytest.raises(IndexError):
+        ranker.rank_forward(Qt, [3, -1, 49])
 
 
 def test_topk_kernel_total_order_and_padding(dev):

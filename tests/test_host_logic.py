@@ -104,3 +104,68 @@ def test_index_part_loader_validates_and_maps(tmp_path):
         load_index_part(str(tmp_path / "3.pt"), verbose=False)
     torch.save([good[:3], good[3:]], str(tmp_path / "4.pt"))                        # legacy list-of-batches part
     assert torch.equal(load_index_part(str(tmp_path / "4.pt"), verbose=False), good)
+
+
+def test_part_loader_does_not_fall_back_to_full_pickle(tmp_path, monkeypatch):
+    """A part the weights-only unpickler refuses is NOT retried with pickle unless the caller opts in."""
+    import pickle
+
+    class Payload:                                        # stands in for "anything the safe loader refuses"
+        def __reduce__(self):
+            return (list, ([1.0],))
+
+    path = str(tmp_path / "0.pt")
+    with open(path, "wb") as fh:
+        pickle.dump(Payload(), fh)
+    monkeypatch.delenv("COLBERT_B200_ALLOW_PICKLE", raising=False)
+    with pytest.raises(RuntimeError, match="weights-only"):
+        load_index_part(path, verbose=False)
+    # opting in reaches the unsafe loader (which then fails on the content checks, not on the load policy)
+    with pytest.raises((TypeError, ValueError, RuntimeError)) as ei:
+        load_index_part(path, verbose=False, allow_pickle=True)
+    assert "weights-only" not in str(ei.value)
+
+
+def test_get_representation_multiview_switch():
+    """BaseModel.get_representation (reference BaseModel.py:21-27): with enable_multiview the first q_view / d_view
+    hidden states are kept, projected and L2-normalised; without it every position is."""
+    from types import SimpleNamespace
+    from colbert_b200.modeling.BaseModel import BaseModel
+    torch.manual_seed(0)
+    m = BaseModel()
+    m.linear = torch.nn.Linear(24, 16, bias=False)
+    hidden = torch.randn(3, 40, 24)
+    mv = SimpleNamespace(q_view=8, d_view=16)
+    for enable in (True, False):
+        m.args = SimpleNamespace(enable_multiview=enable, dense_multiview_args=mv)
+        for is_query in (True, False):
+            out = m.get_representation(hidden, is_query)
+            rows = (mv.q_view if is_query else mv.d_view) if enable else 40
+            expect = torch.nn.functional.normalize(hidden[:, :rows] @ m.linear.weight.t(), p=2, dim=2)
+            assert tuple(out.shape) == (3, rows, 16)
+            torch.testing.assert_close(out, expect)
+            torch.testing.assert_close(out.norm(dim=2), torch.ones(3, rows))      # unit rows ⇒ every q·d ∈ [-1, 1]
+    # against the reference's own method when the reference tree is here (this container; absent on the GPU box)
+    ref_root = "/root/reference"
+    if os.path.isdir(os.path.join(ref_root, "colbert")):
+        import importlib.util
+        spec = importlib.util.spec_from_file_location("_ref_BaseModel", os.path.join(ref_root, "colbert/modeling/BaseModel.py"))
+        ref = importlib.util.module_from_spec(spec)
+        spec.loader.exec_module(ref)
+        r = ref.BaseModel()
+        r.linear = m.linear
+        for enable in (True, False):
+            r.args = m.args = SimpleNamespace(enable_multiview=enable, dense_multiview_args=mv)
+            for is_query in (True, False):
+                assert torch.equal(r.get_representation(hidden, is_query), m.get_representation(hidden, is_query))
+
+
+def test_strides_setter_refreshes_the_ctypes_copy():
+    """ColbertRanker.strides is a property: assigning the corpus-wide list (what ShardedColbertRanker does) rebuilds
+    the ctypes array the single-call path passes to the library (a stale copy applied the wrong floor)."""
+    from colbert_b200.ranking.colbert_ranker import ColbertRanker
+    r = ColbertRanker.__new__(ColbertRanker)
+    r.strides = [3, 9]
+    assert list(r._strides_c) == [3, 9] and r.strides == [3, 9]
+    r.strides = [5, 10, 20, 40]
+    assert list(r._strides_c) == [5, 10, 20, 40] and r._views is None

@@ -56,9 +56,14 @@ class OracleShardedRanker(ShardedColbertRanker):
                 out[b, : keys.shape[0]] = keys
         return torch.from_numpy(out.view(np.int64))
 
+    def _local_num_docs(self):
+        return self.hi - self.lo
+
     def _local_exhaustive_keys(self, Q, k):
+        # rank_exhaustive asks for k_local = min(k, documents of this shard) keys and pads the list itself
+        assert k <= self.hi - self.lo
         Qn = Q.numpy()
-        out = np.zeros((Qn.shape[0], k), dtype=np.uint64)          # key 0 = padding: a shard smaller than k
+        out = np.zeros((Qn.shape[0], k), dtype=np.uint64)
         pids = np.arange(self.lo, self.hi, dtype=np.int64)
         for b in range(Qn.shape[0]):
             s = O.maxsim_exact(self.store, self.dl, self.pf, self.strides, Qn[b], pids - self.lo)
