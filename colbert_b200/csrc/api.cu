@@ -21,7 +21,8 @@ int64_t topk_max_candidates();
 int gather_dispatch(const void*, int, int64_t, int, const int64_t*, const int32_t*, int64_t, const int64_t*, int64_t,
                     int, float*, uint8_t*, cudaStream_t);
 
-int partition_dispatch(const int64_t*, const int64_t*, int64_t, int64_t, int64_t, int64_t*, int64_t*, int64_t*, cudaStream_t);
+int partition_dispatch(const int64_t*, const int64_t*, int64_t, int64_t, int64_t, int64_t*, int64_t*, void*, cudaStream_t);
+size_t partition_workspace_bytes(int64_t);
 size_t doc_end_bits_bytes(int64_t);
 int doc_end_bits_dispatch(const int64_t*, int64_t, int64_t, uint32_t*, cudaStream_t);
 size_t exhaustive_workspace_bytes(int64_t);
@@ -381,7 +382,7 @@ int cbk_gather_rows(const void* d_store, int store_dtype, int64_t n_store_rows, 
                          d_out_D, d_out_mask, static_cast<cudaStream_t>(stream));
 }
 
-size_t cbk_partition_workspace_bytes(int64_t n_queries) { return static_cast<size_t>(n_queries > 0 ? n_queries : 1) * sizeof(int64_t); }
+size_t cbk_partition_workspace_bytes(int64_t n_queries) { return cbk::partition_workspace_bytes(n_queries); }
 
 int cbk_partition_candidates(const int64_t* d_cand_pids, const int64_t* d_cand_rowptr, int64_t n_queries, int64_t pid_lo,
                              int64_t pid_hi, int64_t* d_out_pids, int64_t* d_out_rowptr, void* d_workspace,

@@ -1,9 +1,12 @@
 // Candidate routing for a pid-range-sharded store (the reference's ranker is
 // single-GPU, so this has no counterpart there): from the replicated CSR candidate lists keep, per
 // query and in order, the candidates whose global pid lies in this shard's range [pid_lo, pid_hi).
-// Three tiny launches: count per query (one warp per query) → exclusive scan of the counts →
-// ordered scatter (one warp per query, ballot compaction).  Pure integer, HBM-bound work:
-// 8 B read per candidate twice, 8 B written per kept candidate.
+// ONE launch (single pass with decoupled look-back): a CTA takes tiles of 32 queries in ticket order, counts the kept
+// candidates of each (one warp per query, 4 queries per warp), publishes the tile's total, finds its global base by
+// looking back over the totals / inclusive prefixes of the tiles before it, and scatters — the candidate ids are read
+// from HBM once (the second read of a tile's 256 KB comes out of L1/L2).  Pure integer, HBM-bound work: 8 B read per
+// candidate, 8 B written per kept candidate.  (The three-launch form — count, scan, scatter — is still used by the
+// candidate-generation post-processing below.)
 #include <algorithm>
 
 #include "cbk_common.cuh"
@@ -85,6 +88,100 @@ scatter_in_range_kernel(const int64_t* __restrict__ pids, const int64_t* __restr
       if (keep) out_pids[dst + __popc(m & ((1u << lane) - 1u))] = p;
       dst += __popc(m);
     }
+  }
+}
+
+// ---- single-pass routing ---------------------------------------------------------------------------------
+constexpr int kPartWarps = 8;
+constexpr int kPartQPerWarp = 4;
+constexpr int kPartTileQ = kPartWarps * kPartQPerWarp;      // queries per tile
+constexpr uint64_t kPartAgg = 1ull << 62;                   // state = flag | value: tile total published
+constexpr uint64_t kPartIncl = 2ull << 62;                  // inclusive prefix published
+constexpr uint64_t kPartVal = (1ull << 62) - 1;
+
+// state[0] = ticket counter, state[1 + t] = tile t's status word; zeroed by the caller before every launch
+__global__ void __launch_bounds__(kPartWarps * 32)
+partition_single_pass_kernel(const int64_t* __restrict__ pids, const int64_t* __restrict__ rowptr, int64_t n_queries,
+                             int64_t lo, int64_t hi, int64_t* __restrict__ out_pids, int64_t* __restrict__ out_rowptr,
+                             unsigned long long* __restrict__ state) {
+  __shared__ int64_t s_cnt[kPartTileQ];
+  __shared__ int64_t s_base;
+  __shared__ int64_t s_tile;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int64_t n_tiles = (n_queries + kPartTileQ - 1) / kPartTileQ;
+  while (true) {
+    if (threadIdx.x == 0) s_tile = static_cast<int64_t>(atomicAdd(&state[0], 1ull));
+    __syncthreads();
+    const int64_t tile = s_tile;
+    if (tile >= n_tiles) break;
+    const int64_t q0 = tile * kPartTileQ;
+    // ---- count -----------------------------------------------------------------------------------------
+#pragma unroll
+    for (int j = 0; j < kPartQPerWarp; ++j) {
+      const int64_t q = q0 + warp * kPartQPerWarp + j;
+      int c = 0;
+      if (q < n_queries) {
+        const int64_t beg = rowptr[q], end = rowptr[q + 1];
+        for (int64_t i = beg + lane; i < end; i += 32) {
+          const int64_t p = pids[i];
+          c += (p >= lo && p < hi) ? 1 : 0;
+        }
+      }
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) c += __shfl_xor_sync(0xffffffffu, c, o);
+      if (lane == 0) s_cnt[warp * kPartQPerWarp + j] = c;
+    }
+    __syncthreads();
+    // ---- tile scan + decoupled look-back (warp 0) -----------------------------------------------------------
+    if (warp == 0) {
+      const int64_t mine = s_cnt[lane];
+      int64_t incl = mine;
+#pragma unroll
+      for (int o = 1; o < 32; o <<= 1) {
+        const int64_t t = __shfl_up_sync(0xffffffffu, incl, o);
+        if (lane >= o) incl += t;
+      }
+      const int64_t total = __shfl_sync(0xffffffffu, incl, 31);
+      s_cnt[lane] = incl - mine;                              // exclusive offset of query `lane` inside the tile
+      int64_t base = 0;
+      if (lane == 0) {
+        volatile unsigned long long* st = state + 1;
+        if (tile > 0) {
+          st[tile] = kPartAgg | static_cast<unsigned long long>(total);
+          __threadfence();
+          for (int64_t t = tile - 1; t >= 0; --t) {             // tiles are ticketed in order: predecessors are running
+            unsigned long long w;
+            do { w = st[t]; } while (w == 0ull);
+            base += static_cast<int64_t>(w & kPartVal);
+            if (w & kPartIncl) break;
+          }
+        }
+        __threadfence();
+        st[tile] = kPartIncl | static_cast<unsigned long long>(base + total);
+        s_base = base;
+        if (tile == n_tiles - 1) out_rowptr[n_queries] = base + total;
+      }
+    }
+    __syncthreads();
+    // ---- ordered scatter ----------------------------------------------------------------------------------
+    const int64_t base = s_base;
+#pragma unroll
+    for (int j = 0; j < kPartQPerWarp; ++j) {
+      const int64_t q = q0 + warp * kPartQPerWarp + j;
+      if (q >= n_queries) continue;
+      const int64_t beg = rowptr[q], end = rowptr[q + 1];
+      int64_t dst = base + s_cnt[warp * kPartQPerWarp + j];
+      if (lane == 0) out_rowptr[q] = dst;
+      for (int64_t i0 = beg; i0 < end; i0 += 32) {
+        const int64_t i = i0 + lane;
+        const int64_t p = i < end ? pids[i] : -1;
+        const bool keep = i < end && p >= lo && p < hi;
+        const unsigned int m = __ballot_sync(0xffffffffu, keep);
+        if (keep) out_pids[dst + __popc(m & ((1u << lane) - 1u))] = p;
+        dst += __popc(m);
+      }
+    }
+    __syncthreads();                                         // s_cnt / s_base / s_tile are reused by the next tile
   }
 }
 
@@ -198,16 +295,20 @@ int unique_pids_dispatch(const int64_t* d_emb_ids, int64_t n_queries, int n_ids,
   return CBK_OK;
 }
 
+size_t partition_workspace_bytes(int64_t n_queries) {
+  const int64_t n_tiles = (std::max<int64_t>(n_queries, 1) + kPartTileQ - 1) / kPartTileQ;
+  return static_cast<size_t>(n_tiles + 1) * sizeof(unsigned long long);
+}
+
 int partition_dispatch(const int64_t* d_pids, const int64_t* d_rowptr, int64_t n_queries, int64_t lo, int64_t hi,
-                       int64_t* d_out_pids, int64_t* d_out_rowptr, int64_t* d_counts, cudaStream_t stream) {
-  const int grid = static_cast<int>(std::max<int64_t>(1, std::min<int64_t>((n_queries + 7) / 8, static_cast<int64_t>(sm_count()) * 8)));
-  count_in_range_kernel<<<grid, 256, 0, stream>>>(d_pids, d_rowptr, n_queries, lo, hi, d_counts);
+                       int64_t* d_out_pids, int64_t* d_out_rowptr, void* d_workspace, cudaStream_t stream) {
+  const int64_t n_tiles = (n_queries + kPartTileQ - 1) / kPartTileQ;
+  CBK_CUDA(cudaMemsetAsync(d_workspace, 0, partition_workspace_bytes(n_queries), stream));
+  const int grid = static_cast<int>(std::max<int64_t>(1, std::min<int64_t>(n_tiles, static_cast<int64_t>(sm_count()) * 8)));
+  partition_single_pass_kernel<<<grid, kPartWarps * 32, 0, stream>>>(d_pids, d_rowptr, n_queries, lo, hi, d_out_pids, d_out_rowptr,
+                                                                    static_cast<unsigned long long*>(d_workspace));
   CBK_CUDA(cudaGetLastError());
-  exclusive_scan_kernel<<<1, 1024, 0, stream>>>(d_counts, n_queries, d_out_rowptr);
-  CBK_CUDA(cudaGetLastError());
-  scatter_in_range_kernel<<<grid, 256, 0, stream>>>(d_pids, d_rowptr, n_queries, lo, hi, d_out_rowptr, d_out_pids);
-  CBK_CUDA(cudaGetLastError());
-  count_launch(3);
+  count_launch();
   return CBK_OK;
 }
 

@@ -41,47 +41,93 @@ class RerankPipeline:
         self.slots = slots
         assert n_queries % self.world == 0, "the batch must split evenly over the ranks"
         self.slice = n_queries // self.world
+        #: rows of the batch whose results THIS rank hands back (every rank holds the full replicated result on the
+        #: device; each copies only its own 1/world slice to the host, together they return the whole batch)
+        self.result_rows = (self.rank * self.slice, (self.rank + 1) * self.slice)
+        # The tensor-core kernels round the query to fp16 on load, so fp16 queries on the wire give bit-identical
+        # scores at half the bytes; the exceptions multiply differently and keep fp32 on the wire.
+        flags = int(getattr(local, "kernel_flags", 0))
+        from .. import _lib
+        self.fp16_wire_ok = (self.dim % 64 == 0 and self.dim <= 1024
+                             and not flags & (_lib.CBK_FLAG_BF16_NATIVE_MMA | _lib.CBK_FLAG_RERANK_GENERIC))
         dev = self.device
         self.copy_stream = torch.cuda.Stream(device=dev)
         self.Q_dev = [torch.empty((n_queries, q_len, self.dim), dtype=torch.float32, device=dev) for _ in range(slots)]
         self.C_dev = [torch.empty((n_queries, n_cand), dtype=torch.int64, device=dev) for _ in range(slots)]
-        self.out_pids = [torch.empty((n_queries, self.k), dtype=torch.int64).pin_memory() for _ in range(slots)]
-        self.out_scores = [torch.empty((n_queries, self.k), dtype=torch.float32).pin_memory() for _ in range(slots)]
+        self.Q16_dev = [None] * slots           # staging for 16-bit queries / 32-bit pids on the wire, made on first use
+        self.C32_dev = [None] * slots
+        lo, hi = self.result_rows
+        self.out_pids = [torch.empty((hi - lo, self.k), dtype=torch.int64).pin_memory() for _ in range(slots)]
+        self.out_scores = [torch.empty((hi - lo, self.k), dtype=torch.float32).pin_memory() for _ in range(slots)]
         self.ev_in = [torch.cuda.Event() for _ in range(slots)]
         self.ev_done = [torch.cuda.Event() for _ in range(slots)]
         self._i = 0
         # the input all-gather runs on the copy stream, concurrently with the key all-gather of the previous step on
         # the compute stream: it needs its own communicator (collective call: every rank builds its pipeline)
         self.in_group = dist.new_group(ranks=list(range(self.world))) if self.world > 1 else None
-        self.h2d_bytes_per_step = (self.slice * q_len * self.dim * 4 + self.slice * n_cand * 8) * self.world
-        self.d2h_bytes_per_step = n_queries * self.k * 12 * self.world
+        self.h2d_bytes_per_step = 0             # set by the first submit (depends on the dtypes handed in)
+        self.d2h_bytes_per_step = n_queries * self.k * 12        # all ranks together: each its own slice
+        self._wire = None
+
+    def describe(self) -> str:
+        return ("colbert_b200.ranking.pipeline.RerankPipeline.submit/result (pinned host in, pinned host out, 2-slot stream "
+                f"pipeline; wire dtypes {self._wire}; every rank uploads 1/{self.world} of the batch and downloads "
+                f"1/{self.world} of the result)")
+
+    def _upload(self, s: int, host: torch.Tensor, full: torch.Tensor, lo: int, hi: int) -> None:
+        """host[lo:hi] → full[lo:hi] (H2D), then — sharded — all-gather IN PLACE: the send buffer is this rank's own
+        slice of the receive buffer, so no staging copy is made."""
+        full[lo:hi].copy_(host[lo:hi], non_blocking=True)
+        if self.world > 1:
+            flat = full.view(self.world, -1)
+            dist.all_gather_into_tensor(flat, flat[self.rank], group=self.in_group)
 
     def submit(self, Q_host: torch.Tensor, cand_host: torch.Tensor) -> int:
-        """Queue one step; returns the slot to pass to :meth:`result`.  ``Q_host`` ``[n_queries, q_len, dim]`` fp32
-        and ``cand_host`` ``[n_queries, n_cand]`` int64, both pinned and identical on every rank."""
+        """Queue one step; returns the slot to pass to :meth:`result`.  ``Q_host`` ``[n_queries, q_len, dim]`` fp32 or
+        fp16 and ``cand_host`` ``[n_queries, n_cand]`` int64 or int32 (pids < 2^31), both pinned and identical on every
+        rank.  16-bit queries / 32-bit pids halve the bytes on PCIe and NVLink and are widened on the device; the scores
+        are bit-identical to the fp32 / int64 submission (the kernel rounds the query to fp16 itself)."""
         assert Q_host.is_pinned() and cand_host.is_pinned(), "inputs must be pinned host tensors"
+        assert Q_host.dtype in (torch.float32, torch.float16) and cand_host.dtype in (torch.int64, torch.int32)
+        if Q_host.dtype == torch.float16 and not self.fp16_wire_ok:
+            raise ValueError("fp16 queries on the wire need a kernel that rounds the query to fp16 (dim multiple of 64, "
+                             "no CBK_FLAG_BF16_NATIVE_MMA / CBK_FLAG_RERANK_GENERIC): pass fp32")
         s = self._i % self.slots
         self._i += 1
         compute = torch.cuda.current_stream(self.device)
         lo, hi = self.rank * self.slice, (self.rank + 1) * self.slice
+        dev = self.device
         with torch.cuda.stream(self.copy_stream):
             self.copy_stream.wait_event(self.ev_done[s])            # the slot's previous step no longer reads the buffers
-            self.Q_dev[s][lo:hi].copy_(Q_host[lo:hi], non_blocking=True)
-            self.C_dev[s][lo:hi].copy_(cand_host[lo:hi], non_blocking=True)
-            if self.world > 1:                                      # slices → full replicated batch over NVLink
-                dist.all_gather_into_tensor(self.Q_dev[s].view(self.n_queries * self.q_len, self.dim),
-                                            self.Q_dev[s][lo:hi].reshape(self.slice * self.q_len, self.dim).clone(),
-                                            group=self.in_group)
-                dist.all_gather_into_tensor(self.C_dev[s], self.C_dev[s][lo:hi].clone(), group=self.in_group)
+            if Q_host.dtype == torch.float16:
+                if self.Q16_dev[s] is None:
+                    self.Q16_dev[s] = torch.empty((self.n_queries, self.q_len, self.dim), dtype=torch.float16, device=dev)
+                self._upload(s, Q_host, self.Q16_dev[s], lo, hi)
+                self.Q_dev[s].copy_(self.Q16_dev[s])                # exact widening
+            else:
+                self._upload(s, Q_host, self.Q_dev[s], lo, hi)
+            if cand_host.dtype == torch.int32:
+                if self.C32_dev[s] is None:
+                    self.C32_dev[s] = torch.empty((self.n_queries, self.n_cand), dtype=torch.int32, device=dev)
+                self._upload(s, cand_host, self.C32_dev[s], lo, hi)
+                self.C_dev[s].copy_(self.C32_dev[s])
+            else:
+                self._upload(s, cand_host, self.C_dev[s], lo, hi)
             self.ev_in[s].record(self.copy_stream)
+        if self._wire is None:
+            self._wire = f"Q {str(Q_host.dtype).replace('torch.', '')}, pids {str(cand_host.dtype).replace('torch.', '')}"
+            self.h2d_bytes_per_step = (self.slice * self.q_len * self.dim * Q_host.element_size()
+                                       + self.slice * self.n_cand * cand_host.element_size()) * self.world
         compute.wait_event(self.ev_in[s])
         pids, scores = self.ranker.rank_forward_batch(self.Q_dev[s], self.C_dev[s], depth=self.depth)
-        self.out_pids[s].copy_(pids, non_blocking=True)
-        self.out_scores[s].copy_(scores, non_blocking=True)
+        r0, r1 = self.result_rows
+        self.out_pids[s].copy_(pids[r0:r1], non_blocking=True)
+        self.out_scores[s].copy_(scores[r0:r1], non_blocking=True)
         self.ev_done[s].record(compute)
         return s
 
     def result(self, slot: int) -> Tuple[torch.Tensor, torch.Tensor]:
-        """Block until the step in ``slot`` has finished; → (pids [n_queries,k] int64, scores [n_queries,k] fp32) on the host."""
+        """Block until the step in ``slot`` has finished; → (pids [rows,k] int64, scores [rows,k] fp32) on the host for
+        the queries ``result_rows`` of the batch (all of them on a single GPU; this rank's 1/world slice when sharded)."""
         self.ev_done[slot].synchronize()
         return self.out_pids[slot], self.out_scores[slot]

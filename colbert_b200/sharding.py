@@ -62,6 +62,9 @@ class ShardedColbertRanker:
             local.strides = self.strides
             local.pid_base = self.pid_base
             local.kernel_flags |= CBK_FLAG_SKIP_FOREIGN_PIDS
+        self._comm_stream = None
+        #: when set to a list, every MaxSim launch of rank_forward_batch appends its (start, end) CUDA events to it
+        self.maxsim_events = None
 
     @classmethod
     def from_global_tensors(cls, embeddings: torch.Tensor, doclens, device, group=None, store_dtype=None):
@@ -88,7 +91,13 @@ class ShardedColbertRanker:
         """Route this shard's share of every candidate list, score it, keep the local top-k as packed keys."""
         n_docs = self.local.doclens.numel()
         my_pids, my_rowptr = kernels.partition_candidates(cand_pids, cand_rowptr, self.pid_base, self.pid_base + n_docs)
+        if self.maxsim_events is not None:
+            ev = (torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True))
+            ev[0].record()
         scores = self.local.score_candidates(Q, my_pids, my_rowptr)
+        if self.maxsim_events is not None:
+            ev[1].record()
+            self.maxsim_events.append(ev)
         return kernels.topk_per_query(scores, my_pids, my_rowptr, k, max_cand,
                                       flags=CBK_TOPK_NEG_INF_IS_PADDING, as_keys=True)
 
@@ -126,17 +135,28 @@ class ShardedColbertRanker:
         return self._merge(self._exchange(keys), int(k))
 
     def rank_forward_batch(self, Q: torch.Tensor, cand_pids: torch.Tensor, cand_rowptr: Optional[torch.Tensor] = None,
-                           depth: Optional[int] = 10, max_cand: Optional[int] = None):
-        """Same contract as ``ColbertRanker.rank_forward_batch`` with GLOBAL pids; identical on all ranks."""
+                           depth: Optional[int] = 10, max_cand: Optional[int] = None, chunks: Optional[int] = None):
+        """Same contract as ``ColbertRanker.rank_forward_batch`` with GLOBAL pids; identical on all ranks.
+
+        ``chunks`` (equal-length lists ``[B, n]`` on more than one GPU): the batch is scored in that many query chunks,
+        and the key all-gather + merge of chunk i run on a second stream underneath the MaxSim of chunk i+1 — the
+        exchange is latency- and skew-bound (it waits for the slowest rank), so hiding it keeps the tensor pipes busy.
+        Default: 4 chunks from 2048 queries up, else 1.  The result does not depend on it."""
         dev = self.local.device if self.local is not None else Q.device
         Q = Q.to(dev, dtype=torch.float32, non_blocking=True).contiguous()
         B = Q.size(0)
         cand_pids = cand_pids.to(dev, non_blocking=True)
-        if cand_rowptr is None:
+        dense = cand_rowptr is None
+        if dense:
             assert cand_pids.dim() == 2 and cand_pids.size(0) == B
             n = cand_pids.size(1)
-            cand_rowptr = torch.arange(0, (B + 1) * n, n, dtype=torch.int64, device=dev)
             max_cand = n
+            if chunks is None:
+                chunks = 4 if (self.world > 1 and B >= 2048) else 1
+            chunks = max(1, min(int(chunks), B))
+            if chunks > 1 and Q.is_cuda:
+                return self._rank_forward_chunked(Q, cand_pids.contiguous(), n, depth, chunks)
+            cand_rowptr = torch.arange(0, (B + 1) * n, n, dtype=torch.int64, device=dev)
             cand_pids = cand_pids.reshape(-1)
         else:
             cand_rowptr = cand_rowptr.to(dev, non_blocking=True)
@@ -146,3 +166,31 @@ class ShardedColbertRanker:
         k = max_cand if depth is None else min(int(depth), max_cand)
         keys = self._local_topk_keys(Q, cand_pids, cand_rowptr, k, max_cand)
         return self._merge(self._exchange(keys), k)
+
+    def _rank_forward_chunked(self, Q: torch.Tensor, cand: torch.Tensor, n: int, depth: Optional[int], chunks: int):
+        dev = Q.device
+        B = Q.size(0)
+        k = n if depth is None else min(int(depth), n)
+        compute = torch.cuda.current_stream(dev)
+        if self._comm_stream is None:
+            self._comm_stream = torch.cuda.Stream(device=dev)
+        comm = self._comm_stream
+        out_p = torch.empty((B, k), dtype=torch.int64, device=dev)
+        out_s = torch.empty((B, k), dtype=torch.float32, device=dev)
+        comm.wait_stream(compute)                                   # out_* exist before the side stream writes them
+        for c in range(chunks):
+            q0, q1 = B * c // chunks, B * (c + 1) // chunks
+            rowptr = torch.arange(0, (q1 - q0 + 1) * n, n, dtype=torch.int64, device=dev)
+            keys = self._local_topk_keys(Q[q0:q1], cand[q0:q1].reshape(-1), rowptr, k, n)
+            ready = torch.cuda.Event()
+            ready.record(compute)
+            keys.record_stream(comm)
+            with torch.cuda.stream(comm):
+                comm.wait_event(ready)
+                p, s = self._merge(self._exchange(keys), k)
+                out_p[q0:q1].copy_(p)
+                out_s[q0:q1].copy_(s)
+        compute.wait_stream(comm)
+        out_p.record_stream(comm)
+        out_s.record_stream(comm)
+        return out_p, out_s

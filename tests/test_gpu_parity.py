@@ -394,6 +394,11 @@ def test_sharded_ranker_world1(dev):
     p1, s1 = single.rank_forward_batch(Q, cand, depth=10)
     p2, s2 = sharded.rank_forward_batch(Q, cand, depth=10)
     assert torch.equal(p1, p2) and torch.equal(s1, s2)
+    # query chunks with the exchange + merge on a side stream: same result for any chunk count
+    for chunks in (2, 3, 4):
+        p3, s3 = sharded.rank_forward_batch(Q, cand, depth=10, chunks=chunks)
+        torch.cuda.synchronize()
+        assert torch.equal(p1, p3) and torch.equal(s1, s3)
 
 
 def test_partition_candidates_matches_numpy(dev):
@@ -491,6 +496,19 @@ def test_rerank_pipeline_matches_direct_call(dev):
     for (Q, cand), (p, s) in zip(batches, outs):
         rp, rs = ranker.rank_forward_batch(Q, cand, depth=10)
         assert torch.equal(p, rp.cpu()) and torch.equal(s, rs.cpu())
+    # fp16 queries / int32 pids on the wire: half the bytes, BIT-IDENTICAL results (the kernel rounds Q to fp16 itself)
+    pipe16 = RerankPipeline(ranker, B, 32, n, depth=10)
+    for (Q, cand), (p, s) in zip(batches, outs):
+        h = pipe16.submit(Q.to(torch.float16).pin_memory(), cand.to(torch.int32).pin_memory())
+        p16, s16 = pipe16.result(h)
+        assert torch.equal(p16, p) and torch.equal(s16, s)
+    assert pipe16.h2d_bytes_per_step * 2 == pipe.h2d_bytes_per_step
+    # a store multiplied as native bf16 rounds the query differently: fp16 on the wire is refused there
+    from colbert_b200 import _lib
+    r2 = make_ranker(index, dev, torch.bfloat16)
+    r2.kernel_flags |= _lib.CBK_FLAG_BF16_NATIVE_MMA
+    with pytest.raises(ValueError):
+        RerankPipeline(r2, B, 32, n).submit(batches[0][0].to(torch.float16).pin_memory(), batches[0][1])
 
 
 # ------------------------------------------------------------------------------------------------
