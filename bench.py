@@ -192,9 +192,10 @@ class CpuArm:
             self.kind = "reference"
             cr, BaseModel, shims = ref_loader.load(cpu=not native_gpu)
             self.shims = shims
-            with tempfile.TemporaryDirectory() as d, shims():
-                synthetic.write_index(index, d)
-                self.ranker = cr.ColbertRanker(d, model=BaseModel, dim=128)
+            import contextlib
+            with tempfile.TemporaryDirectory() as d, shims(), contextlib.redirect_stdout(sys.stderr):
+                synthetic.write_index(index, d)                     # (the reference prints its progress to stdout;
+                self.ranker = cr.ColbertRanker(d, model=BaseModel, dim=128)   # stdout carries the ONE JSON line)
             self.what = ("the reference's own ColbertRanker.rank_forward + BaseModel.score (unmodified files staged in "
                          "oracle/_ref, " + ("DEVICE='cuda' as its author deploys it: CPU index_select -> pinned buffer "
                                             "-> H2D -> einsum on the GPU" if native_gpu else "DEVICE='cpu'") + ")")
@@ -207,20 +208,20 @@ class CpuArm:
             self.ranker = CpuRankerPort(store, index.doclens.tolist(), max_candidates=n_cand)
             self.shims = None
             self.what = "oracle/ref_port_torch.py (the reference's op sequence on torch CPU ops)"
-        self._call(0)                                                   # warm-up
+        self.run(only=[0])                                              # warm-up
 
     def _call(self, b):
         Qt = self.Q[b].unsqueeze(0).permute(0, 2, 1)
         return self.ranker.rank_forward(Qt, self.cand_lists[b], depth=self.depth)
 
-    def run(self):
+    def run(self, only=None):
         """one pass over the sample → seconds"""
         ctx = self.shims() if self.shims is not None else None
         if ctx is not None:
             ctx.__enter__()
         try:
             t0 = time.perf_counter()
-            for b in range(self.n_queries):
+            for b in (range(self.n_queries) if only is None else only):
                 self._call(b)
             if self.native_gpu:
                 self.torch.cuda.synchronize()
@@ -431,7 +432,8 @@ def timed_region(torch, dist, world, step, warmup, min_steps, min_ms=1500.0, max
 
 def secondary_multiview(torch, sampler, dev, args, cand_dev, rowptr, d_view, q_view, dtype, peaks):
     """configs[2]: multi-view rerank (enable_multiview: every document is d_view rows, every query q_view rows, max over
-    views = max over the document's rows), same 4096 x 1000 candidate lists as the headline."""
+    views = max over the document's rows), same 4096 x 1000 candidate lists as the headline.  d_view == 0: the headline
+    workload itself (doclen U[1,180], 32 query rows) on a store of another dtype."""
     from colbert_b200 import kernels
     from colbert_b200.ranking import ColbertRanker
     store, doclens = build_store(torch, dev, args.docs, 128, dtype, seed=777 + d_view, doclen_fixed=d_view)
@@ -449,15 +451,22 @@ def secondary_multiview(torch, sampler, dev, args, cand_dev, rowptr, d_view, q_v
 
     steps, ms_total, kern_ms, win = timed_region(torch, None, 1, step, args.warmup, args.steps)
     n_cand = cand_dev.numel()
-    algo = n_cand * d_view * 128 * 2
+    algo = int(ranker._doclens_dev[cand_dev].to(torch.int64).sum().item()) * 128 * 2
     achieved = algo / (kern_ms * 1e-3) / 1e9
-    out = {"workload": f"multi-view rerank: {n_q} queries x {args.cands} candidates, q_view {q_view}, d_view {d_view}, dim 128, "
-                       f"{args.dtype} store of {args.docs} docs ({store.numel() * 2 / 1e9:.1f} GB), top-{k} "
-                       "(BASELINE.json configs[2]" + ("" if d_view == 8 else "; the author's dense.yaml operating point is 16 x 16") + ")",
+    dname = str(dtype).replace("torch.", "").replace("bfloat16", "bf16").replace("float16", "fp16")
+    if d_view:
+        what = (f"multi-view rerank: {n_q} queries x {args.cands} candidates, q_view {q_view}, d_view {d_view}, dim 128, "
+                f"{dname} store of {args.docs} docs ({store.numel() * 2 / 1e9:.1f} GB), top-{k} (BASELINE.json configs[2]"
+                + ("" if d_view == 8 else "; the author's dense.yaml operating point is 16 x 16") + ")")
+    else:
+        what = (f"rerank: {n_q} queries x {args.cands} candidates, q_len {q_view}, dim 128, doclen U[1,180], {dname} store of "
+                f"{args.docs} docs ({store.numel() * 2 / 1e9:.1f} GB), top-{k} (configs[1] on the reference's own index "
+                "dtype: the store whose scores meet 1e-3 against the reference's goldens)")
+    out = {"workload": what,
            "value": n_cand * steps / (ms_total * 1e-3), "unit": UNIT, "steps": steps, "ms_per_step": ms_total / steps,
            "roofline": {"bound": "hbm", "achieved": achieved, "peak": peaks["hbm_gbs"], "unit": "GB/s",
                         "frac": achieved / peaks["hbm_gbs"], "kernel_ms": kern_ms, "algorithmic_bytes_per_launch": algo,
-                        "kernel": "maxsim_rerank_kernel (multi-view instantiation)", "traffic": None},
+                        "kernel": "maxsim_rerank_kernel" + (" (multi-view instantiation)" if d_view else ""), "traffic": None},
            "clocks": sampler.window(*win)}
     del store, ranker
     torch.cuda.empty_cache()
@@ -722,6 +731,9 @@ def run_ours(args, rank, world, local_rank):
         if world == 1:
             secondary["multiview_8x8"] = secondary_multiview(torch, sampler, dev, args, cand_dev, rowptr, 8, 8, dtype, peaks)
             secondary["multiview_16x16"] = secondary_multiview(torch, sampler, dev, args, cand_dev, rowptr, 16, 16, dtype, peaks)
+            if dtype != torch.float16:
+                secondary["rerank_fp16_store"] = secondary_multiview(torch, sampler, dev, args, cand_dev, rowptr, 0, 32,
+                                                                     torch.float16, peaks)
         del cand_dev
         torch.cuda.empty_cache()
         secondary["exhaustive"] = secondary_exhaustive(torch, dist, sampler, dev, args, rank, world, peaks)
