@@ -114,23 +114,22 @@ struct __align__(16) PendBuf {
 __device__ __noinline__ void flush_pending(PendBuf* pb, int n, float* __restrict__ dst_first, bool write) {
   __syncwarp();
   const int lane = threadIdx.x & 31;
-  if (lane < n) {
-    const int doclen = pb->len[lane];
-    const int n_strides = pb->n_strides;
-    float floor_v = n_strides > 0 ? 0.f : -INFINITY;
-    for (int i = 0; i < n_strides; ++i)
-      if (pb->strides[i] == doclen) floor_v = -INFINITY;
-    const float* row = pb->v[lane];
-    float s0 = 0.f, s1 = 0.f, s2 = 0.f, s3 = 0.f;
-#pragma unroll
-    for (int i = 0; i < 32; i += 4) {
-      s0 += fmaxf(row[i], floor_v);
-      s1 += fmaxf(row[i + 1], floor_v);
-      s2 += fmaxf(row[i + 2], floor_v);
-      s3 += fmaxf(row[i + 3], floor_v);
-    }
-    if (write) dst_first[lane] = (s0 + s1) + (s2 + s3);
-  }
+  static_assert(kPend == 8, "flush_pending maps lane -> (document = lane / 4, quarter of the query rows = lane % 4)");
+  const int d = lane >> 2, qtr = lane & 3;
+  const int doclen = pb->len[d];                      // (documents >= n: stale values, computed and dropped)
+  const int n_strides = pb->n_strides;
+  float floor_v = n_strides > 0 ? 0.f : -INFINITY;
+  for (int i = 0; i < n_strides; ++i)
+    if (pb->strides[i] == doclen) floor_v = -INFINITY;
+  const float* row = pb->v[d] + qtr * 8;              // bank (33 d + 8 qtr + i) % 32: conflict-free across the warp
+  float s0 = fmaxf(row[0], floor_v) + fmaxf(row[1], floor_v);
+  float s1 = fmaxf(row[2], floor_v) + fmaxf(row[3], floor_v);
+  float s2 = fmaxf(row[4], floor_v) + fmaxf(row[5], floor_v);
+  float s3 = fmaxf(row[6], floor_v) + fmaxf(row[7], floor_v);
+  float sum = (s0 + s1) + (s2 + s3);
+  sum += __shfl_xor_sync(0xffffffffu, sum, 1);
+  sum += __shfl_xor_sync(0xffffffffu, sum, 2);
+  if (write && qtr == 0 && d < n) dst_first[d] = sum;
   __syncwarp();
 }
 
@@ -165,6 +164,25 @@ __device__ __noinline__ EpiState close_docs_in_group(PendBuf* pb, EpiState st, f
     }
   }
   return st;
+}
+
+// Exactly ONE document ends inside the 8 columns x[0..7], at column e (warp-uniform): → head = max(r, x[0..e]) closes
+// that document, tail = max(x[e+1..7]) opens the next one (-inf when e == 7).  A switch on e: one indirect branch and
+// four or five 3-input maxima instead of eight compare / branch / max rounds.
+__device__ __forceinline__ void split8(const uint32_t* v, int e, float r, float& head, float& tail) {
+  const float x0 = __uint_as_float(v[0]), x1 = __uint_as_float(v[1]), x2 = __uint_as_float(v[2]), x3 = __uint_as_float(v[3]);
+  const float x4 = __uint_as_float(v[4]), x5 = __uint_as_float(v[5]), x6 = __uint_as_float(v[6]), x7 = __uint_as_float(v[7]);
+  const float ninf = -INFINITY;
+  switch (e) {
+    case 0: head = fmaxf(r, x0); tail = fmaxf(fmaxf(fmaxf(x1, x2), x3), fmaxf(fmaxf(fmaxf(x4, x5), x6), x7)); break;
+    case 1: head = fmaxf(fmaxf(r, x0), x1); tail = fmaxf(fmaxf(fmaxf(x2, x3), x4), fmaxf(fmaxf(x5, x6), x7)); break;
+    case 2: head = fmaxf(fmaxf(fmaxf(r, x0), x1), x2); tail = fmaxf(fmaxf(fmaxf(x3, x4), x5), fmaxf(x6, x7)); break;
+    case 3: head = fmaxf(fmaxf(fmaxf(r, x0), x1), fmaxf(x2, x3)); tail = fmaxf(fmaxf(fmaxf(x4, x5), x6), x7); break;
+    case 4: head = fmaxf(fmaxf(fmaxf(r, x0), x1), fmaxf(fmaxf(x2, x3), x4)); tail = fmaxf(fmaxf(x5, x6), x7); break;
+    case 5: head = fmaxf(fmaxf(fmaxf(r, x0), x1), fmaxf(fmaxf(fmaxf(x2, x3), x4), x5)); tail = fmaxf(x6, x7); break;
+    case 6: head = fmaxf(fmaxf(fmaxf(fmaxf(r, x0), x1), x2), fmaxf(fmaxf(fmaxf(x3, x4), x5), x6)); tail = x7; break;
+    default: head = fmaxf(fmaxf(fmaxf(fmaxf(r, x0), x1), x2), fmaxf(fmaxf(fmaxf(x3, x4), x5), fmaxf(x6, x7))); tail = ninf; break;
+  }
 }
 
 // max of 8 consecutive accumulator columns and the running value
@@ -473,6 +491,18 @@ maxsim_exhaustive_kernel(const __grid_constant__ ExhMaps maps, const uint32_t* _
               const uint32_t m8 = (m >> (8 * s8)) & 0xffu;
               if (m8 == 0u) {
                 st.r = max8(v + 8 * s8, st.r);
+              } else if ((m8 & (m8 - 1u)) == 0u) {   // one document ends in these 8 columns (any document of 8+ rows)
+                const int e = 31 - __clz(static_cast<int>(m8));
+                float head, tail;
+                split8(v + 8 * s8, e, st.r, head, tail);
+                const int slot = st.docs_done & (kPend - 1);
+                const int end1 = col + 8 * s8 + e + 1;
+                pb->v[slot][lane] = head;
+                if (lane == 0) pb->len[slot] = end1 - st.doc_start;
+                st.doc_start = end1;
+                ++st.docs_done;
+                st.r = tail;
+                if ((st.docs_done & (kPend - 1)) == 0) flush_pending(pb, kPend, dst_row + (st.docs_done - kPend), write != 0);
               } else {
                 const uint32_t* x = v + 8 * s8;
                 st = close_docs_in_group(pb, st, __uint_as_float(x[0]), __uint_as_float(x[1]), __uint_as_float(x[2]),
