@@ -12,7 +12,8 @@ import os
 from typing import Optional
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "csrc", "libcolbert_b200.so")
+# COLBERT_B200_LIB: another build of the same library (A/B experiments on kernel variants); default = the in-tree build
+LIB_PATH = os.environ.get("COLBERT_B200_LIB") or os.path.join(_HERE, "csrc", "libcolbert_b200.so")
 
 CBK_F16, CBK_BF16, CBK_F32 = 0, 1, 2
 CBK_MASK_NONE, CBK_MASK_U8, CBK_MASK_I64, CBK_MASK_F32 = 0, 1, 2, 3
@@ -22,6 +23,8 @@ CBK_FLAG_BF16_NATIVE_MMA = 1
 CBK_FLAG_SKIP_FOREIGN_PIDS = 2
 CBK_FLAG_RERANK_TCGEN05 = 4
 CBK_FLAG_RERANK_GENERIC = 8
+CBK_FLAG_FIXED_DOCLEN = 16
+CBK_ABI_VERSION = 2
 CBK_TOPK_NEG_INF_IS_PADDING = 1
 
 # name → (restype, argtypes); mirrors include/colbert_b200.h one to one
@@ -32,7 +35,7 @@ SIGNATURES = {
     "cbk_device_supported": (C.c_int, [C.c_int]),
     "cbk_launch_count": (C.c_uint64, []),
     "cbk_maxsim_rerank_workspace_bytes": (_sz, []),
-    "cbk_maxsim_rerank": (C.c_int, [_vp, _i32, _i64, _i32, _vp, _vp, _i64, _i64, _vp, _i32, _vp, _i32, _i64,
+    "cbk_maxsim_rerank": (C.c_int, [_vp, _i32, _i64, _i32, _vp, _vp, _i64, _i64, _vp, _i32, _vp, _vp, _i32, _i64,
                                     _vp, _vp, _i64, _vp, _vp, _sz, _i32, _vp]),
     "cbk_topk_max_candidates": (_i64, []),
     "cbk_topk_per_query": (C.c_int, [_vp, _vp, _vp, _i64, _i64, _i32, _i32, _vp, _vp, _vp]),
@@ -84,8 +87,8 @@ def load() -> C.CDLL:
     for name, (res, args) in SIGNATURES.items():
         fn = getattr(lib, name)          # AttributeError if the symbol is not exported
         fn.restype, fn.argtypes = res, args
-    if lib.cbk_abi_version() != 1:
-        raise RuntimeError(f"ABI version mismatch: library reports {lib.cbk_abi_version()}, binding expects 1")
+    if lib.cbk_abi_version() != CBK_ABI_VERSION:
+        raise RuntimeError(f"ABI version mismatch: library reports {lib.cbk_abi_version()}, binding expects {CBK_ABI_VERSION}")
     _lib = lib
     return lib
 

@@ -13,7 +13,7 @@ namespace cbk {
 
 // dispatchers implemented in the kernel translation units
 int rerank_dispatch(const void*, int, int64_t, int, const int64_t*, const int32_t*, int64_t, int64_t, const int32_t*, int,
-                    const float*, int, int64_t, const int64_t*, const int64_t*, int64_t, float*, void*, int, cudaStream_t);
+                    const float*, const int32_t*, int, int64_t, const int64_t*, const int64_t*, int64_t, float*, void*, int, cudaStream_t);
 int topk_dispatch(const float*, const int64_t*, const int64_t*, int64_t, int64_t, int, int, float*, int64_t*, uint64_t*,
                   cudaStream_t);
 int merge_dispatch(const uint64_t*, int, int64_t, int, int, float*, int64_t*, cudaStream_t);
@@ -33,12 +33,12 @@ int topk_dense_dispatch(const float*, int64_t, int64_t, int, int64_t, int, float
 int emb2pid_dispatch(const int64_t*, int64_t, int32_t*, cudaStream_t);
 int unique_pids_dispatch(const int64_t*, int64_t, int, const int32_t*, int64_t, int64_t*, int64_t*, void*, cudaStream_t);
 int rerank_generic_dispatch(const void*, int, int64_t, int, const int64_t*, const int32_t*, int64_t, int64_t, const int32_t*, int,
-                            const float*, int, int64_t, const int64_t*, const int64_t*, float*, int, cudaStream_t);
+                            const float*, const int32_t*, int, int64_t, const int64_t*, const int64_t*, float*, int, cudaStream_t);
 bool rerank_wide_supports(int dim);
 int rerank_wide_dispatch(const void*, int, int64_t, int, const int64_t*, const int32_t*, int64_t, int64_t, const int32_t*, int,
-                         const float*, int, int64_t, const int64_t*, const int64_t*, int64_t, float*, void*, int, cudaStream_t);
+                         const float*, const int32_t*, int, int64_t, const int64_t*, const int64_t*, int64_t, float*, void*, int, cudaStream_t);
 int rerank_umma_dispatch(const void*, int, int64_t, int, const int64_t*, const int32_t*, int64_t, int64_t, const int32_t*, int,
-                         const float*, int, int64_t, const int64_t*, const int64_t*, int64_t, float*, void*, int, cudaStream_t);
+                         const float*, const int32_t*, int, int64_t, const int64_t*, const int64_t*, int64_t, float*, void*, int, cudaStream_t);
 int umma_probe_dispatch(const void*, const void*, int, int, int, float*, cudaStream_t);
 int umma_rate_dispatch(int, int, int, int, int, long long*, cudaStream_t);
 int mask_cast_dispatch(const void*, int, int64_t, int, const void*, int, void*, int, cudaStream_t);
@@ -191,11 +191,12 @@ size_t cbk_maxsim_rerank_workspace_bytes(void) { return 256; }
 
 int cbk_maxsim_rerank(const void* d_store, int store_dtype, int64_t n_store_rows, int dim, const int64_t* d_pfxsum,
                       const int32_t* d_doclens, int64_t n_docs, int64_t pid_base, const int32_t* strides, int n_strides,
-                      const float* d_Q,
+                      const float* d_Q, const int32_t* d_q_lens,
                       int q_len, int64_t n_queries, const int64_t* d_cand_pids, const int64_t* d_cand_rowptr,
                       int64_t n_cand_total, float* d_out_scores, void* d_workspace, size_t workspace_bytes,
                       int flags, void* stream) {
-  CBK_CHECK_ARG(d_store && d_pfxsum && d_doclens && d_Q && d_cand_pids && d_cand_rowptr && d_out_scores,
+  const bool fixed_len = (flags & CBK_FLAG_FIXED_DOCLEN) && n_strides == 1 && dim == 128;   // metadata arrays unused
+  CBK_CHECK_ARG(d_store && (fixed_len || (d_pfxsum && d_doclens)) && d_Q && d_cand_pids && d_cand_rowptr && d_out_scores,
                 "cbk_maxsim_rerank: null pointer argument");
   CBK_CHECK_ARG(store_dtype == CBK_F16 || store_dtype == CBK_BF16, "cbk_maxsim_rerank: unknown store dtype %d", store_dtype);
   CBK_CHECK_ARG(n_store_rows > 0 && n_docs > 0 && n_queries > 0 && n_cand_total >= 0,
@@ -220,18 +221,18 @@ int cbk_maxsim_rerank(const void* d_store, int store_dtype, int64_t n_store_rows
   if (dim != 128 && !(flags & CBK_FLAG_RERANK_GENERIC) && rerank_wide_supports(dim) &&
       (reinterpret_cast<uintptr_t>(d_store) & 0xf) == 0)
     return rerank_wide_dispatch(d_store, store_dtype, n_store_rows, dim, d_pfxsum, d_doclens, n_docs, pid_base, strides, n_strides,
-                                d_Q, q_len, n_queries, d_cand_pids, d_cand_rowptr, n_cand_total, d_out_scores, d_workspace, flags,
-                                static_cast<cudaStream_t>(stream));   // K-split tensor-core kernel: dim = 64, 192, …, 768, 1024
+                                d_Q, d_q_lens, q_len, n_queries, d_cand_pids, d_cand_rowptr, n_cand_total, d_out_scores, d_workspace,
+                                flags, static_cast<cudaStream_t>(stream));   // K-split tensor-core kernel: dim = 64, 192, …, 768, 1024
   if (dim != 128)   // any other width (CUDA cores)
     return rerank_generic_dispatch(d_store, store_dtype, n_store_rows, dim, d_pfxsum, d_doclens, n_docs, pid_base, strides,
-                                   n_strides, d_Q, q_len, n_queries, d_cand_pids, d_cand_rowptr, d_out_scores, flags,
+                                   n_strides, d_Q, d_q_lens, q_len, n_queries, d_cand_pids, d_cand_rowptr, d_out_scores, flags,
                                    static_cast<cudaStream_t>(stream));
   if (flags & CBK_FLAG_RERANK_TCGEN05)
     return rerank_umma_dispatch(d_store, store_dtype, n_store_rows, dim, d_pfxsum, d_doclens, n_docs, pid_base, strides,
-                                n_strides, d_Q, q_len, n_queries, d_cand_pids, d_cand_rowptr, n_cand_total, d_out_scores,
+                                n_strides, d_Q, d_q_lens, q_len, n_queries, d_cand_pids, d_cand_rowptr, n_cand_total, d_out_scores,
                                 d_workspace, flags, static_cast<cudaStream_t>(stream));
   return rerank_dispatch(d_store, store_dtype, n_store_rows, dim, d_pfxsum, d_doclens, n_docs, pid_base, strides, n_strides, d_Q,
-                         q_len, n_queries, d_cand_pids, d_cand_rowptr, n_cand_total, d_out_scores, d_workspace, flags,
+                         d_q_lens, q_len, n_queries, d_cand_pids, d_cand_rowptr, n_cand_total, d_out_scores, d_workspace, flags,
                          static_cast<cudaStream_t>(stream));
 }
 
@@ -333,7 +334,7 @@ int cbk_rank_forward_host(const void* d_store, int store_dtype, int64_t n_store_
   const int64_t* d_pids = reinterpret_cast<const int64_t*>(dp + L.pids);
   float* d_scores = reinterpret_cast<float*>(dp + L.scores);
   int rc = cbk_maxsim_rerank(d_store, store_dtype, n_store_rows, dim, d_pfxsum, d_doclens, n_docs, pid_base, strides, n_strides,
-                             reinterpret_cast<const float*>(dp + L.q), q_len, 1, d_pids, d_rowptr, n, d_scores, dp, 256,
+                             reinterpret_cast<const float*>(dp + L.q), nullptr, q_len, 1, d_pids, d_rowptr, n, d_scores, dp, 256,
                              flags, stream);
   if (rc != CBK_OK) return rc;
   // the k winners go straight into the page-locked scratch when the device can address it (unified addressing maps

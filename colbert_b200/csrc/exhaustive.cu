@@ -23,6 +23,7 @@
 // so the query is split into bf16 hi + lo parts and each tile is multiplied twice into the same
 // accumulator (K = 256); fp16 stores need one pass over K.
 #include <algorithm>
+#include <cstdio>
 #include <cstdlib>
 
 #include "umma.cuh"
@@ -40,8 +41,14 @@ constexpr int kAccSlots = 4;              // × 128 TMEM columns
 constexpr int kTileBytes = kTileTok * 256;
 constexpr int kEpiGroups = 4;             // epilogue warp groups (4 warps each, one per TMEM lane quadrant)
 constexpr int kIssuers = 2;               // MMA-issuing warps: one warp sustains one 128x128x16 MMA per ~90 cycles, two reach the 64-cycle floor
-constexpr int kIssuer1Warp = 2 + kEpiGroups * 4;   // warp 1 issues for groups 0-1, this warp for groups 2-3
-constexpr int kExhThreads = 64 + kEpiGroups * 128 + 32;
+// Warp roles, by warpgroup: warps 0-15 = four epilogue groups (group = warp / 4, TMEM lane quadrant = warp % 4),
+// warp 16 = TMA producer, warps 17-18 = MMA issuers, warp 19 idle.
+constexpr int kEpiWarps = kEpiGroups * 4;
+constexpr int kProducerWarp = kEpiWarps;
+constexpr int kIssuer0Warp = kEpiWarps + 1;        // issues for groups 0-1
+constexpr int kIssuer1Warp = kEpiWarps + 2;        // issues for groups 2-3
+constexpr int kExhThreads = (kEpiWarps + 4) * 32;
+
 
 struct StrideSet {
   int n;
@@ -193,12 +200,57 @@ __device__ __forceinline__ float max8(const uint32_t* v, float r) {
   return fmaxf(fmaxf(x0, x1), x2);
 }
 
+// One 32-column chunk of an accumulator: fold the columns into the running maximum of the open document, closing
+// every document whose last row lies inside the chunk (m: bit j = column j ends a document; col = row index of
+// column 0 relative to the warp's sub-range).
+__device__ __forceinline__ void drain_chunk(const uint32_t (&v)[32], uint32_t m, int col, PendBuf* pb, EpiState& st,
+                                            float* dst_row, int write, int lane) {
+  if (m == 0u) {   // no document ends inside these 32 columns (the common case): one max tree
+    const float y0 = max8(v, st.r), y1 = max8(v + 8, -INFINITY), y2 = max8(v + 16, -INFINITY), y3 = max8(v + 24, -INFINITY);
+    st.r = fmaxf(fmaxf(y0, y1), fmaxf(y2, y3));
+    return;
+  }
+#pragma unroll
+  for (int s8 = 0; s8 < 4; ++s8) {   // 8 columns at a time: most groups of 8 still hold no document end
+    const uint32_t m8 = (m >> (8 * s8)) & 0xffu;
+    if (m8 == 0u) {
+      st.r = max8(v + 8 * s8, st.r);
+    } else if ((m8 & (m8 - 1u)) == 0u) {   // one document ends in these 8 columns (any document of 8+ rows)
+      const int e = 31 - __clz(static_cast<int>(m8));
+      float head, tail;
+      split8(v + 8 * s8, e, st.r, head, tail);       // inline: as an out-of-line call this path cost 12 % at Nq = 16
+      const int slot = st.docs_done & (kPend - 1);
+      const int end1 = col + 8 * s8 + e + 1;
+      pb->v[slot][lane] = head;
+      if (lane == 0) pb->len[slot] = end1 - st.doc_start;
+      st.doc_start = end1;
+      ++st.docs_done;
+      st.r = tail;
+      if ((st.docs_done & (kPend - 1)) == 0) flush_pending(pb, kPend, dst_row + (st.docs_done - kPend), write != 0);
+    } else {
+      const uint32_t* x = v + 8 * s8;
+      st = close_docs_in_group(pb, st, __uint_as_float(x[0]), __uint_as_float(x[1]), __uint_as_float(x[2]),
+                               __uint_as_float(x[3]), __uint_as_float(x[4]), __uint_as_float(x[5]),
+                               __uint_as_float(x[6]), __uint_as_float(x[7]), m8, col + 8 * s8, dst_row, write);
+    }
+  }
+}
+
 // =====================================================================================================
+// kStats: per-role cycle accounting (debug builds of the launch: CBK_EXH_STATS=1), four counters per warp:
+//   producer  [0] waiting for a free stage                                              [3] total
+//   issuers   [0] waiting for a full stage   [1] waiting for a free accumulator         [3] total
+//   epilogue  [0] waiting for a full accumulator   [1] draining it   [2] tile prologue   [3] total
+template <bool kStats>
 __global__ void __launch_bounds__(kExhThreads, 1)
 maxsim_exhaustive_kernel(const __grid_constant__ ExhMaps maps, const uint32_t* __restrict__ doc_end_bits,
                          const int64_t* __restrict__ pfxsum, const int64_t* __restrict__ cta_doc_start,
                          StrideSet strides, int n_queries, int n_qblocks, int parts, int64_t n_docs, uint32_t idesc,
-                         float* __restrict__ scores) {
+                         float* __restrict__ scores, long long* __restrict__ stats) {
+  long long sc0 = 0, sc1 = 0, sc2 = 0;
+  const long long sc_begin = kStats ? clock64() : 0;
+#define CBK_T0() long long _t0 = kStats ? clock64() : 0
+#define CBK_T1(acc) if (kStats) acc += clock64() - _t0
   extern __shared__ uint8_t smem_raw[];
   __shared__ __align__(8) uint64_t bar_a_full, bar_pass_done;
   __shared__ __align__(8) uint64_t bar_b_full[kMaxBStages], bar_b_empty[kMaxBStages];
@@ -209,9 +261,9 @@ maxsim_exhaustive_kernel(const __grid_constant__ ExhMaps maps, const uint32_t* _
   __shared__ PendBuf s_pend[kEpiGroups * 4];
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-  if (warp >= 2 && warp < kIssuer1Warp && lane <= CBK_MAX_STRIDES) {
-    if (lane == 0) s_pend[warp - 2].n_strides = strides.n;
-    else s_pend[warp - 2].strides[lane - 1] = strides.v[lane - 1];
+  if (warp < kEpiWarps && lane <= CBK_MAX_STRIDES) {
+    if (lane == 0) s_pend[warp].n_strides = strides.n;
+    else s_pend[warp].strides[lane - 1] = strides.v[lane - 1];
   }
   const uint32_t raw = smem_u32(smem_raw);
   const uint32_t a_addr = (raw + 1023u) & ~1023u;              // kABlocks × 32 KB
@@ -233,7 +285,7 @@ maxsim_exhaustive_kernel(const __grid_constant__ ExhMaps maps, const uint32_t* _
     }
     fence_mbar_init();
   }
-  if (warp == 1) {
+  if (warp == kIssuer0Warp) {
     umma::tmem_alloc(smem_u32(&tmem_base_smem), 512);
     umma::tmem_relinquish();
   }
@@ -275,7 +327,8 @@ maxsim_exhaustive_kernel(const __grid_constant__ ExhMaps maps, const uint32_t* _
     return t0;
   };
 
-  if (warp == 0) {
+  if (warp >= kEpiWarps) {
+   if (warp == kProducerWarp) {
     // ===================================== TMA producer =============================================
     // (whole warp, uniform control flow; one elected lane issues — see elect_one in cbk_common.cuh)
     {
@@ -314,7 +367,7 @@ maxsim_exhaustive_kernel(const __grid_constant__ ExhMaps maps, const uint32_t* _
           for (int s2 = 0; s2 < kEpiGroups; ++s2) {
             if (t >= nt[s2]) continue;
             const uint32_t st = it % kBStages;
-            mbar_wait(smem_u32(&bar_b_empty[st]), ((it / kBStages) & 1u) ^ 1u);
+            { CBK_T0(); mbar_wait(smem_u32(&bar_b_empty[st]), ((it / kBStages) & 1u) ^ 1u); CBK_T1(sc0); }
             const uint32_t full = smem_u32(&bar_b_full[st]);
             const uint32_t dst = b_addr + st * kTileBytes;
             const int row = static_cast<int>(t0[s2]) + t * kTileTok;
@@ -328,7 +381,7 @@ maxsim_exhaustive_kernel(const __grid_constant__ ExhMaps maps, const uint32_t* _
           }
       }
     }
-  } else if (warp == 1 || warp == kIssuer1Warp) {
+  } else if (warp == kIssuer0Warp || warp == kIssuer1Warp) {
     // ===================================== MMA issuers ==============================================
     // Two warps, each with uniform control flow and one elected lane issuing (see elect_one in cbk_common.cuh):
     // issuer w feeds epilogue groups 2w and 2w+1.  A single issuing warp sustains one 128x128x16 MMA per ~90
@@ -336,7 +389,7 @@ maxsim_exhaustive_kernel(const __grid_constant__ ExhMaps maps, const uint32_t* _
     // so their loop is kept short: barrier addresses and descriptor words are formed once, ring positions advance
     // by increments, and there is one copy of the issue code.  Both issuers walk every tile (wait for it, commit
     // its release) even when it carries no accumulator of theirs, which keeps the stage barriers' counts fixed.
-    const int w = warp == 1 ? 0 : 1;
+    const int w = warp - kIssuer0Warp;
     const uint32_t bfull0 = hold(smem_u32(&bar_b_full[0])), bempty0 = hold(smem_u32(&bar_b_empty[0]));
     const uint32_t accfull0 = hold(smem_u32(&bar_acc_full[0])), accempty0 = hold(smem_u32(&bar_acc_empty[0]));
     const uint32_t a_lo0 = hold(umma::desc_lo_sw128(a_addr)), b_lo0 = hold(umma::desc_lo_sw128(b_addr));
@@ -357,14 +410,14 @@ maxsim_exhaustive_kernel(const __grid_constant__ ExhMaps maps, const uint32_t* _
         for (int s2 = 0; s2 < n_sub; ++s2) {
           const int nts = s2 == 0 ? nt0 : (s2 == 1 ? nt1 : (s2 == 2 ? nt2 : nt3));
           if (t >= nts) continue;
-          mbar_wait(bfull0 + 8 * st, st_parity);
+          { CBK_T0(); mbar_wait(bfull0 + 8 * st, st_parity); CBK_T1(sc0); }
           umma::fence_after_sync();
           const uint32_t b_lo = b_lo0 + st * kTileDesc;
 #pragma unroll 1
           for (int a = 0; a < qb; ++a) {
             const uint32_t g = static_cast<uint32_t>(s2 * qb_eff + a);     // epilogue group = TMEM slot
             if (static_cast<int>(g >> 1) != w) continue;
-            mbar_wait(accempty0 + 8 * g, ((empty_parity >> g) & 1u) ^ 1u);
+            { CBK_T0(); mbar_wait(accempty0 + 8 * g, ((empty_parity >> g) & 1u) ^ 1u); CBK_T1(sc1); }
             empty_parity ^= 1u << g;
             umma::fence_after_sync();
             const uint32_t d_tmem = tmem + g * kTileTok;
@@ -397,12 +450,13 @@ maxsim_exhaustive_kernel(const __grid_constant__ ExhMaps maps, const uint32_t* _
       if (elect_one()) umma::commit(smem_u32(&bar_pass_done));
       __syncwarp();
     }
+   }
   } else {
-    // ===================================== epilogue (warps 2..17) ===================================
-    const int grp = (warp - 2) >> 2;                 // epilogue group
+    // ===================================== epilogue (warps 0..15) ===================================
+    const int grp = warp >> 2;                       // epilogue group
     const int quad = warp & 3;                       // TMEM lane quadrant this warp may read = query within the block
     const uint32_t lane_base = static_cast<uint32_t>(quad * 32) << 16;
-    PendBuf* const pb = &s_pend[warp - 2];
+    PendBuf* const pb = &s_pend[warp];
     uint32_t full_parity = 0;                        // parity of this group's next wait on its accumulator-full barrier
     for (int p = 0; p < n_passes; ++p) {
       const int qb = min(qb_max, n_qblocks - p * qb_max);
@@ -446,16 +500,24 @@ maxsim_exhaustive_kernel(const __grid_constant__ ExhMaps maps, const uint32_t* _
       st.doc_start = 0;
       st.docs_done = 0;
 
+      // document-end bits of a tile: 5 words from the bitmap, loaded ONE TILE AHEAD so that their latency is never exposed
+      uint32_t wnext[5] = {0u, 0u, 0u, 0u, 0u};
+      if (active && my_nt > 0) {
+#pragma unroll
+        for (int i = 0; i < 5; ++i) wnext[i] = wp[i];
+      }
       for (int t = 0; t < max_nt; ++t) {
         if (!active || t >= my_nt) continue;
 
         // 128 document-end bits of this tile, shifted so that bit j of word c is column 32c + j
-        uint32_t wraw[5];
-#pragma unroll
-        for (int i = 0; i < 5; ++i) wraw[i] = wp[4 * t + i];
+        const long long t_tile = kStats ? clock64() : 0;
         uint32_t ends[4];
 #pragma unroll
-        for (int c = 0; c < 4; ++c) ends[c] = __funnelshift_r(wraw[c], wraw[c + 1], sh);
+        for (int c = 0; c < 4; ++c) ends[c] = __funnelshift_r(wnext[c], wnext[c + 1], sh);
+        if (t + 1 < my_nt) {
+#pragma unroll
+          for (int i = 0; i < 5; ++i) wnext[i] = wp[4 * (t + 1) + i];
+        }
         const int left = my_rows - t * kTileTok;                   // rows of my sub-range in this tile and after
         if (left < kTileTok) {                                     // last tile: drop the ends that belong to my neighbour
 #pragma unroll
@@ -466,10 +528,18 @@ maxsim_exhaustive_kernel(const __grid_constant__ ExhMaps maps, const uint32_t* _
           }
         }
 
+        const long long t_wait = kStats ? clock64() : 0;
         mbar_wait(smem_u32(&bar_acc_full[grp]), full_parity);      // group g owns TMEM slot g
+        const long long t_drain = kStats ? clock64() : 0;
+        if (kStats) { sc2 += t_wait - t_tile; sc0 += t_drain - t_wait; }
         full_parity ^= 1u;
         umma::fence_after_sync();
         const uint32_t t_addr = tmem + lane_base + grp * kTileTok;
+        const int col0 = t * kTileTok;
+        // One 32-column chunk in registers at a time.  Measured and NOT adopted (B200, Nq = 16, 1.1 M-document shard):
+        // a second register buffer with the load of chunk c+1 in flight while chunk c is folded — 13.0 ms against 9.3 ms
+        // (with setmaxnreg moving registers from the producer / issuer warpgroup to the epilogue warpgroups so that
+        // nothing spills; a warp with a tcgen05.ld outstanding does not overlap it with its own arithmetic here).
         uint32_t m = ends[0], m1 = ends[1], m2 = ends[2], m3 = ends[3];
 #pragma unroll 1
         for (int c = 0; c < 4; ++c) {
@@ -481,52 +551,59 @@ maxsim_exhaustive_kernel(const __grid_constant__ ExhMaps maps, const uint32_t* _
             __syncwarp();
             if (lane == 0) mbar_arrive(smem_u32(&bar_acc_empty[grp]));
           }
-          if (m == 0u) {   // no document ends inside these 32 columns (the common case): one max tree
-            const float y0 = max8(v, st.r), y1 = max8(v + 8, -INFINITY), y2 = max8(v + 16, -INFINITY), y3 = max8(v + 24, -INFINITY);
-            st.r = fmaxf(fmaxf(y0, y1), fmaxf(y2, y3));
-          } else {
-            const int col = t * kTileTok + c * 32;
-#pragma unroll
-            for (int s8 = 0; s8 < 4; ++s8) {   // 8 columns at a time: most groups of 8 still hold no document end
-              const uint32_t m8 = (m >> (8 * s8)) & 0xffu;
-              if (m8 == 0u) {
-                st.r = max8(v + 8 * s8, st.r);
-              } else if ((m8 & (m8 - 1u)) == 0u) {   // one document ends in these 8 columns (any document of 8+ rows)
-                const int e = 31 - __clz(static_cast<int>(m8));
-                float head, tail;
-                split8(v + 8 * s8, e, st.r, head, tail);
-                const int slot = st.docs_done & (kPend - 1);
-                const int end1 = col + 8 * s8 + e + 1;
-                pb->v[slot][lane] = head;
-                if (lane == 0) pb->len[slot] = end1 - st.doc_start;
-                st.doc_start = end1;
-                ++st.docs_done;
-                st.r = tail;
-                if ((st.docs_done & (kPend - 1)) == 0) flush_pending(pb, kPend, dst_row + (st.docs_done - kPend), write != 0);
-              } else {
-                const uint32_t* x = v + 8 * s8;
-                st = close_docs_in_group(pb, st, __uint_as_float(x[0]), __uint_as_float(x[1]), __uint_as_float(x[2]),
-                                         __uint_as_float(x[3]), __uint_as_float(x[4]), __uint_as_float(x[5]),
-                                         __uint_as_float(x[6]), __uint_as_float(x[7]), m8, col + 8 * s8, dst_row, write);
-              }
-            }
-          }
+          drain_chunk(v, m, col0 + c * 32, pb, st, dst_row, write, lane);
           m = m1;
           m1 = m2;
           m2 = m3;
         }
+        if (kStats) sc1 += clock64() - t_drain;
       }
       const int n_pend = st.docs_done & (kPend - 1);
       if (n_pend > 0) flush_pending(pb, n_pend, dst_row + (st.docs_done - n_pend), write != 0);
     }
   }
 
+  if (kStats && lane == 0) {
+    long long* o = stats + (static_cast<int64_t>(blockIdx.x) * (kExhThreads / 32) + warp) * 4;
+    o[0] = sc0; o[1] = sc1; o[2] = sc2; o[3] = clock64() - sc_begin;
+  }
+#undef CBK_T0
+#undef CBK_T1
   umma::fence_before_sync();
   __syncthreads();
-  if (warp == 1) umma::tmem_dealloc(tmem, 512);
+  if (warp == kIssuer0Warp) umma::tmem_dealloc(tmem, 512);
 }
 
 }  // namespace
+
+// Profiling aid (CBK_EXH_STATS=1): the instrumented instantiation, synchronous, per-role mean cycle counts to stderr.
+static int exhaustive_launch_with_stats(const ExhMaps& maps, const uint32_t* bits, const int64_t* pfxsum, const int64_t* ranges,
+                                        const StrideSet& ss, int n_queries, int n_qblocks, int parts, int64_t n_docs,
+                                        uint32_t idesc, float* out, int n_ctas, size_t smem, cudaStream_t stream) {
+  constexpr int kW = kExhThreads / 32;
+  long long* d_stats = nullptr;
+  const size_t bytes = static_cast<size_t>(n_ctas) * kW * 4 * sizeof(long long);
+  CBK_CUDA(cudaMalloc(&d_stats, bytes));
+  CBK_CUDA(cudaMemsetAsync(d_stats, 0, bytes, stream));
+  CBK_CUDA(cudaFuncSetAttribute(maxsim_exhaustive_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
+  maxsim_exhaustive_kernel<true><<<n_ctas, kExhThreads, smem, stream>>>(maps, bits, pfxsum, ranges, ss, n_queries, n_qblocks, parts,
+                                                                      n_docs, idesc, out, d_stats);
+  CBK_CUDA(cudaGetLastError());
+  CBK_CUDA(cudaStreamSynchronize(stream));
+  long long* h = static_cast<long long*>(std::malloc(bytes));
+  CBK_CUDA(cudaMemcpy(h, d_stats, bytes, cudaMemcpyDeviceToHost));
+  cudaFree(d_stats);
+  double acc[kW][4] = {};
+  for (int c = 0; c < n_ctas; ++c)
+    for (int w = 0; w < kW; ++w)
+      for (int k = 0; k < 4; ++k) acc[w][k] += static_cast<double>(h[(static_cast<size_t>(c) * kW + w) * 4 + k]) / n_ctas;
+  std::free(h);
+  std::fprintf(stderr, "[exh stats] n_queries=%d qblocks=%d ctas=%d (mean cycles per CTA)\n", n_queries, n_qblocks, n_ctas);
+  for (int w = 0; w < kW; ++w)
+    std::fprintf(stderr, "[exh stats] warp %2d: c0 %.0f c1 %.0f c2 %.0f total %.0f\n", w, acc[w][0], acc[w][1], acc[w][2], acc[w][3]);
+  count_launch(3);
+  return CBK_OK;
+}
 
 size_t doc_end_bits_bytes(int64_t n_store_rows) {
   return static_cast<size_t>((n_store_rows + 31) / 32 + 8) * sizeof(uint32_t);   // +8 words: tiles read 5 words past their start
@@ -582,10 +659,13 @@ int exhaustive_dispatch(const void* d_store, int store_dtype, int64_t n_store_ro
   const uint32_t fmt = bf16 ? umma::kFmtBF16 : umma::kFmtF16;
   const uint32_t idesc = umma::make_idesc(128, kTileTok, fmt, fmt);
   const size_t smem = 1024 + static_cast<size_t>(kSmemTiles) * kTileBytes;
-  CBK_CUDA(cudaFuncSetAttribute(maxsim_exhaustive_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
-  maxsim_exhaustive_kernel<<<n_ctas, kExhThreads, smem, stream>>>(maps, d_doc_end_bits, d_pfxsum, d_ranges, ss,
-                                                                static_cast<int>(n_queries), n_qblocks, parts, n_docs, idesc,
-                                                                d_out_scores);
+  static const bool want_stats = std::getenv("CBK_EXH_STATS") != nullptr;     // profiling aid, never set in production
+  if (want_stats) return exhaustive_launch_with_stats(maps, d_doc_end_bits, d_pfxsum, d_ranges, ss, static_cast<int>(n_queries),
+                                                      n_qblocks, parts, n_docs, idesc, d_out_scores, n_ctas, smem, stream);
+  CBK_CUDA(cudaFuncSetAttribute(maxsim_exhaustive_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
+  maxsim_exhaustive_kernel<false><<<n_ctas, kExhThreads, smem, stream>>>(maps, d_doc_end_bits, d_pfxsum, d_ranges, ss,
+                                                                       static_cast<int>(n_queries), n_qblocks, parts, n_docs, idesc,
+                                                                       d_out_scores, nullptr);
   CBK_CUDA(cudaGetLastError());
   count_launch(3);
   return CBK_OK;

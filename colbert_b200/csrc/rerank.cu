@@ -18,6 +18,7 @@
 //     reduces with warp shuffles; only one fp32 per candidate is ever written;
 //   * work is handed out in segments of 64 consecutive candidates through one atomic counter.
 #include <algorithm>
+#include <cstdlib>
 
 #include "cbk_common.cuh"
 
@@ -70,15 +71,18 @@ __device__ __forceinline__ uint32_t bf16x2_to_f16x2(uint32_t v) {
 // kShort: every document has at most 8 rows (multi-view indexes: d_view rows per document) — the ring is cut into 8 stages of
 // 8 rows instead of 4 of 16, which more than doubles the bytes a warp keeps in flight, and the second 8-token sub-tile
 // is not computed.
-template <typename T, bool kCvtBf16, bool kShort>
+// kFixed (CBK_FLAG_FIXED_DOCLEN): every document has exactly strides.v[0] rows (multi-view indexes again): document p
+// starts at row p · d, so the segment prologue reads neither pfxsum nor doclens (two dependent random 32-byte sectors per
+// 2-KB candidate otherwise), and the zero floor never applies (the single stride IS the document length).
+template <typename T, bool kCvtBf16, bool kShort, bool kFixed>
 __global__ void __launch_bounds__(kWarps * 32, kCtasPerSm)
 maxsim_rerank_kernel(const __grid_constant__ TmapSet tmaps, const int64_t* __restrict__ pfxsum,
                      const int32_t* __restrict__ doclens, int64_t n_docs, int64_t pid_base, int skip_foreign,
                      StrideSet strides,
-                     const float* __restrict__ Q, int q_len, int64_t n_queries,
+                     const float* __restrict__ Q, const int32_t* __restrict__ q_lens, int q_len, int64_t n_queries,
                      const int64_t* __restrict__ cand_pids, const int64_t* __restrict__ rowptr,
                      int64_t n_cand_bound, int seg_cands, float* __restrict__ out,
-                     unsigned int* __restrict__ seg_counter) {
+                     unsigned int* __restrict__ seg_counter, int probe_gather_only) {
   extern __shared__ uint8_t smem_raw[];
   constexpr int kTR = kShort ? 8 : kTileRows;             // rows per tile
   constexpr int kST = kShort ? 2 * kStages : kStages;     // stages of the ring (same 16 KB either way)
@@ -132,8 +136,13 @@ maxsim_rerank_kernel(const __grid_constant__ TmapSet tmaps, const int64_t* __res
       if (i < nc) {
         const int64_t pid = cand_pids[c0 + i] - pid_base;
         if (pid >= 0 && pid < n_docs) {
-          row = static_cast<int>(pfxsum[pid]);
-          len = doclens[pid];
+          if (kFixed) {
+            len = strides.v[0];
+            row = static_cast<int>(pid) * len;
+          } else {
+            row = static_cast<int>(pfxsum[pid]);
+            len = doclens[pid];
+          }
         }
         if (len <= 0) out[c0 + i] = len == 0 ? 0.f : (skip_foreign ? -INFINITY : __int_as_float(0x7fc00000));
       }
@@ -197,6 +206,7 @@ maxsim_rerank_kernel(const __grid_constant__ TmapSet tmaps, const int64_t* __res
         // ---- (re)load the query as A fragments, fp32 → T with round-to-nearest ------------------
         cur_q = q;
         const float* Qq = Q + q * static_cast<int64_t>(q_len) * kDim;
+        const int ql = q_lens ? min(q_len, q_lens[q]) : q_len;   // rows at or past this query's own length read as zero
 #pragma unroll
         for (int mt = 0; mt < 2; ++mt) {
           const int r0 = mt * 16 + (lane >> 2);
@@ -205,11 +215,11 @@ maxsim_rerank_kernel(const __grid_constant__ TmapSet tmaps, const int64_t* __res
           for (int ks = 0; ks < 8; ++ks) {
             const int k0 = ks * 16 + 2 * (lane & 3);
             float2 v00 = make_float2(0.f, 0.f), v10 = v00, v01 = v00, v11 = v00;
-            if (r0 < q_len) {
+            if (r0 < ql) {
               v00 = *reinterpret_cast<const float2*>(Qq + r0 * kDim + k0);
               v01 = *reinterpret_cast<const float2*>(Qq + r0 * kDim + k0 + 8);
             }
-            if (r1 < q_len) {
+            if (r1 < ql) {
               v10 = *reinterpret_cast<const float2*>(Qq + r1 * kDim + k0);
               v11 = *reinterpret_cast<const float2*>(Qq + r1 * kDim + k0 + 8);
             }
@@ -255,9 +265,10 @@ maxsim_rerank_kernel(const __grid_constant__ TmapSet tmaps, const int64_t* __res
             ldmatrix_x4(sbase + prow * 128 + (((chunk ^ prow) & 7) << 4), dst[s][0], dst[s][1], dst[s][2], dst[s][3]);
           }
         };
-        load_b(0, bq[0]);
+        if (!probe_gather_only) load_b(0, bq[0]);
 #pragma unroll
         for (int p = 0; p < 4; ++p) {
+          if (probe_gather_only) break;       // CBK_RERANK_PROBE=1: the gather alone (what the streaming structure sustains)
           if (p < 3) load_b(p + 1, bq[(p + 1) & 1]);
 #pragma unroll
           for (int s = 0; s < kSub; ++s) {
@@ -304,7 +315,7 @@ maxsim_rerank_kernel(const __grid_constant__ TmapSet tmaps, const int64_t* __res
       }
 
       // ---- per-candidate epilogue: max across the 4 lanes of a row, floor, sum over query rows ----
-      bool do_floor = strides.n > 0;
+      bool do_floor = !kFixed && strides.n > 0;
 #pragma unroll
       for (int i = 0; i < CBK_MAX_STRIDES; ++i)
         if (i < strides.n && strides.v[i] == len) do_floor = false;
@@ -330,12 +341,13 @@ maxsim_rerank_kernel(const __grid_constant__ TmapSet tmaps, const int64_t* __res
   }
 }
 
-template <typename T, bool kCvtBf16, bool kShort>
+template <typename T, bool kCvtBf16, bool kShort, bool kFixed>
 int launch(const TmapSet& tmaps, const int64_t* pfxsum, const int32_t* doclens, int64_t n_docs, int64_t pid_base,
-           int skip_foreign, const StrideSet& strides, const float* Q, int q_len, int64_t n_queries, const int64_t* cand_pids,
+           int skip_foreign, const StrideSet& strides, const float* Q, const int32_t* q_lens, int q_len, int64_t n_queries, const int64_t* cand_pids,
            const int64_t* rowptr, int64_t n_cand, float* out, unsigned int* counter, cudaStream_t stream) {
+  static const int probe = std::getenv("CBK_RERANK_PROBE") != nullptr;     // profiling aid, never set in production
   const size_t smem = kWarps * sizeof(WarpSmem) + 1024;
-  CBK_CUDA(cudaFuncSetAttribute(maxsim_rerank_kernel<T, kCvtBf16, kShort>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+  CBK_CUDA(cudaFuncSetAttribute(maxsim_rerank_kernel<T, kCvtBf16, kShort, kFixed>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                 static_cast<int>(smem)));
   // work unit = segment of consecutive candidates claimed by one warp: 64 for big batches (amortises the claim and
   // the metadata fetch), down to 1 for a single query so that each of its ~1000 candidates gets a warp of its own
@@ -345,8 +357,9 @@ int launch(const TmapSet& tmaps, const int64_t* pfxsum, const int32_t* doclens, 
   const int64_t n_segs = (n_cand + seg_cands - 1) / seg_cands;
   const int64_t want = (n_segs + kWarps - 1) / kWarps;
   const int grid = static_cast<int>(std::max<int64_t>(1, std::min<int64_t>(want, static_cast<int64_t>(sm_count()) * kCtasPerSm)));
-  maxsim_rerank_kernel<T, kCvtBf16, kShort><<<grid, kWarps * 32, smem, stream>>>(tmaps, pfxsum, doclens, n_docs, pid_base, skip_foreign, strides, Q, q_len,
-                                                              n_queries, cand_pids, rowptr, n_cand, seg_cands, out, counter);
+  maxsim_rerank_kernel<T, kCvtBf16, kShort, kFixed><<<grid, kWarps * 32, smem, stream>>>(tmaps, pfxsum, doclens, n_docs, pid_base, skip_foreign, strides, Q, q_lens, q_len,
+                                                              n_queries, cand_pids, rowptr, n_cand, seg_cands, out, counter,
+                                                              probe);
   CBK_CUDA(cudaGetLastError());
   count_launch();
   return CBK_OK;
@@ -356,7 +369,7 @@ int launch(const TmapSet& tmaps, const int64_t* pfxsum, const int32_t* doclens, 
 
 int rerank_dispatch(const void* d_store, int store_dtype, int64_t n_store_rows, int dim, const int64_t* d_pfxsum,
                     const int32_t* d_doclens, int64_t n_docs, int64_t pid_base, const int32_t* strides, int n_strides,
-                    const float* d_Q, int q_len, int64_t n_queries, const int64_t* d_cand_pids,
+                    const float* d_Q, const int32_t* d_q_lens, int q_len, int64_t n_queries, const int64_t* d_cand_pids,
                     const int64_t* d_cand_rowptr, int64_t n_cand_total, float* d_out_scores, void* d_workspace,
                     int flags, cudaStream_t stream) {
   // tensor maps depend only on (base, rows): keep the last set per thread instead of re-encoding
@@ -386,14 +399,17 @@ int rerank_dispatch(const void* d_store, int store_dtype, int64_t n_store_rows, 
     for (int i = 0; i < n_strides; ++i) max_len = std::max(max_len, static_cast<int>(strides[i]));
   }
   // (forcing this instantiation on long documents is slower: configs[1] 16.9 vs 15.4 ms — twice the TMA ops and waits)
-#define CBK_LAUNCH(T, CVT)                                                                                                  \
-  (max_len <= 8 ? launch<T, CVT, true>(tmaps, d_pfxsum, d_doclens, n_docs, pid_base, skip, ss, d_Q, q_len, n_queries,       \
-                                       d_cand_pids, d_cand_rowptr, n_cand_total, d_out_scores, counter, stream)              \
-                : launch<T, CVT, false>(tmaps, d_pfxsum, d_doclens, n_docs, pid_base, skip, ss, d_Q, q_len, n_queries,      \
-                                        d_cand_pids, d_cand_rowptr, n_cand_total, d_out_scores, counter, stream))
+#define CBK_ARGS tmaps, d_pfxsum, d_doclens, n_docs, pid_base, skip, ss, d_Q, d_q_lens, q_len, n_queries, d_cand_pids, d_cand_rowptr, \
+                 n_cand_total, d_out_scores, counter, stream
+  // CBK_FLAG_FIXED_DOCLEN: the caller guarantees doclens[p] == strides[0] for every document
+  const bool fixed = (flags & CBK_FLAG_FIXED_DOCLEN) && n_strides == 1 && strides[0] > 0;
+#define CBK_LAUNCH(T, CVT)                                                                                     \
+  (fixed ? (max_len <= 8 ? launch<T, CVT, true, true>(CBK_ARGS) : launch<T, CVT, false, true>(CBK_ARGS))       \
+         : (max_len <= 8 ? launch<T, CVT, true, false>(CBK_ARGS) : launch<T, CVT, false, false>(CBK_ARGS)))
   if (store_dtype == CBK_F16) return CBK_LAUNCH(__half, false);
   if (flags & CBK_FLAG_BF16_NATIVE_MMA) return CBK_LAUNCH(__nv_bfloat16, false);
   return CBK_LAUNCH(__half, true);
+#undef CBK_ARGS
 #undef CBK_LAUNCH
 }
 

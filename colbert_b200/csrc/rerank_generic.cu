@@ -21,15 +21,16 @@ template <typename T>
 __global__ void __launch_bounds__(256)
 maxsim_generic_kernel(const T* __restrict__ store, int64_t n_store_rows, int dim, const int64_t* __restrict__ pfxsum,
                       const int32_t* __restrict__ doclens, int64_t n_docs, int64_t pid_base, int skip_foreign,
-                      StrideSet strides, const float* __restrict__ Q, int q_len, const int64_t* __restrict__ cand_pids,
+                      StrideSet strides, const float* __restrict__ Q, const int32_t* __restrict__ q_lens, int q_len, const int64_t* __restrict__ cand_pids,
                       const int64_t* __restrict__ rowptr, float* __restrict__ out) {
   extern __shared__ float sQ[];   // [32][dim + 1]
   const int64_t q = blockIdx.x;
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, n_warps = blockDim.x >> 5;
   const int pitch = dim + 1;
+  const int ql = q_lens ? min(q_len, q_lens[q]) : q_len;   // rows at or past this query's own length read as zero
   for (int i = threadIdx.x; i < 32 * dim; i += blockDim.x) {
     const int r = i / dim, c = i - r * dim;
-    sQ[r * pitch + c] = r < q_len ? Q[(q * q_len + r) * dim + c] : 0.f;
+    sQ[r * pitch + c] = r < ql ? Q[(q * q_len + r) * dim + c] : 0.f;
   }
   __syncthreads();
   const int64_t beg = rowptr[q], end = rowptr[q + 1];
@@ -64,7 +65,7 @@ maxsim_generic_kernel(const T* __restrict__ store, int64_t n_store_rows, int dim
 
 int rerank_generic_dispatch(const void* d_store, int store_dtype, int64_t n_store_rows, int dim, const int64_t* d_pfxsum,
                             const int32_t* d_doclens, int64_t n_docs, int64_t pid_base, const int32_t* strides,
-                            int n_strides, const float* d_Q, int q_len, int64_t n_queries, const int64_t* d_cand_pids,
+                            int n_strides, const float* d_Q, const int32_t* d_q_lens, int q_len, int64_t n_queries, const int64_t* d_cand_pids,
                             const int64_t* d_cand_rowptr, float* d_out_scores, int flags, cudaStream_t stream) {
   StrideSet ss;
   ss.n = n_strides;
@@ -79,12 +80,12 @@ int rerank_generic_dispatch(const void* d_store, int store_dtype, int64_t n_stor
   if (store_dtype == CBK_F16) {
     CBK_CUDA(cudaFuncSetAttribute(maxsim_generic_kernel<__half>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
     maxsim_generic_kernel<__half><<<grid, 256, smem, stream>>>(static_cast<const __half*>(d_store), n_store_rows, dim, d_pfxsum,
-                                                               d_doclens, n_docs, pid_base, skip, ss, d_Q, q_len, d_cand_pids,
+                                                               d_doclens, n_docs, pid_base, skip, ss, d_Q, d_q_lens, q_len, d_cand_pids,
                                                                d_cand_rowptr, d_out_scores);
   } else {
     CBK_CUDA(cudaFuncSetAttribute(maxsim_generic_kernel<__nv_bfloat16>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
     maxsim_generic_kernel<__nv_bfloat16><<<grid, 256, smem, stream>>>(static_cast<const __nv_bfloat16*>(d_store), n_store_rows, dim,
-                                                                      d_pfxsum, d_doclens, n_docs, pid_base, skip, ss, d_Q, q_len,
+                                                                      d_pfxsum, d_doclens, n_docs, pid_base, skip, ss, d_Q, d_q_lens, q_len,
                                                                       d_cand_pids, d_cand_rowptr, d_out_scores);
   }
   CBK_CUDA(cudaGetLastError());

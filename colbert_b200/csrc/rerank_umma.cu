@@ -101,7 +101,7 @@ template <typename T, int kN>
 __global__ void __launch_bounds__(kThreads, kN == 32 ? 4 : 3)
 maxsim_rerank_umma_kernel(const __grid_constant__ TileMaps maps, const int64_t* __restrict__ pfxsum,
                           const int32_t* __restrict__ doclens, int64_t n_docs, int64_t pid_base, int skip_foreign,
-                          StrideSet strides, const float* __restrict__ Q, int q_len, int64_t n_queries,
+                          StrideSet strides, const float* __restrict__ Q, const int32_t* __restrict__ q_lens, int q_len, int64_t n_queries,
                           const int64_t* __restrict__ cand_pids, const int64_t* __restrict__ rowptr,
                           int64_t n_cand_bound, int seg_cands, int ring_bytes, uint32_t idesc, float* __restrict__ out,
                           unsigned int* __restrict__ seg_counter) {
@@ -244,6 +244,7 @@ maxsim_rerank_umma_kernel(const __grid_constant__ TileMaps maps, const int64_t* 
           ++qseq;
           wait_items_done(last_item_of_buf[qbuf] + 1);
           const float* Qq = Q + q * static_cast<int64_t>(q_len) * kDim;
+          const int ql = q_lens ? min(q_len, q_lens[q]) : q_len;   // rows at or past this query's own length read as zero
           uint8_t* dstb = q_ptr + qbuf * kQBufBytes;
           // element (row r, column k) → half h = k / 64, 16-byte chunk (k % 64) / 8 XOR (r & 7) (SWIZZLE_128B);
           // 4 chunks (8 float4 loads) per lane are in flight at a time
@@ -257,7 +258,7 @@ maxsim_rerank_umma_kernel(const __grid_constant__ TileMaps maps, const int64_t* 
               const int r = e / (kDim / 8), ch = e % (kDim / 8);
               const int qr = r & 31;                             // rows 32-63 (bf16 store): lo part of row r-32
               f[u][0] = f[u][1] = make_float4(0.f, 0.f, 0.f, 0.f);
-              if (qr < q_len) {
+              if (qr < ql) {
                 const float4* src = reinterpret_cast<const float4*>(Qq + qr * kDim + ch * 8);
                 f[u][0] = src[0];
                 f[u][1] = src[1];
@@ -497,7 +498,7 @@ maxsim_rerank_umma_kernel(const __grid_constant__ TileMaps maps, const int64_t* 
 
 int rerank_umma_dispatch(const void* d_store, int store_dtype, int64_t n_store_rows, int dim, const int64_t* d_pfxsum,
                          const int32_t* d_doclens, int64_t n_docs, int64_t pid_base, const int32_t* strides, int n_strides,
-                         const float* d_Q, int q_len, int64_t n_queries, const int64_t* d_cand_pids,
+                         const float* d_Q, const int32_t* d_q_lens, int q_len, int64_t n_queries, const int64_t* d_cand_pids,
                          const int64_t* d_cand_rowptr, int64_t n_cand_total, float* d_out_scores, void* d_workspace,
                          int flags, cudaStream_t stream) {
   static thread_local TileMaps maps;
@@ -531,13 +532,13 @@ int rerank_umma_dispatch(const void* d_store, int store_dtype, int64_t n_store_r
   if (bf16) {
     auto kern = maxsim_rerank_umma_kernel<__nv_bfloat16, 64>;
     CBK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
-    kern<<<grid, kThreads, smem, stream>>>(maps, d_pfxsum, d_doclens, n_docs, pid_base, skip, ss, d_Q, q_len, n_queries,
+    kern<<<grid, kThreads, smem, stream>>>(maps, d_pfxsum, d_doclens, n_docs, pid_base, skip, ss, d_Q, d_q_lens, q_len, n_queries,
                                            d_cand_pids, d_cand_rowptr, n_cand_total, seg_cands, ring_bytes,
                                            umma::make_idesc(128, 64, umma::kFmtBF16, umma::kFmtBF16), d_out_scores, counter);
   } else {
     auto kern = maxsim_rerank_umma_kernel<__half, 32>;
     CBK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
-    kern<<<grid, kThreads, smem, stream>>>(maps, d_pfxsum, d_doclens, n_docs, pid_base, skip, ss, d_Q, q_len, n_queries,
+    kern<<<grid, kThreads, smem, stream>>>(maps, d_pfxsum, d_doclens, n_docs, pid_base, skip, ss, d_Q, d_q_lens, q_len, n_queries,
                                            d_cand_pids, d_cand_rowptr, n_cand_total, seg_cands, ring_bytes,
                                            umma::make_idesc(128, 32, umma::kFmtF16, umma::kFmtF16), d_out_scores, counter);
   }

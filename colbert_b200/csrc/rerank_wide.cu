@@ -64,7 +64,7 @@ template <typename T, bool kCvtBf16, int kMaxKs, int kCtas>
 __global__ void __launch_bounds__(kWThreads, kCtas)
 maxsim_wide_kernel(const __grid_constant__ CUtensorMap tmap, const int64_t* __restrict__ pfxsum,
                    const int32_t* __restrict__ doclens, int64_t n_docs, int64_t pid_base, int skip_foreign, StrideSet strides,
-                   const float* __restrict__ Q, int q_len, int dim, int64_t n_queries, const int64_t* __restrict__ cand_pids,
+                   const float* __restrict__ Q, const int32_t* __restrict__ q_lens, int q_len, int dim, int64_t n_queries, const int64_t* __restrict__ cand_pids,
                    const int64_t* __restrict__ rowptr, int64_t n_cand_bound, int n_stages, float* __restrict__ out,
                    unsigned int* __restrict__ seg_counter) {
   extern __shared__ uint8_t smem_raw[];
@@ -177,6 +177,7 @@ maxsim_wide_kernel(const __grid_constant__ CUtensorMap tmap, const int64_t* __re
         // ---- (re)load my slice of the query as A fragments, fp32 → T with round-to-nearest ----------------------
         cur_q = q;
         const float* Qq = Q + q * static_cast<int64_t>(q_len) * dim;
+        const int ql = q_lens ? min(q_len, q_lens[q]) : q_len;   // rows at or past this query's own length read as zero
 #pragma unroll
         for (int mt = 0; mt < 2; ++mt) {
           const int r0 = mt * 16 + (lane >> 2);
@@ -186,11 +187,11 @@ maxsim_wide_kernel(const __grid_constant__ CUtensorMap tmap, const int64_t* __re
             if (j < my_nks) {
               const int k0 = (my_ks0 + j) * 16 + 2 * (lane & 3);
               float2 v00 = make_float2(0.f, 0.f), v10 = v00, v01 = v00, v11 = v00;
-              if (r0 < q_len) {
+              if (r0 < ql) {
                 v00 = *reinterpret_cast<const float2*>(Qq + static_cast<int64_t>(r0) * dim + k0);
                 v01 = *reinterpret_cast<const float2*>(Qq + static_cast<int64_t>(r0) * dim + k0 + 8);
               }
-              if (r1 < q_len) {
+              if (r1 < ql) {
                 v10 = *reinterpret_cast<const float2*>(Qq + static_cast<int64_t>(r1) * dim + k0);
                 v11 = *reinterpret_cast<const float2*>(Qq + static_cast<int64_t>(r1) * dim + k0 + 8);
               }
@@ -295,7 +296,7 @@ maxsim_wide_kernel(const __grid_constant__ CUtensorMap tmap, const int64_t* __re
 
 template <typename T, bool kCvtBf16, int kMaxKs, int kCtas>
 int launch_wide_as(const CUtensorMap& tmap, const int64_t* pfxsum, const int32_t* doclens, int64_t n_docs, int64_t pid_base,
-                   int skip_foreign, const StrideSet& strides, const float* Q, int q_len, int dim, int64_t n_queries,
+                   int skip_foreign, const StrideSet& strides, const float* Q, const int32_t* q_lens, int q_len, int dim, int64_t n_queries,
                    const int64_t* cand_pids, const int64_t* rowptr, int64_t n_cand, float* out, unsigned int* counter,
                    cudaStream_t stream) {
   const size_t tile_bytes = static_cast<size_t>(dim) * 2 * kWTileRows;
@@ -307,7 +308,7 @@ int launch_wide_as(const CUtensorMap& tmap, const int64_t* pfxsum, const int32_t
   CBK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
   const int64_t n_segs = (n_cand + kWSegCands - 1) / kWSegCands;
   const int grid = static_cast<int>(std::max<int64_t>(1, std::min<int64_t>(n_segs, static_cast<int64_t>(sm_count()) * kCtas)));
-  kern<<<grid, kWThreads, smem, stream>>>(tmap, pfxsum, doclens, n_docs, pid_base, skip_foreign, strides, Q, q_len, dim, n_queries,
+  kern<<<grid, kWThreads, smem, stream>>>(tmap, pfxsum, doclens, n_docs, pid_base, skip_foreign, strides, Q, q_lens, q_len, dim, n_queries,
                                          cand_pids, rowptr, n_cand, n_stages, out, counter);
   CBK_CUDA(cudaGetLastError());
   count_launch();
@@ -316,16 +317,16 @@ int launch_wide_as(const CUtensorMap& tmap, const int64_t* pfxsum, const int32_t
 
 template <typename T, bool kCvtBf16>
 int launch_wide(const CUtensorMap& tmap, const int64_t* pfxsum, const int32_t* doclens, int64_t n_docs, int64_t pid_base,
-                int skip_foreign, const StrideSet& strides, const float* Q, int q_len, int dim, int64_t n_queries,
+                int skip_foreign, const StrideSet& strides, const float* Q, const int32_t* q_lens, int q_len, int dim, int64_t n_queries,
                 const int64_t* cand_pids, const int64_t* rowptr, int64_t n_cand, float* out, unsigned int* counter,
                 cudaStream_t stream) {
   if (dim <= 384)
-    return launch_wide_as<T, kCvtBf16, 3, 2>(tmap, pfxsum, doclens, n_docs, pid_base, skip_foreign, strides, Q, q_len, dim, n_queries,
+    return launch_wide_as<T, kCvtBf16, 3, 2>(tmap, pfxsum, doclens, n_docs, pid_base, skip_foreign, strides, Q, q_lens, q_len, dim, n_queries,
                                              cand_pids, rowptr, n_cand, out, counter, stream);
   if (dim <= 768)
-    return launch_wide_as<T, kCvtBf16, 6, 2>(tmap, pfxsum, doclens, n_docs, pid_base, skip_foreign, strides, Q, q_len, dim, n_queries,
+    return launch_wide_as<T, kCvtBf16, 6, 2>(tmap, pfxsum, doclens, n_docs, pid_base, skip_foreign, strides, Q, q_lens, q_len, dim, n_queries,
                                              cand_pids, rowptr, n_cand, out, counter, stream);
-  return launch_wide_as<T, kCvtBf16, 8, 1>(tmap, pfxsum, doclens, n_docs, pid_base, skip_foreign, strides, Q, q_len, dim, n_queries,
+  return launch_wide_as<T, kCvtBf16, 8, 1>(tmap, pfxsum, doclens, n_docs, pid_base, skip_foreign, strides, Q, q_lens, q_len, dim, n_queries,
                                            cand_pids, rowptr, n_cand, out, counter, stream);
 }
 
@@ -335,7 +336,7 @@ bool rerank_wide_supports(int dim) { return dim % 64 == 0 && dim >= 64 && dim <=
 
 int rerank_wide_dispatch(const void* d_store, int store_dtype, int64_t n_store_rows, int dim, const int64_t* d_pfxsum,
                          const int32_t* d_doclens, int64_t n_docs, int64_t pid_base, const int32_t* strides, int n_strides,
-                         const float* d_Q, int q_len, int64_t n_queries, const int64_t* d_cand_pids,
+                         const float* d_Q, const int32_t* d_q_lens, int q_len, int64_t n_queries, const int64_t* d_cand_pids,
                          const int64_t* d_cand_rowptr, int64_t n_cand_total, float* d_out_scores, void* d_workspace,
                          int flags, cudaStream_t stream) {
   static thread_local CUtensorMap tmap;
@@ -357,12 +358,12 @@ int rerank_wide_dispatch(const void* d_store, int store_dtype, int64_t n_store_r
   unsigned int* counter = static_cast<unsigned int*>(d_workspace);
   CBK_CUDA(cudaMemsetAsync(counter, 0, sizeof(unsigned int), stream));
   if (store_dtype == CBK_F16)
-    return launch_wide<__half, false>(tmap, d_pfxsum, d_doclens, n_docs, pid_base, skip, ss, d_Q, q_len, dim, n_queries, d_cand_pids,
+    return launch_wide<__half, false>(tmap, d_pfxsum, d_doclens, n_docs, pid_base, skip, ss, d_Q, d_q_lens, q_len, dim, n_queries, d_cand_pids,
                                       d_cand_rowptr, n_cand_total, d_out_scores, counter, stream);
   if (flags & CBK_FLAG_BF16_NATIVE_MMA)
-    return launch_wide<__nv_bfloat16, false>(tmap, d_pfxsum, d_doclens, n_docs, pid_base, skip, ss, d_Q, q_len, dim, n_queries,
+    return launch_wide<__nv_bfloat16, false>(tmap, d_pfxsum, d_doclens, n_docs, pid_base, skip, ss, d_Q, d_q_lens, q_len, dim, n_queries,
                                              d_cand_pids, d_cand_rowptr, n_cand_total, d_out_scores, counter, stream);
-  return launch_wide<__half, true>(tmap, d_pfxsum, d_doclens, n_docs, pid_base, skip, ss, d_Q, q_len, dim, n_queries, d_cand_pids,
+  return launch_wide<__half, true>(tmap, d_pfxsum, d_doclens, n_docs, pid_base, skip, ss, d_Q, d_q_lens, q_len, dim, n_queries, d_cand_pids,
                                    d_cand_rowptr, n_cand_total, d_out_scores, counter, stream);
 }
 

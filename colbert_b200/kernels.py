@@ -42,11 +42,13 @@ def _workspace(device: torch.device) -> torch.Tensor:
 
 def maxsim_rerank(store: torch.Tensor, pfxsum: torch.Tensor, doclens: torch.Tensor, strides: Sequence[int],
                   Q: torch.Tensor, cand_pids: torch.Tensor, cand_rowptr: torch.Tensor,
-                  out: Optional[torch.Tensor] = None, flags: int = 0, pid_base: int = 0) -> torch.Tensor:
+                  out: Optional[torch.Tensor] = None, flags: int = 0, pid_base: int = 0,
+                  q_lens: Optional[torch.Tensor] = None) -> torch.Tensor:
     """scores[c] for the CSR candidate lists; see cbk_maxsim_rerank in include/colbert_b200.h.
 
     store [rows, dim] fp16|bf16 · pfxsum [n_docs+1] int64 · doclens [n_docs] int32 · Q [B, q_len, dim] fp32
-    cand_pids [n] int64 · cand_rowptr [B+1] int64  → fp32 [n] (all on the store's device)."""
+    cand_pids [n] int64 · cand_rowptr [B+1] int64 · q_lens None | [B] int32 (real rows per query; the rest of the
+    q_len slots is padding)  → fp32 [n] (all on the store's device)."""
     lib = _lib.load()
     dev = store.device
     _need(store, "store", store.dtype, dev)
@@ -60,6 +62,10 @@ def maxsim_rerank(store: torch.Tensor, pfxsum: torch.Tensor, doclens: torch.Tens
     n_q, q_len, dim = Q.shape
     if cand_rowptr.numel() != n_q + 1:
         raise ValueError("cand_rowptr must have B+1 entries")
+    if q_lens is not None:
+        _need(q_lens, "q_lens", torch.int32, dev)
+        if q_lens.numel() != n_q:
+            raise ValueError("q_lens must have one entry per query")
     n = cand_pids.numel()
     if out is None:
         out = torch.empty(n, dtype=torch.float32, device=dev)
@@ -72,7 +78,7 @@ def maxsim_rerank(store: torch.Tensor, pfxsum: torch.Tensor, doclens: torch.Tens
     with torch.cuda.device(dev):
         rc = lib.cbk_maxsim_rerank(_ptr(store), _lib.dtype_code(store.dtype), store.size(0), dim, _ptr(pfxsum),
                                    _ptr(doclens), doclens.numel(), int(pid_base), C.cast(st, C.c_void_p),
-                                   len(strides), _ptr(Q),
+                                   len(strides), _ptr(Q), _ptr(q_lens),
                                    q_len, n_q, _ptr(cand_pids), _ptr(cand_rowptr), n, _ptr(out), _ptr(ws),
                                    ws.numel(), int(flags), C.c_void_p(_lib.current_stream_ptr(dev)))
     _lib.check("cbk_maxsim_rerank", rc)

@@ -157,6 +157,10 @@ class ColbertRanker:
         self.doclens_pfxsum = torch.zeros(self.doclens.numel() + 1, dtype=torch.int64)
         torch.cumsum(self.doclens, 0, out=self.doclens_pfxsum[1:])
         self.dim = self.tensor.size(-1)
+        # every document has the same number of rows (enable_multiview: d_view embeddings per document)? → the kernel can
+        # compute offsets as pid * d instead of looking them up (CBK_FLAG_FIXED_DOCLEN)
+        dl_min, dl_max = int(self.doclens.min()), int(self.doclens.max())
+        self._doclen_const = dl_min if dl_min == dl_max and dl_min > 0 else 0
         strides = [torch_percentile(self.doclens, p) for p in [25, 50, 75]]
         strides.append(self.doclens.max().item())
         self.strides = sorted(list(set(strides)))
@@ -196,31 +200,49 @@ class ColbertRanker:
             out.append(torch.as_strided(tensor, (rows, stride, self.dim), (self.dim, self.dim, 1)))
         return out
 
+    @property
+    def effective_flags(self) -> int:
+        """``kernel_flags`` plus what the index itself implies: CBK_FLAG_FIXED_DOCLEN when every document has the same
+        number of rows and that number is the only stride (so no floor can apply)."""
+        flags = int(self.kernel_flags)
+        if getattr(self, "_doclen_const", 0) and self.strides == [self._doclen_const]:
+            flags |= kernels._lib.CBK_FLAG_FIXED_DOCLEN
+        return flags
+
     # -- the batched primitive everything else goes through -----------------------------------------
-    def score_candidates(self, Q: torch.Tensor, cand_pids: torch.Tensor, cand_rowptr: torch.Tensor) -> torch.Tensor:
+    def score_candidates(self, Q: torch.Tensor, cand_pids: torch.Tensor, cand_rowptr: torch.Tensor,
+                         q_lens: Optional[torch.Tensor] = None) -> torch.Tensor:
         """fp32 scores, one per candidate, in candidate order.  ``Q`` is ``[B, q_len, dim]`` fp32 on the
-        device; query rows beyond 32 are scored in 32-row slices whose partial sums are added."""
+        device; query rows beyond 32 are scored in 32-row slices whose partial sums are added.  ``q_lens``
+        (``[B]`` int32 on the device, optional): query b has only ``q_lens[b]`` real rows, the rest is padding."""
         B, q_len, dim = Q.shape
+        flags = self.effective_flags
         if q_len <= kernels._lib.CBK_MAX_QLEN:
             return kernels.maxsim_rerank(self.tensor, self._pfxsum_dev, self._doclens_dev, self.strides, Q,
-                                         cand_pids, cand_rowptr, flags=self.kernel_flags, pid_base=self.pid_base)
+                                         cand_pids, cand_rowptr, flags=flags, pid_base=self.pid_base, q_lens=q_lens)
         total = None
         for lo in range(0, q_len, kernels._lib.CBK_MAX_QLEN):
+            ql = None if q_lens is None else (q_lens - lo).clamp_(min=0)
             part = kernels.maxsim_rerank(self.tensor, self._pfxsum_dev, self._doclens_dev, self.strides,
                                          Q[:, lo: lo + kernels._lib.CBK_MAX_QLEN].contiguous(), cand_pids, cand_rowptr,
-                                         flags=self.kernel_flags, pid_base=self.pid_base)
+                                         flags=flags, pid_base=self.pid_base, q_lens=ql)
             total = part if total is None else total.add_(part)
         return total
 
     def rank_forward_batch(self, Q: torch.Tensor, cand_pids: torch.Tensor, cand_rowptr: Optional[torch.Tensor] = None,
-                           depth: Optional[int] = 10, max_cand: Optional[int] = None
-                           ) -> Tuple[torch.Tensor, torch.Tensor]:
+                           depth: Optional[int] = 10, max_cand: Optional[int] = None,
+                           q_lens: Optional[torch.Tensor] = None) -> Tuple[torch.Tensor, torch.Tensor]:
         """Many queries, each with its own candidates, in one MaxSim launch + one top-k launch.
 
         ``Q``: ``[B, q_len, dim]`` fp32 (host — ideally pinned — or device).  ``cand_pids``: ``[B, n]``
-        int64 for equal-length lists, or flat ``[N]`` with ``cand_rowptr`` ``[B+1]``.
+        int64 for equal-length lists, or flat ``[N]`` with ``cand_rowptr`` ``[B+1]`` (ragged lists).
+        ``q_lens``: optional ``[B]`` real row count of each query (queries of different lengths padded to ``q_len``
+        rows — what the reference's server does one query at a time with ``keep_nonzero``,
+        dense_server_client.py:44-46).
         → ``(pids [B, k] int64, scores [B, k] fp32)`` on the device, score-descending; k = depth
         (None: the longest list); shorter lists are padded with (-1, -inf)."""
+        if q_lens is not None:
+            q_lens = torch.as_tensor(q_lens).to(self.device, dtype=torch.int32, non_blocking=True).contiguous()
         Q = Q.to(self.device, dtype=self.maxsim_dtype, non_blocking=True).contiguous()
         B = Q.size(0)
         cand_pids = cand_pids.to(self.device, non_blocking=True)
@@ -235,7 +257,7 @@ class ColbertRanker:
             if max_cand is None:
                 max_cand = int((cand_rowptr[1:] - cand_rowptr[:-1]).max().item())
         cand_pids = cand_pids.contiguous()
-        scores = self.score_candidates(Q, cand_pids, cand_rowptr)
+        scores = self.score_candidates(Q, cand_pids, cand_rowptr, q_lens)
         k = max_cand if depth is None else min(int(depth), max_cand)
         top_scores, top_pids = kernels.topk_per_query(scores, cand_pids, cand_rowptr, k, max_cand)
         return top_pids, top_scores
@@ -412,7 +434,7 @@ class ColbertRanker:
                                            C.cast(self._strides_c, C.c_void_p), len(self.strides), q0.data_ptr(), q_len,
                                            dim_major, pid_ptr, n, k, C.cast(out_pids, C.c_void_p),
                                            C.cast(out_scores, C.c_void_p), d_scr.data_ptr(), h_scr.data_ptr(),
-                                           d_scr.numel(), int(self.kernel_flags),
+                                           d_scr.numel(), int(self.effective_flags),
                                            C.c_void_p(kernels._lib.current_stream_ptr(self.device)))
         finally:
             if switch:

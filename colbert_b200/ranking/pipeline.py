@@ -46,7 +46,7 @@ class RerankPipeline:
         self.result_rows = (self.rank * self.slice, (self.rank + 1) * self.slice)
         # The tensor-core kernels round the query to fp16 on load, so fp16 queries on the wire give bit-identical
         # scores at half the bytes; the exceptions multiply differently and keep fp32 on the wire.
-        flags = int(getattr(local, "kernel_flags", 0))
+        flags = int(getattr(local, "effective_flags", getattr(local, "kernel_flags", 0)))
         from .. import _lib
         self.fp16_wire_ok = (self.dim % 64 == 0 and self.dim <= 1024
                              and not flags & (_lib.CBK_FLAG_BF16_NATIVE_MMA | _lib.CBK_FLAG_RERANK_GENERIC))
@@ -82,13 +82,22 @@ class RerankPipeline:
             flat = full.view(self.world, -1)
             dist.all_gather_into_tensor(flat, flat[self.rank], group=self.in_group)
 
-    def submit(self, Q_host: torch.Tensor, cand_host: torch.Tensor) -> int:
+    def submit(self, Q_host: torch.Tensor, cand_host: torch.Tensor, q_lens: Optional[torch.Tensor] = None,
+               cand_rowptr: Optional[torch.Tensor] = None) -> int:
         """Queue one step; returns the slot to pass to :meth:`result`.  ``Q_host`` ``[n_queries, q_len, dim]`` fp32 or
         fp16 and ``cand_host`` ``[n_queries, n_cand]`` int64 or int32 (pids < 2^31), both pinned and identical on every
         rank.  16-bit queries / 32-bit pids halve the bytes on PCIe and NVLink and are widened on the device; the scores
-        are bit-identical to the fp32 / int64 submission (the kernel rounds the query to fp16 itself)."""
+        are bit-identical to the fp32 / int64 submission (the kernel rounds the query to fp16 itself).
+
+        ``q_lens`` (host ``[n_queries]`` ints, optional): real row count of each query; the remaining rows of its
+        ``q_len`` slots are padding (queries of different lengths in one batch — the reference's server strips the
+        padding one query at a time, dense_server_client.py:44-46).
+        ``cand_rowptr`` (host ``[n_queries + 1]`` int64, optional): RAGGED candidate lists — ``cand_host`` is then the
+        flat concatenation (at most ``n_queries * n_cand`` pids, no list longer than ``n_cand``)."""
         assert Q_host.is_pinned() and cand_host.is_pinned(), "inputs must be pinned host tensors"
         assert Q_host.dtype in (torch.float32, torch.float16) and cand_host.dtype in (torch.int64, torch.int32)
+        if cand_rowptr is not None:
+            return self._submit_ragged(Q_host, cand_host, cand_rowptr, q_lens)
         if Q_host.dtype == torch.float16 and not self.fp16_wire_ok:
             raise ValueError("fp16 queries on the wire need a kernel that rounds the query to fp16 (dim multiple of 64, "
                              "no CBK_FLAG_BF16_NATIVE_MMA / CBK_FLAG_RERANK_GENERIC): pass fp32")
@@ -119,7 +128,42 @@ class RerankPipeline:
             self.h2d_bytes_per_step = (self.slice * self.q_len * self.dim * Q_host.element_size()
                                        + self.slice * self.n_cand * cand_host.element_size()) * self.world
         compute.wait_event(self.ev_in[s])
-        pids, scores = self.ranker.rank_forward_batch(self.Q_dev[s], self.C_dev[s], depth=self.depth)
+        extra = {} if q_lens is None else {"q_lens": torch.as_tensor(q_lens, dtype=torch.int32)}
+        pids, scores = self.ranker.rank_forward_batch(self.Q_dev[s], self.C_dev[s], depth=self.depth, **extra)
+        r0, r1 = self.result_rows
+        self.out_pids[s].copy_(pids[r0:r1], non_blocking=True)
+        self.out_scores[s].copy_(scores[r0:r1], non_blocking=True)
+        self.ev_done[s].record(compute)
+        return s
+
+    def _submit_ragged(self, Q_host, cand_host, cand_rowptr, q_lens) -> int:
+        """Ragged lists: every rank uploads the whole (flat) batch itself — list boundaries do not fall on rank slices."""
+        s = self._i % self.slots
+        self._i += 1
+        compute = torch.cuda.current_stream(self.device)
+        rp = torch.as_tensor(cand_rowptr, dtype=torch.int64)
+        total = int(rp[-1])
+        assert rp.numel() == self.n_queries + 1 and total <= self.n_queries * self.n_cand
+        assert int((rp[1:] - rp[:-1]).max()) <= self.n_cand, "a candidate list is longer than the pipeline was built for"
+        with torch.cuda.stream(self.copy_stream):
+            self.copy_stream.wait_event(self.ev_done[s])
+            self.Q_dev[s].copy_(Q_host, non_blocking=True)                           # (widens fp16 on the way)
+            flat = self.C_dev[s].view(-1)[:total]
+            flat.copy_(cand_host.view(-1)[:total], non_blocking=True)
+            rp_dev = rp.to(self.device, non_blocking=True)
+            ql_dev = None if q_lens is None else torch.as_tensor(q_lens, dtype=torch.int32).to(self.device, non_blocking=True)
+            self.ev_in[s].record(self.copy_stream)
+        if self._wire is None:
+            self._wire = f"Q {str(Q_host.dtype).replace('torch.', '')}, pids {str(cand_host.dtype).replace('torch.', '')}, ragged"
+            self.h2d_bytes_per_step = (Q_host.numel() * Q_host.element_size() + total * cand_host.element_size()
+                                       + rp.numel() * 8) * self.world
+        compute.wait_event(self.ev_in[s])
+        for t in (rp_dev, ql_dev):
+            if t is not None:
+                t.record_stream(compute)
+        extra = {} if ql_dev is None else {"q_lens": ql_dev}
+        pids, scores = self.ranker.rank_forward_batch(self.Q_dev[s], flat, rp_dev, depth=self.depth, max_cand=self.n_cand,
+                                                      **extra)
         r0, r1 = self.result_rows
         self.out_pids[s].copy_(pids[r0:r1], non_blocking=True)
         self.out_scores[s].copy_(scores[r0:r1], non_blocking=True)
@@ -131,3 +175,76 @@ class RerankPipeline:
         the queries ``result_rows`` of the batch (all of them on a single GPU; this rank's 1/world slice when sharded)."""
         self.ev_done[slot].synchronize()
         return self.out_pids[slot], self.out_scores[slot]
+
+
+class GraphedRerank:
+    """Low-batch latency path: host inputs → H2D → MaxSim → top-k → D2H captured ONCE in a CUDA graph and replayed per
+    call (single GPU).  The reference's serving loop handles one query per call (``DenseRetrieverServer.retrieve`` →
+    ``ColbertRetriever.search`` → ``rank_forward``, dense_server_client.py:36-49); here a call carries ``batch`` queries
+    of up to ``q_len`` rows (``q_lens`` says how many are real) with up to ``n_cand`` candidates each, and costs one
+    graph launch instead of four library calls + two copies.
+
+        g = GraphedRerank(ranker, batch=8, q_len=32, n_cand=1000, depth=10)
+        pids, scores = g(Q[8, 32, dim] fp32, cand[8, 1000] int64, q_lens=[...])     # host tensors in, host tensors out
+    """
+
+    def __init__(self, ranker, batch: int, q_len: int, n_cand: int, depth: int = 10):
+        from .. import kernels
+        self.ranker, self.batch, self.q_len, self.n_cand = ranker, batch, q_len, n_cand
+        self.k = min(int(depth), n_cand)
+        dev = self.device = ranker.device
+        dim = ranker.dim
+        self.h_Q = torch.zeros((batch, q_len, dim), dtype=torch.float32).pin_memory()
+        self.h_C = torch.zeros((batch, n_cand), dtype=torch.int64).pin_memory()
+        self.h_ql = torch.full((batch,), q_len, dtype=torch.int32).pin_memory()
+        self.h_rp = torch.arange(0, (batch + 1) * n_cand, n_cand, dtype=torch.int64).pin_memory()
+        self.h_pids = torch.empty((batch, self.k), dtype=torch.int64).pin_memory()
+        self.h_scores = torch.empty((batch, self.k), dtype=torch.float32).pin_memory()
+        self.d_Q, self.d_C = torch.zeros_like(self.h_Q, device=dev), torch.zeros_like(self.h_C, device=dev)
+        self.d_ql, self.d_rp = torch.zeros_like(self.h_ql, device=dev), torch.zeros_like(self.h_rp, device=dev)
+        self.stream = torch.cuda.Stream(device=dev)
+
+        def body():
+            self.d_Q.copy_(self.h_Q, non_blocking=True)
+            self.d_C.copy_(self.h_C, non_blocking=True)
+            self.d_ql.copy_(self.h_ql, non_blocking=True)
+            self.d_rp.copy_(self.h_rp, non_blocking=True)
+            flat = self.d_C.view(-1)
+            scores = ranker.score_candidates(self.d_Q, flat, self.d_rp, self.d_ql)
+            s, p = kernels.topk_per_query(scores, flat, self.d_rp, self.k, n_cand)
+            self.h_pids.copy_(p, non_blocking=True)
+            self.h_scores.copy_(s, non_blocking=True)
+
+        with torch.cuda.stream(self.stream):
+            for _ in range(2):                      # warm up outside capture: tensor maps, function attributes, allocator
+                body()
+            self.stream.synchronize()
+            self.graph = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(self.graph, stream=self.stream):
+                body()
+
+    def __call__(self, Q: torch.Tensor, cand: torch.Tensor, q_lens=None, cand_rowptr=None) -> Tuple[torch.Tensor, torch.Tensor]:
+        """``Q`` ``[b ≤ batch, q_len, dim]`` fp32, ``cand`` ``[b, n ≤ n_cand]`` int64 (or flat + ``cand_rowptr`` for ragged
+        lists) → (pids ``[b, k]``, scores ``[b, k]``) host tensors (views of the pinned result buffers: copy them if they
+        must outlive the next call); lists shorter than k are padded with (-1, -inf)."""
+        b = Q.size(0)
+        assert b <= self.batch and Q.size(1) <= self.q_len
+        self.h_Q[:b, : Q.size(1)].copy_(Q)
+        if Q.size(1) < self.q_len:
+            self.h_Q[:b, Q.size(1):].zero_()
+        self.h_ql[:b] = Q.size(1) if q_lens is None else torch.as_tensor(q_lens, dtype=torch.int32)
+        if cand_rowptr is None:
+            n = cand.size(1)
+            assert cand.size(0) == b and n <= self.n_cand
+            self.h_C.view(-1)[: b * n].copy_(cand.reshape(-1))
+            self.h_rp[: b + 1] = torch.arange(0, (b + 1) * n, n, dtype=torch.int64)
+        else:
+            rp = torch.as_tensor(cand_rowptr, dtype=torch.int64)
+            assert rp.numel() == b + 1 and int(rp[-1]) <= self.batch * self.n_cand
+            self.h_C.view(-1)[: int(rp[-1])].copy_(cand.reshape(-1)[: int(rp[-1])])
+            self.h_rp[: b + 1] = rp
+        self.h_rp[b + 1:] = self.h_rp[b]                       # unused queries: empty lists
+        with torch.cuda.stream(self.stream):
+            self.graph.replay()
+        self.stream.synchronize()
+        return self.h_pids[:b], self.h_scores[:b]

@@ -87,14 +87,14 @@ class ShardedColbertRanker:
 
     # ---- the four stages; the CPU (gloo) tests override the two device stages -----------------------
     def _local_topk_keys(self, Q: torch.Tensor, cand_pids: torch.Tensor, cand_rowptr: torch.Tensor, k: int,
-                         max_cand: int) -> torch.Tensor:
+                         max_cand: int, q_lens: Optional[torch.Tensor] = None) -> torch.Tensor:
         """Route this shard's share of every candidate list, score it, keep the local top-k as packed keys."""
         n_docs = self.local.doclens.numel()
         my_pids, my_rowptr = kernels.partition_candidates(cand_pids, cand_rowptr, self.pid_base, self.pid_base + n_docs)
         if self.maxsim_events is not None:
             ev = (torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True))
             ev[0].record()
-        scores = self.local.score_candidates(Q, my_pids, my_rowptr)
+        scores = self.local.score_candidates(Q, my_pids, my_rowptr, q_lens)
         if self.maxsim_events is not None:
             ev[1].record()
             self.maxsim_events.append(ev)
@@ -135,7 +135,8 @@ class ShardedColbertRanker:
         return self._merge(self._exchange(keys), int(k))
 
     def rank_forward_batch(self, Q: torch.Tensor, cand_pids: torch.Tensor, cand_rowptr: Optional[torch.Tensor] = None,
-                           depth: Optional[int] = 10, max_cand: Optional[int] = None, chunks: Optional[int] = None):
+                           depth: Optional[int] = 10, max_cand: Optional[int] = None, chunks: Optional[int] = None,
+                           q_lens: Optional[torch.Tensor] = None):
         """Same contract as ``ColbertRanker.rank_forward_batch`` with GLOBAL pids; identical on all ranks.
 
         ``chunks`` (equal-length lists ``[B, n]`` on more than one GPU): the batch is scored in that many query chunks,
@@ -146,6 +147,9 @@ class ShardedColbertRanker:
         Q = Q.to(dev, dtype=torch.float32, non_blocking=True).contiguous()
         B = Q.size(0)
         cand_pids = cand_pids.to(dev, non_blocking=True)
+        extra = {}
+        if q_lens is not None:
+            extra["q_lens"] = torch.as_tensor(q_lens).to(dev, dtype=torch.int32, non_blocking=True).contiguous()
         dense = cand_rowptr is None
         if dense:
             assert cand_pids.dim() == 2 and cand_pids.size(0) == B
@@ -155,7 +159,7 @@ class ShardedColbertRanker:
                 chunks = 4 if (self.world > 1 and B >= 2048) else 1
             chunks = max(1, min(int(chunks), B))
             if chunks > 1 and Q.is_cuda:
-                return self._rank_forward_chunked(Q, cand_pids.contiguous(), n, depth, chunks)
+                return self._rank_forward_chunked(Q, cand_pids.contiguous(), n, depth, chunks, extra.get("q_lens"))
             cand_rowptr = torch.arange(0, (B + 1) * n, n, dtype=torch.int64, device=dev)
             cand_pids = cand_pids.reshape(-1)
         else:
@@ -164,10 +168,11 @@ class ShardedColbertRanker:
                 max_cand = int((cand_rowptr[1:] - cand_rowptr[:-1]).max().item())
         cand_pids = cand_pids.contiguous()
         k = max_cand if depth is None else min(int(depth), max_cand)
-        keys = self._local_topk_keys(Q, cand_pids, cand_rowptr, k, max_cand)
+        keys = self._local_topk_keys(Q, cand_pids, cand_rowptr, k, max_cand, **extra)
         return self._merge(self._exchange(keys), k)
 
-    def _rank_forward_chunked(self, Q: torch.Tensor, cand: torch.Tensor, n: int, depth: Optional[int], chunks: int):
+    def _rank_forward_chunked(self, Q: torch.Tensor, cand: torch.Tensor, n: int, depth: Optional[int], chunks: int,
+                              q_lens: Optional[torch.Tensor] = None):
         dev = Q.device
         B = Q.size(0)
         k = n if depth is None else min(int(depth), n)
@@ -181,7 +186,8 @@ class ShardedColbertRanker:
         for c in range(chunks):
             q0, q1 = B * c // chunks, B * (c + 1) // chunks
             rowptr = torch.arange(0, (q1 - q0 + 1) * n, n, dtype=torch.int64, device=dev)
-            keys = self._local_topk_keys(Q[q0:q1], cand[q0:q1].reshape(-1), rowptr, k, n)
+            keys = self._local_topk_keys(Q[q0:q1], cand[q0:q1].reshape(-1), rowptr, k, n,
+                                         **({} if q_lens is None else {"q_lens": q_lens[q0:q1].contiguous()}))
             ready = torch.cuda.Event()
             ready.record(compute)
             keys.record_stream(comm)

@@ -38,13 +38,14 @@
 extern "C" {
 #endif
 
-#define CBK_ABI_VERSION 1
+#define CBK_ABI_VERSION 2
 #define CBK_MAX_STRIDES 8      /* the reference produces at most 4 (percentiles 25/50/75 + max) */
 #define CBK_MAX_QLEN 32        /* query rows per launch; longer queries are split by the caller  */
 #define CBK_FLAG_BF16_NATIVE_MMA 1
 #define CBK_FLAG_RERANK_TCGEN05 4       /* score with the tcgen05 / TMEM kernel instead of the mma.sync one */
 #define CBK_FLAG_SKIP_FOREIGN_PIDS 2   /* sharded stores: a pid outside this shard scores -inf, not NaN */
 #define CBK_FLAG_RERANK_GENERIC 8       /* dim != 128: score with the CUDA-core kernel even where the tensor-core one applies */
+#define CBK_FLAG_FIXED_DOCLEN 16        /* every document has exactly strides[0] rows (multi-view index): offsets are pid * strides[0] */
 #define CBK_TOPK_NEG_INF_IS_PADDING 1  /* top-k: candidates scored -inf are dropped (sharded rerank) */
 
 typedef enum cbk_status {
@@ -96,6 +97,10 @@ uint64_t cbk_launch_count(void);
  *                  SURVEY.md §8e); candidates carry global pids, document p is local row block p - pid_base
  *   strides        host array of n_strides ints (colbert_ranker.py:36-40), may be NULL when n_strides == 0
  *   d_Q            [n_queries, q_len, dim] fp32 row-major (the reference's Q.permute(0,2,1), l.111)
+ *   d_q_lens       NULL, or [n_queries] int32: query q has only q_lens[q] (<= q_len) real rows, the rest of its q_len
+ *                  slots is padding and is read as zero whatever it holds (a zero row adds exactly 0 to every score).
+ *                  This is what replaces the reference server's per-query keep_nonzero / qd_mask_to_realinput
+ *                  (colbert/training/dense_server_client.py:44-46) when queries of different lengths share a batch.
  *   d_cand_pids    [n_cand_total] int64, concatenated candidate lists
  *   d_cand_rowptr  [n_queries + 1] int64, query q owns candidates rowptr[q] .. rowptr[q+1]-1;
  *                  the number of candidates actually scored is rowptr[n_queries], read on the device;
@@ -112,6 +117,10 @@ uint64_t cbk_launch_count(void);
  *                  (11 significant bits; measured worst relative score error 2e-4).  With the flag the
  *                  bf16 values are multiplied directly with the query rounded to bf16 (8 bits; 1.2e-3,
  *                  outside the 1e-3 parity tolerance but safe for stores beyond fp16's range).
+ *                  CBK_FLAG_FIXED_DOCLEN (with n_strides == 1): the caller guarantees that every document has
+ *                  exactly strides[0] rows — the layout of an enable_multiview index, where a document is its
+ *                  d_view view embeddings (BaseModel.py:21-27).  Document p then starts at row (p - pid_base) *
+ *                  strides[0]; d_pfxsum / d_doclens are not read (dim == 128 kernel; ignored by the others).
  *
  * Supported: 1 ≤ q_len ≤ CBK_MAX_QLEN, n_store_rows < 2^31; dim == 128 runs the TMA + tensor-core kernel the
  * benchmarks quote, any other multiple of 64 up to 1024 (the author's configuration: 768) a K-split TMA + tensor-core
@@ -124,7 +133,7 @@ size_t cbk_maxsim_rerank_workspace_bytes(void);
 int cbk_maxsim_rerank(const void* d_store, int store_dtype, int64_t n_store_rows, int dim,
                       const int64_t* d_pfxsum, const int32_t* d_doclens, int64_t n_docs, int64_t pid_base,
                       const int32_t* strides, int n_strides,
-                      const float* d_Q, int q_len, int64_t n_queries,
+                      const float* d_Q, const int32_t* d_q_lens, int q_len, int64_t n_queries,
                       const int64_t* d_cand_pids, const int64_t* d_cand_rowptr, int64_t n_cand_total,
                       float* d_out_scores, void* d_workspace, size_t workspace_bytes, int flags, void* stream);
 

@@ -35,7 +35,7 @@ def test_binding_covers_every_declared_symbol(built_lib):
     from colbert_b200 import _lib
     assert sorted(_lib.SIGNATURES) == declared_symbols()
     lib = _lib.load()
-    assert lib.cbk_abi_version() == 1
+    assert lib.cbk_abi_version() == 2
     assert lib.cbk_topk_max_candidates() == 16384          # the reference's BSIZE
     assert lib.cbk_maxsim_rerank_workspace_bytes() >= 4
 
@@ -52,7 +52,7 @@ def test_library_is_sm100a_and_uses_tma(built_lib):
 def test_invalid_arguments_are_reported_not_crashed(built_lib):
     from colbert_b200 import _lib
     lib = _lib.load()
-    rc = lib.cbk_maxsim_rerank(None, 0, 10, 128, None, None, 1, 0, None, 0, None, 32, 1, None, None, 0, None, None, 0, 0, None)
+    rc = lib.cbk_maxsim_rerank(None, 0, 10, 128, None, None, 1, 0, None, 0, None, None, 32, 1, None, None, 0, None, None, 0, 0, None)
     assert rc == -1 and b"null pointer" in lib.cbk_last_error()
     rc = lib.cbk_topk_per_query(None, None, None, 1, 1, 1, 0, None, None, None)
     assert rc == -1
