@@ -30,7 +30,6 @@ constexpr int kDim = 128;
 constexpr int kTileRows = 16;
 constexpr int kStages = 4;
 constexpr int kWarps = 4;
-constexpr int kCtasPerSm = 3;
 constexpr int kSegCands = 64;
 // Tried and dropped: prefetching tiles into L2 (cp.async.bulk.prefetch.tensor) 4-16 tiles ahead of the ring
 // so that a stage turns over in an L2 round trip.  Measured on B200, configs[1]: 14.2 / 13.4 ms (bf16 / fp16 store)
@@ -48,13 +47,30 @@ struct TmapSet {
   CUtensorMap m[kTileRows];
 };
 
+template <int kRingBytes>
 struct __align__(1024) WarpSmem {
-  uint8_t tiles[kStages * kTileBytes];   // 4 stages of 16 rows, or 8 stages of 8 rows (kShort)
+  uint8_t tiles[kRingBytes];  // 16 KB: 4 stages of 16 rows, or 8 stages of 8 rows (kShort); 8 KB: 4 stages of 8 rows (kLean)
   int2 meta[kSegCands];     // compacted list of scorable candidates: .x = first store row, .y = doclen (> 0)
   uint64_t full[2 * kStages];
   uint8_t cidx[kSegCands];  // position of each compacted entry inside the segment
 };
-static_assert(sizeof(WarpSmem) % 1024 == 0, "per-warp smem must keep 1024-B swizzle-atom alignment");
+static_assert(sizeof(WarpSmem<16384>) % 1024 == 0 && sizeof(WarpSmem<8192>) % 1024 == 0,
+              "per-warp smem must keep 1024-B swizzle-atom alignment");
+
+// How an instantiation is shaped.  kLean = short documents AND at most 16 query rows — the multi-view operating point
+// (q_view, d_view <= 8..16): one m-tile of query fragments (32 registers instead of 64) and an 8 KB ring per warp let
+// 5 CTAs = 20 warps live on an SM instead of 12.  ncu on the 12-warp version of this workload: issue slots 50 % busy
+// with 3 warps per scheduler each waiting ~6 cycles per instruction on its own previous result — latency-bound, so the
+// cure is more warps, not fewer instructions.
+template <bool kShort, int kMT>
+struct Shape {
+  static constexpr bool kLean = kShort && kMT == 1;
+  static constexpr int kCtas = kLean ? 5 : 3;
+  static constexpr int kRing = kLean ? 8192 : 16384;
+  static constexpr int kTR = kShort ? 8 : kTileRows;        // rows per tile
+  static constexpr int kTB = kTR * kDim * 2;                // bytes per stage
+  static constexpr int kST = kRing / kTB;                   // stages of the ring
+};
 
 // two bf16 packed in a 32-bit register → two fp16 (exact for |x| in fp16's normal range, i.e. for
 // the unit-norm embeddings ColBERT stores; tiny values land on fp16 subnormals)
@@ -74,8 +90,8 @@ __device__ __forceinline__ uint32_t bf16x2_to_f16x2(uint32_t v) {
 // kFixed (CBK_FLAG_FIXED_DOCLEN): every document has exactly strides.v[0] rows (multi-view indexes again): document p
 // starts at row p · d, so the segment prologue reads neither pfxsum nor doclens (two dependent random 32-byte sectors per
 // 2-KB candidate otherwise), and the zero floor never applies (the single stride IS the document length).
-template <typename T, bool kCvtBf16, bool kShort, bool kFixed>
-__global__ void __launch_bounds__(kWarps * 32, kCtasPerSm)
+template <typename T, bool kCvtBf16, bool kShort, bool kFixed, int kMT>
+__global__ void __launch_bounds__(kWarps * 32, Shape<kShort, kMT>::kCtas)
 maxsim_rerank_kernel(const __grid_constant__ TmapSet tmaps, const int64_t* __restrict__ pfxsum,
                      const int32_t* __restrict__ doclens, int64_t n_docs, int64_t pid_base, int skip_foreign,
                      StrideSet strides,
@@ -84,15 +100,15 @@ maxsim_rerank_kernel(const __grid_constant__ TmapSet tmaps, const int64_t* __res
                      int64_t n_cand_bound, int seg_cands, float* __restrict__ out,
                      unsigned int* __restrict__ seg_counter, int probe_gather_only) {
   extern __shared__ uint8_t smem_raw[];
-  constexpr int kTR = kShort ? 8 : kTileRows;             // rows per tile
-  constexpr int kST = kShort ? 2 * kStages : kStages;     // stages of the ring (same 16 KB either way)
-  constexpr int kTB = kTR * kDim * 2;                     // bytes per stage
+  using Sh = Shape<kShort, kMT>;
+  constexpr int kTR = Sh::kTR, kST = Sh::kST, kTB = Sh::kTB;
   constexpr int kSub = kShort ? 1 : 2;                    // 8-token sub-tiles per tile
+  using WarpSmemT = WarpSmem<Sh::kRing>;
   const int lane = threadIdx.x & 31;
   const int warp = threadIdx.x >> 5;
   const uint32_t raw_addr = smem_u32(smem_raw);
   const uint32_t pad = ((raw_addr + 1023u) & ~1023u) - raw_addr;
-  WarpSmem* ws = reinterpret_cast<WarpSmem*>(smem_raw + pad) + warp;
+  WarpSmemT* ws = reinterpret_cast<WarpSmemT*>(smem_raw + pad) + warp;
   const uint32_t tiles_addr = smem_u32(&ws->tiles[0]);
   const uint32_t full_addr = smem_u32(&ws->full[0]);
 
@@ -106,12 +122,12 @@ maxsim_rerank_kernel(const __grid_constant__ TmapSet tmaps, const int64_t* __res
   // the candidate count lives on the device (a routed list's length is only known there); the host
   // passes an upper bound that sizes the grid
   const int64_t n_cand = min(rowptr[n_queries], n_cand_bound);
-  const int n_mt = q_len > 16 ? 2 : 1;
+  const int n_mt = kMT == 1 ? 1 : (q_len > 16 ? 2 : 1);
   const int64_t n_segs = (n_cand + seg_cands - 1) / seg_cands;
   uint32_t issued = 0;    // tiles handed to the TMA so far   → stage = issued % kST
   uint32_t consumed = 0;  // tiles multiplied so far          → stage / parity of the next wait
   int64_t cur_q = -1;
-  uint32_t qa[2][8][4];   // A fragments of the current query: [m-tile][k-step][reg]
+  uint32_t qa[kMT][8][4];   // A fragments of the current query: [m-tile][k-step][reg]
 
   // ldmatrix addressing that does not depend on the tile: row (lane & 7) of matrix (lane >> 3)
   const int lrow = lane & 7;
@@ -208,7 +224,7 @@ maxsim_rerank_kernel(const __grid_constant__ TmapSet tmaps, const int64_t* __res
         const float* Qq = Q + q * static_cast<int64_t>(q_len) * kDim;
         const int ql = q_lens ? min(q_len, q_lens[q]) : q_len;   // rows at or past this query's own length read as zero
 #pragma unroll
-        for (int mt = 0; mt < 2; ++mt) {
+        for (int mt = 0; mt < kMT; ++mt) {
           const int r0 = mt * 16 + (lane >> 2);
           const int r1 = r0 + 8;
 #pragma unroll
@@ -281,9 +297,9 @@ maxsim_rerank_kernel(const __grid_constant__ TmapSet tmaps, const int64_t* __res
             }
             mma_16816<T>(acc[s][0], qa[0][2 * p], b0, b1);
             mma_16816<T>(acc[s][0], qa[0][2 * p + 1], b2, b3);
-            if (n_mt > 1) {
-              mma_16816<T>(acc[s][1], qa[1][2 * p], b0, b1);
-              mma_16816<T>(acc[s][1], qa[1][2 * p + 1], b2, b3);
+            if (kMT > 1 && n_mt > 1) {
+              mma_16816<T>(acc[s][1], qa[kMT - 1][2 * p], b0, b1);
+              mma_16816<T>(acc[s][1], qa[kMT - 1][2 * p + 1], b2, b3);
             }
           }
         }
@@ -341,13 +357,15 @@ maxsim_rerank_kernel(const __grid_constant__ TmapSet tmaps, const int64_t* __res
   }
 }
 
-template <typename T, bool kCvtBf16, bool kShort, bool kFixed>
+template <typename T, bool kCvtBf16, bool kShort, bool kFixed, int kMT>
 int launch(const TmapSet& tmaps, const int64_t* pfxsum, const int32_t* doclens, int64_t n_docs, int64_t pid_base,
            int skip_foreign, const StrideSet& strides, const float* Q, const int32_t* q_lens, int q_len, int64_t n_queries, const int64_t* cand_pids,
            const int64_t* rowptr, int64_t n_cand, float* out, unsigned int* counter, cudaStream_t stream) {
   static const int probe = std::getenv("CBK_RERANK_PROBE") != nullptr;     // profiling aid, never set in production
-  const size_t smem = kWarps * sizeof(WarpSmem) + 1024;
-  CBK_CUDA(cudaFuncSetAttribute(maxsim_rerank_kernel<T, kCvtBf16, kShort, kFixed>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+  using Sh = Shape<kShort, kMT>;
+  constexpr int kCtasPerSm = Sh::kCtas;
+  const size_t smem = kWarps * sizeof(WarpSmem<Sh::kRing>) + 1024;
+  CBK_CUDA(cudaFuncSetAttribute(maxsim_rerank_kernel<T, kCvtBf16, kShort, kFixed, kMT>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                 static_cast<int>(smem)));
   // work unit = segment of consecutive candidates claimed by one warp: 64 for big batches (amortises the claim and
   // the metadata fetch), down to 1 for a single query so that each of its ~1000 candidates gets a warp of its own
@@ -357,7 +375,7 @@ int launch(const TmapSet& tmaps, const int64_t* pfxsum, const int32_t* doclens, 
   const int64_t n_segs = (n_cand + seg_cands - 1) / seg_cands;
   const int64_t want = (n_segs + kWarps - 1) / kWarps;
   const int grid = static_cast<int>(std::max<int64_t>(1, std::min<int64_t>(want, static_cast<int64_t>(sm_count()) * kCtasPerSm)));
-  maxsim_rerank_kernel<T, kCvtBf16, kShort, kFixed><<<grid, kWarps * 32, smem, stream>>>(tmaps, pfxsum, doclens, n_docs, pid_base, skip_foreign, strides, Q, q_lens, q_len,
+  maxsim_rerank_kernel<T, kCvtBf16, kShort, kFixed, kMT><<<grid, kWarps * 32, smem, stream>>>(tmaps, pfxsum, doclens, n_docs, pid_base, skip_foreign, strides, Q, q_lens, q_len,
                                                               n_queries, cand_pids, rowptr, n_cand, seg_cands, out, counter,
                                                               probe);
   CBK_CUDA(cudaGetLastError());
@@ -403,9 +421,13 @@ int rerank_dispatch(const void* d_store, int store_dtype, int64_t n_store_rows, 
                  n_cand_total, d_out_scores, counter, stream
   // CBK_FLAG_FIXED_DOCLEN: the caller guarantees doclens[p] == strides[0] for every document
   const bool fixed = (flags & CBK_FLAG_FIXED_DOCLEN) && n_strides == 1 && strides[0] > 0;
-#define CBK_LAUNCH(T, CVT)                                                                                     \
-  (fixed ? (max_len <= 8 ? launch<T, CVT, true, true>(CBK_ARGS) : launch<T, CVT, false, true>(CBK_ARGS))       \
-         : (max_len <= 8 ? launch<T, CVT, true, false>(CBK_ARGS) : launch<T, CVT, false, false>(CBK_ARGS)))
+  // multi-view operating point (documents of at most 8 rows, queries of at most 16): the lean instantiation
+  const bool lean = max_len <= 8 && q_len <= 16;
+#define CBK_LAUNCH(T, CVT)                                                                                            \
+  (fixed ? (lean ? launch<T, CVT, true, true, 1>(CBK_ARGS)                                                            \
+                 : (max_len <= 8 ? launch<T, CVT, true, true, 2>(CBK_ARGS) : launch<T, CVT, false, true, 2>(CBK_ARGS))) \
+         : (lean ? launch<T, CVT, true, false, 1>(CBK_ARGS)                                                           \
+                 : (max_len <= 8 ? launch<T, CVT, true, false, 2>(CBK_ARGS) : launch<T, CVT, false, false, 2>(CBK_ARGS))))
   if (store_dtype == CBK_F16) return CBK_LAUNCH(__half, false);
   if (flags & CBK_FLAG_BF16_NATIVE_MMA) return CBK_LAUNCH(__nv_bfloat16, false);
   return CBK_LAUNCH(__half, true);
