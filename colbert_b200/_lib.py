@@ -24,7 +24,7 @@ CBK_FLAG_SKIP_FOREIGN_PIDS = 2
 CBK_FLAG_RERANK_TCGEN05 = 4
 CBK_FLAG_RERANK_GENERIC = 8
 CBK_FLAG_FIXED_DOCLEN = 16
-CBK_ABI_VERSION = 2
+CBK_ABI_VERSION = 3
 CBK_TOPK_NEG_INF_IS_PADDING = 1
 
 # name → (restype, argtypes); mirrors include/colbert_b200.h one to one
@@ -60,6 +60,9 @@ SIGNATURES = {
     "cbk_selftest_umma_gemm": (C.c_int, [_vp, _vp, _i32, _i32, _i32, _vp, _vp]),
     "cbk_selftest_umma_rate": (C.c_int, [_i32, _i32, _i32, _i32, _i32, _vp, _vp]),
     "cbk_mask_cast_rows": (C.c_int, [_vp, _i32, _i64, _i32, _vp, _i32, _vp, _i32, _vp]),
+    "cbk_score_allpairs_fwd": (C.c_int, [_vp, _vp, _i32, _i64, _i32, _i64, _i32, _i32, _vp, _vp, _vp]),
+    "cbk_score_allpairs_bwd": (C.c_int, [_vp, _vp, _i32, _i64, _i32, _i64, _i32, _i32, _vp, _vp, _vp, _i32, _vp, _i32,
+                                         _vp, _vp, _vp]),
 }
 
 

@@ -42,6 +42,10 @@ int rerank_umma_dispatch(const void*, int, int64_t, int, const int64_t*, const i
 int umma_probe_dispatch(const void*, const void*, int, int, int, float*, cudaStream_t);
 int umma_rate_dispatch(int, int, int, int, int, long long*, cudaStream_t);
 int mask_cast_dispatch(const void*, int, int64_t, int, const void*, int, void*, int, cudaStream_t);
+int score_allpairs_fwd_dispatch(const void*, const void*, int, int64_t, int, int64_t, int, int, float*, int32_t*, cudaStream_t);
+bool score_allpairs_bwd_fits(int64_t, int, int);
+int score_allpairs_bwd_dispatch(const void*, const void*, int, int64_t, int, int64_t, int, int, const float*, const int32_t*, const void*,
+                                int, const void*, int, float*, float*, cudaStream_t);
 
 namespace {
 thread_local char g_err[512] = "";
@@ -151,6 +155,34 @@ int make_store_tensor_map_3d_wide(CUtensorMap* out, const void* base, int64_t ro
   if (r != CUDA_SUCCESS) {
     set_error("cuTensorMapEncodeTiled (3-D, dim %d) failed with CUresult %d (rows %lld box_rows %d)", dim, static_cast<int>(r),
               static_cast<long long>(rows), box_rows);
+    return CBK_ERR_CUDA;
+  }
+  return CBK_OK;
+}
+
+int make_rows_tensor_map(CUtensorMap* out, const void* base, int64_t rows, int dim, int box_rows) {
+  return make_store_tensor_map(out, base, rows, dim, 64, box_rows);
+}
+
+// Packed queries [n_queries, m, dim] seen as {dim, m, n_queries} with a box of {64, 32, 4}: one op brings a K slab of a
+// block of 4 queries as 128 rows ([query][row][64 columns], 128-B swizzle); rows >= m and queries >= n_queries are
+// outside the tensor and arrive as zeros, so nothing has to be padded in memory.
+int make_query_block_tensor_map(CUtensorMap* out, const void* base, int64_t n_queries, int m, int dim) {
+  EncodeTiledFn fn = encode_tiled_fn();
+  if (!fn) {
+    set_error("cuTensorMapEncodeTiled is not available from the installed driver");
+    return CBK_ERR_CUDA;
+  }
+  const cuuint64_t gdim[3] = {static_cast<cuuint64_t>(dim), static_cast<cuuint64_t>(m), static_cast<cuuint64_t>(n_queries)};
+  const cuuint64_t gstride[2] = {static_cast<cuuint64_t>(dim) * 2, static_cast<cuuint64_t>(m) * dim * 2};
+  const cuuint32_t box[3] = {64, 32, 4};
+  const cuuint32_t estride[3] = {1, 1, 1};
+  CUresult r = fn(out, CU_TENSOR_MAP_DATA_TYPE_UINT16, 3, const_cast<void*>(base), gdim, gstride, box, estride,
+                  CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                  CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) {
+    set_error("cuTensorMapEncodeTiled (query blocks) failed with CUresult %d (queries %lld m %d dim %d)", static_cast<int>(r),
+              static_cast<long long>(n_queries), m, dim);
     return CBK_ERR_CUDA;
   }
   return CBK_OK;
@@ -411,6 +443,48 @@ int cbk_mask_cast_rows(const void* d_src, int src_dtype, int64_t n_rows, int dim
   if (rc != CBK_OK) return rc;
   return mask_cast_dispatch(d_src, src_dtype, n_rows, dim, mask_dtype == CBK_MASK_NONE ? nullptr : d_mask, mask_dtype,
                             d_out, out_dtype, static_cast<cudaStream_t>(stream));
+}
+
+static int check_allpairs_shape(const char* fn, int dtype, int64_t nq, int m, int64_t nd, int n, int dim) {
+  CBK_CHECK_ARG(nq > 0 && m > 0 && nd > 0 && n > 0 && dim > 0, "%s: sizes must be positive", fn);
+  CBK_CHECK_ARG(dtype == CBK_F16 || dtype == CBK_BF16, "%s: operands must be CBK_F16 or CBK_BF16 (got %d)", fn, dtype);
+  CBK_CHECK_SUPPORTED(m <= CBK_MAX_QLEN, "%s: %d query rows; at most %d per call", fn, m, CBK_MAX_QLEN);
+  CBK_CHECK_SUPPORTED(dim % 64 == 0 && dim <= 1024, "%s: dim %d; the tensor-core path needs a multiple of 64 up to 1024", fn, dim);
+  CBK_CHECK_SUPPORTED(nd * n < (1ll << 31) - 512 && nq * m < (1ll << 31), "%s: more than 2^31 rows", fn);
+  return CBK_OK;
+}
+
+int cbk_score_allpairs_fwd(const void* d_Qp, const void* d_Dp, int dtype, int64_t n_queries, int m, int64_t n_docs, int n, int dim,
+                           float* d_out_scores, int32_t* d_out_argmax, void* stream) {
+  CBK_CHECK_ARG(d_Qp && d_Dp && d_out_scores, "cbk_score_allpairs_fwd: null pointer argument");
+  int rc = check_allpairs_shape("cbk_score_allpairs_fwd", dtype, n_queries, m, n_docs, n, dim);
+  if (rc != CBK_OK) return rc;
+  CBK_CHECK_ARG((reinterpret_cast<uintptr_t>(d_Qp) & 15) == 0 && (reinterpret_cast<uintptr_t>(d_Dp) & 15) == 0,
+                "cbk_score_allpairs_fwd: operands must be 16-byte aligned");
+  rc = check_device();
+  if (rc != CBK_OK) return rc;
+  return score_allpairs_fwd_dispatch(d_Qp, d_Dp, dtype, n_queries, m, n_docs, n, dim, d_out_scores, d_out_argmax,
+                                     static_cast<cudaStream_t>(stream));
+}
+
+int cbk_score_allpairs_bwd(const void* d_Qp, const void* d_Dp, int dtype, int64_t n_queries, int m, int64_t n_docs, int n, int dim,
+                           const float* d_grad_scores, const int32_t* d_argmax, const void* d_q_mask, int q_mask_dtype,
+                           const void* d_d_mask, int d_mask_dtype, float* d_grad_Q, float* d_grad_D, void* stream) {
+  CBK_CHECK_ARG(d_Qp && d_Dp && d_grad_scores && d_argmax, "cbk_score_allpairs_bwd: null pointer argument");
+  CBK_CHECK_ARG(d_grad_Q || d_grad_D, "cbk_score_allpairs_bwd: neither gradient requested");
+  CBK_CHECK_ARG((q_mask_dtype == CBK_MASK_NONE || d_q_mask) && (d_mask_dtype == CBK_MASK_NONE || d_d_mask),
+                "cbk_score_allpairs_bwd: mask dtype given but mask is NULL");
+  int rc = check_allpairs_shape("cbk_score_allpairs_bwd", dtype, n_queries, m, n_docs, n, dim);
+  if (rc != CBK_OK) return rc;
+  CBK_CHECK_SUPPORTED(!d_grad_D || score_allpairs_bwd_fits(n_queries, m, n),
+                      "cbk_score_allpairs_bwd: %lld query rows x %d document rows do not fit the per-document bucket sort "
+                      "(at most 65535 query rows in total)", static_cast<long long>(n_queries * m), n);
+  rc = check_device();
+  if (rc != CBK_OK) return rc;
+  return score_allpairs_bwd_dispatch(d_Qp, d_Dp, dtype, n_queries, m, n_docs, n, dim, d_grad_scores, d_argmax,
+                                     q_mask_dtype == CBK_MASK_NONE ? nullptr : d_q_mask, q_mask_dtype,
+                                     d_mask_dtype == CBK_MASK_NONE ? nullptr : d_d_mask, d_mask_dtype, d_grad_Q, d_grad_D,
+                                     static_cast<cudaStream_t>(stream));
 }
 
 int cbk_build_emb2pid(const int64_t* d_pfxsum, int64_t n_docs, int32_t* d_emb2pid, void* stream) {

@@ -48,6 +48,7 @@ constexpr int kProducerWarp = kEpiWarps;
 constexpr int kIssuer0Warp = kEpiWarps + 1;        // issues for groups 0-1
 constexpr int kIssuer1Warp = kEpiWarps + 2;        // issues for groups 2-3
 constexpr int kExhThreads = (kEpiWarps + 4) * 32;
+constexpr int kEndsRing = 16;             // tiles whose document-end words are staged in shared memory (producer → epilogue)
 
 
 struct StrideSet {
@@ -173,31 +174,49 @@ __device__ __noinline__ EpiState close_docs_in_group(PendBuf* pb, EpiState st, f
   return st;
 }
 
-// Exactly ONE document ends inside the 8 columns x[0..7], at column e (warp-uniform): → head = max(r, x[0..e]) closes
-// that document, tail = max(x[e+1..7]) opens the next one (-inf when e == 7).  A switch on e: one indirect branch and
-// four or five 3-input maxima instead of eight compare / branch / max rounds.
-__device__ __forceinline__ void split8(const uint32_t* v, int e, float r, float& head, float& tail) {
-  const float x0 = __uint_as_float(v[0]), x1 = __uint_as_float(v[1]), x2 = __uint_as_float(v[2]), x3 = __uint_as_float(v[3]);
-  const float x4 = __uint_as_float(v[4]), x5 = __uint_as_float(v[5]), x6 = __uint_as_float(v[6]), x7 = __uint_as_float(v[7]);
-  const float ninf = -INFINITY;
-  switch (e) {
-    case 0: head = fmaxf(r, x0); tail = fmaxf(fmaxf(fmaxf(x1, x2), x3), fmaxf(fmaxf(fmaxf(x4, x5), x6), x7)); break;
-    case 1: head = fmaxf(fmaxf(r, x0), x1); tail = fmaxf(fmaxf(fmaxf(x2, x3), x4), fmaxf(fmaxf(x5, x6), x7)); break;
-    case 2: head = fmaxf(fmaxf(fmaxf(r, x0), x1), x2); tail = fmaxf(fmaxf(fmaxf(x3, x4), x5), fmaxf(x6, x7)); break;
-    case 3: head = fmaxf(fmaxf(fmaxf(r, x0), x1), fmaxf(x2, x3)); tail = fmaxf(fmaxf(fmaxf(x4, x5), x6), x7); break;
-    case 4: head = fmaxf(fmaxf(fmaxf(r, x0), x1), fmaxf(fmaxf(x2, x3), x4)); tail = fmaxf(fmaxf(x5, x6), x7); break;
-    case 5: head = fmaxf(fmaxf(fmaxf(r, x0), x1), fmaxf(fmaxf(fmaxf(x2, x3), x4), x5)); tail = fmaxf(x6, x7); break;
-    case 6: head = fmaxf(fmaxf(fmaxf(fmaxf(r, x0), x1), x2), fmaxf(fmaxf(fmaxf(x3, x4), x5), x6)); tail = x7; break;
-    default: head = fmaxf(fmaxf(fmaxf(fmaxf(r, x0), x1), x2), fmaxf(fmaxf(fmaxf(x3, x4), x5), fmaxf(x6, x7))); tail = ninf; break;
-  }
-}
-
 // max of 8 consecutive accumulator columns and the running value
 __device__ __forceinline__ float max8(const uint32_t* v, float r) {
   const float x0 = fmaxf(fmaxf(__uint_as_float(v[0]), __uint_as_float(v[1])), __uint_as_float(v[2]));
   const float x1 = fmaxf(fmaxf(__uint_as_float(v[3]), __uint_as_float(v[4])), __uint_as_float(v[5]));
   const float x2 = fmaxf(fmaxf(__uint_as_float(v[6]), __uint_as_float(v[7])), r);
   return fmaxf(fmaxf(x0, x1), x2);
+}
+
+// max of accumulator columns v[L .. R-1] as a ternary tree (one FMNMX3 per node)
+template <int L, int R>
+__device__ __forceinline__ float max_range(const uint32_t (&v)[32]) {
+  constexpr int n = R - L;
+  static_assert(n >= 1, "empty range");
+  if constexpr (n == 1) {
+    return __uint_as_float(v[L]);
+  } else if constexpr (n == 2) {
+    return fmaxf(__uint_as_float(v[L]), __uint_as_float(v[L + 1]));
+  } else {
+    constexpr int a = L + (n + 2) / 3, b = a + (R - a + 1) / 2;
+    return fmaxf(fmaxf(max_range<L, a>(v), max_range<a, b>(v)), max_range<b, R>(v));
+  }
+}
+
+// Exactly ONE document ends inside the 32 columns, at column E: head = max(r, v[0..E]) closes it, tail = max(v[E+1..31])
+// opens the next one.  One straight-line copy per E (16-17 three-input maxima each), selected by a jump table: a chunk
+// with a document end costs about as many instructions as one without.
+template <int E>
+__device__ __forceinline__ void split32(const uint32_t (&v)[32], float r, float& head, float& tail) {
+  head = fmaxf(r, max_range<0, E + 1>(v));
+  if constexpr (E < 31) tail = max_range<E + 1, 32>(v);
+  else tail = -INFINITY;
+}
+
+__device__ __forceinline__ void split32_at(const uint32_t (&v)[32], int e, float r, float& head, float& tail) {
+#define CBK_S32(E) case E: split32<E>(v, r, head, tail); break;
+  switch (e) {
+    CBK_S32(0) CBK_S32(1) CBK_S32(2) CBK_S32(3) CBK_S32(4) CBK_S32(5) CBK_S32(6) CBK_S32(7)
+    CBK_S32(8) CBK_S32(9) CBK_S32(10) CBK_S32(11) CBK_S32(12) CBK_S32(13) CBK_S32(14) CBK_S32(15)
+    CBK_S32(16) CBK_S32(17) CBK_S32(18) CBK_S32(19) CBK_S32(20) CBK_S32(21) CBK_S32(22) CBK_S32(23)
+    CBK_S32(24) CBK_S32(25) CBK_S32(26) CBK_S32(27) CBK_S32(28) CBK_S32(29) CBK_S32(30)
+    default: split32<31>(v, r, head, tail); break;
+  }
+#undef CBK_S32
 }
 
 // One 32-column chunk of an accumulator: fold the columns into the running maximum of the open document, closing
@@ -210,23 +229,26 @@ __device__ __forceinline__ void drain_chunk(const uint32_t (&v)[32], uint32_t m,
     st.r = fmaxf(fmaxf(y0, y1), fmaxf(y2, y3));
     return;
   }
+  if ((m & (m - 1u)) == 0u) {   // one document ends in these 32 columns (any index whose documents have 32+ rows)
+    const int e = 31 - __clz(static_cast<int>(m));
+    float head, tail;
+    split32_at(v, e, st.r, head, tail);
+    const int slot = st.docs_done & (kPend - 1);
+    const int end1 = col + e + 1;
+    pb->v[slot][lane] = head;
+    if (lane == 0) pb->len[slot] = end1 - st.doc_start;
+    st.doc_start = end1;
+    ++st.docs_done;
+    st.r = tail;
+    if ((st.docs_done & (kPend - 1)) == 0) flush_pending(pb, kPend, dst_row + (st.docs_done - kPend), write != 0);
+    return;
+  }
+  // several documents end inside the chunk (documents shorter than 32 rows): 8 columns at a time, out of line
 #pragma unroll
-  for (int s8 = 0; s8 < 4; ++s8) {   // 8 columns at a time: most groups of 8 still hold no document end
+  for (int s8 = 0; s8 < 4; ++s8) {
     const uint32_t m8 = (m >> (8 * s8)) & 0xffu;
     if (m8 == 0u) {
       st.r = max8(v + 8 * s8, st.r);
-    } else if ((m8 & (m8 - 1u)) == 0u) {   // one document ends in these 8 columns (any document of 8+ rows)
-      const int e = 31 - __clz(static_cast<int>(m8));
-      float head, tail;
-      split8(v + 8 * s8, e, st.r, head, tail);       // inline: as an out-of-line call this path cost 12 % at Nq = 16
-      const int slot = st.docs_done & (kPend - 1);
-      const int end1 = col + 8 * s8 + e + 1;
-      pb->v[slot][lane] = head;
-      if (lane == 0) pb->len[slot] = end1 - st.doc_start;
-      st.doc_start = end1;
-      ++st.docs_done;
-      st.r = tail;
-      if ((st.docs_done & (kPend - 1)) == 0) flush_pending(pb, kPend, dst_row + (st.docs_done - kPend), write != 0);
     } else {
       const uint32_t* x = v + 8 * s8;
       st = close_docs_in_group(pb, st, __uint_as_float(x[0]), __uint_as_float(x[1]), __uint_as_float(x[2]),
@@ -259,6 +281,11 @@ maxsim_exhaustive_kernel(const __grid_constant__ ExhMaps maps, const uint32_t* _
   __shared__ __align__(8) uint64_t bar_acc_full[kEpiGroups], bar_acc_empty[kEpiGroups];   // group g owns TMEM slot g
   __shared__ uint32_t tmem_base_smem;
   __shared__ PendBuf s_pend[kEpiGroups * 4];
+  // document-end bits of the tiles in flight, one uint4 per tile: word c bit j = column 32c + j is the last row of a
+  // document OF THE TILE'S SUB-RANGE.  Written by the producer warp before it arms the tile's stage barrier (so the
+  // words are visible to whoever observes, through the MMA, that the tile has arrived), read by the 16 epilogue warps:
+  // what used to be 5 global loads, 4 funnel shifts and the last-tile masking in every epilogue warp.
+  __shared__ __align__(16) uint32_t s_ends[kEndsRing][4];
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   if (warp < kEpiWarps && lane <= CBK_MAX_STRIDES) {
@@ -353,13 +380,14 @@ maxsim_exhaustive_kernel(const __grid_constant__ ExhMaps maps, const uint32_t* _
             }
         }
         __syncwarp();
-        int nt[kEpiGroups];
+        int nt[kEpiGroups], rows[kEpiGroups];
         int64_t t0[kEpiGroups];
         int max_nt = 0;
 #pragma unroll
         for (int s2 = 0; s2 < kEpiGroups; ++s2) {
           nt[s2] = s2 < n_sub ? sub_tiles(n_sub, s2) : 0;
           t0[s2] = s2 < n_sub ? sub_tok0(n_sub, s2) : 0;
+          rows[s2] = s2 < n_sub ? static_cast<int>((s2 + 1 < n_sub ? sub_tok0(n_sub, s2 + 1) : rng_tok[kEpiGroups]) - t0[s2]) : 0;
           max_nt = max(max_nt, nt[s2]);
         }
         for (int t = 0; t < max_nt; ++t)
@@ -367,7 +395,18 @@ maxsim_exhaustive_kernel(const __grid_constant__ ExhMaps maps, const uint32_t* _
           for (int s2 = 0; s2 < kEpiGroups; ++s2) {
             if (t >= nt[s2]) continue;
             const uint32_t st = it % kBStages;
+            // document-end words of this tile (lanes 0-4 fetch one bitmap word each; they arrive while the warp waits
+            // for the stage): bit j of word c = column 32c + j, ends past the sub-range's last row belong to a neighbour
+            const uint32_t bw = lane < 5 ? doc_end_bits[(t0[s2] >> 5) + 4 * t + lane] : 0u;
             { CBK_T0(); mbar_wait(smem_u32(&bar_b_empty[st]), ((it / kBStages) & 1u) ^ 1u); CBK_T1(sc0); }
+            {
+              uint32_t e = __funnelshift_r(bw, __shfl_down_sync(0xffffffffu, bw, 1), static_cast<uint32_t>(t0[s2]) & 31u);
+              const int l = rows[s2] - t * kTileTok - 32 * lane;
+              if (l <= 0) e = 0u;
+              else if (l < 32) e &= (1u << l) - 1u;
+              if (lane < 4) s_ends[it % kEndsRing][lane] = e;
+              __syncwarp();
+            }
             const uint32_t full = smem_u32(&bar_b_full[st]);
             const uint32_t dst = b_addr + st * kTileBytes;
             const int row = static_cast<int>(t0[s2]) + t * kTileTok;
@@ -458,6 +497,7 @@ maxsim_exhaustive_kernel(const __grid_constant__ ExhMaps maps, const uint32_t* _
     const uint32_t lane_base = static_cast<uint32_t>(quad * 32) << 16;
     PendBuf* const pb = &s_pend[warp];
     uint32_t full_parity = 0;                        // parity of this group's next wait on its accumulator-full barrier
+    uint32_t item = 0;                               // tiles the producer has numbered so far (all passes): index into s_ends
     for (int p = 0; p < n_passes; ++p) {
       const int qb = min(qb_max, n_qblocks - p * qb_max);
       const int n_sub = qb == 1 ? 4 : (qb == 2 ? 2 : 1);
@@ -485,11 +525,6 @@ maxsim_exhaustive_kernel(const __grid_constant__ ExhMaps maps, const uint32_t* _
       const int q = (p * qb_max + my_a) * 4 + quad;
       const int write = active && q < n_queries;
       float* const dst_row = scores + static_cast<int64_t>(write ? q : 0) * n_docs + my_d0;   // score of my first document
-      // document-end bits of my rows: bit (my_tok0 & 31) of word wp[0] is my first row; everything below is
-      // 32-bit arithmetic relative to the start of the sub-range
-      const uint32_t* const wp = doc_end_bits + (my_tok0 >> 5);
-      const int sh = static_cast<int>(my_tok0 & 31);
-      const int my_rows = static_cast<int>(my_tok1 - my_tok0);
       int my_nt = 0;
 #pragma unroll
       for (int s2 = 0; s2 < kEpiGroups; ++s2)
@@ -500,33 +535,16 @@ maxsim_exhaustive_kernel(const __grid_constant__ ExhMaps maps, const uint32_t* _
       st.doc_start = 0;
       st.docs_done = 0;
 
-      // document-end bits of a tile: 5 words from the bitmap, loaded ONE TILE AHEAD so that their latency is never exposed
-      uint32_t wnext[5] = {0u, 0u, 0u, 0u, 0u};
-      if (active && my_nt > 0) {
-#pragma unroll
-        for (int i = 0; i < 5; ++i) wnext[i] = wp[i];
-      }
       for (int t = 0; t < max_nt; ++t) {
+        // position of tile (t, my_s) in the producer's order (tiles of row t in sub-range order), then advance past row t
+        uint32_t my_item = item;
+#pragma unroll
+        for (int s2 = 0; s2 < kEpiGroups; ++s2) {
+          if (s2 < my_s && t < nt[s2]) ++my_item;
+          if (t < nt[s2]) ++item;
+        }
         if (!active || t >= my_nt) continue;
-
-        // 128 document-end bits of this tile, shifted so that bit j of word c is column 32c + j
         const long long t_tile = kStats ? clock64() : 0;
-        uint32_t ends[4];
-#pragma unroll
-        for (int c = 0; c < 4; ++c) ends[c] = __funnelshift_r(wnext[c], wnext[c + 1], sh);
-        if (t + 1 < my_nt) {
-#pragma unroll
-          for (int i = 0; i < 5; ++i) wnext[i] = wp[4 * (t + 1) + i];
-        }
-        const int left = my_rows - t * kTileTok;                   // rows of my sub-range in this tile and after
-        if (left < kTileTok) {                                     // last tile: drop the ends that belong to my neighbour
-#pragma unroll
-          for (int c = 0; c < 4; ++c) {
-            const int l = left - 32 * c;
-            if (l <= 0) ends[c] = 0u;
-            else if (l < 32) ends[c] &= (1u << l) - 1u;
-          }
-        }
 
         const long long t_wait = kStats ? clock64() : 0;
         mbar_wait(smem_u32(&bar_acc_full[grp]), full_parity);      // group g owns TMEM slot g
@@ -540,7 +558,9 @@ maxsim_exhaustive_kernel(const __grid_constant__ ExhMaps maps, const uint32_t* _
         // a second register buffer with the load of chunk c+1 in flight while chunk c is folded — 13.0 ms against 9.3 ms
         // (with setmaxnreg moving registers from the producer / issuer warpgroup to the epilogue warpgroups so that
         // nothing spills; a warp with a tcgen05.ld outstanding does not overlap it with its own arithmetic here).
-        uint32_t m = ends[0], m1 = ends[1], m2 = ends[2], m3 = ends[3];
+        // 128 document-end bits of this tile, staged by the producer: bit j of word c is column 32c + j
+        const uint4 ends = *reinterpret_cast<const uint4*>(&s_ends[my_item % kEndsRing][0]);
+        uint32_t m = ends.x, m1 = ends.y, m2 = ends.z, m3 = ends.w;
 #pragma unroll 1
         for (int c = 0; c < 4; ++c) {
           uint32_t v[32];

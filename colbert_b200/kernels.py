@@ -172,6 +172,64 @@ def mask_cast_rows(src: torch.Tensor, mask: Optional[torch.Tensor], out_dtype: t
     return out
 
 
+def score_allpairs_supported(m: int, dim: int) -> bool:
+    """Shapes cbk_score_allpairs_fwd / _bwd implement: at most CBK_MAX_QLEN query rows, width a multiple of 64 up to 1024."""
+    return 0 < m <= _lib.CBK_MAX_QLEN and dim % 64 == 0 and 0 < dim <= 1024
+
+
+def score_allpairs_fwd(Qp: torch.Tensor, Dp: torch.Tensor, want_argmax: bool = True):
+    """scores [q, d] fp32 (and argmax [q, d, m] int32) of the masked 16-bit operands Qp [q, m, h], Dp [d, n, h];
+    see cbk_score_allpairs_fwd."""
+    lib = _lib.load()
+    dev = Dp.device
+    _need(Dp, "Dp", Dp.dtype, dev)
+    _need(Qp, "Qp", Dp.dtype, dev)
+    nq, m, h = Qp.shape
+    nd, n, h2 = Dp.shape
+    if h != h2:
+        raise ValueError(f"widths differ: {tuple(Qp.shape)} vs {tuple(Dp.shape)}")
+    scores = torch.empty((nq, nd), dtype=torch.float32, device=dev)
+    argmax = torch.empty((nq, nd, m), dtype=torch.int32, device=dev) if want_argmax else None
+    with torch.cuda.device(dev):
+        rc = lib.cbk_score_allpairs_fwd(_ptr(Qp), _ptr(Dp), _lib.dtype_code(Dp.dtype), nq, m, nd, n, h, _ptr(scores),
+                                        _ptr(argmax), C.c_void_p(_lib.current_stream_ptr(dev)))
+    _lib.check("cbk_score_allpairs_fwd", rc)
+    return scores, argmax
+
+
+def score_allpairs_bwd(Qp: torch.Tensor, Dp: torch.Tensor, grad_scores: torch.Tensor, argmax: torch.Tensor,
+                       q_mask: Optional[torch.Tensor], d_mask: Optional[torch.Tensor], want_dq: bool = True,
+                       want_dd: bool = True):
+    """(grad_Q [q, m, h], grad_D [d, n, h]) fp32 for the upstream gradient grad_scores [q, d]; see cbk_score_allpairs_bwd."""
+    lib = _lib.load()
+    dev = Dp.device
+    _need(Dp, "Dp", Dp.dtype, dev)
+    _need(Qp, "Qp", Dp.dtype, dev)
+    _need(grad_scores, "grad_scores", torch.float32, dev)
+    _need(argmax, "argmax", torch.int32, dev)
+    nq, m, h = Qp.shape
+    nd, n, _ = Dp.shape
+    if tuple(grad_scores.shape) != (nq, nd) or tuple(argmax.shape) != (nq, nd, m):
+        raise ValueError("grad_scores must be [q, d] and argmax [q, d, m]")
+    codes = []
+    for name, mk, rows in (("q_mask", q_mask, nq * m), ("d_mask", d_mask, nd * n)):
+        if mk is None:
+            codes.append(_lib.CBK_MASK_NONE)
+            continue
+        _need(mk, name, mk.dtype, dev)
+        if mk.numel() != rows:
+            raise ValueError(f"{name} must have one entry per row")
+        codes.append(_lib.mask_code(mk.dtype))
+    dq = torch.empty((nq, m, h), dtype=torch.float32, device=dev) if want_dq else None
+    dd = torch.empty((nd, n, h), dtype=torch.float32, device=dev) if want_dd else None
+    with torch.cuda.device(dev):
+        rc = lib.cbk_score_allpairs_bwd(_ptr(Qp), _ptr(Dp), _lib.dtype_code(Dp.dtype), nq, m, nd, n, h, _ptr(grad_scores),
+                                        _ptr(argmax), _ptr(q_mask), codes[0], _ptr(d_mask), codes[1], _ptr(dq), _ptr(dd),
+                                        C.c_void_p(_lib.current_stream_ptr(dev)))
+    _lib.check("cbk_score_allpairs_bwd", rc)
+    return dq, dd
+
+
 def partition_candidates(cand_pids: torch.Tensor, cand_rowptr: torch.Tensor, pid_lo: int, pid_hi: int):
     """Keep, per query and in order, the candidates with pid in [pid_lo, pid_hi) → (pids [n_total] int64 of
     which the first rowptr[-1] are valid, rowptr [B+1] int64); no host synchronisation.

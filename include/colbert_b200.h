@@ -38,7 +38,7 @@
 extern "C" {
 #endif
 
-#define CBK_ABI_VERSION 2
+#define CBK_ABI_VERSION 3
 #define CBK_MAX_STRIDES 8      /* the reference produces at most 4 (percentiles 25/50/75 + max) */
 #define CBK_MAX_QLEN 32        /* query rows per launch; longer queries are split by the caller  */
 #define CBK_FLAG_BF16_NATIVE_MMA 1
@@ -249,6 +249,31 @@ int cbk_embedding_ids_to_pids(const int64_t* d_emb_ids, int64_t n_queries, int n
  * ------------------------------------------------------------------------------------------------ */
 int cbk_mask_cast_rows(const void* d_src, int src_dtype, int64_t n_rows, int dim, const void* d_mask, int mask_dtype,
                        void* d_out, int out_dtype, void* stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * All-pairs MaxSim of padded batches, forward and backward — BaseModel.score as the reference trains with it
+ * (BaseModel.py:39-46 called from colbert/modeling/colbert_model.py:87-95 on the all-gathered Q / D of
+ * colbert/training/training_utils.py:35-45), at any width that is a multiple of 64 up to 1024 (the author's: 768).
+ *
+ *   d_Qp  [n_queries, m, dim], d_Dp [n_docs, n, dim]: the MASKED operands in 16 bits (dtype CBK_F16 | CBK_BF16), i.e. the
+ *         outputs of cbk_mask_cast_rows(Q, q_mask) and cbk_mask_cast_rows(D, d_mask) — BaseModel.py:41-42 fused with the
+ *         cast.  A masked slot is a zero row and scores exactly 0, as in the reference.  m <= CBK_MAX_QLEN.
+ *   cbk_score_allpairs_fwd   d_out_scores [n_queries, n_docs] fp32 = Σ_m max_n Qp[q,m]·Dp[d,n] (fp32 accumulation on
+ *                            tcgen05 tensor cores; `simmat` of BaseModel.py:43 is never written);
+ *                            d_out_argmax [n_queries, n_docs, m] int32 = the maximising n (first one on ties, like
+ *                            torch.max on the CPU), or NULL when no backward pass will follow.
+ *   cbk_score_allpairs_bwd   gradients of Σ_{q,d} grad_scores[q,d]·scores[q,d] with respect to the UNMASKED inputs:
+ *                              d_grad_Q [n_queries, m, dim] fp32 = q_mask[q,m] · Σ_d grad[q,d] · Dp[d, argmax[q,d,m]]
+ *                              d_grad_D [n_docs, n, dim]   fp32 = d_mask[d,n] · Σ_{(q,m): argmax[q,d,m]=n} grad[q,d] · Qp[q,m]
+ *                            (what autograd derives for BaseModel.py:41-45); either may be NULL.  Masks as for
+ *                            cbk_mask_cast_rows (CBK_MASK_NONE: all ones).  Sums run in a fixed order: results are
+ *                            bit-reproducible.  d_grad_D needs n_queries * m <= 65535.
+ * ------------------------------------------------------------------------------------------------ */
+int cbk_score_allpairs_fwd(const void* d_Qp, const void* d_Dp, int dtype, int64_t n_queries, int m, int64_t n_docs, int n, int dim,
+                           float* d_out_scores, int32_t* d_out_argmax, void* stream);
+int cbk_score_allpairs_bwd(const void* d_Qp, const void* d_Dp, int dtype, int64_t n_queries, int m, int64_t n_docs, int n, int dim,
+                           const float* d_grad_scores, const int32_t* d_argmax, const void* d_q_mask, int q_mask_dtype,
+                           const void* d_d_mask, int d_mask_dtype, float* d_grad_Q, float* d_grad_D, void* stream);
 
 /* ------------------------------------------------------------------------------------------------
  * Exhaustive, query-batched MaxSim — every document of the store against a batch of queries: the

@@ -145,6 +145,38 @@ def score_allpairs(Q: np.ndarray, D: np.ndarray, q_mask: np.ndarray, d_mask: np.
     return out
 
 
+def score_allpairs_grad(Q: np.ndarray, D: np.ndarray, q_mask: np.ndarray, d_mask: np.ndarray, W: np.ndarray):
+    """What autograd derives for BaseModel.score (reference colbert/modeling/BaseModel.py:41-45) as the reference
+    trains with it (colbert/modeling/colbert_model.py:87-95): for L = Σ_{q,d} W[q,d]·scores[q,d]
+
+        n*(q,d,m) = argmax_n simmat[q,d,m,n]                    (first maximal n, like torch.max on the CPU)
+        dL/dQ[q,m] = q_mask[q,m] · Σ_d W[q,d] · (D·d_mask)[d, n*(q,d,m)]
+        dL/dD[d,n] = d_mask[d,n] · Σ_{(q,m): n*(q,d,m) = n} W[q,d] · (Q·q_mask)[q,m]
+
+    → (scores [q,d], dQ [q,m,h], dD [d,n,h], argmax [q,d,m]), all float32 / int64."""
+    qm = q_mask.astype(np.float32)
+    dm = d_mask.astype(np.float32)
+    Qm = Q.astype(np.float32) * qm[..., None]
+    Dm = D.astype(np.float32) * dm[..., None]
+    nq, m, h = Qm.shape
+    nd, n, _ = Dm.shape
+    scores = np.empty((nq, nd), dtype=np.float32)
+    arg = np.empty((nq, nd, m), dtype=np.int64)
+    dQ = np.zeros_like(Qm)
+    dD = np.zeros_like(Dm)
+    Dt = Dm.reshape(nd * n, h).T
+    for qi in range(nq):
+        sim = (Qm[qi] @ Dt).reshape(m, nd, n)
+        a = sim.argmax(-1)                                   # [m, d]
+        arg[qi] = a.T
+        scores[qi] = np.take_along_axis(sim, a[..., None], -1)[..., 0].sum(0, dtype=np.float32)
+        for di in range(nd):
+            rows = Dm[di, a[:, di]]                          # [m, h]
+            dQ[qi] += W[qi, di] * rows
+            np.add.at(dD[di], a[:, di], W[qi, di] * Qm[qi])
+    return scores, dQ * qm[..., None], dD * dm[..., None], arg
+
+
 # --------------------------------------------------------------------------------------------
 # rank_forward (reference rows a9-a15), faithful op sequence
 # --------------------------------------------------------------------------------------------

@@ -108,9 +108,39 @@ def run_score_cases():
     return out
 
 
+def run_score_grad_cases():
+    """BaseModel.score under autograd, as the reference trains with it (colbert_model.py:87-95): scores and the gradients
+    of Σ scores * W with respect to Q and D, from the reference's own ops on the CPU in fp32."""
+    out = {}
+    rng = np.random.default_rng(4242)
+    for name, (nq, m, nd, n, h) in {"g_small": (3, 5, 4, 7, 64), "g_mid": (6, 32, 12, 40, 128),
+                                    "g_views": (4, 16, 9, 16, 128), "g_wide": (2, 8, 3, 40, 768),
+                                    "g_tiles": (5, 32, 3, 300, 64)}.items():
+        Qn = rng.standard_normal((nq, m, h), dtype=np.float32)
+        Dn = rng.standard_normal((nd, n, h), dtype=np.float32)
+        Qn /= np.linalg.norm(Qn, axis=-1, keepdims=True)
+        Dn /= np.linalg.norm(Dn, axis=-1, keepdims=True)
+        Q16, D16 = Qn.astype(np.float16), Dn.astype(np.float16)      # inputs are stored (and differentiated) at fp16 values
+        qlen = rng.integers(1, m + 1, size=nq)
+        dlen = rng.integers(1, n + 1, size=nd)
+        qmask = (np.arange(m)[None, :] < qlen[:, None]).astype(np.int64)
+        dmask = (np.arange(n)[None, :] < dlen[:, None]).astype(np.int64)
+        W = rng.standard_normal((nq, nd), dtype=np.float32)
+        Qt = torch.from_numpy(Q16.astype(np.float32)).requires_grad_(True)
+        Dt = torch.from_numpy(D16.astype(np.float32)).requires_grad_(True)
+        s = BaseModel.score(Qt, Dt, torch.from_numpy(qmask), torch.from_numpy(dmask))
+        (s * torch.from_numpy(W)).sum().backward()
+        out[f"{name}_Q"], out[f"{name}_D"], out[f"{name}_qmask"], out[f"{name}_dmask"] = Q16, D16, qmask, dmask
+        out[f"{name}_W"], out[f"{name}_score"] = W, s.detach().numpy()
+        out[f"{name}_dQ"], out[f"{name}_dD"] = Qt.grad.numpy(), Dt.grad.numpy()
+    return out
+
+
 def main():
     np.savez_compressed(os.path.join(HERE, "score_cases.npz"), **run_score_cases())
     print("wrote score_cases.npz")
+    np.savez_compressed(os.path.join(HERE, "score_grad_cases.npz"), **run_score_grad_cases())
+    print("wrote score_grad_cases.npz")
     for case in CASES:
         res = run_reference_case(case)
         path = os.path.join(HERE, f"rank_{case['name']}.npz")

@@ -35,7 +35,7 @@ def test_binding_covers_every_declared_symbol(built_lib):
     from colbert_b200 import _lib
     assert sorted(_lib.SIGNATURES) == declared_symbols()
     lib = _lib.load()
-    assert lib.cbk_abi_version() == 2
+    assert lib.cbk_abi_version() == 3
     assert lib.cbk_topk_max_candidates() == 16384          # the reference's BSIZE
     assert lib.cbk_maxsim_rerank_workspace_bytes() >= 4
 

@@ -129,3 +129,15 @@ def test_torch_port_matches_reference(golden_dir, case):
         Qt = torch.from_numpy(Q).unsqueeze(0).permute(0, 2, 1)
         p, s = port.rank_forward(Qt, pids.tolist(), depth=None)
         _check_topk(p, s, g[f"q{qi}_all_pids"], g[f"q{qi}_all_scores"], RTOL)
+
+
+@pytest.mark.parametrize("name", ["g_small", "g_mid", "g_views", "g_wide", "g_tiles"])
+def test_score_allpairs_grad_matches_reference_autograd(golden_dir, name):
+    """oracle backward of BaseModel.score == the reference's own ops under torch autograd (BaseModel.py:41-45)."""
+    g = np.load(os.path.join(golden_dir, "score_grad_cases.npz"))
+    Q, D = g[f"{name}_Q"].astype(np.float32), g[f"{name}_D"].astype(np.float32)
+    s, dQ, dD, _ = O.score_allpairs_grad(Q, D, g[f"{name}_qmask"], g[f"{name}_dmask"], g[f"{name}_W"])
+    np.testing.assert_allclose(s, g[f"{name}_score"], rtol=0, atol=2e-5)
+    # a different arg-max on a near-tie would show up as an O(1) difference: the tolerance only covers summation order
+    np.testing.assert_allclose(dQ, g[f"{name}_dQ"], rtol=0, atol=2e-5)
+    np.testing.assert_allclose(dD, g[f"{name}_dD"], rtol=0, atol=2e-5)
