@@ -555,9 +555,11 @@ maxsim_exhaustive_kernel(const __grid_constant__ ExhMaps maps, const uint32_t* _
         const uint32_t t_addr = tmem + lane_base + grp * kTileTok;
         const int col0 = t * kTileTok;
         // One 32-column chunk in registers at a time.  Measured and NOT adopted (B200, Nq = 16, 1.1 M-document shard):
-        // a second register buffer with the load of chunk c+1 in flight while chunk c is folded — 13.0 ms against 9.3 ms
-        // (with setmaxnreg moving registers from the producer / issuer warpgroup to the epilogue warpgroups so that
-        // nothing spills; a warp with a tcgen05.ld outstanding does not overlap it with its own arithmetic here).
+        // a second register buffer with the load of chunk c+1 in flight while chunk c is folded — 13.0 ms against 9.3 ms;
+        // two 64-column loads per accumulator, the slot handed back after the second — 10.4 ms against 7.9 ms (both with
+        // setmaxnreg moving registers from the producer / issuer warpgroup to the epilogue warpgroups so that the hot
+        // loop does not spill: 128 x 40 + 512 x 104 registers is all a 640-thread CTA owns).  A warp with a tcgen05.ld
+        // outstanding does not overlap it with its own arithmetic here, and the epilogue body doubles in size.
         // 128 document-end bits of this tile, staged by the producer: bit j of word c is column 32c + j
         const uint4 ends = *reinterpret_cast<const uint4*>(&s_ends[my_item % kEndsRing][0]);
         uint32_t m = ends.x, m1 = ends.y, m2 = ends.z, m3 = ends.w;
