@@ -537,6 +537,110 @@ def secondary_exhaustive(torch, dist, sampler, dev, args, rank, world, peaks):
     return out
 
 
+def secondary_allpairs_training(torch, sampler, dev, args, peaks):
+    """BaseModel.score as the reference TRAINS with it — forward + backward over the all-gathered batch
+    of colbert_model.py:87-95 at the author's width (q = 170 questions x 32 rows, d = 340 passages x 384 rows, h = 768)."""
+    from colbert_b200 import kernels
+    from colbert_b200.modeling.BaseModel import BaseModel
+    nq, m, nd, n, h = 170, 32, 340, 384, 768
+    g = torch.Generator(device=dev); g.manual_seed(31337)
+    Q = torch.nn.functional.normalize(torch.randn(nq, m, h, generator=g, device=dev), dim=-1)
+    D = torch.nn.functional.normalize(torch.randn(nd, n, h, generator=g, device=dev), dim=-1)
+    qmask = torch.ones(nq, m, dtype=torch.int64, device=dev)
+    dmask = (torch.arange(n, device=dev)[None, :] < torch.randint(n // 4, n + 1, (nd, 1), generator=g, device=dev)).long()
+    W = torch.randn(nq, nd, generator=g, device=dev)
+    Qp = kernels.mask_cast_rows(Q.reshape(-1, h), qmask.reshape(-1), torch.float16).reshape(nq, m, h)
+    Dp = kernels.mask_cast_rows(D.reshape(-1, h), dmask.reshape(-1), torch.float16).reshape(nd, n, h)
+    flops = 2.0 * nq * m * nd * n * h
+    res = {}
+
+    def fwd_only(ev):
+        if ev: ev[0].record()
+        res["s"], res["a"] = kernels.score_allpairs_fwd(Qp, Dp)
+        if ev: ev[1].record()
+
+    steps, ms_total, fwd_ms, win = timed_region(torch, None, 1, fwd_only, args.warmup, args.steps, min_ms=1000.0)
+    clocks_fwd = sampler.window(*win)
+
+    def train_step(ev):
+        Qa, Da = Q.detach().requires_grad_(True), D.detach().requires_grad_(True)
+        if ev: ev[0].record()
+        (BaseModel.score(Qa, Da, qmask, dmask) * W).sum().backward()
+        if ev: ev[1].record()
+        res["dQ"], res["dD"] = Qa.grad, Da.grad
+
+    steps2, ms_total2, step_ms, win2 = timed_region(torch, None, 1, train_step, args.warmup, args.steps, min_ms=1000.0)
+    ach = flops / (fwd_ms * 1e-3) / 1e12
+    out = {"workload": f"all-pairs MaxSim with backward (training shape, colbert_model.py:87-95): q {nq} x m {m}, d {nd} x n {n}, "
+                       f"h {h}; 16-bit operands (fp16), fp32 accumulation; inputs 0.43 GB fp32 (> L2)",
+           "forward_kernel_ms": fwd_ms, "steps": steps,
+           "roofline": {"bound": "tensor", "achieved": ach, "peak": peaks["tflops_sustained"], "unit": "TFLOP/s",
+                        "frac": ach / peaks["tflops_sustained"], "frac_of_burst_peak": ach / peaks["tflops_burst"],
+                        "algorithmic_flops_per_launch": flops, "kernel": "score_allpairs_fwd_kernel (tcgen05)"},
+           "score_fwd_bwd_ms": step_ms, "score_fwd_bwd_steps": steps2,
+           "score_fwd_bwd_what": "BaseModel.score(Q, D, q_mask, d_mask) under autograd: 2 mask+cast passes, forward kernel, "
+                                 "dQ and dD kernels, fp32 gradients",
+           "clocks": clocks_fwd, "clocks_fwd_bwd": sampler.window(*win2)}
+    if not args.no_parity:
+        # oracle (numpy restatement of BaseModel.py:41-45 and its autograd) on a slice: 3 queries x 5 documents
+        import numpy as np
+        from oracle import maxsim_oracle as O
+        qs, ds = [0, nq // 2, nq - 1], [0, 1, nd // 2, nd - 2, nd - 1]
+        Qh, Dh = Q[qs].half().float().cpu().numpy(), D[ds].half().float().cpu().numpy()
+        rs, _, _, rarg = O.score_allpairs_grad(Qh, Dh, qmask[qs].cpu().numpy(), dmask[ds].cpu().numpy(),
+                                               np.zeros((len(qs), len(ds)), np.float32))
+        got = res["s"][qs][:, ds].cpu().numpy()
+        worst = float(np.abs(got - rs).max() / max(1.0, np.abs(rs).max()))
+        arg_ok = bool((res["a"][qs][:, ds].cpu().numpy() == rarg).all())
+        # whole batch against the reference's op sequence in fp32 on the GPU (BaseModel.py:41-45 on the 16-bit-rounded
+        # inputs): scores; the kernel's arg-max is a true arg-max (an fp32 matmul and the tensor cores sum in different
+        # orders, so among ~2 M (q, d, m) maxima a few near-ties legitimately resolve differently — each is checked to be
+        # within 1e-5 of the maximum); and dQ / dD equal what autograd derives for THAT arg-max (gather / index_add).
+        prev = torch.backends.cuda.matmul.allow_tf32
+        torch.backends.cuda.matmul.allow_tf32 = False
+        try:
+            Qm_, Dm_ = Q.half().float() * qmask[..., None], D.half().float() * dmask[..., None]
+            dQ_ref, dD_ref = torch.zeros_like(Qm_), torch.zeros_like(Dm_)
+            doc_row0 = (torch.arange(nd, device=dev) * n)[None, :, None]
+            s_worst = tie_gap = 0.0
+            flips = 0
+            for lo in range(0, nq, 10):
+                hi = min(nq, lo + 10)
+                sim = torch.einsum("qmh,dnh->qdmn", Qm_[lo:hi], Dm_)
+                mx, ix = sim.max(-1)
+                ours = res["a"][lo:hi].long()
+                at = sim.gather(-1, ours.unsqueeze(-1)).squeeze(-1)
+                tie_gap = max(tie_gap, float((mx - at).max()))
+                flips += int((ix != ours).sum())
+                ref_s = mx.sum(-1)
+                s_worst = max(s_worst, float(((res["s"][lo:hi] - ref_s).abs() / ref_s.abs().clamp_min(1.0)).max()))
+                del sim, mx, ix, at
+                rows = (doc_row0 + ours).reshape(-1)                                        # [c * nd * m] rows of D
+                picked = Dm_.reshape(nd * n, h)[rows].view(hi - lo, nd, m, h)
+                dQ_ref[lo:hi] = (picked * W[lo:hi, :, None, None]).sum(1)
+                del picked
+                contrib = (W[lo:hi, :, None, None] * Qm_[lo:hi, None, :, :]).reshape(-1, h)
+                dD_ref.view(nd * n, h).index_add_(0, rows, contrib)
+                del contrib
+            dQ_ref *= qmask[..., None]
+            dD_ref *= dmask[..., None]
+        finally:
+            torch.backends.cuda.matmul.allow_tf32 = prev
+        gq = float((res["dQ"] - dQ_ref).abs().max() / dQ_ref.abs().max())
+        gd = float((res["dD"] - dD_ref).abs().max() / dD_ref.abs().max())
+        assert worst <= 1e-3 and arg_ok and s_worst <= 1e-3 and tie_gap <= 1e-5 and gq <= 1e-3 and gd <= 1e-3, \
+            (worst, arg_ok, s_worst, tie_gap, gq, gd)
+        out["parity"] = {"scores_worst_rel_vs_oracle": worst, "argmax_equal_to_oracle": arg_ok, "queries": len(qs), "documents": len(ds),
+                         "scores_worst_rel_vs_torch_fp32_full_batch": s_worst,
+                         "argmax_differs_from_torch_fp32": flips, "of": nq * nd * m, "largest_gap_to_the_maximum": tie_gap,
+                         "grad_Q_worst_rel": gq, "grad_D_worst_rel": gd,
+                         "grad_reference": "autograd's formula for the kernel's own arg-max (gather / index_add in torch fp32)",
+                         "tol_rel": 1e-3}
+        del dQ_ref, dD_ref, Qm_, Dm_
+    torch.cuda.empty_cache()
+    return out
+
+
 def run_ours(args, rank, world, local_rank):
     import torch
     import torch.distributed as dist
@@ -737,6 +841,8 @@ def run_ours(args, rank, world, local_rank):
         del cand_dev
         torch.cuda.empty_cache()
         secondary["exhaustive"] = secondary_exhaustive(torch, dist, sampler, dev, args, rank, world, peaks)
+        if world == 1:
+            secondary["allpairs_training"] = secondary_allpairs_training(torch, sampler, dev, args, peaks)
     sampler.stop()
 
     if rank == 0:

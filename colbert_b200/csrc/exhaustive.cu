@@ -48,7 +48,7 @@ constexpr int kProducerWarp = kEpiWarps;
 constexpr int kIssuer0Warp = kEpiWarps + 1;        // issues for groups 0-1
 constexpr int kIssuer1Warp = kEpiWarps + 2;        // issues for groups 2-3
 constexpr int kExhThreads = (kEpiWarps + 4) * 32;
-constexpr int kEndsRing = 16;             // tiles whose document-end words are staged in shared memory (producer → epilogue)
+constexpr int kEndsRing = 8;              // tiles PER SUB-RANGE whose document-end words are staged in shared memory (producer → epilogue)
 
 
 struct StrideSet {
@@ -285,7 +285,10 @@ maxsim_exhaustive_kernel(const __grid_constant__ ExhMaps maps, const uint32_t* _
   // document OF THE TILE'S SUB-RANGE.  Written by the producer warp before it arms the tile's stage barrier (so the
   // words are visible to whoever observes, through the MMA, that the tile has arrived), read by the 16 epilogue warps:
   // what used to be 5 global loads, 4 funnel shifts and the last-tile masking in every epilogue warp.
-  __shared__ __align__(16) uint32_t s_ends[kEndsRing][4];
+  // Indexed [sub-range][tile % kEndsRing]: the producer is never more than 1 + kMaxBStages tiles of a sub-range ahead of
+  // the group that drains it (tile t + 1 cannot be multiplied before the group released tile t, and it read the words
+  // of tile t before that), so 8 entries per sub-range are never overwritten while still unread.
+  __shared__ __align__(16) uint32_t s_ends[kEpiGroups][kEndsRing][4];
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   if (warp < kEpiWarps && lane <= CBK_MAX_STRIDES) {
@@ -364,6 +367,7 @@ maxsim_exhaustive_kernel(const __grid_constant__ ExhMaps maps, const uint32_t* _
         tma_prefetch_desc(&maps.q);
       }
       uint32_t it = 0;
+      uint32_t ring0[kEpiGroups] = {0u, 0u, 0u, 0u};   // tiles of sub-range index s2 in the passes before this one (s_ends position)
       for (int p = 0; p < n_passes; ++p) {
         if (p > 0) mbar_wait(smem_u32(&bar_pass_done), (p - 1) & 1);   // every MMA that read the old A blocks is done
         const int qb = min(qb_max, n_qblocks - p * qb_max);
@@ -404,7 +408,7 @@ maxsim_exhaustive_kernel(const __grid_constant__ ExhMaps maps, const uint32_t* _
               const int l = rows[s2] - t * kTileTok - 32 * lane;
               if (l <= 0) e = 0u;
               else if (l < 32) e &= (1u << l) - 1u;
-              if (lane < 4) s_ends[it % kEndsRing][lane] = e;
+              if (lane < 4) s_ends[s2][(ring0[s2] + t) % kEndsRing][lane] = e;
               __syncwarp();
             }
             const uint32_t full = smem_u32(&bar_b_full[st]);
@@ -418,6 +422,8 @@ maxsim_exhaustive_kernel(const __grid_constant__ ExhMaps maps, const uint32_t* _
             __syncwarp();
             ++it;
           }
+#pragma unroll
+        for (int s2 = 0; s2 < kEpiGroups; ++s2) ring0[s2] += static_cast<uint32_t>(nt[s2]);
       }
     }
   } else if (warp == kIssuer0Warp || warp == kIssuer1Warp) {
@@ -497,7 +503,7 @@ maxsim_exhaustive_kernel(const __grid_constant__ ExhMaps maps, const uint32_t* _
     const uint32_t lane_base = static_cast<uint32_t>(quad * 32) << 16;
     PendBuf* const pb = &s_pend[warp];
     uint32_t full_parity = 0;                        // parity of this group's next wait on its accumulator-full barrier
-    uint32_t item = 0;                               // tiles the producer has numbered so far (all passes): index into s_ends
+    uint32_t ring0[kEpiGroups] = {0u, 0u, 0u, 0u};   // as in the producer: tiles of sub-range index s2 in earlier passes
     for (int p = 0; p < n_passes; ++p) {
       const int qb = min(qb_max, n_qblocks - p * qb_max);
       const int n_sub = qb == 1 ? 4 : (qb == 2 ? 2 : 1);
@@ -526,9 +532,15 @@ maxsim_exhaustive_kernel(const __grid_constant__ ExhMaps maps, const uint32_t* _
       const int write = active && q < n_queries;
       float* const dst_row = scores + static_cast<int64_t>(write ? q : 0) * n_docs + my_d0;   // score of my first document
       int my_nt = 0;
+      uint32_t my_ring0 = 0;
 #pragma unroll
-      for (int s2 = 0; s2 < kEpiGroups; ++s2)
-        if (s2 == my_s) my_nt = nt[s2];
+      for (int s2 = 0; s2 < kEpiGroups; ++s2) {
+        if (s2 == my_s) {
+          my_nt = nt[s2];
+          my_ring0 = ring0[s2];
+        }
+        ring0[s2] += static_cast<uint32_t>(nt[s2]);
+      }
 
       EpiState st;
       st.r = -INFINITY;
@@ -536,13 +548,6 @@ maxsim_exhaustive_kernel(const __grid_constant__ ExhMaps maps, const uint32_t* _
       st.docs_done = 0;
 
       for (int t = 0; t < max_nt; ++t) {
-        // position of tile (t, my_s) in the producer's order (tiles of row t in sub-range order), then advance past row t
-        uint32_t my_item = item;
-#pragma unroll
-        for (int s2 = 0; s2 < kEpiGroups; ++s2) {
-          if (s2 < my_s && t < nt[s2]) ++my_item;
-          if (t < nt[s2]) ++item;
-        }
         if (!active || t >= my_nt) continue;
         const long long t_tile = kStats ? clock64() : 0;
 
@@ -561,7 +566,7 @@ maxsim_exhaustive_kernel(const __grid_constant__ ExhMaps maps, const uint32_t* _
         // loop does not spill: 128 x 40 + 512 x 104 registers is all a 640-thread CTA owns).  A warp with a tcgen05.ld
         // outstanding does not overlap it with its own arithmetic here, and the epilogue body doubles in size.
         // 128 document-end bits of this tile, staged by the producer: bit j of word c is column 32c + j
-        const uint4 ends = *reinterpret_cast<const uint4*>(&s_ends[my_item % kEndsRing][0]);
+        const uint4 ends = *reinterpret_cast<const uint4*>(&s_ends[my_s][(my_ring0 + t) % kEndsRing][0]);
         uint32_t m = ends.x, m1 = ends.y, m2 = ends.z, m3 = ends.w;
 #pragma unroll 1
         for (int c = 0; c < 4; ++c) {
