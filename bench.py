@@ -59,6 +59,9 @@ def parse_args():
     ap.add_argument("--cpu-queries", type=int, default=128, help="bounded CPU-baseline sample (queries)")
     ap.add_argument("--no-secondary", action="store_true", help="skip the `secondary` block (configs[2], [3]/[4])")
     ap.add_argument("--no-parity", action="store_true", help="skip the oracle parity gate")
+    ap.add_argument("--e2e-exchange", default="allgather", choices=["allgather", "replicate"],
+                    help="N > 1: how RerankPipeline distributes the replicated inputs (see its docstring)")
+    ap.add_argument("--chunks", type=int, default=0, help="N > 1: query chunks per sharded step (0 = the ranker's default)")
     ap.add_argument("--parity-queries", type=int, default=8, help="queries re-scored by the oracle (parity gate)")
     ap.add_argument("--exh-docs", type=int, default=1_100_000, help="documents per GPU in the exhaustive secondary "
                     "(configs[3]: 8.8 M passages over 8 GPUs)")
@@ -720,7 +723,7 @@ def run_ours(args, rank, world, local_rank):
             return p, s
         # sharded: the ranker's own batched call — per query chunk: partition -> MaxSim -> local top-k keys, then
         # (second stream, under the next chunk's MaxSim) NCCL all-gather of packed keys + replicated merge
-        return sharded.rank_forward_batch(Q_dev, cand_2d, depth=k)
+        return sharded.rank_forward_batch(Q_dev, cand_2d, depth=k, chunks=args.chunks or None)
 
     for _ in range(args.warmup):
         step_device()
@@ -776,7 +779,7 @@ def run_ours(args, rank, world, local_rank):
     # copies its own inputs host→device and its results device→host inside the timed region; consecutive steps
     # are pipelined over two streams (the copies of step i+1 overlap the scoring of step i).
     from colbert_b200.ranking.pipeline import RerankPipeline
-    pipe = RerankPipeline(sharded or ranker, n_queries, q_len, args.cands, depth=args.depth)
+    pipe = RerankPipeline(sharded or ranker, n_queries, q_len, args.cands, depth=args.depth, input_exchange=args.e2e_exchange)
 
     def run_e2e(n_steps):
         prev, res = None, None

@@ -78,7 +78,8 @@ __device__ __forceinline__ void emit(uint64_t key, int64_t pos, float* out_score
 // it plus the bin that holds it is compacted (≤ kTopkMaxCand keys, normally ≈ k) and only that is sorted.  A level is
 // skipped as soon as the survivors fit.  The score matrix is read three times instead of being bitonic-sorted in
 // 16384-wide chunks (2.0 → 0.2 ms for 16 × 1.1 M scores, k = 1000).
-constexpr int kSelChunk = 16384;          // scores per CTA
+constexpr int kSelChunk = 16384;          // scores per CTA at most; fewer when the batch is small (sel_chunk): a single query over
+                                          // 1.1 M documents would otherwise occupy 68 of 148 SMs
 constexpr int kSelThreads = 256;
 constexpr int kSelBins = 4096;
 
@@ -97,7 +98,7 @@ __device__ __forceinline__ uint32_t sel_key(float x) { return float_to_ordered(x
 // level L histogram of the scores whose resolved prefix matches; hist [n_queries][kSelBins]
 template <int kLevel>
 __global__ void __launch_bounds__(kSelThreads)
-radix_hist_kernel(const float* __restrict__ scores, int64_t n_docs, const SelState* __restrict__ state,
+radix_hist_kernel(const float* __restrict__ scores, int64_t n_docs, int chunk, const SelState* __restrict__ state,
                   uint32_t* __restrict__ hist) {
   __shared__ uint32_t sh[kSelBins];
   const int64_t q = blockIdx.y;
@@ -108,8 +109,8 @@ radix_hist_kernel(const float* __restrict__ scores, int64_t n_docs, const SelSta
   constexpr int kPrevShift = kLevel == 1 ? 20 : 8;       // (unused at level 0: nothing is resolved yet)
   for (int i = threadIdx.x; i < kSelBins; i += kSelThreads) sh[i] = 0;
   __syncthreads();
-  const int64_t first = static_cast<int64_t>(blockIdx.x) * kSelChunk;
-  const int n = static_cast<int>(min(static_cast<int64_t>(kSelChunk), n_docs - first));
+  const int64_t first = static_cast<int64_t>(blockIdx.x) * chunk;
+  const int n = static_cast<int>(min(static_cast<int64_t>(chunk), n_docs - first));
   const float* row = scores + q * n_docs + first;
   for (int i0 = 0; i0 < n; i0 += kSelThreads) {
     const int i = i0 + threadIdx.x;
@@ -179,7 +180,11 @@ radix_select_kernel(uint32_t* __restrict__ hist, SelState* __restrict__ state, i
     stq.bits += kBitsHere;
     stq.k_rem -= s_above;
     const uint32_t n_above_total = static_cast<uint32_t>(k) - stq.k_rem;      // strictly above the bin, all levels
-    if (n_above_total + in_bin <= static_cast<uint32_t>(kTopkMaxCand)) stq.done = 1;
+    // stop refining once the survivors are cheap to sort: one more histogram pass over the row costs less than
+    // sorting 16384 keys in one CTA (0.17 ms), so the early levels only stop at ~4 k survivors
+    const uint32_t limit = kLevel == 2 ? static_cast<uint32_t>(kTopkMaxCand)
+                                       : min(static_cast<uint32_t>(kTopkMaxCand), max(4096u, 2u * static_cast<uint32_t>(k)));
+    if (n_above_total + in_bin <= limit) stq.done = 1;
     else if (kLevel == 2) stq.overflow = 1;                                    // > kTopkMaxCand exact ties with the k-th
     state[q] = stq;
   }
@@ -187,14 +192,14 @@ radix_select_kernel(uint32_t* __restrict__ hist, SelState* __restrict__ state, i
 
 // every score at or above the located bin becomes a packed key in cand[q][0 .. n_cand)
 __global__ void __launch_bounds__(kSelThreads)
-radix_compact_kernel(const float* __restrict__ scores, int64_t n_docs, int64_t pid_base, SelState* __restrict__ state,
+radix_compact_kernel(const float* __restrict__ scores, int64_t n_docs, int chunk, int64_t pid_base, SelState* __restrict__ state,
                      uint64_t* __restrict__ cand) {
   const int64_t q = blockIdx.y;
   const SelState stq = state[q];
   if (stq.overflow) return;
   const int shift = 32 - static_cast<int>(stq.bits);
-  const int64_t first = static_cast<int64_t>(blockIdx.x) * kSelChunk;
-  const int n = static_cast<int>(min(static_cast<int64_t>(kSelChunk), n_docs - first));
+  const int64_t first = static_cast<int64_t>(blockIdx.x) * chunk;
+  const int n = static_cast<int>(min(static_cast<int64_t>(chunk), n_docs - first));
   const float* row = scores + q * n_docs + first;
   uint64_t* cq = cand + q * kTopkMaxCand;
   for (int i0 = 0; i0 < n; i0 += kSelThreads) {
@@ -558,16 +563,20 @@ int topk_dense_dispatch(const float* d_scores, int64_t n_queries, int64_t n_docs
   uint64_t* cand = reinterpret_cast<uint64_t*>(ws + ((radix_zeroed_bytes(n_queries) + 255) & ~static_cast<size_t>(255)));
   void* chunk_ws = ws + radix_workspace_bytes(n_queries);
   CBK_CUDA(cudaMemsetAsync(state, 0, radix_zeroed_bytes(n_queries), stream));
-  const dim3 grid(static_cast<unsigned int>((n_docs + kSelChunk - 1) / kSelChunk), static_cast<unsigned int>(n_queries));
+  // scores per CTA: enough CTAs for four waves over the SMs, between 2048 and kSelChunk scores each
+  int64_t want = (n_docs * n_queries + 4ll * sm_count() - 1) / (4ll * sm_count());
+  want = ((want + kSelThreads - 1) / kSelThreads) * kSelThreads;
+  const int chunk = static_cast<int>(std::min<int64_t>(kSelChunk, std::max<int64_t>(2048, want)));
+  const dim3 grid(static_cast<unsigned int>((n_docs + chunk - 1) / chunk), static_cast<unsigned int>(n_queries));
   const unsigned int nq = static_cast<unsigned int>(n_queries);
   const size_t hstride = static_cast<size_t>(n_queries) * kSelBins;
-  radix_hist_kernel<0><<<grid, kSelThreads, 0, stream>>>(d_scores, n_docs, state, hist);
+  radix_hist_kernel<0><<<grid, kSelThreads, 0, stream>>>(d_scores, n_docs, chunk, state, hist);
   radix_select_kernel<0><<<nq, kSelThreads, 0, stream>>>(hist, state, k);
-  radix_hist_kernel<1><<<grid, kSelThreads, 0, stream>>>(d_scores, n_docs, state, hist + hstride);
+  radix_hist_kernel<1><<<grid, kSelThreads, 0, stream>>>(d_scores, n_docs, chunk, state, hist + hstride);
   radix_select_kernel<1><<<nq, kSelThreads, 0, stream>>>(hist + hstride, state, k);
-  radix_hist_kernel<2><<<grid, kSelThreads, 0, stream>>>(d_scores, n_docs, state, hist + 2 * hstride);
+  radix_hist_kernel<2><<<grid, kSelThreads, 0, stream>>>(d_scores, n_docs, chunk, state, hist + 2 * hstride);
   radix_select_kernel<2><<<nq, kSelThreads, 0, stream>>>(hist + 2 * hstride, state, k);
-  radix_compact_kernel<<<grid, kSelThreads, 0, stream>>>(d_scores, n_docs, pid_base, state, cand);
+  radix_compact_kernel<<<grid, kSelThreads, 0, stream>>>(d_scores, n_docs, chunk, pid_base, state, cand);
   const size_t smem = static_cast<size_t>(kTopkMaxCand) * sizeof(uint64_t);
   CBK_CUDA(cudaFuncSetAttribute(radix_final_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
   radix_final_kernel<<<nq, 1024, smem, stream>>>(cand, state, k, as_keys ? nullptr : d_out_scores, as_keys ? nullptr : d_out_pids,

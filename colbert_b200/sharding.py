@@ -141,8 +141,11 @@ class ShardedColbertRanker:
 
         ``chunks`` (equal-length lists ``[B, n]`` on more than one GPU): the batch is scored in that many query chunks,
         and the key all-gather + merge of chunk i run on a second stream underneath the MaxSim of chunk i+1 — the
-        exchange is latency- and skew-bound (it waits for the slowest rank), so hiding it keeps the tensor pipes busy.
-        Default: 4 chunks from 2048 queries up, else 1.  The result does not depend on it."""
+        exchange is latency- and skew-bound (it waits for the slowest rank).  Measured on 8 x B200 (4096 queries x 1000
+        candidates per GPU, `bench.py --gpus 8 --chunks c`): 16.25 / 16.40 / 16.72 ms per step with 1 / 2 / 4 chunks — the
+        persistent MaxSim kernel fills every SM, so the NCCL kernel of chunk i cannot start before chunk i + 1 drains and
+        each chunk adds its own launch tail: the default is ONE chunk; the option stays for short-kernel regimes.
+        The result does not depend on it."""
         dev = self.local.device if self.local is not None else Q.device
         Q = Q.to(dev, dtype=torch.float32, non_blocking=True).contiguous()
         B = Q.size(0)
@@ -156,7 +159,7 @@ class ShardedColbertRanker:
             n = cand_pids.size(1)
             max_cand = n
             if chunks is None:
-                chunks = 4 if (self.world > 1 and B >= 2048) else 1
+                chunks = 1
             chunks = max(1, min(int(chunks), B))
             if chunks > 1 and Q.is_cuda:
                 return self._rank_forward_chunked(Q, cand_pids.contiguous(), n, depth, chunks, extra.get("q_lens"))
