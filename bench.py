@@ -433,17 +433,20 @@ def timed_region(torch, dist, world, step, warmup, min_steps, min_ms=1500.0, max
     return steps, float(t[0]), float(t[1]), (w0, w1)
 
 
-def secondary_multiview(torch, sampler, dev, args, cand_dev, rowptr, d_view, q_view, dtype, peaks):
+def secondary_multiview(torch, sampler, dev, args, cand_dev, rowptr, d_view, q_view, dtype, peaks, dim=128, n_docs=None):
     """configs[2]: multi-view rerank (enable_multiview: every document is d_view rows, every query q_view rows, max over
     views = max over the document's rows), same 4096 x 1000 candidate lists as the headline.  d_view == 0: the headline
     workload itself (doclen U[1,180], 32 query rows) on a store of another dtype."""
     from colbert_b200 import kernels
     from colbert_b200.ranking import ColbertRanker
-    store, doclens = build_store(torch, dev, args.docs, 128, dtype, seed=777 + d_view, doclen_fixed=d_view)
+    n_docs = n_docs or args.docs
+    store, doclens = build_store(torch, dev, n_docs, dim, dtype, seed=777 + d_view + dim, doclen_fixed=d_view)
     ranker = ColbertRanker.from_store(store, doclens)
     g = torch.Generator(device="cpu"); g.manual_seed(555 + q_view)
     n_q = rowptr.numel() - 1
-    Q = torch.nn.functional.normalize(torch.randn(n_q, q_view, 128, generator=g), p=2, dim=2).to(dev)
+    if n_docs != args.docs:                 # a smaller store: fold the candidate ids into it (lists stay duplicate-free enough)
+        cand_dev = cand_dev % n_docs
+    Q = torch.nn.functional.normalize(torch.randn(n_q, q_view, dim, generator=g), p=2, dim=2).to(dev)
     k = min(args.depth, args.cands)
 
     def step(ev):
@@ -454,13 +457,14 @@ def secondary_multiview(torch, sampler, dev, args, cand_dev, rowptr, d_view, q_v
 
     steps, ms_total, kern_ms, win = timed_region(torch, None, 1, step, args.warmup, args.steps)
     n_cand = cand_dev.numel()
-    algo = int(ranker._doclens_dev[cand_dev].to(torch.int64).sum().item()) * 128 * 2
+    algo = int(ranker._doclens_dev[cand_dev].to(torch.int64).sum().item()) * dim * 2
     achieved = algo / (kern_ms * 1e-3) / 1e9
     dname = str(dtype).replace("torch.", "").replace("bfloat16", "bf16").replace("float16", "fp16")
     if d_view:
-        what = (f"multi-view rerank: {n_q} queries x {args.cands} candidates, q_view {q_view}, d_view {d_view}, dim 128, "
-                f"{dname} store of {args.docs} docs ({store.numel() * 2 / 1e9:.1f} GB), top-{k} (BASELINE.json configs[2]"
-                + ("" if d_view == 8 else "; the author's dense.yaml operating point is 16 x 16") + ")")
+        what = (f"multi-view rerank: {n_q} queries x {args.cands} candidates, q_view {q_view}, d_view {d_view}, dim {dim}, "
+                f"{dname} store of {n_docs} docs ({store.numel() * 2 / 1e9:.1f} GB), top-{k} (BASELINE.json configs[2]"
+                + ("" if d_view == 8 else "; the author's dense.yaml operating point is 16 x 16")
+                + (" at its own width 768, no projection" if dim == 768 else "") + ")")
     else:
         what = (f"rerank: {n_q} queries x {args.cands} candidates, q_len {q_view}, dim 128, doclen U[1,180], {dname} store of "
                 f"{args.docs} docs ({store.numel() * 2 / 1e9:.1f} GB), top-{k} (configs[1] on the reference's own index "
@@ -469,7 +473,8 @@ def secondary_multiview(torch, sampler, dev, args, cand_dev, rowptr, d_view, q_v
            "value": n_cand * steps / (ms_total * 1e-3), "unit": UNIT, "steps": steps, "ms_per_step": ms_total / steps,
            "roofline": {"bound": "hbm", "achieved": achieved, "peak": peaks["hbm_gbs"], "unit": "GB/s",
                         "frac": achieved / peaks["hbm_gbs"], "kernel_ms": kern_ms, "algorithmic_bytes_per_launch": algo,
-                        "kernel": "maxsim_rerank_kernel" + (" (multi-view instantiation)" if d_view else ""), "traffic": None},
+                        "kernel": ("maxsim_mv_wide_kernel (tcgen05 streaming, fixed 16-row documents)" if dim != 128 else
+                                   "maxsim_rerank_kernel" + (" (multi-view instantiation)" if d_view else "")), "traffic": None},
            "clocks": sampler.window(*win)}
     del store, ranker
     torch.cuda.empty_cache()
@@ -838,6 +843,8 @@ def run_ours(args, rank, world, local_rank):
         if world == 1:
             secondary["multiview_8x8"] = secondary_multiview(torch, sampler, dev, args, cand_dev, rowptr, 8, 8, dtype, peaks)
             secondary["multiview_16x16"] = secondary_multiview(torch, sampler, dev, args, cand_dev, rowptr, 16, 16, dtype, peaks)
+            secondary["multiview_16x16_dim768"] = secondary_multiview(torch, sampler, dev, args, cand_dev, rowptr, 16, 16, dtype,
+                                                                      peaks, dim=768, n_docs=min(args.docs, 1_000_000))
             if dtype != torch.float16:
                 secondary["rerank_fp16_store"] = secondary_multiview(torch, sampler, dev, args, cand_dev, rowptr, 0, 32,
                                                                      torch.float16, peaks)

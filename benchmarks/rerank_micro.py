@@ -23,6 +23,7 @@ def main():
     ap.add_argument("--queries", type=int, default=4096)
     ap.add_argument("--cands", type=int, default=1000)
     ap.add_argument("--iters", type=int, default=30)
+    ap.add_argument("--dim", type=int, default=128, help="embedding width (768: the author's un-projected multi-view index)")
     ap.add_argument("--no-fixed", action="store_true", help="score through the looked-up path even on a fixed-doclen index")
     args = ap.parse_args()
     import torch
@@ -31,10 +32,10 @@ def main():
     from colbert_b200.ranking import ColbertRanker
     dev = torch.device("cuda", 0)
     dt = torch.bfloat16 if args.dtype == "bf16" else torch.float16
-    store, doclens = bench.build_store(torch, dev, args.docs, 128, dt, seed=777, doclen_fixed=args.doclen)
+    store, doclens = bench.build_store(torch, dev, args.docs, args.dim, dt, seed=777, doclen_fixed=args.doclen)
     ranker = ColbertRanker.from_store(store, doclens)
     g = torch.Generator().manual_seed(1)
-    Q = torch.nn.functional.normalize(torch.randn(args.queries, args.q_len, 128, generator=g), dim=2).to(dev)
+    Q = torch.nn.functional.normalize(torch.randn(args.queries, args.q_len, args.dim, generator=g), dim=2).to(dev)
     cand = torch.randint(0, args.docs, (args.queries * args.cands,), generator=g, dtype=torch.int64).to(dev)
     rowptr = torch.arange(0, args.queries * args.cands + 1, args.cands, dtype=torch.int64, device=dev)
     flags = ranker.kernel_flags if args.no_fixed else ranker.effective_flags
@@ -52,10 +53,10 @@ def main():
     e1.record()
     torch.cuda.synchronize()
     ms = e0.elapsed_time(e1) / args.iters
-    algo = int(ranker._doclens_dev[cand].to(torch.int64).sum().item()) * 256
+    algo = int(ranker._doclens_dev[cand].to(torch.int64).sum().item()) * args.dim * 2
     peaks_path = os.path.join(ROOT, "MEASURED_PEAKS.json")
     peak = json.load(open(peaks_path))["hbm_gbs"] if os.path.exists(peaks_path) else 6650.0
-    print(json.dumps({"doclen": args.doclen or "U[1,180]", "q_len": args.q_len, "dtype": args.dtype,
+    print(json.dumps({"doclen": args.doclen or "U[1,180]", "dim": args.dim, "q_len": args.q_len, "dtype": args.dtype,
                       "fixed_path": bool(flags & _lib.CBK_FLAG_FIXED_DOCLEN), "probe_gather_only": bool(os.environ.get("CBK_RERANK_PROBE")),
                       "kernel_ms": round(ms, 4), "gbs": round(algo / ms / 1e6, 1), "frac_of_hbm_peak": round(algo / ms / 1e6 / peak, 3),
                       "cands_per_s": round(args.queries * args.cands / ms * 1e3)}), flush=True)

@@ -64,3 +64,78 @@ def test_wide_rerank_foreign_pids_and_rank_forward():
     ranker.kernel_flags = _lib.CBK_FLAG_SKIP_FOREIGN_PIDS
     sc = ranker.score_candidates(torch.from_numpy(Q[None]).to(DEV), bad, rp2).cpu().numpy()
     assert np.isneginf(sc[1]) and np.isneginf(sc[2])
+
+
+@pytest.mark.parametrize("dim", [256, 512, 768, 1024])
+@pytest.mark.parametrize("dt", [torch.float16, torch.bfloat16], ids=["fp16", "bf16"])
+def test_multiview_16_rows_wide_streaming_kernel(dim, dt):
+    """the author's operating point (16 view embeddings per document and per query, un-projected width): the tcgen05
+    streaming kernel (csrc/rerank_mv_wide.cu, taken automatically for a fixed-length store of 16 rows, q_len <= 16) against
+    the oracle and against the K-split and generic kernels — ragged lists (tiles of fewer than 8 candidates, empty lists),
+    short queries, per-query q_lens, pids outside the store."""
+    from colbert_b200 import _lib, synthetic
+    from colbert_b200.ranking import ColbertRanker
+    rng = np.random.default_rng(dim + 1)
+    n_docs = 700
+    doclens = np.full(n_docs, 16, dtype=np.int64)
+    index = synthetic.make_index(1300 + dim, n_docs, dim=dim, doclens=doclens)
+    emb = torch.from_numpy(index.emb).to(dt)
+    ranker = ColbertRanker.from_tensors(emb, index.doclens.tolist(), device=DEV, store_dtype=dt)
+    assert ranker.strides == [16] and ranker.effective_flags & _lib.CBK_FLAG_FIXED_DOCLEN
+    store, pf = O.pad_store(emb.float().numpy()), O.doclens_pfxsum(index.doclens)
+    for q_len in (16, 5):
+        lens = [3, 0, 8, 1000, 17, 64, 1, 300]
+        n_q = len(lens)
+        Q = synthetic.make_queries(1301 + q_len, n_q, q_len, dim)
+        cands = [rng.integers(0, n_docs, size=l).astype(np.int64) for l in lens]
+        flat = np.concatenate(cands)
+        rowptr = np.concatenate([[0], np.cumsum(lens)]).astype(np.int64)
+        ref = np.concatenate([O.maxsim_exact(store, index.doclens, pf, ranker.strides, Q[b], cands[b]) if lens[b] else
+                              np.zeros(0, np.float32) for b in range(n_q)])
+        args = (torch.from_numpy(Q).to(DEV), torch.from_numpy(flat).to(DEV), torch.from_numpy(rowptr).to(DEV))
+        launches0 = _lib.launch_count()
+        got = ranker.score_candidates(*args).cpu().numpy()
+        assert _lib.launch_count() == launches0 + 1
+        rel = np.abs(got - ref) / np.maximum(np.abs(ref), 1.0)
+        assert rel.max() <= SCORE_RTOL, (dim, q_len, rel.max())
+        # bf16 stores: the query enters as bf16 value + bf16 residual, so the only rounding left is the store's own
+        if dt == torch.bfloat16:
+            assert rel.max() <= 5e-5, rel.max()
+        ranker.kernel_flags = _lib.CBK_FLAG_RERANK_GENERIC
+        gen = ranker.score_candidates(*args).cpu().numpy()
+        ranker.kernel_flags = 0
+        assert np.abs(got - gen).max() <= SCORE_RTOL * max(1.0, np.abs(ref).max())
+    # per-query real lengths inside a 16-row slot: rows at or past q_lens[q] are padding whatever they hold
+    q_lens = np.array([16, 1, 9, 16, 4, 12, 16, 7], dtype=np.int32)
+    Qpad = synthetic.make_queries(1400, n_q, 16, dim)
+    got = ranker.score_candidates(torch.from_numpy(Qpad).to(DEV), torch.from_numpy(flat).to(DEV), torch.from_numpy(rowptr).to(DEV),
+                                  q_lens=torch.from_numpy(q_lens).to(DEV)).cpu().numpy()
+    ref = np.concatenate([O.maxsim_exact(store, index.doclens, pf, ranker.strides, Qpad[b][:q_lens[b]], cands[b]) if lens[b] else
+                          np.zeros(0, np.float32) for b in range(n_q)])
+    assert (np.abs(got - ref) / np.maximum(np.abs(ref), 1.0)).max() <= SCORE_RTOL
+    # pids outside the store: NaN, or -inf on a shard
+    bad = torch.tensor([5, n_docs, -1, 7, 8, 9, 10, 11, 12], dtype=torch.int64, device=DEV)
+    rp2 = torch.tensor([0, 9], dtype=torch.int64, device=DEV)
+    sc = ranker.score_candidates(torch.from_numpy(Qpad[:1]).to(DEV), bad, rp2).cpu().numpy()
+    assert np.isnan(sc[1]) and np.isnan(sc[2]) and np.isfinite(np.delete(sc, [1, 2])).all()
+    ranker.kernel_flags = _lib.CBK_FLAG_SKIP_FOREIGN_PIDS
+    sc = ranker.score_candidates(torch.from_numpy(Qpad[:1]).to(DEV), bad, rp2).cpu().numpy()
+    assert np.isneginf(sc[1]) and np.isneginf(sc[2])
+    ranker.kernel_flags = 0
+
+
+def test_multiview_wide_many_ctas_and_query_changes():
+    """enough candidates for every CTA to own a range that spans several queries (query region swapped under the ring)"""
+    from colbert_b200 import synthetic
+    from colbert_b200.ranking import ColbertRanker
+    dim, n_docs, n_q, n_c = 768, 4000, 600, 37
+    index = synthetic.make_index(1500, n_docs, dim=dim, doclens=np.full(n_docs, 16, dtype=np.int64))
+    ranker = ColbertRanker.from_tensors(torch.from_numpy(index.emb), index.doclens.tolist(), device=DEV)
+    store, pf = O.pad_store(index.emb), O.doclens_pfxsum(index.doclens)
+    Q = synthetic.make_queries(1501, n_q, 16, dim)
+    cand = np.random.default_rng(1502).integers(0, n_docs, size=(n_q, n_c)).astype(np.int64)
+    rowptr = torch.arange(0, (n_q + 1) * n_c, n_c, dtype=torch.int64, device=DEV)
+    got = ranker.score_candidates(torch.from_numpy(Q).to(DEV), torch.from_numpy(cand.reshape(-1)).to(DEV), rowptr).cpu().numpy()
+    for b in range(0, n_q, 7):
+        ref = O.maxsim_exact(store, index.doclens, pf, ranker.strides, Q[b], cand[b])
+        assert (np.abs(got[b * n_c:(b + 1) * n_c] - ref) / np.maximum(np.abs(ref), 1.0)).max() <= SCORE_RTOL, b
