@@ -24,6 +24,7 @@ def main():
     ap.add_argument("--cands", type=int, default=1000)
     ap.add_argument("--iters", type=int, default=30)
     ap.add_argument("--dim", type=int, default=128, help="embedding width (768: the author's un-projected multi-view index)")
+    ap.add_argument("--ksplit", action="store_true", help="dim 256 … 1024: the K-split mma.sync kernel instead of the streaming one")
     ap.add_argument("--no-fixed", action="store_true", help="score through the looked-up path even on a fixed-doclen index")
     args = ap.parse_args()
     import torch
@@ -39,6 +40,8 @@ def main():
     cand = torch.randint(0, args.docs, (args.queries * args.cands,), generator=g, dtype=torch.int64).to(dev)
     rowptr = torch.arange(0, args.queries * args.cands + 1, args.cands, dtype=torch.int64, device=dev)
     flags = ranker.kernel_flags if args.no_fixed else ranker.effective_flags
+    if args.ksplit:
+        flags |= _lib.CBK_FLAG_RERANK_KSPLIT
 
     def run():
         return kernels.maxsim_rerank(ranker.tensor, ranker._pfxsum_dev, ranker._doclens_dev, ranker.strides, Q, cand, rowptr,
@@ -57,7 +60,7 @@ def main():
     peaks_path = os.path.join(ROOT, "MEASURED_PEAKS.json")
     peak = json.load(open(peaks_path))["hbm_gbs"] if os.path.exists(peaks_path) else 6650.0
     print(json.dumps({"doclen": args.doclen or "U[1,180]", "dim": args.dim, "q_len": args.q_len, "dtype": args.dtype,
-                      "fixed_path": bool(flags & _lib.CBK_FLAG_FIXED_DOCLEN), "probe_gather_only": bool(os.environ.get("CBK_RERANK_PROBE")),
+                      "fixed_path": bool(flags & _lib.CBK_FLAG_FIXED_DOCLEN), "ksplit": bool(args.ksplit), "probe_gather_only": bool(os.environ.get("CBK_RERANK_PROBE")),
                       "kernel_ms": round(ms, 4), "gbs": round(algo / ms / 1e6, 1), "frac_of_hbm_peak": round(algo / ms / 1e6 / peak, 3),
                       "cands_per_s": round(args.queries * args.cands / ms * 1e3)}), flush=True)
 

@@ -24,6 +24,7 @@ CBK_FLAG_SKIP_FOREIGN_PIDS = 2
 CBK_FLAG_RERANK_TCGEN05 = 4
 CBK_FLAG_RERANK_GENERIC = 8
 CBK_FLAG_FIXED_DOCLEN = 16
+CBK_FLAG_RERANK_KSPLIT = 32
 CBK_ABI_VERSION = 3
 CBK_TOPK_NEG_INF_IS_PADDING = 1
 

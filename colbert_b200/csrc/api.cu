@@ -37,6 +37,10 @@ int rerank_generic_dispatch(const void*, int, int64_t, int, const int64_t*, cons
 bool rerank_wide_supports(int dim);
 int rerank_wide_dispatch(const void*, int, int64_t, int, const int64_t*, const int32_t*, int64_t, int64_t, const int32_t*, int,
                          const float*, const int32_t*, int, int64_t, const int64_t*, const int64_t*, int64_t, float*, void*, int, cudaStream_t);
+bool rerank_wide_stream_supports(int, int, int);
+int rerank_wide_stream_dispatch(const void*, int, int64_t, int, const int64_t*, const int32_t*, int64_t, int64_t, const int32_t*, int,
+                                const float*, const int32_t*, int, int64_t, const int64_t*, const int64_t*, int64_t, float*, int,
+                                cudaStream_t);
 bool rerank_mv_wide_supports(int, int, const int32_t*, int, int);
 int rerank_mv_wide_dispatch(const void*, int, int64_t, int, int64_t, int64_t, const float*, const int32_t*, int, int64_t, const int64_t*,
                             const int64_t*, int64_t, float*, int, cudaStream_t);
@@ -253,10 +257,15 @@ int cbk_maxsim_rerank(const void* d_store, int store_dtype, int64_t n_store_rows
   int rc = check_device();
   if (rc != CBK_OK) return rc;
   if (n_cand_total == 0) return CBK_OK;
-  if (rerank_mv_wide_supports(dim, q_len, strides, n_strides, flags) && (reinterpret_cast<uintptr_t>(d_store) & 0xf) == 0)
+  if (rerank_mv_wide_supports(dim, q_len, strides, n_strides, flags) && !(flags & CBK_FLAG_RERANK_KSPLIT) &&
+      (reinterpret_cast<uintptr_t>(d_store) & 0xf) == 0)
     return rerank_mv_wide_dispatch(d_store, store_dtype, n_store_rows, dim, n_docs, pid_base, d_Q, d_q_lens, q_len, n_queries,
                                    d_cand_pids, d_cand_rowptr, n_cand_total, d_out_scores, flags,
                                    static_cast<cudaStream_t>(stream));   // multi-view 16 x 16 at 256 ... 768 columns: tcgen05 streaming kernel
+  if (rerank_wide_stream_supports(dim, q_len, flags) && (reinterpret_cast<uintptr_t>(d_store) & 0xf) == 0)
+    return rerank_wide_stream_dispatch(d_store, store_dtype, n_store_rows, dim, d_pfxsum, d_doclens, n_docs, pid_base, strides,
+                                       n_strides, d_Q, d_q_lens, q_len, n_queries, d_cand_pids, d_cand_rowptr, n_cand_total,
+                                       d_out_scores, flags, static_cast<cudaStream_t>(stream));   // dim 256 ... 1024: tcgen05 streaming kernel
   if (dim != 128 && !(flags & CBK_FLAG_RERANK_GENERIC) && rerank_wide_supports(dim) &&
       (reinterpret_cast<uintptr_t>(d_store) & 0xf) == 0)
     return rerank_wide_dispatch(d_store, store_dtype, n_store_rows, dim, d_pfxsum, d_doclens, n_docs, pid_base, strides, n_strides,

@@ -16,7 +16,7 @@ from concurrent.futures import ThreadPoolExecutor
 
 HERE = os.path.dirname(os.path.abspath(__file__))
 ROOT = os.path.dirname(os.path.dirname(HERE))
-SOURCES = ["api.cu", "rerank.cu", "topk.cu", "gather.cu", "partition.cu", "umma_probe.cu", "exhaustive.cu", "rerank_generic.cu", "rerank_umma.cu", "rerank_wide.cu", "score_allpairs.cu", "rerank_mv_wide.cu"]
+SOURCES = ["api.cu", "rerank.cu", "topk.cu", "gather.cu", "partition.cu", "umma_probe.cu", "exhaustive.cu", "rerank_generic.cu", "rerank_umma.cu", "rerank_wide.cu", "score_allpairs.cu", "rerank_mv_wide.cu", "rerank_wide_stream.cu"]
 HEADERS = ["cbk_common.cuh", "umma.cuh", os.path.join(ROOT, "include", "colbert_b200.h")]
 LIB = os.path.join(HERE, "libcolbert_b200.so")
 STAMP = os.path.join(HERE, ".build_stamp")

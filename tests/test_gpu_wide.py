@@ -1,5 +1,6 @@
-"""K-split tensor-core rerank kernel for wide embeddings (dim a multiple of 64 other than 128; the author's configuration
-uses 768) against the oracle and against the generic CUDA-core kernel."""
+"""Tensor-core rerank kernels for wide embeddings (dim a multiple of 64 other than 128; the author's configuration uses
+768) against the oracle and against the generic CUDA-core kernel: the tcgen05 streaming kernel (dim 256 … 1024, the default
+there), the K-split mma.sync kernel (dim 64 and 192, or CBK_FLAG_RERANK_KSPLIT), the multi-view streaming kernel."""
 import numpy as np
 import pytest
 import torch
@@ -33,13 +34,14 @@ def test_wide_rerank_matches_oracle_and_generic(dim, dt):
         ref = np.concatenate([O.maxsim_exact(store, index.doclens, pf, ranker.strides, Q[b], cands[b]) if lens[b] else
                               np.zeros(0, np.float32) for b in range(n_q)])
         got = {}
-        for name, flags in (("wide", 0), ("generic", _lib.CBK_FLAG_RERANK_GENERIC)):
+        for name, flags in (("wide", 0), ("ksplit", _lib.CBK_FLAG_RERANK_KSPLIT), ("generic", _lib.CBK_FLAG_RERANK_GENERIC)):
             ranker.kernel_flags = flags
             got[name] = ranker.score_candidates(torch.from_numpy(Q).to(DEV), torch.from_numpy(flat).to(DEV),
                                                 torch.from_numpy(rowptr).to(DEV)).cpu().numpy()
             rel = np.abs(got[name] - ref) / np.maximum(np.abs(ref), 1.0)
             assert rel.max() <= SCORE_RTOL, (dim, q_len, name, rel.max())
         assert np.abs(got["wide"] - got["generic"]).max() <= SCORE_RTOL * max(1.0, np.abs(ref).max())
+        assert np.abs(got["ksplit"] - got["generic"]).max() <= SCORE_RTOL * max(1.0, np.abs(ref).max())
     ranker.kernel_flags = 0
 
 
@@ -139,3 +141,25 @@ def test_multiview_wide_many_ctas_and_query_changes():
     for b in range(0, n_q, 7):
         ref = O.maxsim_exact(store, index.doclens, pf, ranker.strides, Q[b], cand[b])
         assert (np.abs(got[b * n_c:(b + 1) * n_c] - ref) / np.maximum(np.abs(ref), 1.0)).max() <= SCORE_RTOL, b
+
+
+def test_wide_stream_long_documents_and_many_queries():
+    """documents longer than a tile (> 128 rows: the running maximum crosses tiles), every CTA owning a range that spans
+    several queries, lists that end in the middle of a tile, q_len 20 (both halves of the query rows, the second partial)"""
+    from colbert_b200 import synthetic
+    from colbert_b200.ranking import ColbertRanker
+    dim, n_docs, n_q, n_c = 512, 1500, 333, 29
+    rng = np.random.default_rng(1600)
+    doclens = rng.integers(1, 400, size=n_docs).astype(np.int64)
+    index = synthetic.make_index(1601, n_docs, dim=dim, doclens=doclens)
+    for dt in (torch.float16, torch.bfloat16):
+        emb = torch.from_numpy(index.emb).to(dt)
+        ranker = ColbertRanker.from_tensors(emb, index.doclens.tolist(), device=DEV, store_dtype=dt)
+        store, pf = O.pad_store(emb.float().numpy()), O.doclens_pfxsum(index.doclens)
+        Q = synthetic.make_queries(1602, n_q, 20, dim)
+        cand = rng.integers(0, n_docs, size=(n_q, n_c)).astype(np.int64)
+        rowptr = torch.arange(0, (n_q + 1) * n_c, n_c, dtype=torch.int64, device=DEV)
+        got = ranker.score_candidates(torch.from_numpy(Q).to(DEV), torch.from_numpy(cand.reshape(-1)).to(DEV), rowptr).cpu().numpy()
+        for b in range(0, n_q, 11):
+            ref = O.maxsim_exact(store, index.doclens, pf, ranker.strides, Q[b], cand[b])
+            assert (np.abs(got[b * n_c:(b + 1) * n_c] - ref) / np.maximum(np.abs(ref), 1.0)).max() <= SCORE_RTOL, (dt, b)
