@@ -5,23 +5,25 @@
 // A row is up to 2 KB, the path is HBM-bound (≤ 32 FLOP/B).  The K-split mma.sync kernel (rerank_wide.cu) pays a block
 // barrier and an 8-way shared-memory reduction per 16-row tile (0.69 of the copy peak inside bench.py at 768); this kernel
 // streams:
-//   * every candidate document is cut into PIECES of up to 16 rows (the last one holds the remainder); a tile is up to 8
+//   * every candidate document is cut into PIECES of up to 16 rows (the last one holds the remainder); a tile is up to 16
 //     consecutive pieces of candidates of ONE query — piece j occupies accumulator columns 16 j … 16 j + 15 — and one 64-column
-//     K slab of a tile is a ring stage: one TMA box per piece, fetched with a tensor map of exactly the piece's height
+//     K slab of a tile is a ring stage (32 KB): one TMA box per piece, fetched with a tensor map of exactly the piece's height
 //     (one map per height 1 … 16), so no byte outside the candidate documents is read;
 //   * the query is resident in shared memory while the CTA stays on it (dim/64 slabs × 64 rows × 128 B), written by a
 //     dedicated warp from the fp32 query in the K-major 128-byte-swizzled layout: rows 0–31 = the query rounded to the
 //     store's type, rows 32–63 = for bf16 stores the bf16 RESIDUAL of that rounding (zero for fp16 stores), so a bf16 store
 //     is multiplied with 16 significant bits of the query at no extra MMA;
-//   * tcgen05.mma M = 64, N = 128 into one of two 128-column TMEM accumulators; accumulator row m lives in TMEM lane
+//   * tcgen05.mma M = 64, N = 256 into one of two 256-column TMEM accumulators (N = 256 halves the MMAs issued per byte:
+//     one issuing warp sustains an MMA every ~88 cycles, and with N = 128 that, not HBM, set the pace); accumulator row m lives in TMEM lane
 //     (m mod 16) + 32·(m div 16): quadrant w holds query rows 16 w … (w = 0, 1) and their residual products (w = 2, 3);
 //   * epilogue: warp w + 2 passes the residual products through shared memory to warp w, which folds each piece's valid
 //     columns into a running maximum per query row, and at a document's last piece applies the zero floor (doclen ∉ strides,
 //     SURVEY.md §8 a12'), adds up its 16 rows and — together with the other half of the query rows — writes the score at
 //     the candidate's own position.
-// Warp roles: 0–3 epilogue · 4 MMA issuer · 5 query loader · 6–9 TMA producers.  Every role walks the same deterministic
-// piece sequence of the CTA's contiguous candidate range (CandWalker: 32 candidates' metadata fetched at a time, one per
-// lane, the next 32 prefetched).
+// Warp roles: 0–3 epilogue · 4 MMA issuer · 5 query loader · 6–9 TMA producers · 10 planner.  The planner walks the CTA's
+// contiguous candidate range (CandWalker: 32 candidates' metadata fetched at a time, one per lane, the next 32 prefetched),
+// cuts it into tiles and publishes one descriptor per tile in a shared-memory ring; every other role reads descriptors —
+// walking the candidates in each role cost the issuer ~2000 cycles per tile on its critical path.
 #include <algorithm>
 
 #include "umma.cuh"
@@ -33,15 +35,29 @@ int make_store_tensor_map(CUtensorMap* out, const void* base, int64_t rows, int 
 namespace {
 
 constexpr int kWsPieceRows = 16;
-constexpr int kWsTilePieces = 8;
+constexpr int kWsTilePieces = 16;
 constexpr int kWsSlotBytes = kWsPieceRows * 128;                  // a piece's slot in a stage (2 KB)
-constexpr int kWsStageBytes = kWsTilePieces * kWsSlotBytes;       // 16 KB
+constexpr int kWsStageBytes = kWsTilePieces * kWsSlotBytes;       // 32 KB
+constexpr int kWsTileCols = kWsTilePieces * kWsPieceRows;         // 256 accumulator columns
 constexpr int kWsASlabBytes = 64 * 128;
 constexpr int kWsProducers = 4;
-constexpr int kWsIssuerWarp = 4, kWsLoaderWarp = 5, kWsProducer0 = 6;
-constexpr int kWsThreads = (kWsProducer0 + kWsProducers) * 32;
-constexpr int kWsLoBufBytes = 2 * 128 * 16 * 4;                   // residual products: [pair][column][row] fp32
-constexpr int kWsMaxStages = 12;
+constexpr int kWsIssuerWarp = 4, kWsLoaderWarp = 5, kWsProducer0 = 6, kWsPlannerWarp = kWsProducer0 + kWsProducers;
+constexpr int kWsThreads = (kWsPlannerWarp + 1) * 32;
+constexpr int kWsLoBufBytes = 2 * 128 * 16 * 4;                   // residual products of HALF a tile: [pair][column][row] fp32
+constexpr int kWsMaxStages = 6;
+constexpr int kWsDescRing = 8;
+
+// What the planner publishes per tile (n == 0: the range is exhausted).
+struct WsDesc {
+  int n;
+  int pad;
+  int64_t q;
+  int row[kWsTilePieces];
+  int len[kWsTilePieces];
+  int64_t cand[kWsTilePieces];
+  uint8_t v[kWsTilePieces];
+  uint8_t flags[kWsTilePieces];       // bit 0 first piece, bit 1 last piece of its document, bit 2 the zero floor applies
+};
 
 struct WsMaps {
   CUtensorMap m[kWsPieceRows];      // box {64 columns, h rows}, h = 1 … 16
@@ -178,12 +194,15 @@ maxsim_wide_stream_kernel(const __grid_constant__ WsMaps maps, const int64_t* __
   extern __shared__ uint8_t smem_raw[];
   __shared__ __align__(8) uint64_t bar_full[kWsMaxStages], bar_empty[kWsMaxStages];
   __shared__ __align__(8) uint64_t bar_acc_full[2], bar_acc_empty[2], bar_a_full, bar_a_free;
+  __shared__ __align__(8) uint64_t bar_desc_full[kWsDescRing], bar_desc_empty[kWsDescRing];
+  __shared__ __align__(16) WsDesc descs[kWsDescRing];
   __shared__ uint32_t tmem_base_smem;
   __shared__ float half_sum[kWsTilePieces];      // warp 1 → warp 0: sums over query rows 16-31 of the pieces that close a document
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int n_slabs = dim >> 6;
   const bool two_halves = q_len > 16;            // query rows 16-31 exist: quadrant 1 (and 3) take part
+  const uint32_t epi_warps = (two_halves ? 2u : 1u) * (kHasLo ? 2u : 1u);
   const uint32_t a_addr = (smem_u32(smem_raw) + 1023u) & ~1023u;
   const uint32_t b_addr = a_addr + static_cast<uint32_t>(n_slabs) * kWsASlabBytes;
   uint8_t* const smem_al = smem_raw + (a_addr - smem_u32(smem_raw));
@@ -195,17 +214,20 @@ maxsim_wide_stream_kernel(const __grid_constant__ WsMaps maps, const int64_t* __
       mbar_init(smem_u32(&bar_full[s]), 1);
       mbar_init(smem_u32(&bar_empty[s]), 1);
     }
-    const uint32_t epi_warps = (two_halves ? 2u : 1u) * (kHasLo ? 2u : 1u);
     for (int s = 0; s < 2; ++s) {
       mbar_init(smem_u32(&bar_acc_full[s]), 1);
       mbar_init(smem_u32(&bar_acc_empty[s]), epi_warps);
+    }
+    for (int s = 0; s < kWsDescRing; ++s) {
+      mbar_init(smem_u32(&bar_desc_full[s]), 1);
+      mbar_init(smem_u32(&bar_desc_empty[s]), kWsProducers + 2 + epi_warps);    // every reading warp releases a descriptor once
     }
     mbar_init(smem_u32(&bar_a_full), 1);
     mbar_init(smem_u32(&bar_a_free), 1);
     fence_mbar_init();
   }
   if (warp == kWsIssuerWarp) {
-    umma::tmem_alloc(smem_u32(&tmem_base_smem), 256);
+    umma::tmem_alloc(smem_u32(&tmem_base_smem), 512);
     umma::tmem_relinquish();
   }
   umma::fence_before_sync();
@@ -213,24 +235,68 @@ maxsim_wide_stream_kernel(const __grid_constant__ WsMaps maps, const int64_t* __
   umma::fence_after_sync();
   const uint32_t tmem = tmem_base_smem;
 
-  // this CTA's contiguous candidate range
-  const int64_t n_cand = min(rowptr[n_queries], n_cand_bound);
-  const int64_t per = (n_cand + gridDim.x - 1) / gridDim.x;
-  const int64_t c_lo = min(n_cand, per * blockIdx.x), c_hi = min(n_cand, per * (blockIdx.x + 1));
-  CandWalker wk;
-  wk.init(lane, cand_pids, rowptr, pfxsum, doclens, n_docs, pid_base, n_queries, c_lo, c_hi);
-  WsPiece pc;
-  pc.row = 0; pc.v = 0; pc.flags = 0; pc.len = 0; pc.cand = 0;
-  int64_t tile_q = -1;
+  // descriptor ring, reader side: wait for tile `t`'s descriptor / hand it back once its fields are in registers
+  auto desc_wait = [&](uint32_t t) -> const WsDesc* {
+    mbar_wait(smem_u32(&bar_desc_full[t % kWsDescRing]), (t / kWsDescRing) & 1u);
+    return &descs[t % kWsDescRing];
+  };
+  auto desc_release = [&](uint32_t t) {
+    __syncwarp();
+    if (lane == 0) mbar_arrive(smem_u32(&bar_desc_empty[t % kWsDescRing]));
+  };
 
-  if (warp >= kWsProducer0) {
+  if (warp == kWsPlannerWarp) {
+    // ===================================== planner ==================================================
+    const int64_t n_cand = min(rowptr[n_queries], n_cand_bound);
+    const int64_t per = (n_cand + gridDim.x - 1) / gridDim.x;
+    const int64_t c_lo = min(n_cand, per * blockIdx.x), c_hi = min(n_cand, per * (blockIdx.x + 1));
+    CandWalker wk;
+    wk.init(lane, cand_pids, rowptr, pfxsum, doclens, n_docs, pid_base, n_queries, c_lo, c_hi);
+    WsPiece pc;
+    pc.row = 0; pc.v = 0; pc.flags = 0; pc.len = 0; pc.cand = 0;
+    int64_t tile_q = -1;
+    for (uint32_t t = 0;; ++t) {
+      const int n = wk.next_tile<true>(lane, pc, tile_q, out, skip_foreign);
+      mbar_wait(smem_u32(&bar_desc_empty[t % kWsDescRing]), ((t / kWsDescRing) & 1u) ^ 1u);
+      WsDesc* d = &descs[t % kWsDescRing];
+      if (lane < n) {
+        int fl = pc.flags;
+        if (pc.flags & 2) {   // the zero floor of SURVEY.md §8 a12' applies when the document's length is not one of the strides
+          bool floor0 = strides.n > 0;
+          for (int i = 0; i < strides.n; ++i)
+            if (strides.v[i] == pc.len) floor0 = false;
+          if (floor0) fl |= 4;
+        }
+        d->row[lane] = pc.row;
+        d->len[lane] = pc.len;
+        d->cand[lane] = pc.cand;
+        d->v[lane] = static_cast<uint8_t>(pc.v);
+        d->flags[lane] = static_cast<uint8_t>(fl);
+      }
+      if (lane == 0) {
+        d->n = n;
+        d->q = tile_q;
+      }
+      __syncwarp();
+      if (lane == 0) mbar_arrive(smem_u32(&bar_desc_full[t % kWsDescRing]));
+      if (n == 0) break;
+    }
+  } else if (warp >= kWsProducer0) {
     // ===================================== TMA producers ============================================
     const int p = warp - kWsProducer0;
     if (lane == 0 && p == 0) tma_prefetch_desc(&maps.m[kWsPieceRows - 1]);
     uint32_t it = 0;
-    for (int n = wk.next_tile<false>(lane, pc, tile_q, out, skip_foreign); n > 0;
-         n = wk.next_tile<false>(lane, pc, tile_q, out, skip_foreign)) {
-      int rows_total = lane < n ? pc.v : 0;             // bytes of a stage = 128 B × the rows of all its pieces
+    for (uint32_t t = 0;; ++t) {
+      const WsDesc* d = desc_wait(t);
+      const int n = d->n;
+      int my_row = 0, my_v = 0;                          // lane j < n: piece j
+      if (lane < n) {
+        my_row = d->row[lane];
+        my_v = d->v[lane];
+      }
+      desc_release(t);
+      if (n == 0) break;
+      int rows_total = my_v;                            // bytes of a stage = 128 B × the rows of all its pieces
 #pragma unroll
       for (int o = 16; o > 0; o >>= 1) rows_total += __shfl_xor_sync(0xffffffffu, rows_total, o);
       for (int s = 0; s < n_slabs; ++s, ++it) {
@@ -245,8 +311,8 @@ maxsim_wide_stream_kernel(const __grid_constant__ WsMaps maps, const int64_t* __
           __syncwarp();
         }
         for (int j = p; j < n; j += kWsProducers) {     // my pieces of the tile: one box each, of exactly the piece's height
-          const int rj = __shfl_sync(0xffffffffu, pc.row, j);
-          const int vj = __shfl_sync(0xffffffffu, pc.v, j);
+          const int rj = __shfl_sync(0xffffffffu, my_row, j);
+          const int vj = __shfl_sync(0xffffffffu, my_v, j);
           if (elect_one()) tma_load_2d(dst + j * kWsSlotBytes, &maps.m[vj - 1], s * 64, rj, full, kEvictFirst);
         }
         __syncwarp();
@@ -257,10 +323,14 @@ maxsim_wide_stream_kernel(const __grid_constant__ WsMaps maps, const int64_t* __
     const uint32_t full0 = hold(smem_u32(&bar_full[0])), empty0 = hold(smem_u32(&bar_empty[0]));
     const uint32_t a_lo0 = hold(umma::desc_lo_sw128(a_addr)), b_lo0 = hold(umma::desc_lo_sw128(b_addr));
     constexpr uint32_t kStageDesc = kWsStageBytes >> 4, kSlabDesc = kWsASlabBytes >> 4;
-    uint32_t st = 0, st_parity = 0, acc_it = 0, n_q_seen = 0;
+    uint32_t st = 0, st_parity = 0, n_q_seen = 0;
     int64_t cur_q = -1;
-    for (int n = wk.next_tile<false>(lane, pc, tile_q, out, skip_foreign); n > 0;
-         n = wk.next_tile<false>(lane, pc, tile_q, out, skip_foreign), ++acc_it) {
+    for (uint32_t t = 0;; ++t) {
+      const WsDesc* d = desc_wait(t);
+      const int n = d->n;
+      const int64_t tile_q = d->q;
+      desc_release(t);
+      if (n == 0) break;
       if (tile_q != cur_q) {
         // every MMA issued so far read the old query: its completion frees the query region for the loader
         if (cur_q >= 0) {
@@ -272,10 +342,10 @@ maxsim_wide_stream_kernel(const __grid_constant__ WsMaps maps, const int64_t* __
         ++n_q_seen;
         umma::fence_after_sync();
       }
-      const uint32_t slot = acc_it & 1u;
-      mbar_wait(smem_u32(&bar_acc_empty[slot]), ((acc_it >> 1) & 1u) ^ 1u);
+      const uint32_t slot = t & 1u;
+      mbar_wait(smem_u32(&bar_acc_empty[slot]), ((t >> 1) & 1u) ^ 1u);
       umma::fence_after_sync();
-      const uint32_t d_tmem = tmem + slot * 128;
+      const uint32_t d_tmem = tmem + slot * kWsTileCols;
       for (int s = 0; s < n_slabs; ++s) {
         mbar_wait(full0 + 8 * st, st_parity);
         umma::fence_after_sync();
@@ -298,8 +368,12 @@ maxsim_wide_stream_kernel(const __grid_constant__ WsMaps maps, const int64_t* __
     // ===================================== query loader =============================================
     uint32_t n_q_seen = 0;
     int64_t cur_q = -1;
-    for (int n = wk.next_tile<false>(lane, pc, tile_q, out, skip_foreign); n > 0;
-         n = wk.next_tile<false>(lane, pc, tile_q, out, skip_foreign)) {
+    for (uint32_t t = 0;; ++t) {
+      const WsDesc* d = desc_wait(t);
+      const int n = d->n;
+      const int64_t tile_q = d->q;
+      desc_release(t);
+      if (n == 0) break;
       if (tile_q == cur_q) continue;
       cur_q = tile_q;
       if (n_q_seen > 0) mbar_wait(smem_u32(&bar_a_free), (n_q_seen - 1) & 1u);    // the MMAs of the previous query are done
@@ -343,70 +417,83 @@ maxsim_wide_stream_kernel(const __grid_constant__ WsMaps maps, const int64_t* __
       float* const my_lo = lo_buf + half * (128 * 16);
       const int bar_a = 1 + 2 * half, bar_b = 2 + 2 * half;     // named barriers of the (value, residual) warp pair
       float rmax = -INFINITY;                                   // running maximum of the open document, per query row
-      uint32_t acc_it = 0;
-      // only warp 0 writes scores (it also answers for the candidates that have nothing to multiply)
-      for (int n = (warp == 0 ? wk.next_tile<true>(lane, pc, tile_q, out, skip_foreign)
-                              : wk.next_tile<false>(lane, pc, tile_q, out, skip_foreign));
-           n > 0; n = (warp == 0 ? wk.next_tile<true>(lane, pc, tile_q, out, skip_foreign)
-                                 : wk.next_tile<false>(lane, pc, tile_q, out, skip_foreign)),
-               ++acc_it) {
-        const uint32_t slot = acc_it & 1u;
-        mbar_wait(smem_u32(&bar_acc_full[slot]), (acc_it >> 1) & 1u);
+      for (uint32_t t = 0;; ++t) {
+        const WsDesc* d = desc_wait(t);
+        const int n = d->n;
+        int my_v = 0, my_flags = 0;                             // lane j < n: piece j
+        int64_t my_cand = 0;
+        if (lane < n) {
+          my_v = d->v[lane];
+          my_flags = d->flags[lane];
+          my_cand = d->cand[lane];
+        }
+        desc_release(t);
+        if (n == 0) break;
+        const uint32_t slot = t & 1u;
+        mbar_wait(smem_u32(&bar_acc_full[slot]), (t >> 1) & 1u);
         umma::fence_after_sync();
-        const uint32_t t_addr = tmem + lane_base + slot * 128;
-        if (is_lo) {
+        const uint32_t t_addr = tmem + lane_base + slot * kWsTileCols;
+        float closed = 0.f;             // value warps, lane j: sum over my 16 query rows of piece j, if piece j closes a document
+        // the residual products travel through shared memory eight pieces (128 columns) at a time
 #pragma unroll 1
-          for (int j = 0; j < n; ++j) {
+        for (int j0 = 0; j0 < n; j0 += 8) {
+          const int j1 = min(n, j0 + 8);
+          if (is_lo) {
+#pragma unroll 1
+            for (int j = j0; j < j1; ++j) {
+              uint32_t v[16];
+              umma::tmem_ld_32x16(t_addr + j * 16, v);
+              umma::tmem_ld_wait();
+              if (lane < 16) {
+#pragma unroll
+                for (int i = 0; i < 16; ++i) my_lo[((j - j0) * 16 + i) * 16 + lane] = __uint_as_float(v[i]);
+              }
+            }
+            asm volatile("bar.sync %0, 64;" ::"r"(bar_a) : "memory");     // these residual products are in my_lo
+            asm volatile("bar.sync %0, 64;" ::"r"(bar_b) : "memory");     // the value warp has read them
+            continue;
+          }
+          if (kHasLo) asm volatile("bar.sync %0, 64;" ::"r"(bar_a) : "memory");
+#pragma unroll 1
+          for (int j = j0; j < j1; ++j) {
             uint32_t v[16];
             umma::tmem_ld_32x16(t_addr + j * 16, v);
             umma::tmem_ld_wait();
-            if (lane < 16) {
+            const int pv = __shfl_sync(0xffffffffu, my_v, j);
+            const int pf = __shfl_sync(0xffffffffu, my_flags, j);
+            float x[16];
 #pragma unroll
-              for (int i = 0; i < 16; ++i) my_lo[(j * 16 + i) * 16 + lane] = __uint_as_float(v[i]);
+            for (int i = 0; i < 16; ++i) {
+              x[i] = __uint_as_float(v[i]);
+              if (kHasLo && lane < 16) x[i] += my_lo[((j - j0) * 16 + i) * 16 + lane];
+            }
+            float m;
+            if (pv == kWsPieceRows) {     // a full piece (all but the last of a document): plain max tree
+              m = fmaxf(fmaxf(fmaxf(fmaxf(x[0], x[1]), fmaxf(x[2], x[3])), fmaxf(fmaxf(x[4], x[5]), fmaxf(x[6], x[7]))),
+                        fmaxf(fmaxf(fmaxf(x[8], x[9]), fmaxf(x[10], x[11])), fmaxf(fmaxf(x[12], x[13]), fmaxf(x[14], x[15]))));
+            } else {
+              m = -INFINITY;
+#pragma unroll
+              for (int i = 0; i < 16; ++i) m = fmaxf(m, i < pv ? x[i] : -INFINITY);
+            }
+            rmax = (pf & 1) ? m : fmaxf(rmax, m);
+            if (pf & 2) {   // the document ends with this piece: floor, then the sum over my rows (lanes 16-31 hold nothing)
+              float sum = lane < 16 ? fmaxf(rmax, (pf & 4) ? 0.f : -INFINITY) : 0.f;
+              sum += __shfl_xor_sync(0xffffffffu, sum, 8);
+              sum += __shfl_xor_sync(0xffffffffu, sum, 4);
+              sum += __shfl_xor_sync(0xffffffffu, sum, 2);
+              sum += __shfl_xor_sync(0xffffffffu, sum, 1);
+              const float sc = __shfl_sync(0xffffffffu, sum, 0);
+              if (lane == j) closed = sc;
             }
           }
-          umma::fence_before_sync();
-          __syncwarp();
-          if (lane == 0) mbar_arrive(smem_u32(&bar_acc_empty[slot]));
-          asm volatile("bar.sync %0, 64;" ::"r"(bar_a) : "memory");     // the residual products of this tile are in my_lo
-          asm volatile("bar.sync %0, 64;" ::"r"(bar_b) : "memory");     // the value warp has read them
-          continue;
+          if (kHasLo) asm volatile("bar.sync %0, 64;" ::"r"(bar_b) : "memory");
         }
-        if (kHasLo) asm volatile("bar.sync %0, 64;" ::"r"(bar_a) : "memory");
-        float closed = 0.f;             // lane j: sum over my 16 query rows of piece j, if piece j closes a document
-#pragma unroll 1
-        for (int j = 0; j < n; ++j) {
-          uint32_t v[16];
-          umma::tmem_ld_32x16(t_addr + j * 16, v);
-          umma::tmem_ld_wait();
-          const int pv = __shfl_sync(0xffffffffu, pc.v, j);
-          const int pf = __shfl_sync(0xffffffffu, pc.flags, j);
-          float m = -INFINITY;
-#pragma unroll
-          for (int i = 0; i < 16; ++i) {
-            float x = __uint_as_float(v[i]);
-            if (kHasLo && lane < 16) x += my_lo[(j * 16 + i) * 16 + lane];
-            m = fmaxf(m, i < pv ? x : -INFINITY);
-          }
-          rmax = (pf & 1) ? m : fmaxf(rmax, m);
-          if (pf & 2) {   // the document ends with this piece: floor, then the sum over my rows (lanes 16-31 hold nothing)
-            const int len = __shfl_sync(0xffffffffu, pc.len, j);
-            float floor_v = strides.n > 0 ? 0.f : -INFINITY;
-            for (int i = 0; i < strides.n; ++i)
-              if (strides.v[i] == len) floor_v = -INFINITY;
-            float sum = lane < 16 ? fmaxf(rmax, floor_v) : 0.f;
-            sum += __shfl_xor_sync(0xffffffffu, sum, 8);
-            sum += __shfl_xor_sync(0xffffffffu, sum, 4);
-            sum += __shfl_xor_sync(0xffffffffu, sum, 2);
-            sum += __shfl_xor_sync(0xffffffffu, sum, 1);
-            const float sc = __shfl_sync(0xffffffffu, sum, 0);
-            if (lane == j) closed = sc;
-          }
-        }
+        // every column of the slot has been read: hand it back to the MMA warp
         umma::fence_before_sync();
         __syncwarp();
         if (lane == 0) mbar_arrive(smem_u32(&bar_acc_empty[slot]));
-        if (kHasLo) asm volatile("bar.sync %0, 64;" ::"r"(bar_b) : "memory");
+        if (is_lo) continue;
         // the two halves of the query rows meet in shared memory; warp 0 writes the score at the candidate's position
         if (two_halves) {
           if (warp == 1 && lane < n) half_sum[lane] = closed;
@@ -414,21 +501,22 @@ maxsim_wide_stream_kernel(const __grid_constant__ WsMaps maps, const int64_t* __
           if (warp == 0 && lane < n) closed += half_sum[lane];
           asm volatile("bar.sync 6, 64;" ::: "memory");
         }
-        if (warp == 0 && lane < n && (pc.flags & 2)) out[pc.cand] = closed;
+        if (warp == 0 && lane < n && (my_flags & 2)) out[my_cand] = closed;
       }
     }
   }
 
   umma::fence_before_sync();
   __syncthreads();
-  if (warp == kWsIssuerWarp) umma::tmem_dealloc(tmem, 256);
+  if (warp == kWsIssuerWarp) umma::tmem_dealloc(tmem, 512);
 }
 
 }  // namespace
 
-// widths 256 … 1024 in steps of 64, queries of at most 32 rows
+// widths 256 … 768 in steps of 64 (the query region takes dim/64 × 8 KB of shared memory; beyond 768 too little is left for
+// the ring and the K-split kernel serves), queries of at most 32 rows
 bool rerank_wide_stream_supports(int dim, int q_len, int flags) {
-  return dim % 64 == 0 && dim >= 256 && dim <= 1024 && q_len <= 32 &&
+  return dim % 64 == 0 && dim >= 256 && dim <= 768 && q_len <= 32 &&
          !(flags & (CBK_FLAG_BF16_NATIVE_MMA | CBK_FLAG_RERANK_GENERIC | CBK_FLAG_RERANK_KSPLIT));
 }
 
@@ -454,12 +542,12 @@ int rerank_wide_stream_dispatch(const void* d_store, int store_dtype, int64_t n_
   ss.n = n_strides;
   for (int i = 0; i < CBK_MAX_STRIDES; ++i) ss.v[i] = i < n_strides ? strides[i] : -1;
   const int n_slabs = dim / 64;
-  const size_t fixed = 1024 + static_cast<size_t>(n_slabs) * kWsASlabBytes + kWsLoBufBytes;
+  const size_t fixed = 1024 + static_cast<size_t>(n_slabs) * kWsASlabBytes + (store_dtype == CBK_BF16 ? kWsLoBufBytes : 0);
   const int n_stages = static_cast<int>(std::min<size_t>(kWsMaxStages, (220 * 1024 - fixed) / kWsStageBytes));
   const size_t smem = fixed + static_cast<size_t>(n_stages) * kWsStageBytes;
   const bool bf16 = store_dtype == CBK_BF16;
   const uint32_t fmt = bf16 ? umma::kFmtBF16 : umma::kFmtF16;
-  const uint32_t idesc = umma::make_idesc(64, 128, fmt, fmt);
+  const uint32_t idesc = umma::make_idesc(64, kWsTileCols, fmt, fmt);
   // a candidate is at least one piece; ranges shorter than a few tiles are not worth a CTA
   const int grid = static_cast<int>(std::max<int64_t>(1, std::min<int64_t>(sm_count(), (n_cand_total + 31) / 32)));
   const int skip = (flags & CBK_FLAG_SKIP_FOREIGN_PIDS) ? 1 : 0;
