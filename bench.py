@@ -682,7 +682,7 @@ def run_ours(args, rank, world, local_rank):
     # what the serving entry is handed: the encoder's 16-bit query embeddings and 32-bit pids when the kernel rounds the
     # query to fp16 anyway (bit-identical scores, tests/test_gpu_parity.py::test_rerank_pipeline_matches_direct_call),
     # else fp32 / int64
-    wire16 = dim % 64 == 0 and dim <= 1024
+    wire16 = bool(ranker.query_rounded_to_fp16)
     Q_pin = (Q_host.to(torch.float16) if wire16 else Q_host).pin_memory()
     cand_pin = (cand_host.to(torch.int32) if args.docs * world < 2 ** 31 else cand_host).pin_memory()
     Q_dev, cand_dev = Q_host.to(dev), cand_host.to(dev).reshape(-1).contiguous()

@@ -209,6 +209,21 @@ class ColbertRanker:
             flags |= kernels._lib.CBK_FLAG_FIXED_DOCLEN
         return flags
 
+    @property
+    def query_rounded_to_fp16(self) -> bool:
+        """True when the kernel this ranker's calls resolve to rounds the query to fp16 on load — 16-bit queries on the wire
+        (``RerankPipeline``) then give bit-identical scores.  Not the case for the generic kernel (fp32 arithmetic), the
+        bf16-native flag, and bf16 stores on the tcgen05 kernels, which multiply the query as bf16 value + bf16 residual
+        (16 significant bits: more than fp16 carries)."""
+        flags = int(self.effective_flags)
+        L = kernels._lib
+        if flags & (L.CBK_FLAG_BF16_NATIVE_MMA | L.CBK_FLAG_RERANK_GENERIC) or self.dim % 64 != 0 or self.dim > 1024:
+            return False
+        bf16 = self.tensor.dtype == torch.bfloat16
+        if self.dim == 128:
+            return not (bf16 and flags & L.CBK_FLAG_RERANK_TCGEN05)
+        return not (bf16 and 256 <= self.dim and not flags & L.CBK_FLAG_RERANK_KSPLIT)
+
     # -- the batched primitive everything else goes through -----------------------------------------
     def score_candidates(self, Q: torch.Tensor, cand_pids: torch.Tensor, cand_rowptr: torch.Tensor,
                          q_lens: Optional[torch.Tensor] = None) -> torch.Tensor:

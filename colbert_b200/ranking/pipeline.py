@@ -57,10 +57,7 @@ class RerankPipeline:
         self.result_rows = (self.rank * self.slice, (self.rank + 1) * self.slice)
         # The tensor-core kernels round the query to fp16 on load, so fp16 queries on the wire give bit-identical
         # scores at half the bytes; the exceptions multiply differently and keep fp32 on the wire.
-        flags = int(getattr(local, "effective_flags", getattr(local, "kernel_flags", 0)))
-        from .. import _lib
-        self.fp16_wire_ok = (self.dim % 64 == 0 and self.dim <= 1024
-                             and not flags & (_lib.CBK_FLAG_BF16_NATIVE_MMA | _lib.CBK_FLAG_RERANK_GENERIC))
+        self.fp16_wire_ok = bool(local.query_rounded_to_fp16)
         dev = self.device
         self.copy_stream = torch.cuda.Stream(device=dev)
         self.Q_dev = [torch.empty((n_queries, q_len, self.dim), dtype=torch.float32, device=dev) for _ in range(slots)]
