@@ -35,7 +35,10 @@ class RerankPipeline:
         the whole batch through its own PCIe link — copy engines only, no SM and no collective on the input side.
         Measured on 8 x B200 (4096 queries x 1000 candidates per GPU, 16-bit queries / 32-bit pids, device step 15.5-16.3 ms):
         all-gather 17.4 ms per step end to end, replicate 21.0 ms (8 x 400 MB per step out of one host's memory) — hence
-        the default."""
+        the default.  ``"p2p"``: each rank uploads its slice into a SYMMETRIC buffer (torch.distributed._symmetric_memory) and
+        pulls the other ranks' slices with peer-to-peer copies — copy engines over NVLink, no SM: unlike the NCCL kernel of
+        "allgather" they run underneath the persistent MaxSim kernel of the previous step.  Falls back to "allgather" when
+        symmetric memory cannot be set up."""
         self.ranker = ranker
         local = getattr(ranker, "local", ranker)
         self.device = local.device
@@ -45,7 +48,7 @@ class RerankPipeline:
         self.rank = ranker.rank if sharded else 0
         self.group = ranker.group if sharded else None
         self.n_queries, self.q_len, self.n_cand = n_queries, q_len, n_cand
-        assert input_exchange in ("allgather", "replicate")
+        assert input_exchange in ("allgather", "replicate", "p2p")
         self.input_exchange = input_exchange if self.world > 1 else "replicate"
         self.k = min(int(depth), n_cand)
         self.depth = depth
@@ -72,15 +75,46 @@ class RerankPipeline:
         self._i = 0
         # the input all-gather runs on the copy stream, concurrently with the key all-gather of the previous step on
         # the compute stream: it needs its own communicator (collective call: every rank builds its pipeline)
+        self._sym = None
+        if self.world > 1 and self.input_exchange == "p2p":
+            try:
+                self._setup_p2p()
+            except Exception as e:                              # no peer access / no symmetric-memory support on this box
+                import warnings
+                warnings.warn(f"RerankPipeline: symmetric-memory input exchange unavailable ({e!r}); using the NCCL all-gather")
+                self.input_exchange = "allgather"
         self.in_group = (dist.new_group(ranks=list(range(self.world)))
                          if self.world > 1 and self.input_exchange == "allgather" else None)
         self.h2d_bytes_per_step = 0             # set by the first submit (depends on the dtypes handed in)
         self.d2h_bytes_per_step = n_queries * self.k * 12        # all ranks together: each its own slice
         self._wire = None
 
+    def _setup_p2p(self) -> None:
+        """One symmetric allocation per slot: [queries at up to 4 B per element | pids at up to 8 B]; typed views of it (mine
+        and every peer's) are made on first use of a wire dtype."""
+        import torch.distributed._symmetric_memory as symm_mem
+        group = self.group if self.group is not None else dist.group.WORLD
+        self._sym_q_bytes = self.n_queries * self.q_len * self.dim * 4
+        self._sym_c_bytes = self.n_queries * self.n_cand * 8
+        self._sym = symm_mem.empty((self.slots, self._sym_q_bytes + self._sym_c_bytes), dtype=torch.uint8, device=self.device)
+        self._sym_hdl = symm_mem.rendezvous(self._sym, group)
+        self._sym_peers = [self._sym_hdl.get_buffer(p, tuple(self._sym.shape), torch.uint8) for p in range(self.world)]
+        self._sym_views = {}
+
+    def _sym_view(self, s: int, which: str, dtype: torch.dtype, shape):
+        """→ list over ranks of the typed view of slot ``s``'s query / pid region in that rank's symmetric buffer"""
+        key = (s, which, dtype)
+        if key not in self._sym_views:
+            off = 0 if which == "q" else self._sym_q_bytes
+            nbytes = int(torch.tensor([], dtype=dtype).element_size()) * int(torch.Size(shape).numel())
+            self._sym_views[key] = [b[s, off: off + nbytes].view(dtype).view(shape) for b in self._sym_peers]
+        return self._sym_views[key]
+
     def describe(self) -> str:
-        up = (f"every rank uploads 1/{self.world} of the batch (all-gathered over NVLink)" if self.input_exchange == "allgather"
-              else "every rank uploads the whole batch through its own PCIe link")
+        up = {"allgather": f"every rank uploads 1/{self.world} of the batch (all-gathered over NVLink by NCCL)",
+              "p2p": f"every rank uploads 1/{self.world} of the batch into symmetric memory and pulls the other slices with "
+                     "peer-to-peer copies (copy engines over NVLink)",
+              "replicate": "every rank uploads the whole batch through its own PCIe link"}[self.input_exchange]
         return ("colbert_b200.ranking.pipeline.RerankPipeline.submit/result (pinned host in, pinned host out, 2-slot stream "
                 f"pipeline; wire dtypes {self._wire}; {up} and downloads 1/{self.world} of the result)")
 
@@ -118,7 +152,26 @@ class RerankPipeline:
         compute = torch.cuda.current_stream(self.device)
         lo, hi = self.rank * self.slice, (self.rank + 1) * self.slice
         dev = self.device
-        with torch.cuda.stream(self.copy_stream):
+        if self.input_exchange == "p2p":
+            with torch.cuda.stream(self.copy_stream):
+                self.copy_stream.wait_event(self.ev_done[s])
+                qv = self._sym_view(s, "q", Q_host.dtype, (self.n_queries, self.q_len, self.dim))
+                cv = self._sym_view(s, "c", cand_host.dtype, (self.n_queries, self.n_cand))
+                qv[self.rank][lo:hi].copy_(Q_host[lo:hi], non_blocking=True)          # my slice → my symmetric buffer
+                cv[self.rank][lo:hi].copy_(cand_host[lo:hi], non_blocking=True)
+                self._sym_hdl.barrier(channel=s)                                      # every rank's slice is in place
+                for step in range(1, self.world):                                     # pull the others', staggered by rank
+                    p = (self.rank + step) % self.world
+                    plo, phi = p * self.slice, (p + 1) * self.slice
+                    qv[self.rank][plo:phi].copy_(qv[p][plo:phi], non_blocking=True)
+                    cv[self.rank][plo:phi].copy_(cv[p][plo:phi], non_blocking=True)
+                # (no second barrier: a peer's pull of my slice precedes its scoring of this step, and my next write to this
+                #  slot follows my scoring of this step, which ends in a collective that peer takes part in)
+                self.Q_dev[s].copy_(qv[self.rank])                                    # widen (or copy) into the kernel's types
+                self.C_dev[s].copy_(cv[self.rank])
+                self.ev_in[s].record(self.copy_stream)
+        else:
+          with torch.cuda.stream(self.copy_stream):
             self.copy_stream.wait_event(self.ev_done[s])            # the slot's previous step no longer reads the buffers
             if Q_host.dtype == torch.float16:
                 if self.Q16_dev[s] is None:
@@ -137,7 +190,7 @@ class RerankPipeline:
             self.ev_in[s].record(self.copy_stream)
         if self._wire is None:
             self._wire = f"Q {str(Q_host.dtype).replace('torch.', '')}, pids {str(cand_host.dtype).replace('torch.', '')}"
-            rows = self.slice if self.input_exchange == "allgather" else self.n_queries
+            rows = self.n_queries if self.input_exchange == "replicate" else self.slice
             self.h2d_bytes_per_step = (rows * self.q_len * self.dim * Q_host.element_size()
                                        + rows * self.n_cand * cand_host.element_size()) * self.world
         compute.wait_event(self.ev_in[s])
