@@ -59,7 +59,7 @@ def parse_args():
     ap.add_argument("--cpu-queries", type=int, default=128, help="bounded CPU-baseline sample (queries)")
     ap.add_argument("--no-secondary", action="store_true", help="skip the `secondary` block (configs[2], [3]/[4])")
     ap.add_argument("--no-parity", action="store_true", help="skip the oracle parity gate")
-    ap.add_argument("--e2e-exchange", default="allgather", choices=["allgather", "replicate", "p2p"],
+    ap.add_argument("--e2e-exchange", default="p2p", choices=["allgather", "replicate", "p2p"],
                     help="N > 1: how RerankPipeline distributes the replicated inputs (see its docstring)")
     ap.add_argument("--chunks", type=int, default=0, help="N > 1: query chunks per sharded step (0 = the ranker's default)")
     ap.add_argument("--parity-queries", type=int, default=8, help="queries re-scored by the oracle (parity gate)")

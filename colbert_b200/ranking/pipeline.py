@@ -25,7 +25,7 @@ import torch.distributed as dist
 
 class RerankPipeline:
     def __init__(self, ranker, n_queries: int, q_len: int, n_cand: int, depth: int = 10, slots: int = 2,
-                 input_exchange: str = "allgather"):
+                 input_exchange: str = "p2p"):
         """``ranker``: ``ColbertRanker`` or ``ShardedColbertRanker``.  Every step carries ``n_queries`` queries
         of ``q_len`` rows and ``n_cand`` candidates each (equal-length lists).
 
@@ -37,8 +37,10 @@ class RerankPipeline:
         all-gather 17.4 ms per step end to end, replicate 21.0 ms (8 x 400 MB per step out of one host's memory) — hence
         the default.  ``"p2p"``: each rank uploads its slice into a SYMMETRIC buffer (torch.distributed._symmetric_memory) and
         pulls the other ranks' slices with peer-to-peer copies — copy engines over NVLink, no SM: unlike the NCCL kernel of
-        "allgather" they run underneath the persistent MaxSim kernel of the previous step.  Falls back to "allgather" when
-        symmetric memory cannot be set up."""
+        "allgather" they run underneath the persistent MaxSim kernel of the previous step (8 x B200: 17.05 ms per step end to
+        end against 17.4 ms, device step 16.2 ms; what is left is the widening of the 16-bit queries / 32-bit pids, two small
+        kernels that do have to wait for SMs).  The default; falls back to "allgather" when symmetric memory cannot be
+        set up."""
         self.ranker = ranker
         local = getattr(ranker, "local", ranker)
         self.device = local.device
