@@ -58,12 +58,18 @@ SIGNATURES = {
                                         _i32, _vp]),
     "cbk_topk_dense_workspace_bytes": (_sz, [_i64, _i64, _i32]),
     "cbk_topk_dense": (C.c_int, [_vp, _i64, _i64, _i32, _i64, _i32, _vp, _vp, _vp, _sz, _vp]),
-    "cbk_selftest_umma_gemm": (C.c_int, [_vp, _vp, _i32, _i32, _i32, _vp, _vp]),
-    "cbk_selftest_umma_rate": (C.c_int, [_i32, _i32, _i32, _i32, _i32, _vp, _vp]),
     "cbk_mask_cast_rows": (C.c_int, [_vp, _i32, _i64, _i32, _vp, _i32, _vp, _i32, _vp]),
     "cbk_score_allpairs_fwd": (C.c_int, [_vp, _vp, _i32, _i64, _i32, _i64, _i32, _i32, _vp, _vp, _vp]),
     "cbk_score_allpairs_bwd": (C.c_int, [_vp, _vp, _i32, _i64, _i32, _i64, _i32, _i32, _vp, _vp, _vp, _i32, _vp, _i32,
                                          _vp, _vp, _vp]),
+}
+
+
+# include/colbert_b200_probe.h — libcolbert_b200_probe.so (tests / benchmarks only, not the product library)
+PROBE_LIB_PATH = os.path.join(_HERE, "csrc", "libcolbert_b200_probe.so")
+PROBE_SIGNATURES = {
+    "cbk_selftest_umma_gemm": (C.c_int, [_vp, _vp, _i32, _i32, _i32, _vp, _vp]),
+    "cbk_selftest_umma_rate": (C.c_int, [_i32, _i32, _i32, _i32, _i32, _vp, _vp]),
 }
 
 
@@ -87,13 +93,33 @@ def load() -> C.CDLL:
         raise RuntimeError(
             f"{LIB_PATH} is missing: the CUDA extension has not been built. Run "
             "`python -m colbert_b200.csrc.build` (nvcc, sm_100a). colbert_b200 has no CPU fallback.")
-    lib = C.CDLL(LIB_PATH)
+    lib = C.CDLL(LIB_PATH, mode=C.RTLD_GLOBAL)       # the probe library resolves its cbk:: helpers against this one
     for name, (res, args) in SIGNATURES.items():
         fn = getattr(lib, name)          # AttributeError if the symbol is not exported
         fn.restype, fn.argtypes = res, args
     if lib.cbk_abi_version() != CBK_ABI_VERSION:
         raise RuntimeError(f"ABI version mismatch: library reports {lib.cbk_abi_version()}, binding expects {CBK_ABI_VERSION}")
     _lib = lib
+    return lib
+
+
+_probe: Optional[C.CDLL] = None
+
+
+def load_probe() -> C.CDLL:
+    """The probe library (self-test and issue-rate probes of the tcgen05 building blocks); the product library is loaded
+    first — the probes report errors and count launches through it."""
+    global _probe
+    if _probe is not None:
+        return _probe
+    load()
+    if not os.path.exists(PROBE_LIB_PATH):
+        raise RuntimeError(f"{PROBE_LIB_PATH} is missing: run `python -m colbert_b200.csrc.build`")
+    lib = C.CDLL(PROBE_LIB_PATH)
+    for name, (res, args) in PROBE_SIGNATURES.items():
+        fn = getattr(lib, name)
+        fn.restype, fn.argtypes = res, args
+    _probe = lib
     return lib
 
 

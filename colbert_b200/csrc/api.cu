@@ -46,8 +46,6 @@ int rerank_mv_wide_dispatch(const void*, int, int64_t, int, int64_t, int64_t, co
                             const int64_t*, int64_t, float*, int, cudaStream_t);
 int rerank_umma_dispatch(const void*, int, int64_t, int, const int64_t*, const int32_t*, int64_t, int64_t, const int32_t*, int,
                          const float*, const int32_t*, int, int64_t, const int64_t*, const int64_t*, int64_t, float*, void*, int, cudaStream_t);
-int umma_probe_dispatch(const void*, const void*, int, int, int, float*, cudaStream_t);
-int umma_rate_dispatch(int, int, int, int, int, long long*, cudaStream_t);
 int mask_cast_dispatch(const void*, int, int64_t, int, const void*, int, void*, int, cudaStream_t);
 int score_allpairs_fwd_dispatch(const void*, const void*, int, int64_t, int, int64_t, int, int, float*, int32_t*, cudaStream_t);
 bool score_allpairs_bwd_fits(int64_t, int, int);
@@ -589,21 +587,6 @@ int cbk_topk_dense(const float* d_scores, int64_t n_queries, int64_t n_docs, int
   if (rc != CBK_OK) return rc;
   return topk_dense_dispatch(d_scores, n_queries, n_docs, k, pid_base, as_keys, d_out_scores, d_out_pids, d_workspace,
                              static_cast<cudaStream_t>(stream));
-}
-
-int cbk_selftest_umma_rate(int N, int mode, int iters, int n_acc, int ctas_per_sm, int64_t* d_cycles, void* stream) {
-  int rc = check_device();
-  if (rc != CBK_OK) return rc;
-  return umma_rate_dispatch(N, mode, iters, n_acc, ctas_per_sm, reinterpret_cast<long long*>(d_cycles),
-                            static_cast<cudaStream_t>(stream));
-}
-
-int cbk_selftest_umma_gemm(const void* d_A, const void* d_B, int N, int a_bf16, int b_bf16, float* d_C, void* stream) {
-  CBK_CHECK_ARG(d_A && d_B && d_C, "cbk_selftest_umma_gemm: null pointer argument");
-  CBK_CHECK_SUPPORTED(N >= 16 && N <= 256 && N % 16 == 0, "cbk_selftest_umma_gemm: N %d must be a multiple of 16 in [16, 256]", N);
-  int rc = check_device();
-  if (rc != CBK_OK) return rc;
-  return umma_probe_dispatch(d_A, d_B, N, a_bf16, b_bf16, d_C, static_cast<cudaStream_t>(stream));
 }
 
 }  // extern "C"

@@ -16,9 +16,14 @@ from concurrent.futures import ThreadPoolExecutor
 
 HERE = os.path.dirname(os.path.abspath(__file__))
 ROOT = os.path.dirname(os.path.dirname(HERE))
-SOURCES = ["api.cu", "rerank.cu", "topk.cu", "gather.cu", "partition.cu", "umma_probe.cu", "exhaustive.cu", "rerank_generic.cu", "rerank_umma.cu", "rerank_wide.cu", "score_allpairs.cu", "rerank_mv_wide.cu", "rerank_wide_stream.cu"]
-HEADERS = ["cbk_common.cuh", "umma.cuh", os.path.join(ROOT, "include", "colbert_b200.h")]
+SOURCES = ["api.cu", "rerank.cu", "topk.cu", "gather.cu", "partition.cu", "exhaustive.cu", "rerank_generic.cu", "rerank_umma.cu", "rerank_wide.cu", "score_allpairs.cu", "rerank_mv_wide.cu", "rerank_wide_stream.cu"]
+# self-test / issue-rate probes of the tcgen05 building blocks: a separate library (tests and benchmarks only), linked against
+# the product library for error reporting and launch accounting
+PROBE_SOURCES = ["umma_probe.cu"]
+HEADERS = ["cbk_common.cuh", "umma.cuh", os.path.join(ROOT, "include", "colbert_b200.h"),
+           os.path.join(ROOT, "include", "colbert_b200_probe.h")]
 LIB = os.path.join(HERE, "libcolbert_b200.so")
+PROBE_LIB = os.path.join(HERE, "libcolbert_b200_probe.so")
 STAMP = os.path.join(HERE, ".build_stamp")
 
 NVCC_FLAGS = [
@@ -39,7 +44,7 @@ def _nvcc() -> str:
 
 def _digest() -> str:
     h = hashlib.sha256()
-    for f in SOURCES + HEADERS + [os.path.abspath(__file__)]:
+    for f in SOURCES + PROBE_SOURCES + HEADERS + [os.path.abspath(__file__)]:
         path = f if os.path.isabs(f) else os.path.join(HERE, f)
         with open(path, "rb") as fh:
             h.update(fh.read())
@@ -49,7 +54,8 @@ def _digest() -> str:
 
 def build(force: bool = False, verbose: bool = False) -> str:
     digest = _digest()
-    if not force and os.path.exists(LIB) and os.path.exists(STAMP) and open(STAMP).read().strip() == digest:
+    if (not force and os.path.exists(LIB) and os.path.exists(PROBE_LIB) and os.path.exists(STAMP)
+            and open(STAMP).read().strip() == digest):
         return LIB
     nvcc = _nvcc()
     objdir = os.path.join(HERE, "build")
@@ -68,12 +74,18 @@ def build(force: bool = False, verbose: bool = False) -> str:
             print(log, file=sys.stderr)
         return obj
 
-    with ThreadPoolExecutor(max_workers=min(8, len(SOURCES))) as ex:
-        objs = list(ex.map(compile_one, SOURCES))
+    with ThreadPoolExecutor(max_workers=min(8, len(SOURCES) + len(PROBE_SOURCES))) as ex:
+        all_objs = list(ex.map(compile_one, SOURCES + PROBE_SOURCES))
+    objs, probe_objs = all_objs[:len(SOURCES)], all_objs[len(SOURCES):]
     link = [nvcc, "-shared", "-o", LIB, *objs, "-gencode", "arch=compute_100a,code=sm_100a", "-cudart", "static"]
     res = subprocess.run(link, capture_output=True, text=True)
     if res.returncode != 0:
         raise RuntimeError("link failed:\n" + res.stdout + res.stderr)
+    link = [nvcc, "-shared", "-o", PROBE_LIB, *probe_objs, "-gencode", "arch=compute_100a,code=sm_100a", "-cudart", "static",
+            "-L" + HERE, "-lcolbert_b200", "-Xlinker", "-rpath", "-Xlinker", "$ORIGIN"]
+    res = subprocess.run(link, capture_output=True, text=True)
+    if res.returncode != 0:
+        raise RuntimeError("link of the probe library failed:\n" + res.stdout + res.stderr)
     with open(STAMP, "w") as fh:
         fh.write(digest)
     return LIB

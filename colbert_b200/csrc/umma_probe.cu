@@ -282,3 +282,31 @@ int umma_probe_dispatch(const void* d_A, const void* d_B, int N, int a_bf16, int
 }
 
 }  // namespace cbk
+
+// ---- entry points of libcolbert_b200_probe.so (include/colbert_b200_probe.h) ---------------------------------------
+static int probe_check_device() {
+  int dev = 0, major = 0;
+  CBK_CUDA(cudaGetDevice(&dev));
+  CBK_CUDA(cudaDeviceGetAttribute(&major, cudaDevAttrComputeCapabilityMajor, dev));
+  CBK_CHECK_SUPPORTED(major == 10, "device %d has compute capability major %d; the probes are sm_100a only", dev, major);
+  return CBK_OK;
+}
+
+extern "C" {
+
+int cbk_selftest_umma_rate(int N, int mode, int iters, int n_acc, int ctas_per_sm, int64_t* d_cycles, void* stream) {
+  int rc = probe_check_device();
+  if (rc != CBK_OK) return rc;
+  return cbk::umma_rate_dispatch(N, mode, iters, n_acc, ctas_per_sm, reinterpret_cast<long long*>(d_cycles),
+                                 static_cast<cudaStream_t>(stream));
+}
+
+int cbk_selftest_umma_gemm(const void* d_A, const void* d_B, int N, int a_bf16, int b_bf16, float* d_C, void* stream) {
+  CBK_CHECK_ARG(d_A && d_B && d_C, "cbk_selftest_umma_gemm: null pointer argument");
+  CBK_CHECK_SUPPORTED(N >= 16 && N <= 256 && N % 16 == 0, "cbk_selftest_umma_gemm: N %d must be a multiple of 16 in [16, 256]", N);
+  int rc = probe_check_device();
+  if (rc != CBK_OK) return rc;
+  return cbk::umma_probe_dispatch(d_A, d_B, N, a_bf16, b_bf16, d_C, static_cast<cudaStream_t>(stream));
+}
+
+}  // extern "C"

@@ -252,7 +252,7 @@ def partition_candidates(cand_pids: torch.Tensor, cand_rowptr: torch.Tensor, pid
 def selftest_umma_gemm(A: torch.Tensor, B: torch.Tensor, tma_3d: bool = False) -> torch.Tensor:
     """C[128, N] = A[128,128] · B[N,128]^T through TMA → tcgen05.mma → TMEM → tcgen05.ld (one CTA).
     ``tma_3d``: load each operand with ONE 3-D TMA op instead of one op per 64-column half."""
-    lib = _lib.load()
+    lib = _lib.load_probe()
     dev = A.device
     _need(A, "A", A.dtype, dev)
     _need(B, "B", B.dtype, dev)
@@ -270,7 +270,7 @@ def selftest_umma_gemm(A: torch.Tensor, B: torch.Tensor, tma_3d: bool = False) -
 def selftest_umma_rate(N: int, mode: int, iters: int, n_acc: int, ctas_per_sm: int = 1, device=None) -> torch.Tensor:
     """Cycles each CTA took to issue and retire ``iters`` tiles of [128, N] += A[128,128] · B[N,128]^T
     (cbk_selftest_umma_rate; mode 0 = both operands from shared memory, 1 = A from TMEM)."""
-    lib = _lib.load()
+    lib = _lib.load_probe()
     dev = torch.device(device if device is not None else "cuda:0")
     n_sm = torch.cuda.get_device_properties(dev).multi_processor_count
     out = torch.zeros(n_sm * ctas_per_sm, dtype=torch.int64, device=dev)

@@ -308,24 +308,6 @@ size_t cbk_topk_dense_workspace_bytes(int64_t n_queries, int64_t n_docs, int k);
 int cbk_topk_dense(const float* d_scores, int64_t n_queries, int64_t n_docs, int k, int64_t pid_base, int as_keys,
                    float* d_out_scores, int64_t* d_out_pids, void* d_workspace, size_t workspace_bytes, void* stream);
 
-/* ------------------------------------------------------------------------------------------------
- * Self-test of the tcgen05 / TMEM / TMA building blocks the query-batched kernels are made of:
- *     C[128, N] = A[128, 128] · B[N, 128]^T      16-bit inputs (a_bf16 / b_bf16: 0 = fp16, 1 = bf16), fp32 out
- * N a multiple of 16 in [16, 256]; one CTA.  Bit 1 of a_bf16 selects the 3-D tensor-map variant (one TMA op
- * per operand instead of one per 64-column half).  Not part of the scoring path.
- * ------------------------------------------------------------------------------------------------ */
-int cbk_selftest_umma_gemm(const void* d_A, const void* d_B, int N, int a_bf16, int b_bf16, float* d_C, void* stream);
-
-/* Issue-rate probe for the same building block: ctas_per_sm CTAs per SM each run `iters` tiles of
- * [128, N] += A[128, 128] · B[N, 128]^T over resident shared-memory operands, rotating over n_acc TMEM
- * accumulators; d_cycles [n_SMs * ctas_per_sm] int64 receives the clock cycles each CTA took.  mode bits:
- * 1 = A operand from TMEM, 4 = issue through elect.sync on a converged warp (otherwise thread 0 in a divergent
- * branch), 2 = (with 4) two issuing warps, 16 = sixteen more warps read the accumulators back meanwhile.
- * mode 8: TMEM read rate instead — N = warps per CTA (4/8/12/16), n_acc = loads between waits (1/2).
- * Used to place the tensor-bound kernels against what the MMA shape itself can sustain
- * (benchmarks/umma_rate.py).  Not part of the scoring path. */
-int cbk_selftest_umma_rate(int N, int mode, int iters, int n_acc, int ctas_per_sm, int64_t* d_cycles, void* stream);
-
 #ifdef __cplusplus
 }
 #endif

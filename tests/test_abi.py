@@ -10,10 +10,11 @@ import pytest
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 HEADER = os.path.join(ROOT, "include", "colbert_b200.h")
+PROBE_HEADER = os.path.join(ROOT, "include", "colbert_b200_probe.h")
 
 
-def declared_symbols():
-    text = open(HEADER).read()
+def declared_symbols(header=HEADER):
+    text = open(header).read()
     text = re.sub(r"/\*.*?\*/", "", text, flags=re.S)
     return sorted(set(re.findall(r"\b(cbk_[a-z0-9_]+)\s*\(", text)))
 
@@ -40,6 +41,17 @@ def test_binding_covers_every_declared_symbol(built_lib):
     assert lib.cbk_maxsim_rerank_workspace_bytes() >= 4
 
 
+def test_probe_library_is_separate(built_lib):
+    """the tcgen05 self-test / rate probes are not in the product library; their own library exports what its header declares"""
+    from colbert_b200 import _lib
+    product = C.CDLL(built_lib)
+    probe = _lib.load_probe()
+    syms = declared_symbols(PROBE_HEADER)
+    assert syms == sorted(_lib.PROBE_SIGNATURES) and syms
+    for name in syms:
+        assert hasattr(probe, name) and not hasattr(product, name)
+
+
 def test_library_is_sm100a_and_uses_tma(built_lib):
     """The kernels are compiled for sm_100a and the rerank kernel really stages through TMA."""
     elf = subprocess.run(["cuobjdump", "-lelf", built_lib], capture_output=True, text=True).stdout
@@ -62,7 +74,7 @@ def test_invalid_arguments_are_reported_not_crashed(built_lib):
     assert rc == -1 and b"cbk_rank_forward_host" in lib.cbk_last_error()
     assert lib.cbk_rank_forward_scratch_bytes(1000, 32, 128, 10) >= 1000 * 12 + 32 * 128 * 4 + 256
     assert lib.cbk_rank_forward_scratch_bytes(0, 32, 128, 10) == 0
-    rc = lib.cbk_selftest_umma_rate(128, 2, 100, 4, 1, None, None)                 # no output buffer
+    rc = _lib.load_probe().cbk_selftest_umma_rate(128, 2, 100, 4, 1, None, None)   # no output buffer
     assert rc != 0
     with pytest.raises(_lib.CbkError):
         _lib.check("cbk_gather_rows", rc)
