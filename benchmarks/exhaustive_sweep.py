@@ -23,6 +23,9 @@ def main():
     ap.add_argument("--doclen", type=int, default=0, help="0: U[20,120] (mean 70, config 4); else fixed (config 5)")
     ap.add_argument("--dtype", default="fp16", choices=["fp16", "bf16"])
     ap.add_argument("--k", type=int, default=1000)
+    ap.add_argument("--dim", type=int, default=128, help="embedding width; other than 128 needs a fixed --doclen and fp16 "
+                                                         "(multi-view store scored by the all-pairs kernel)")
+    ap.add_argument("--q-len", type=int, default=32)
     ap.add_argument("--iters", type=int, default=5)
     args = ap.parse_args()
     import torch
@@ -36,16 +39,16 @@ def main():
     else:
         doclens = torch.randint(20, 121, (args.docs,), generator=g, dtype=torch.int64)
     total = int(doclens.sum())
-    store = torch.zeros(total + 512, 128, dtype=dt, device=dev)
+    store = torch.zeros(total + 512, args.dim, dtype=dt, device=dev)
     gg = torch.Generator(device=dev).manual_seed(8)
     for s in range(0, total, 1 << 22):
         e = min(total, s + (1 << 22))
-        store[s:e] = torch.nn.functional.normalize(torch.randn(e - s, 128, generator=gg, device=dev), dim=1).to(dt)
+        store[s:e] = torch.nn.functional.normalize(torch.randn(e - s, args.dim, generator=gg, device=dev), dim=1).to(dt)
     ranker = ColbertRanker.from_store(store, doclens)
     peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json"))) if os.path.exists(os.path.join(ROOT, "MEASURED_PEAKS.json")) else {}
     hbm_peak, tf_peak = peaks.get("hbm_gbs", 6650.0), peaks.get("bf16_tflops_sustained", 1400.0)
     for nq in [int(x) for x in args.nq.split(",")]:
-        Q = torch.nn.functional.normalize(torch.randn(nq, 32, 128, generator=g), dim=2).to(dev)
+        Q = torch.nn.functional.normalize(torch.randn(nq, args.q_len, args.dim, generator=g), dim=2).to(dev)
         out = torch.empty((nq, args.docs), dtype=torch.float32, device=dev)
         for _ in range(2):
             ranker.score_all(Q)
@@ -60,10 +63,10 @@ def main():
         e2.record()
         torch.cuda.synchronize()
         ms, ms_topk = e0.elapsed_time(e1) / args.iters, e1.elapsed_time(e2) / args.iters
-        gbs = total * 256 / (ms * 1e-3) / 1e9
-        tfl = 2.0 * 32 * nq * 128 * total / (ms * 1e-3) / 1e12
+        gbs = total * args.dim * 2 / (ms * 1e-3) / 1e9
+        tfl = 2.0 * args.q_len * nq * args.dim * total / (ms * 1e-3) / 1e12
         print(json.dumps({"nq": nq, "doclen": args.doclen or "U[20,120]", "dtype": args.dtype, "docs": args.docs,
-                          "tokens": total, "store_gb": total * 256 / 1e9, "ms_score": round(ms, 3), "ms_topk": round(ms_topk, 3),
+                          "dim": args.dim, "q_len": args.q_len, "tokens": total, "store_gb": total * args.dim * 2 / 1e9, "ms_score": round(ms, 3), "ms_topk": round(ms_topk, 3),
                           "docs_scored_per_s": nq * args.docs / ((ms + ms_topk) * 1e-3),
                           "hbm_gbs": round(gbs, 1), "hbm_frac": round(gbs / hbm_peak, 3),
                           "tflops": round(tfl, 1), "tensor_frac_of_sustained": round(tfl / tf_peak, 3)}), flush=True)

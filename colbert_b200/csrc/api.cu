@@ -169,10 +169,10 @@ int make_rows_tensor_map(CUtensorMap* out, const void* base, int64_t rows, int d
   return make_store_tensor_map(out, base, rows, dim, 64, box_rows);
 }
 
-// Packed queries [n_queries, m, dim] seen as {dim, m, n_queries} with a box of {64, 32, 4}: one op brings a K slab of a
-// block of 4 queries as 128 rows ([query][row][64 columns], 128-B swizzle); rows >= m and queries >= n_queries are
-// outside the tensor and arrive as zeros, so nothing has to be padded in memory.
-int make_query_block_tensor_map(CUtensorMap* out, const void* base, int64_t n_queries, int m, int dim) {
+// Packed queries [n_queries, m, dim] seen as {dim, m, n_queries} with a box of {64, rpq, 128 / rpq}: one op brings a K slab
+// of a block of 4 queries x 32 row slots (or 8 x 16) as 128 rows ([query][row][64 columns], 128-B swizzle); rows >= m and
+// queries >= n_queries are outside the tensor and arrive as zeros, so nothing has to be padded in memory.
+int make_query_block_tensor_map(CUtensorMap* out, const void* base, int64_t n_queries, int m, int dim, int rows_per_query) {
   EncodeTiledFn fn = encode_tiled_fn();
   if (!fn) {
     set_error("cuTensorMapEncodeTiled is not available from the installed driver");
@@ -180,7 +180,7 @@ int make_query_block_tensor_map(CUtensorMap* out, const void* base, int64_t n_qu
   }
   const cuuint64_t gdim[3] = {static_cast<cuuint64_t>(dim), static_cast<cuuint64_t>(m), static_cast<cuuint64_t>(n_queries)};
   const cuuint64_t gstride[2] = {static_cast<cuuint64_t>(dim) * 2, static_cast<cuuint64_t>(m) * dim * 2};
-  const cuuint32_t box[3] = {64, 32, 4};
+  const cuuint32_t box[3] = {64, static_cast<cuuint32_t>(rows_per_query), static_cast<cuuint32_t>(128 / rows_per_query)};
   const cuuint32_t estride[3] = {1, 1, 1};
   CUresult r = fn(out, CU_TENSOR_MAP_DATA_TYPE_UINT16, 3, const_cast<void*>(base), gdim, gstride, box, estride,
                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,

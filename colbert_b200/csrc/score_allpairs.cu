@@ -32,7 +32,7 @@
 namespace cbk {
 
 int make_rows_tensor_map(CUtensorMap* out, const void* base, int64_t rows, int dim, int box_rows);
-int make_query_block_tensor_map(CUtensorMap* out, const void* base, int64_t n_queries, int m, int dim);
+int make_query_block_tensor_map(CUtensorMap* out, const void* base, int64_t n_queries, int m, int dim, int rows_per_query);
 
 namespace {
 
@@ -44,7 +44,8 @@ constexpr int kApStageBytes = kApABytes + kApBBytes;
 constexpr int kApThreads = 6 * 32;            // warp 0 TMA producer, warp 1 MMA issuer, warps 2-5 epilogue
 
 struct ApMaps {
-  CUtensorMap q;   // packed queries as {h, m, q}: box {64, 32, 4} = one 128-row block of 4 queries, rows >= m / queries >= q zero-filled
+  CUtensorMap q;   // packed queries as {h, m, q}: box {64, rpq, 128 / rpq} = one 128-row block of 4 queries x 32 row slots (or, for
+                   // m <= 16, 8 queries x 16), rows >= m / queries >= q zero-filled
   CUtensorMap d;   // packed documents as [d*n, h]: box {64, 256}, rows past the end zero-filled
 };
 
@@ -59,7 +60,7 @@ struct ApMaps {
   }
 
 __global__ void __launch_bounds__(kApThreads, 1)
-score_allpairs_fwd_kernel(const __grid_constant__ ApMaps maps, int nq, int m, int nd, int n, int n_slabs, int dpi,
+score_allpairs_fwd_kernel(const __grid_constant__ ApMaps maps, int nq, int m, int rpq, int nd, int n, int n_slabs, int dpi,
                           int n_qblocks, int n_items, uint32_t idesc, float* __restrict__ scores,
                           int32_t* __restrict__ argmax) {
   extern __shared__ uint8_t smem_raw[];
@@ -119,7 +120,7 @@ score_allpairs_fwd_kernel(const __grid_constant__ ApMaps maps, int nq, int m, in
           const uint32_t dst = stage0 + st * kApStageBytes;
           if (elect_one()) {
             mbar_arrive_expect_tx(full, kApStageBytes);
-            tma_load_3d(dst, &maps.q, ks * 64, 0, qb * 4, full, kEvictLast);
+            tma_load_3d(dst, &maps.q, ks * 64, 0, qb * (128 / rpq), full, kEvictLast);
             tma_load_2d(dst + kApABytes, &maps.d, ks * 64, static_cast<int>(row0 + static_cast<int64_t>(t) * kApTileN), full,
                         kEvictNormal);
           }
@@ -164,14 +165,15 @@ score_allpairs_fwd_kernel(const __grid_constant__ ApMaps maps, int nq, int m, in
     }
   } else {
     // ===================================== epilogue (warps 2..5) ====================================
-    const int quad = warp & 3;                                   // TMEM lane quadrant this warp may read = query within the block
-    const uint32_t lane_base = static_cast<uint32_t>(quad * 32) << 16;
+    const int quad = warp & 3;                                   // TMEM lane quadrant this warp may read: 32 accumulator rows =
+    const uint32_t lane_base = static_cast<uint32_t>(quad * 32) << 16;   // one query (rpq = 32) or two (rpq = 16: multi-view shapes)
+    const int row_in_q = lane & (rpq - 1);                       // this lane's query row
     uint32_t acc_it = 0;
     for (int i = blockIdx.x; i < n_items; i += gridDim.x) {
       int d0, nd_i;
       item_docs(i, d0, nd_i);
       const int qb = i % n_qblocks;
-      const int q = qb * 4 + quad;
+      const int q = qb * (128 / rpq) + quad * (32 / rpq) + lane / rpq;     // this lane's query
       const bool write = q < nq;
       const int n_rows = nd_i * n;
       const int n_tiles = (n_rows + kApTileN - 1) / kApTileN;
@@ -222,15 +224,15 @@ score_allpairs_fwd_kernel(const __grid_constant__ ApMaps maps, int nq, int m, in
               CBK_AP_FOLD(__uint_as_float(v[j]), r0 + j);
               if (r0 + j == next_end) {   // warp-uniform: last row of the open document
                 float s = best;
-                s += __shfl_xor_sync(0xffffffffu, s, 16);
+                if (rpq == 32) s += __shfl_xor_sync(0xffffffffu, s, 16);
                 s += __shfl_xor_sync(0xffffffffu, s, 8);
                 s += __shfl_xor_sync(0xffffffffu, s, 4);
                 s += __shfl_xor_sync(0xffffffffu, s, 2);
                 s += __shfl_xor_sync(0xffffffffu, s, 1);
                 if (write) {
                   const int64_t o = static_cast<int64_t>(q) * nd + doc;
-                  if (lane == 0) scores[o] = s;
-                  if (argmax != nullptr && lane < m) argmax[o * m + lane] = bi - (next_end - (n - 1));
+                  if (row_in_q == 0) scores[o] = s;
+                  if (argmax != nullptr && row_in_q < m) argmax[o * m + row_in_q] = bi - (next_end - (n - 1));
                 }
                 ++doc;
                 best = -INFINITY;
@@ -400,18 +402,34 @@ score_allpairs_bwd_dd_kernel(const T* __restrict__ Qp, const int32_t* __restrict
     if (lane == 0) off_s[n] = carry;
   }
   __syncthreads();
-  // ordered fill: the thread that owns bucket b walks every entry in ascending order and appends its own
-  for (int b = tid; b < n; b += kDdThreads) {
-    int pos = off_s[b];
-    if (cnt_s[b] == 0) continue;
-    const uint4* p = reinterpret_cast<const uint4*>(idx_s);
-    for (int e8 = 0; e8 < E8 / 8; ++e8) {
-      const uint4 u = p[e8];
-      const uint32_t w[4] = {u.x, u.y, u.z, u.w};
+  // ordered fill.  Many buckets (n > 64): the thread that owns bucket b walks every entry in ascending order and appends its
+  // own.  Few buckets (multi-view shapes, n = d_view): one warp per bucket walks the entries 32 at a time and compacts the
+  // matches with a ballot — still ascending, and every thread of the CTA is busy instead of n of them.
+  if (n > 64) {
+    for (int b = tid; b < n; b += kDdThreads) {
+      int pos = off_s[b];
+      if (cnt_s[b] == 0) continue;
+      const uint4* p = reinterpret_cast<const uint4*>(idx_s);
+      for (int e8 = 0; e8 < E8 / 8; ++e8) {
+        const uint4 u = p[e8];
+        const uint32_t w[4] = {u.x, u.y, u.z, u.w};
 #pragma unroll
-      for (int k = 0; k < 4; ++k) {
-        if (static_cast<int>(w[k] & 0xffffu) == b) list_s[pos++] = static_cast<uint16_t>(e8 * 8 + 2 * k);
-        if (static_cast<int>(w[k] >> 16) == b) list_s[pos++] = static_cast<uint16_t>(e8 * 8 + 2 * k + 1);
+        for (int k = 0; k < 4; ++k) {
+          if (static_cast<int>(w[k] & 0xffffu) == b) list_s[pos++] = static_cast<uint16_t>(e8 * 8 + 2 * k);
+          if (static_cast<int>(w[k] >> 16) == b) list_s[pos++] = static_cast<uint16_t>(e8 * 8 + 2 * k + 1);
+        }
+      }
+    }
+  } else {
+    for (int b = warp; b < n; b += kDdThreads / 32) {
+      int pos = off_s[b];
+      if (cnt_s[b] == 0) continue;
+      for (int e0 = 0; e0 < E8; e0 += 32) {
+        const int e = e0 + lane;
+        const bool hit = e < E8 && static_cast<int>(idx_s[e]) == b;
+        const uint32_t mask = __ballot_sync(0xffffffffu, hit);
+        if (hit) list_s[pos + __popc(mask & ((1u << lane) - 1u))] = static_cast<uint16_t>(e);
+        pos += __popc(mask);
       }
     }
   }
@@ -469,11 +487,13 @@ int docs_per_item(int nd, int n) {
 int score_allpairs_fwd_dispatch(const void* d_Qp, const void* d_Dp, int dtype, int64_t nq, int m, int64_t nd, int n, int dim,
                                 float* d_scores, int32_t* d_argmax, cudaStream_t stream) {
   ApMaps maps;
-  int rc = make_query_block_tensor_map(&maps.q, d_Qp, nq, m, dim);
+  const int rpq = m <= 16 ? 16 : 32;                  // accumulator rows per query: short (multi-view) queries share a quadrant
+  int rc = make_query_block_tensor_map(&maps.q, d_Qp, nq, m, dim, rpq);
   if (rc != CBK_OK) return rc;
   rc = make_rows_tensor_map(&maps.d, d_Dp, nd * n, dim, kApTileN);
   if (rc != CBK_OK) return rc;
-  const int n_qblocks = static_cast<int>((nq + 3) / 4);
+  const int qpb = 128 / rpq;
+  const int n_qblocks = static_cast<int>((nq + qpb - 1) / qpb);
   const int dpi = docs_per_item(static_cast<int>(nd), n);
   const int n_ranges = static_cast<int>((nd + dpi - 1) / dpi);
   const int64_t n_items64 = static_cast<int64_t>(n_ranges) * n_qblocks;
@@ -484,7 +504,7 @@ int score_allpairs_fwd_dispatch(const void* d_Qp, const void* d_Dp, int dtype, i
   const size_t smem = 1024 + static_cast<size_t>(kApStages) * kApStageBytes;
   CBK_CUDA(cudaFuncSetAttribute(score_allpairs_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
   const int grid = std::min(n_items, sm_count());
-  score_allpairs_fwd_kernel<<<grid, kApThreads, smem, stream>>>(maps, static_cast<int>(nq), m, static_cast<int>(nd), n, dim / 64, dpi,
+  score_allpairs_fwd_kernel<<<grid, kApThreads, smem, stream>>>(maps, static_cast<int>(nq), m, rpq, static_cast<int>(nd), n, dim / 64, dpi,
                                                               n_qblocks, n_items, idesc, d_scores, d_argmax);
   CBK_CUDA(cudaGetLastError());
   count_launch();

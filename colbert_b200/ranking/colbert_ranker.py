@@ -279,11 +279,22 @@ class ColbertRanker:
 
     def score_all(self, Q: torch.Tensor) -> torch.Tensor:
         """fp32 ``[B, n_docs]``: every document of this store against every query (``Q`` ``[B, q_len ≤ 32, dim]``
-        fp32 on the device) — the query-batched tcgen05 kernel.  The kernel walks the
-        store row by row, so documents without rows are taken out first and get the score the reference gives
-        them (0, see tests/test_oracle_properties.py)."""
+        fp32 on the device) — the query-batched tcgen05 kernel (dim 128), or, for a fixed-length
+        fp16 store at another width (multi-view index, dim = 64 k up to 1024), the all-pairs kernel over the store seen as a
+        padded batch.  The dim-128 kernel walks the store row by row, so documents without rows are taken out first and
+        get the score the reference gives them (0, see tests/test_oracle_properties.py)."""
         if int(self.doclens.max()) == 0:
             return torch.zeros((Q.size(0), self.doclens.numel()), dtype=torch.float32, device=self.device)
+        d = getattr(self, "_doclen_const", 0)
+        if (self.dim != 128 and d and self.strides == [d] and self.tensor.dtype == torch.float16
+                and kernels.score_allpairs_supported(Q.size(1), self.dim)):
+            # A fixed-length (multi-view) store at a wide width — the author's 16 views x 768: the flat store IS the padded
+            # batch [n_docs, d_view, dim] of BaseModel.score, so the tcgen05 all-pairs kernel scores it in place (no floor can
+            # apply: the single stride is the document length).  The query is rounded to fp16 as everywhere else.
+            n_docs = int(self.doclens.numel())
+            Qp = kernels.mask_cast_rows(Q.reshape(-1, self.dim), None, torch.float16).reshape(Q.size(0), Q.size(1), self.dim)
+            Dp = self.tensor[: n_docs * d].view(n_docs, d, self.dim)
+            return kernels.score_allpairs_fwd(Qp, Dp, want_argmax=False)[0]
         if getattr(self, "_doc_end_bits", None) is None:
             nonempty = self.doclens > 0
             if bool(nonempty.all()):

@@ -156,3 +156,30 @@ def test_exhaustive_tiny_corpora(n_docs):
     assert np.abs(got - ref).max() <= SCORE_RTOL * max(1.0, np.abs(ref).max())
     pids, scores = ranker.rank_exhaustive(torch.from_numpy(Q), k=1000)
     assert pids.shape == (3, n_docs) and sorted(pids[0].tolist()) == list(range(n_docs))
+
+
+@pytest.mark.parametrize("dim,d_view,q_view", [(768, 16, 16), (256, 8, 8), (512, 16, 32)])
+def test_exhaustive_on_a_wide_multiview_store(dim, d_view, q_view):
+    """a fixed-length fp16 store at the author's un-projected width: score_all / rank_exhaustive run the all-pairs tcgen05
+    kernel over the store seen as [n_docs, d_view, dim]"""
+    import numpy as np
+    import torch
+    from colbert_b200 import synthetic
+    from colbert_b200.ranking import ColbertRanker
+    from oracle import maxsim_oracle as O
+    from parity_utils import SCORE_RTOL, check_topk
+    dev = torch.device("cuda", 0)
+    n_docs, nq, k = 3001, 5, 50
+    index = synthetic.make_index(2100 + dim, n_docs, dim=dim, doclens=np.full(n_docs, d_view, dtype=np.int64))
+    ranker = ColbertRanker.from_tensors(torch.from_numpy(index.emb), index.doclens.tolist(), device=dev)
+    Q = synthetic.make_queries(2101, nq, q_view, dim)
+    dense = ranker.score_all(torch.from_numpy(Q).to(dev)).cpu().numpy()
+    assert dense.shape == (nq, n_docs)
+    store, pf = O.pad_store(index.emb), O.doclens_pfxsum(index.doclens)
+    pids_all = np.arange(n_docs, dtype=np.int64)
+    p, s = ranker.rank_exhaustive(torch.from_numpy(Q), k=k)
+    for b in range(nq):
+        ref = O.maxsim_exact(store, index.doclens, pf, ranker.strides, Q[b], pids_all)
+        assert (np.abs(dense[b] - ref) / np.maximum(np.abs(ref), 1.0)).max() <= SCORE_RTOL
+        rp, rs = O.topk_desc(ref, pids_all, k)
+        check_topk(p[b].cpu().numpy(), s[b].cpu().numpy(), rp, rs, SCORE_RTOL, *O.topk_desc(ref, pids_all, None))
