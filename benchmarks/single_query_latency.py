@@ -67,7 +67,22 @@ def main():
     e1.record()
     torch.cuda.synchronize()
     kern_ms = e0.elapsed_time(e1) / args.iters
+    # the CUDA-graph low-batch entry (H2D + MaxSim + top-k + D2H replayed as one graph): 1 and 8 queries per call
+    from colbert_b200.ranking.pipeline import GraphedRerank
+    graph_ms = {}
+    for b in (1, 8):
+        g = GraphedRerank(ranker, batch=b, q_len=32, n_cand=args.cands, depth=10)
+        Qb = torch.from_numpy(Q[:b])
+        Cb = torch.from_numpy(np.stack([cand[i] for i in range(b)]))
+        for _ in range(10):
+            g(Qb, Cb)
+        t0 = time.perf_counter()
+        for _ in range(args.iters):
+            g(Qb, Cb)
+        graph_ms[b] = (time.perf_counter() - t0) / args.iters * 1e3
     print(json.dumps({"call": "rank_forward(Q[1,128,32], 1000 pids, depth=10)", "gpu_ms_per_call": round(gpu_ms, 4),
+                      "graphed_rerank_ms_per_call_batch1": round(graph_ms[1], 4),
+                      "graphed_rerank_ms_per_call_batch8": round(graph_ms[8], 4),
                       "gpu_ms_per_call_dim_major_q": round(gpu_dm_ms, 4), "gpu_ms_per_call_general_path": round(gpu_general_ms, 4),
                       "gpu_maxsim_kernel_ms": round(kern_ms, 4),
                       "cpu_reference": "python bench.py --impl reference  (candidates/s of the CPU port; 1000 / value = s per call)"}))
