@@ -25,6 +25,7 @@
 // cuts it into tiles and publishes one descriptor per tile in a shared-memory ring; every other role reads descriptors —
 // walking the candidates in each role cost the issuer ~2000 cycles per tile on its critical path.
 #include <algorithm>
+#include <cstdlib>
 
 #include "umma.cuh"
 
@@ -190,7 +191,7 @@ maxsim_wide_stream_kernel(const __grid_constant__ WsMaps maps, const int64_t* __
                           int64_t n_docs, int64_t pid_base, int skip_foreign, WsStrides strides, const float* __restrict__ Q,
                           const int32_t* __restrict__ q_lens, int q_len, int dim, int64_t n_queries,
                           const int64_t* __restrict__ cand_pids, const int64_t* __restrict__ rowptr, int64_t n_cand_bound,
-                          int n_stages, uint32_t idesc, float* __restrict__ out) {
+                          int n_stages, uint32_t idesc, float* __restrict__ out, int probe_stream_only) {
   extern __shared__ uint8_t smem_raw[];
   __shared__ __align__(8) uint64_t bar_full[kWsMaxStages], bar_empty[kWsMaxStages];
   __shared__ __align__(8) uint64_t bar_acc_full[2], bar_acc_empty[2], bar_a_full, bar_a_free;
@@ -433,6 +434,12 @@ maxsim_wide_stream_kernel(const __grid_constant__ WsMaps maps, const int64_t* __
         mbar_wait(smem_u32(&bar_acc_full[slot]), (t >> 1) & 1u);
         umma::fence_after_sync();
         const uint32_t t_addr = tmem + lane_base + slot * kWsTileCols;
+        if (probe_stream_only) {        // CBK_WS_PROBE=1: what gather + MMA sustain without the epilogue arithmetic (scores are not written)
+          umma::fence_before_sync();
+          __syncwarp();
+          if (lane == 0) mbar_arrive(smem_u32(&bar_acc_empty[slot]));
+          continue;
+        }
         float closed = 0.f;             // value warps, lane j: sum over my 16 query rows of piece j, if piece j closes a document
         // the residual products travel through shared memory eight pieces (128 columns) at a time
 #pragma unroll 1
@@ -516,6 +523,9 @@ maxsim_wide_stream_kernel(const __grid_constant__ WsMaps maps, const int64_t* __
 // widths 256 … 768 in steps of 64 (the query region takes dim/64 × 8 KB of shared memory; beyond 768 too little is left for
 // the ring and the K-split kernel serves), queries of at most 32 rows
 bool rerank_wide_stream_supports(int dim, int q_len, int flags) {
+  // (dim 128 stays with the per-warp mma.sync kernel of rerank.cu: measured there, this structure reaches 0.30 of the copy
+  //  peak — 0.75 with the epilogue arithmetic switched off — against 0.97: at 256 B per row the per-piece work of the
+  //  planner, the producers and the single epilogue warp pair outweighs the bytes)
   return dim % 64 == 0 && dim >= 256 && dim <= 768 && q_len <= 32 &&
          !(flags & (CBK_FLAG_BF16_NATIVE_MMA | CBK_FLAG_RERANK_GENERIC | CBK_FLAG_RERANK_KSPLIT));
 }
@@ -551,18 +561,19 @@ int rerank_wide_stream_dispatch(const void* d_store, int store_dtype, int64_t n_
   // a candidate is at least one piece; ranges shorter than a few tiles are not worth a CTA
   const int grid = static_cast<int>(std::max<int64_t>(1, std::min<int64_t>(sm_count(), (n_cand_total + 31) / 32)));
   const int skip = (flags & CBK_FLAG_SKIP_FOREIGN_PIDS) ? 1 : 0;
+  static const int probe = std::getenv("CBK_WS_PROBE") != nullptr;          // profiling aid, never set in production
   if (bf16) {
     CBK_CUDA(cudaFuncSetAttribute(maxsim_wide_stream_kernel<__nv_bfloat16, true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                   static_cast<int>(smem)));
     maxsim_wide_stream_kernel<__nv_bfloat16, true><<<grid, kWsThreads, smem, stream>>>(
         maps, d_pfxsum, d_doclens, n_docs, pid_base, skip, ss, d_Q, d_q_lens, q_len, dim, n_queries, d_cand_pids, d_cand_rowptr,
-        n_cand_total, n_stages, idesc, d_out_scores);
+        n_cand_total, n_stages, idesc, d_out_scores, probe);
   } else {
     CBK_CUDA(cudaFuncSetAttribute(maxsim_wide_stream_kernel<__half, false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                   static_cast<int>(smem)));
     maxsim_wide_stream_kernel<__half, false><<<grid, kWsThreads, smem, stream>>>(
         maps, d_pfxsum, d_doclens, n_docs, pid_base, skip, ss, d_Q, d_q_lens, q_len, dim, n_queries, d_cand_pids, d_cand_rowptr,
-        n_cand_total, n_stages, idesc, d_out_scores);
+        n_cand_total, n_stages, idesc, d_out_scores, probe);
   }
   CBK_CUDA(cudaGetLastError());
   count_launch();
