@@ -16,11 +16,16 @@
 //   * tcgen05.mma M = 64, N = 256 into one of two 256-column TMEM accumulators (N = 256 halves the MMAs issued per byte:
 //     one issuing warp sustains an MMA every ~88 cycles, and with N = 128 that, not HBM, set the pace); accumulator row m lives in TMEM lane
 //     (m mod 16) + 32·(m div 16): quadrant w holds query rows 16 w … (w = 0, 1) and their residual products (w = 2, 3);
-//   * epilogue: warp w + 2 passes the residual products through shared memory to warp w, which folds each piece's valid
-//     columns into a running maximum per query row, and at a document's last piece applies the zero floor (doclen ∉ strides,
-//     SURVEY.md §8 a12'), adds up its 16 rows and — together with the other half of the query rows — writes the score at
-//     the candidate's own position.
-// Warp roles: 0–3 epilogue · 4 MMA issuer · 5 query loader · 6–9 TMA producers · 10 planner.  The planner walks the CTA's
+//   * epilogue: FOUR teams of up to four warps (one per TMEM quadrant); team k owns the documents whose running number is
+//     k mod 4, so a document's running maximum never leaves one warp while four documents are folded at a time (with a single
+//     team the epilogue, not HBM, set the pace below dim 768: 0.58 of the copy peak at dim 256, 0.96 with the arithmetic
+//     switched off).  In a team, the warp of quadrant w + 2 passes the residual products of a piece to the warp of quadrant w
+//     through a two-slot shared-memory buffer guarded by mbarriers; that warp folds the piece's valid columns into the running
+//     maximum per query row and, at a document's last piece, applies the zero floor (doclen ∉ strides, SURVEY.md §8 a12'),
+//     adds up its 16 rows and adds the sum to the score at the candidate's own position (two commutative additions into a
+//     zeroed score when the query has more than 16 rows: bit-reproducible).
+// Warp roles: 0–15 epilogue (quadrant = warp mod 4, team = warp div 4) · 16 MMA issuer · 17 query loader · 18–21 TMA
+// producers · 22 planner.  The planner walks the CTA's
 // contiguous candidate range (CandWalker: 32 candidates' metadata fetched at a time, one per lane, the next 32 prefetched),
 // cuts it into tiles and publishes one descriptor per tile in a shared-memory ring; every other role reads descriptors —
 // walking the candidates in each role cost the issuer ~2000 cycles per tile on its critical path.
@@ -42,9 +47,12 @@ constexpr int kWsStageBytes = kWsTilePieces * kWsSlotBytes;       // 32 KB
 constexpr int kWsTileCols = kWsTilePieces * kWsPieceRows;         // 256 accumulator columns
 constexpr int kWsASlabBytes = 64 * 128;
 constexpr int kWsProducers = 4;
-constexpr int kWsIssuerWarp = 4, kWsLoaderWarp = 5, kWsProducer0 = 6, kWsPlannerWarp = kWsProducer0 + kWsProducers;
+constexpr int kWsTeams = 4;                                       // epilogue teams: documents are dealt round-robin to them
+constexpr int kWsEpiWarps = 4 * kWsTeams;
+constexpr int kWsIssuerWarp = kWsEpiWarps, kWsLoaderWarp = kWsEpiWarps + 1, kWsProducer0 = kWsEpiWarps + 2,
+              kWsPlannerWarp = kWsProducer0 + kWsProducers;
 constexpr int kWsThreads = (kWsPlannerWarp + 1) * 32;
-constexpr int kWsLoBufBytes = 2 * 128 * 16 * 4;                   // residual products of HALF a tile: [pair][column][row] fp32
+constexpr int kWsLoBufBytes = 2 * kWsTeams * 2 * 16 * 16 * 4;     // residual products: [query-row half][team][slot][column][row] fp32
 constexpr int kWsMaxStages = 6;
 constexpr int kWsDescRing = 8;
 
@@ -57,7 +65,8 @@ struct WsDesc {
   int len[kWsTilePieces];
   int64_t cand[kWsTilePieces];
   uint8_t v[kWsTilePieces];
-  uint8_t flags[kWsTilePieces];       // bit 0 first piece, bit 1 last piece of its document, bit 2 the zero floor applies
+  uint8_t flags[kWsTilePieces];       // bit 0 first piece, bit 1 last piece of its document, bit 2 the zero floor applies,
+                                      // bits 3-4 the epilogue team that owns the document
 };
 
 struct WsMaps {
@@ -94,6 +103,7 @@ struct CandWalker {
   int64_t q, q_end;                 // query of the candidate being cut
   int64_t cur_c, cur_q;
   int cur_row, cur_len, cur_left;   // cur_left > 0: a document is being cut
+  int doc_seq;                      // documents cut so far (the open one included): deals them to the epilogue teams
 
   __device__ __forceinline__ void fetch(int lane, int64_t c0, int& row, int& len, int& n) {
     n = static_cast<int>(max(static_cast<int64_t>(0), min(static_cast<int64_t>(32), c_hi - c0)));
@@ -118,7 +128,7 @@ struct CandWalker {
     q = a;
     q_end = rp[q + 1];
     win_c0 = lo; win_n = 0; pos = 0;
-    cur_left = 0; cur_c = -1; cur_q = -1; cur_row = 0; cur_len = 0;
+    cur_left = 0; cur_c = -1; cur_q = -1; cur_row = 0; cur_len = 0; doc_seq = 0;
     nxt_c0 = lo;
     fetch(lane, lo, nxt_row, nxt_len, nxt_n);
     c_fetch = lo + 32;
@@ -153,6 +163,7 @@ struct CandWalker {
           q_end = rowptr[q + 1];
         }
         cur_c = c; cur_q = q; cur_row = row; cur_len = len; cur_left = len;
+        ++doc_seq;
       }
       if (n > 0 && cur_q != tile_q) break;       // the tile closes at a query boundary; the document stays pending
       tile_q = cur_q;
@@ -160,7 +171,7 @@ struct CandWalker {
       if (lane == n) {
         pc.row = cur_row + (cur_len - cur_left);
         pc.v = v;
-        pc.flags = (cur_left == cur_len ? 1 : 0) | (cur_left <= kWsPieceRows ? 2 : 0);
+        pc.flags = (cur_left == cur_len ? 1 : 0) | (cur_left <= kWsPieceRows ? 2 : 0) | ((doc_seq & (kWsTeams - 1)) << 3);
         pc.len = cur_len;
         pc.cand = cur_c;
       }
@@ -197,13 +208,13 @@ maxsim_wide_stream_kernel(const __grid_constant__ WsMaps maps, const int64_t* __
   __shared__ __align__(8) uint64_t bar_acc_full[2], bar_acc_empty[2], bar_a_full, bar_a_free;
   __shared__ __align__(8) uint64_t bar_desc_full[kWsDescRing], bar_desc_empty[kWsDescRing];
   __shared__ __align__(16) WsDesc descs[kWsDescRing];
+  __shared__ __align__(8) uint64_t bar_lo_ready[2 * kWsTeams][2], bar_lo_free[2 * kWsTeams][2];   // [half * teams + team][slot]
   __shared__ uint32_t tmem_base_smem;
-  __shared__ float half_sum[kWsTilePieces];      // warp 1 → warp 0: sums over query rows 16-31 of the pieces that close a document
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int n_slabs = dim >> 6;
   const bool two_halves = q_len > 16;            // query rows 16-31 exist: quadrant 1 (and 3) take part
-  const uint32_t epi_warps = (two_halves ? 2u : 1u) * (kHasLo ? 2u : 1u);
+  const uint32_t epi_warps = kWsTeams * (two_halves ? 2u : 1u) * (kHasLo ? 2u : 1u);
   const uint32_t a_addr = (smem_u32(smem_raw) + 1023u) & ~1023u;
   const uint32_t b_addr = a_addr + static_cast<uint32_t>(n_slabs) * kWsASlabBytes;
   uint8_t* const smem_al = smem_raw + (a_addr - smem_u32(smem_raw));
@@ -225,6 +236,11 @@ maxsim_wide_stream_kernel(const __grid_constant__ WsMaps maps, const int64_t* __
     }
     mbar_init(smem_u32(&bar_a_full), 1);
     mbar_init(smem_u32(&bar_a_free), 1);
+    for (int i = 0; i < 2 * kWsTeams; ++i)
+      for (int sl = 0; sl < 2; ++sl) {
+        mbar_init(smem_u32(&bar_lo_ready[i][sl]), 1);
+        mbar_init(smem_u32(&bar_lo_free[i][sl]), 1);
+      }
     fence_mbar_init();
   }
   if (warp == kWsIssuerWarp) {
@@ -408,16 +424,20 @@ maxsim_wide_stream_kernel(const __grid_constant__ WsMaps maps, const int64_t* __
       ++n_q_seen;
     }
   } else {
-    // ===================================== epilogue (warps 0..3) ====================================
-    // warp w < 2: TMEM quadrant w = query rows 16 w … 16 w + 15; warp w + 2: the residual products of the same rows
-    const bool is_lo = warp >= 2;
-    const int half = warp & 1;
+    // ===================================== epilogue (warps 0..15) ===================================
+    // quadrant qd = warp % 4: qd < 2 holds query rows 16 qd … 16 qd + 15, qd + 2 the residual products of the same rows;
+    // team = warp / 4 owns the documents whose running number is team (mod 4)
+    const int qd = warp & 3, team = warp >> 2;
+    const bool is_lo = qd >= 2;
+    const int half = qd & 1;
     const bool active = (half == 0 || two_halves) && (!is_lo || kHasLo);
     if (active) {
-      const uint32_t lane_base = static_cast<uint32_t>(warp * 32) << 16;
-      float* const my_lo = lo_buf + half * (128 * 16);
-      const int bar_a = 1 + 2 * half, bar_b = 2 + 2 * half;     // named barriers of the (value, residual) warp pair
-      float rmax = -INFINITY;                                   // running maximum of the open document, per query row
+      const uint32_t lane_base = static_cast<uint32_t>(qd * 32) << 16;
+      const int pair = half * kWsTeams + team;
+      float* const my_lo = lo_buf + pair * (2 * 16 * 16);          // two slots of [column][row]
+      const uint32_t ready0 = smem_u32(&bar_lo_ready[pair][0]), free0 = smem_u32(&bar_lo_free[pair][0]);
+      uint32_t n_mine = 0;                                      // my pieces so far: slot = n_mine & 1, phase = n_mine >> 1
+      float rmax = -INFINITY;                                   // running maximum of my open document, per query row
       for (uint32_t t = 0;; ++t) {
         const WsDesc* d = desc_wait(t);
         const int n = d->n;
@@ -430,49 +450,44 @@ maxsim_wide_stream_kernel(const __grid_constant__ WsMaps maps, const int64_t* __
         }
         desc_release(t);
         if (n == 0) break;
+        uint32_t mine = __ballot_sync(0xffffffffu, lane < n && ((my_flags >> 3) & (kWsTeams - 1)) == team);
         const uint32_t slot = t & 1u;
         mbar_wait(smem_u32(&bar_acc_full[slot]), (t >> 1) & 1u);
         umma::fence_after_sync();
         const uint32_t t_addr = tmem + lane_base + slot * kWsTileCols;
-        if (probe_stream_only) {        // CBK_WS_PROBE=1: what gather + MMA sustain without the epilogue arithmetic (scores are not written)
-          umma::fence_before_sync();
-          __syncwarp();
-          if (lane == 0) mbar_arrive(smem_u32(&bar_acc_empty[slot]));
-          continue;
-        }
-        float closed = 0.f;             // value warps, lane j: sum over my 16 query rows of piece j, if piece j closes a document
-        // the residual products travel through shared memory eight pieces (128 columns) at a time
-#pragma unroll 1
-        for (int j0 = 0; j0 < n; j0 += 8) {
-          const int j1 = min(n, j0 + 8);
-          if (is_lo) {
-#pragma unroll 1
-            for (int j = j0; j < j1; ++j) {
-              uint32_t v[16];
-              umma::tmem_ld_32x16(t_addr + j * 16, v);
-              umma::tmem_ld_wait();
-              if (lane < 16) {
-#pragma unroll
-                for (int i = 0; i < 16; ++i) my_lo[((j - j0) * 16 + i) * 16 + lane] = __uint_as_float(v[i]);
-              }
-            }
-            asm volatile("bar.sync %0, 64;" ::"r"(bar_a) : "memory");     // these residual products are in my_lo
-            asm volatile("bar.sync %0, 64;" ::"r"(bar_b) : "memory");     // the value warp has read them
-            continue;
-          }
-          if (kHasLo) asm volatile("bar.sync %0, 64;" ::"r"(bar_a) : "memory");
-#pragma unroll 1
-          for (int j = j0; j < j1; ++j) {
+        if (!probe_stream_only) {       // (CBK_WS_PROBE=1: what gather + MMA sustain without the epilogue arithmetic)
+          while (mine) {
+            const int j = __ffs(mine) - 1;
+            mine &= mine - 1u;
             uint32_t v[16];
             umma::tmem_ld_32x16(t_addr + j * 16, v);
             umma::tmem_ld_wait();
+            const uint32_t sl = n_mine & 1u, ph = (n_mine >> 1) & 1u;
+            ++n_mine;
+            if (is_lo) {
+              // residual products of this piece → slot sl, once the value warp has read what was there two pieces ago
+              mbar_wait(free0 + 8 * sl, ph ^ 1u);
+              if (lane < 16) {
+#pragma unroll
+                for (int i = 0; i < 16; ++i) my_lo[(sl * 16 + i) * 16 + lane] = __uint_as_float(v[i]);
+              }
+              __syncwarp();
+              if (lane == 0) mbar_arrive(ready0 + 8 * sl);
+              continue;
+            }
             const int pv = __shfl_sync(0xffffffffu, my_v, j);
             const int pf = __shfl_sync(0xffffffffu, my_flags, j);
             float x[16];
 #pragma unroll
-            for (int i = 0; i < 16; ++i) {
-              x[i] = __uint_as_float(v[i]);
-              if (kHasLo && lane < 16) x[i] += my_lo[((j - j0) * 16 + i) * 16 + lane];
+            for (int i = 0; i < 16; ++i) x[i] = __uint_as_float(v[i]);
+            if (kHasLo) {
+              mbar_wait(ready0 + 8 * sl, ph);
+              if (lane < 16) {
+#pragma unroll
+                for (int i = 0; i < 16; ++i) x[i] += my_lo[(sl * 16 + i) * 16 + lane];
+              }
+              __syncwarp();
+              if (lane == 0) mbar_arrive(free0 + 8 * sl);
             }
             float m;
             if (pv == kWsPieceRows) {     // a full piece (all but the last of a document): plain max tree
@@ -490,25 +505,18 @@ maxsim_wide_stream_kernel(const __grid_constant__ WsMaps maps, const int64_t* __
               sum += __shfl_xor_sync(0xffffffffu, sum, 4);
               sum += __shfl_xor_sync(0xffffffffu, sum, 2);
               sum += __shfl_xor_sync(0xffffffffu, sum, 1);
-              const float sc = __shfl_sync(0xffffffffu, sum, 0);
-              if (lane == j) closed = sc;
+              const int64_t cand = __shfl_sync(0xffffffffu, my_cand, j);
+              if (lane == 0) {
+                if (two_halves) atomicAdd(out + cand, sum);      // two commutative additions into a zeroed score
+                else out[cand] = sum;
+              }
             }
           }
-          if (kHasLo) asm volatile("bar.sync %0, 64;" ::"r"(bar_b) : "memory");
         }
-        // every column of the slot has been read: hand it back to the MMA warp
+        // every column I needed has been read: hand the slot back to the MMA warp
         umma::fence_before_sync();
         __syncwarp();
         if (lane == 0) mbar_arrive(smem_u32(&bar_acc_empty[slot]));
-        if (is_lo) continue;
-        // the two halves of the query rows meet in shared memory; warp 0 writes the score at the candidate's position
-        if (two_halves) {
-          if (warp == 1 && lane < n) half_sum[lane] = closed;
-          asm volatile("bar.sync 5, 64;" ::: "memory");
-          if (warp == 0 && lane < n) closed += half_sum[lane];
-          asm volatile("bar.sync 6, 64;" ::: "memory");
-        }
-        if (warp == 0 && lane < n && (my_flags & 2)) out[my_cand] = closed;
       }
     }
   }
@@ -562,6 +570,7 @@ int rerank_wide_stream_dispatch(const void* d_store, int store_dtype, int64_t n_
   const int grid = static_cast<int>(std::max<int64_t>(1, std::min<int64_t>(sm_count(), (n_cand_total + 31) / 32)));
   const int skip = (flags & CBK_FLAG_SKIP_FOREIGN_PIDS) ? 1 : 0;
   static const int probe = std::getenv("CBK_WS_PROBE") != nullptr;          // profiling aid, never set in production
+  if (q_len > 16) CBK_CUDA(cudaMemsetAsync(d_out_scores, 0, static_cast<size_t>(n_cand_total) * sizeof(float), stream));
   if (bf16) {
     CBK_CUDA(cudaFuncSetAttribute(maxsim_wide_stream_kernel<__nv_bfloat16, true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                   static_cast<int>(smem)));
