@@ -163,3 +163,22 @@ def test_wide_stream_long_documents_and_many_queries():
         for b in range(0, n_q, 11):
             ref = O.maxsim_exact(store, index.doclens, pf, ranker.strides, Q[b], cand[b])
             assert (np.abs(got[b * n_c:(b + 1) * n_c] - ref) / np.maximum(np.abs(ref), 1.0)).max() <= SCORE_RTOL, (dt, b)
+
+
+def test_wide_stream_scores_are_bit_reproducible():
+    """q_len > 16: the two halves of the query rows are ADDED into a zeroed score (two commutative additions) — the result
+    must not depend on which epilogue team gets there first"""
+    from colbert_b200 import synthetic
+    from colbert_b200.ranking import ColbertRanker
+    dim, n_docs, n_q, n_c = 384, 2000, 64, 200
+    rng = np.random.default_rng(1700)
+    doclens = rng.integers(1, 181, size=n_docs).astype(np.int64)
+    index = synthetic.make_index(1701, n_docs, dim=dim, doclens=doclens)
+    emb = torch.from_numpy(index.emb).to(torch.bfloat16)
+    ranker = ColbertRanker.from_tensors(emb, index.doclens.tolist(), device=DEV, store_dtype=torch.bfloat16)
+    Q = torch.from_numpy(synthetic.make_queries(1702, n_q, 32, dim)).to(DEV)
+    cand = torch.from_numpy(rng.integers(0, n_docs, size=n_q * n_c).astype(np.int64)).to(DEV)
+    rowptr = torch.arange(0, (n_q + 1) * n_c, n_c, dtype=torch.int64, device=DEV)
+    a = ranker.score_candidates(Q, cand, rowptr).clone()
+    for _ in range(3):
+        assert torch.equal(a, ranker.score_candidates(Q, cand, rowptr))
