@@ -474,8 +474,8 @@ def secondary_multiview(torch, sampler, dev, args, cand_dev, rowptr, d_view, q_v
            "value": n_cand * steps / (ms_total * 1e-3), "unit": UNIT, "steps": steps, "ms_per_step": ms_total / steps,
            "roofline": {"bound": "hbm", "achieved": achieved, "peak": peaks["hbm_gbs"], "unit": "GB/s",
                         "frac": achieved / peaks["hbm_gbs"], "kernel_ms": kern_ms, "algorithmic_bytes_per_launch": algo,
-                        "kernel": (("maxsim_mv_wide_kernel (tcgen05 streaming, fixed 16-row documents)" if d_view else
-                                    "maxsim_wide_stream_kernel (tcgen05 streaming, ragged documents)") if dim != 128 else
+                        "kernel": (("maxsim_wide_stream_kernel (tcgen05 streaming, fixed 16-row documents: no metadata lookups)"
+                                    if d_view else "maxsim_wide_stream_kernel (tcgen05 streaming, ragged documents)") if dim != 128 else
                                    "maxsim_rerank_kernel" + (" (multi-view instantiation)" if d_view else "")), "traffic": None},
            "clocks": sampler.window(*win)}
     del store, ranker

@@ -41,9 +41,6 @@ bool rerank_wide_stream_supports(int, int, int);
 int rerank_wide_stream_dispatch(const void*, int, int64_t, int, const int64_t*, const int32_t*, int64_t, int64_t, const int32_t*, int,
                                 const float*, const int32_t*, int, int64_t, const int64_t*, const int64_t*, int64_t, float*, int,
                                 cudaStream_t);
-bool rerank_mv_wide_supports(int, int, const int32_t*, int, int);
-int rerank_mv_wide_dispatch(const void*, int, int64_t, int, int64_t, int64_t, const float*, const int32_t*, int, int64_t, const int64_t*,
-                            const int64_t*, int64_t, float*, int, cudaStream_t);
 int rerank_umma_dispatch(const void*, int, int64_t, int, const int64_t*, const int32_t*, int64_t, int64_t, const int32_t*, int,
                          const float*, const int32_t*, int, int64_t, const int64_t*, const int64_t*, int64_t, float*, void*, int, cudaStream_t);
 int mask_cast_dispatch(const void*, int, int64_t, int, const void*, int, void*, int, cudaStream_t);
@@ -232,7 +229,8 @@ int cbk_maxsim_rerank(const void* d_store, int store_dtype, int64_t n_store_rows
                       int q_len, int64_t n_queries, const int64_t* d_cand_pids, const int64_t* d_cand_rowptr,
                       int64_t n_cand_total, float* d_out_scores, void* d_workspace, size_t workspace_bytes,
                       int flags, void* stream) {
-  const bool fixed_len = (flags & CBK_FLAG_FIXED_DOCLEN) && n_strides == 1 && dim == 128;   // metadata arrays unused
+  const bool fixed_len = (flags & CBK_FLAG_FIXED_DOCLEN) && n_strides == 1 &&
+                         (dim == 128 || rerank_wide_stream_supports(dim, q_len, flags));   // metadata arrays unused
   CBK_CHECK_ARG(d_store && (fixed_len || (d_pfxsum && d_doclens)) && d_Q && d_cand_pids && d_cand_rowptr && d_out_scores,
                 "cbk_maxsim_rerank: null pointer argument");
   CBK_CHECK_ARG(store_dtype == CBK_F16 || store_dtype == CBK_BF16, "cbk_maxsim_rerank: unknown store dtype %d", store_dtype);
@@ -255,11 +253,6 @@ int cbk_maxsim_rerank(const void* d_store, int store_dtype, int64_t n_store_rows
   int rc = check_device();
   if (rc != CBK_OK) return rc;
   if (n_cand_total == 0) return CBK_OK;
-  if (rerank_mv_wide_supports(dim, q_len, strides, n_strides, flags) && !(flags & CBK_FLAG_RERANK_KSPLIT) &&
-      (reinterpret_cast<uintptr_t>(d_store) & 0xf) == 0)
-    return rerank_mv_wide_dispatch(d_store, store_dtype, n_store_rows, dim, n_docs, pid_base, d_Q, d_q_lens, q_len, n_queries,
-                                   d_cand_pids, d_cand_rowptr, n_cand_total, d_out_scores, flags,
-                                   static_cast<cudaStream_t>(stream));   // multi-view 16 x 16 at 256 ... 768 columns: tcgen05 streaming kernel
   if (rerank_wide_stream_supports(dim, q_len, flags) && (reinterpret_cast<uintptr_t>(d_store) & 0xf) == 0)
     return rerank_wide_stream_dispatch(d_store, store_dtype, n_store_rows, dim, d_pfxsum, d_doclens, n_docs, pid_base, strides,
                                        n_strides, d_Q, d_q_lens, q_len, n_queries, d_cand_pids, d_cand_rowptr, n_cand_total,

@@ -16,7 +16,7 @@ from concurrent.futures import ThreadPoolExecutor
 
 HERE = os.path.dirname(os.path.abspath(__file__))
 ROOT = os.path.dirname(os.path.dirname(HERE))
-SOURCES = ["api.cu", "rerank.cu", "topk.cu", "gather.cu", "partition.cu", "exhaustive.cu", "rerank_generic.cu", "rerank_umma.cu", "rerank_wide.cu", "score_allpairs.cu", "rerank_mv_wide.cu", "rerank_wide_stream.cu"]
+SOURCES = ["api.cu", "rerank.cu", "topk.cu", "gather.cu", "partition.cu", "exhaustive.cu", "rerank_generic.cu", "rerank_umma.cu", "rerank_wide.cu", "score_allpairs.cu", "rerank_wide_stream.cu"]
 # self-test / issue-rate probes of the tcgen05 building blocks: a separate library (tests and benchmarks only), linked against
 # the product library for error reporting and launch accounting
 PROBE_SOURCES = ["umma_probe.cu"]

@@ -1,6 +1,8 @@
-// MaxSim rerank for wide embeddings (dim = 64·k, 256 … 1024; the author's index is 768 wide, reference
-// proj_conf/dense.yaml:8) on tcgen05 / TMEM / TMA — the general form of rerank_mv_wide.cu: documents of any length, queries of
-// up to 32 rows, zero-floor rule.  Same contract as cbk_maxsim_rerank (reference colbert_ranker.py:88-126, BaseModel.py:39-46).
+// MaxSim rerank for wide embeddings (dim = 64·k, 256 … 768; the author's index is 768 wide, reference
+// proj_conf/dense.yaml:8) on tcgen05 / TMEM / TMA: documents of any length — including the author's multi-view layout of
+// exactly 16 view embeddings per document and per query (dense.yaml:29-32, BaseModel.get_representation BaseModel.py:21-27),
+// for which CBK_FLAG_FIXED_DOCLEN skips the pfxsum / doclens lookups — queries of up to 32 rows, zero-floor rule.  Same
+// contract as cbk_maxsim_rerank (reference colbert_ranker.py:88-126, BaseModel.py:39-46).
 //
 // A row is up to 2 KB, the path is HBM-bound (≤ 32 FLOP/B).  The K-split mma.sync kernel (rerank_wide.cu) pays a block
 // barrier and an 8-way shared-memory reduction per 16-row tile (0.69 of the copy peak inside bench.py at 768); this kernel
@@ -95,6 +97,7 @@ struct CandWalker {
   const int64_t* pfxsum;
   const int32_t* doclens;
   int64_t n_docs, pid_base, c_hi;
+  int fixed_len;                    // > 0: every document has exactly this many rows (CBK_FLAG_FIXED_DOCLEN): no metadata is read
   int64_t c_fetch;                  // first candidate of the window AFTER the prefetched one
   int64_t win_c0;
   int win_n, pos;
@@ -112,14 +115,14 @@ struct CandWalker {
     if (lane < n) {
       const int64_t p = cand_pids[c0 + lane] - pid_base;
       if (p >= 0 && p < n_docs) {
-        row = static_cast<int>(pfxsum[p]);
-        len = doclens[p];
+        row = fixed_len > 0 ? static_cast<int>(p) * fixed_len : static_cast<int>(pfxsum[p]);
+        len = fixed_len > 0 ? fixed_len : doclens[p];
       }
     }
   }
   __device__ __forceinline__ void init(int lane, const int64_t* cp, const int64_t* rp, const int64_t* pf, const int32_t* dl,
-                                       int64_t nd, int64_t pb, int64_t n_queries, int64_t lo, int64_t hi) {
-    cand_pids = cp; rowptr = rp; pfxsum = pf; doclens = dl; n_docs = nd; pid_base = pb; c_hi = hi;
+                                       int64_t nd, int64_t pb, int fixed, int64_t n_queries, int64_t lo, int64_t hi) {
+    cand_pids = cp; rowptr = rp; pfxsum = pf; doclens = dl; n_docs = nd; pid_base = pb; c_hi = hi; fixed_len = fixed;
     int64_t a = 0, b = n_queries - 1;      // last query whose list starts at or before lo
     while (a < b) {
       const int64_t mid = (a + b + 1) >> 1;
@@ -199,7 +202,8 @@ __device__ __forceinline__ void ws_split<__nv_bfloat16>(float x, __nv_bfloat16& 
 template <typename T, bool kHasLo>
 __global__ void __launch_bounds__(kWsThreads, 1)
 maxsim_wide_stream_kernel(const __grid_constant__ WsMaps maps, const int64_t* __restrict__ pfxsum, const int32_t* __restrict__ doclens,
-                          int64_t n_docs, int64_t pid_base, int skip_foreign, WsStrides strides, const float* __restrict__ Q,
+                          int64_t n_docs, int64_t pid_base, int fixed_len, int skip_foreign, WsStrides strides,
+                          const float* __restrict__ Q,
                           const int32_t* __restrict__ q_lens, int q_len, int dim, int64_t n_queries,
                           const int64_t* __restrict__ cand_pids, const int64_t* __restrict__ rowptr, int64_t n_cand_bound,
                           int n_stages, uint32_t idesc, float* __restrict__ out, int probe_stream_only) {
@@ -268,7 +272,7 @@ maxsim_wide_stream_kernel(const __grid_constant__ WsMaps maps, const int64_t* __
     const int64_t per = (n_cand + gridDim.x - 1) / gridDim.x;
     const int64_t c_lo = min(n_cand, per * blockIdx.x), c_hi = min(n_cand, per * (blockIdx.x + 1));
     CandWalker wk;
-    wk.init(lane, cand_pids, rowptr, pfxsum, doclens, n_docs, pid_base, n_queries, c_lo, c_hi);
+    wk.init(lane, cand_pids, rowptr, pfxsum, doclens, n_docs, pid_base, fixed_len, n_queries, c_lo, c_hi);
     WsPiece pc;
     pc.row = 0; pc.v = 0; pc.flags = 0; pc.len = 0; pc.cand = 0;
     int64_t tile_q = -1;
@@ -569,19 +573,23 @@ int rerank_wide_stream_dispatch(const void* d_store, int store_dtype, int64_t n_
   // a candidate is at least one piece; ranges shorter than a few tiles are not worth a CTA
   const int grid = static_cast<int>(std::max<int64_t>(1, std::min<int64_t>(sm_count(), (n_cand_total + 31) / 32)));
   const int skip = (flags & CBK_FLAG_SKIP_FOREIGN_PIDS) ? 1 : 0;
+  // CBK_FLAG_FIXED_DOCLEN: the caller guarantees doclens[p] == strides[0] for every document (multi-view index)
+  const int fixed_len = ((flags & CBK_FLAG_FIXED_DOCLEN) && n_strides == 1 && strides[0] > 0) ? strides[0] : 0;
   static const int probe = std::getenv("CBK_WS_PROBE") != nullptr;          // profiling aid, never set in production
   if (q_len > 16) CBK_CUDA(cudaMemsetAsync(d_out_scores, 0, static_cast<size_t>(n_cand_total) * sizeof(float), stream));
   if (bf16) {
     CBK_CUDA(cudaFuncSetAttribute(maxsim_wide_stream_kernel<__nv_bfloat16, true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                   static_cast<int>(smem)));
     maxsim_wide_stream_kernel<__nv_bfloat16, true><<<grid, kWsThreads, smem, stream>>>(
-        maps, d_pfxsum, d_doclens, n_docs, pid_base, skip, ss, d_Q, d_q_lens, q_len, dim, n_queries, d_cand_pids, d_cand_rowptr,
+        maps, d_pfxsum, d_doclens, n_docs, pid_base, fixed_len, skip, ss, d_Q, d_q_lens, q_len, dim, n_queries, d_cand_pids,
+        d_cand_rowptr,
         n_cand_total, n_stages, idesc, d_out_scores, probe);
   } else {
     CBK_CUDA(cudaFuncSetAttribute(maxsim_wide_stream_kernel<__half, false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                   static_cast<int>(smem)));
     maxsim_wide_stream_kernel<__half, false><<<grid, kWsThreads, smem, stream>>>(
-        maps, d_pfxsum, d_doclens, n_docs, pid_base, skip, ss, d_Q, d_q_lens, q_len, dim, n_queries, d_cand_pids, d_cand_rowptr,
+        maps, d_pfxsum, d_doclens, n_docs, pid_base, fixed_len, skip, ss, d_Q, d_q_lens, q_len, dim, n_queries, d_cand_pids,
+        d_cand_rowptr,
         n_cand_total, n_stages, idesc, d_out_scores, probe);
   }
   CBK_CUDA(cudaGetLastError());

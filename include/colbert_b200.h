@@ -121,12 +121,12 @@ uint64_t cbk_launch_count(void);
  *                  CBK_FLAG_FIXED_DOCLEN (with n_strides == 1): the caller guarantees that every document has
  *                  exactly strides[0] rows — the layout of an enable_multiview index, where a document is its
  *                  d_view view embeddings (BaseModel.py:21-27).  Document p then starts at row (p - pid_base) *
- *                  strides[0]; d_pfxsum / d_doclens are not read (dim == 128 kernel; ignored by the others).
+ *                  strides[0]; d_pfxsum / d_doclens are not read (dim == 128 and dim 256 … 768 kernels; ignored by the others).
  *
  * Supported: 1 ≤ q_len ≤ CBK_MAX_QLEN, n_store_rows < 2^31; dim == 128 runs the TMA + tensor-core kernel the
- * benchmarks quote; a multiple of 64 from 256 to 1024 (the author's configuration: 768) a tcgen05 streaming kernel
- * (a specialised one for fixed 16-row documents — the author's multi-view index — and a general one; CBK_FLAG_RERANK_KSPLIT
- * selects the older K-split mma.sync kernel, which also serves dim 64 and 192); any other dim in [1, 1536] a generic
+ * benchmarks quote; a multiple of 64 from 256 to 768 (the author's configuration: 768) a tcgen05 streaming kernel
+ * (ragged documents, or — CBK_FLAG_FIXED_DOCLEN — the author's fixed-length multi-view index without metadata lookups;
+ * CBK_FLAG_RERANK_KSPLIT selects the older K-split mma.sync kernel, which also serves dim 64, 192 and 832 … 1024); any other dim in [1, 1536] a generic
  * CUDA-core kernel with the same results contract (fp32 arithmetic; CBK_FLAG_RERANK_GENERIC forces it).  pids are range-checked on
  * the device; an out-of-range pid yields NaN at its position.
  * ------------------------------------------------------------------------------------------------ */

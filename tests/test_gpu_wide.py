@@ -1,6 +1,7 @@
 """Tensor-core rerank kernels for wide embeddings (dim a multiple of 64 other than 128; the author's configuration uses
-768) against the oracle and against the generic CUDA-core kernel: the tcgen05 streaming kernel (dim 256 … 1024, the default
-there), the K-split mma.sync kernel (dim 64 and 192, or CBK_FLAG_RERANK_KSPLIT), the multi-view streaming kernel."""
+768) against the oracle and against the generic CUDA-core kernel: the tcgen05 streaming kernel (dim 256 … 768, the default
+there, ragged and fixed-length multi-view stores), the K-split mma.sync kernel (dim 64, 192, 832 … 1024, or
+CBK_FLAG_RERANK_KSPLIT)."""
 import numpy as np
 import pytest
 import torch
@@ -71,10 +72,10 @@ def test_wide_rerank_foreign_pids_and_rank_forward():
 @pytest.mark.parametrize("dim", [256, 512, 768, 1024])
 @pytest.mark.parametrize("dt", [torch.float16, torch.bfloat16], ids=["fp16", "bf16"])
 def test_multiview_16_rows_wide_streaming_kernel(dim, dt):
-    """the author's operating point (16 view embeddings per document and per query, un-projected width): the tcgen05
-    streaming kernel (csrc/rerank_mv_wide.cu, taken automatically for a fixed-length store of 16 rows, q_len <= 16) against
-    the oracle and against the K-split and generic kernels — ragged lists (tiles of fewer than 8 candidates, empty lists),
-    short queries, per-query q_lens, pids outside the store."""
+    """the author's operating point (16 view embeddings per document and per query, un-projected width): a fixed-length
+    store (CBK_FLAG_FIXED_DOCLEN: row = pid * 16, no metadata lookups) through the tcgen05 streaming kernel (dim <= 768; 1024:
+    the K-split kernel) against the oracle and the generic kernel — ragged lists, empty lists, short queries, per-query
+    q_lens, pids outside the store."""
     from colbert_b200 import _lib, synthetic
     from colbert_b200.ranking import ColbertRanker
     rng = np.random.default_rng(dim + 1)
@@ -101,7 +102,7 @@ def test_multiview_16_rows_wide_streaming_kernel(dim, dt):
         rel = np.abs(got - ref) / np.maximum(np.abs(ref), 1.0)
         assert rel.max() <= SCORE_RTOL, (dim, q_len, rel.max())
         # bf16 stores: the query enters as bf16 value + bf16 residual, so the only rounding left is the store's own
-        if dt == torch.bfloat16:
+        if dt == torch.bfloat16 and dim <= 768:
             assert rel.max() <= 5e-5, rel.max()
         ranker.kernel_flags = _lib.CBK_FLAG_RERANK_GENERIC
         gen = ranker.score_candidates(*args).cpu().numpy()
