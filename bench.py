@@ -61,6 +61,9 @@ def parse_args():
     ap.add_argument("--no-parity", action="store_true", help="skip the oracle parity gate")
     ap.add_argument("--e2e-exchange", default="p2p", choices=["allgather", "replicate", "p2p"],
                     help="N > 1: how RerankPipeline distributes the replicated inputs (see its docstring)")
+    ap.add_argument("--wire", default="compact", choices=["compact", "native"],
+                    help="what the serving entry is handed: compact = 16-bit queries / 32-bit pids (widened on the device), "
+                         "native = the kernel's own fp32 / int64 (twice the bytes, no widening kernels)")
     ap.add_argument("--chunks", type=int, default=0, help="N > 1: query chunks per sharded step (0 = the ranker's default)")
     ap.add_argument("--parity-queries", type=int, default=8, help="queries re-scored by the oracle (parity gate)")
     ap.add_argument("--exh-docs", type=int, default=1_100_000, help="documents per GPU in the exhaustive secondary "
@@ -682,9 +685,10 @@ def run_ours(args, rank, world, local_rank):
     # what the serving entry is handed: the encoder's 16-bit query embeddings and 32-bit pids when the kernel rounds the
     # query to fp16 anyway (bit-identical scores, tests/test_gpu_parity.py::test_rerank_pipeline_matches_direct_call),
     # else fp32 / int64
-    wire16 = bool(ranker.query_rounded_to_fp16)
+    compact = args.wire == "compact"
+    wire16 = compact and bool(ranker.query_rounded_to_fp16)
     Q_pin = (Q_host.to(torch.float16) if wire16 else Q_host).pin_memory()
-    cand_pin = (cand_host.to(torch.int32) if args.docs * world < 2 ** 31 else cand_host).pin_memory()
+    cand_pin = (cand_host.to(torch.int32) if compact and args.docs * world < 2 ** 31 else cand_host).pin_memory()
     Q_dev, cand_dev = Q_host.to(dev), cand_host.to(dev).reshape(-1).contiguous()
     n_cand_total = n_queries * args.cands
     rowptr = torch.arange(0, n_cand_total + 1, args.cands, dtype=torch.int64, device=dev)
