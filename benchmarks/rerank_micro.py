@@ -24,7 +24,7 @@ def main():
     ap.add_argument("--cands", type=int, default=1000)
     ap.add_argument("--iters", type=int, default=30)
     ap.add_argument("--dim", type=int, default=128, help="embedding width (768: the author's un-projected multi-view index)")
-    ap.add_argument("--ksplit", action="store_true", help="dim 256 … 1024: the K-split mma.sync kernel instead of the streaming one")
+    ap.add_argument("--ksplit", action="store_true", help="dim 192 … 1024: the K-split mma.sync kernel instead of the streaming one")
     ap.add_argument("--no-fixed", action="store_true", help="score through the looked-up path even on a fixed-doclen index")
     args = ap.parse_args()
     import torch

@@ -1,7 +1,7 @@
 #!/usr/bin/env python
 """Rerank throughput for embeddings wider than 128 (the author's configuration: dim = 768, reference proj_conf/dense.yaml:8),
-as achieved HBM GB/s: the default kernel for the width (dim 256 … 768: the tcgen05 streaming kernel, csrc/rerank_wide_stream.cu;
-other multiples of 64: the K-split mma.sync kernel, csrc/rerank_wide.cu), the K-split kernel forced (CBK_FLAG_RERANK_KSPLIT)
+as achieved HBM GB/s: the default kernel for the width (dim 192 … 1024: the tcgen05 streaming kernel, csrc/rerank_wide_stream.cu;
+dim 64: the K-split mma.sync kernel, csrc/rerank_wide.cu), the K-split kernel forced (CBK_FLAG_RERANK_KSPLIT)
 and the generic CUDA-core kernel.
 
     python benchmarks/wide_dim.py [--dims 768,1024,256] [--store-gb 10] [--queries 256] [--cands 1000]

@@ -1,4 +1,4 @@
-// MaxSim rerank for wide embeddings (dim = 64·k, 256 … 768; the author's index is 768 wide, reference
+// MaxSim rerank for wide embeddings (dim = 64·k, 192 … 1024; the author's index is 768 wide, reference
 // proj_conf/dense.yaml:8) on tcgen05 / TMEM / TMA: documents of any length — including the author's multi-view layout of
 // exactly 16 view embeddings per document and per query (dense.yaml:29-32, BaseModel.get_representation BaseModel.py:21-27),
 // for which CBK_FLAG_FIXED_DOCLEN skips the pfxsum / doclens lookups — queries of up to 32 rows, zero-floor rule.  Same
@@ -532,13 +532,13 @@ maxsim_wide_stream_kernel(const __grid_constant__ WsMaps maps, const int64_t* __
 
 }  // namespace
 
-// widths 256 … 768 in steps of 64 (the query region takes dim/64 × 8 KB of shared memory; beyond 768 too little is left for
-// the ring and the K-split kernel serves), queries of at most 32 rows
+// widths 192 … 1024 in steps of 64 (the query region takes dim/64 × 8 KB of shared memory and the ring what is left: 3 stages
+// of 32 KB at 768, 2 at 1024 — still ahead of the K-split kernel there, 0.83 vs 0.69 of the copy peak), queries of at most 32 rows
 bool rerank_wide_stream_supports(int dim, int q_len, int flags) {
   // (dim 128 stays with the per-warp mma.sync kernel of rerank.cu: measured there, this structure reaches 0.30 of the copy
   //  peak — 0.75 with the epilogue arithmetic switched off — against 0.97: at 256 B per row the per-piece work of the
   //  planner, the producers and the single epilogue warp pair outweighs the bytes)
-  return dim % 64 == 0 && dim >= 256 && dim <= 768 && q_len <= 32 &&
+  return dim % 64 == 0 && dim >= 192 && dim <= 1024 && q_len <= 32 &&
          !(flags & (CBK_FLAG_BF16_NATIVE_MMA | CBK_FLAG_RERANK_GENERIC | CBK_FLAG_RERANK_KSPLIT));
 }
 

@@ -46,7 +46,7 @@ extern "C" {
 #define CBK_FLAG_SKIP_FOREIGN_PIDS 2   /* sharded stores: a pid outside this shard scores -inf, not NaN */
 #define CBK_FLAG_RERANK_GENERIC 8       /* dim != 128: score with the CUDA-core kernel even where the tensor-core one applies */
 #define CBK_FLAG_FIXED_DOCLEN 16        /* every document has exactly strides[0] rows (multi-view index): offsets are pid * strides[0] */
-#define CBK_FLAG_RERANK_KSPLIT 32        /* dim = 256 … 1024: score with the K-split mma.sync kernel instead of the tcgen05 streaming one */
+#define CBK_FLAG_RERANK_KSPLIT 32        /* dim = 192 … 1024: score with the K-split mma.sync kernel instead of the tcgen05 streaming one */
 #define CBK_TOPK_NEG_INF_IS_PADDING 1  /* top-k: candidates scored -inf are dropped (sharded rerank) */
 
 typedef enum cbk_status {
@@ -121,12 +121,12 @@ uint64_t cbk_launch_count(void);
  *                  CBK_FLAG_FIXED_DOCLEN (with n_strides == 1): the caller guarantees that every document has
  *                  exactly strides[0] rows — the layout of an enable_multiview index, where a document is its
  *                  d_view view embeddings (BaseModel.py:21-27).  Document p then starts at row (p - pid_base) *
- *                  strides[0]; d_pfxsum / d_doclens are not read (dim == 128 and dim 256 … 768 kernels; ignored by the others).
+ *                  strides[0]; d_pfxsum / d_doclens are not read (dim == 128 and dim 192 … 1024 kernels; ignored by the others).
  *
  * Supported: 1 ≤ q_len ≤ CBK_MAX_QLEN, n_store_rows < 2^31; dim == 128 runs the TMA + tensor-core kernel the
- * benchmarks quote; a multiple of 64 from 256 to 768 (the author's configuration: 768) a tcgen05 streaming kernel
+ * benchmarks quote; a multiple of 64 from 192 to 1024 (the author's configuration: 768) a tcgen05 streaming kernel
  * (ragged documents, or — CBK_FLAG_FIXED_DOCLEN — the author's fixed-length multi-view index without metadata lookups;
- * CBK_FLAG_RERANK_KSPLIT selects the older K-split mma.sync kernel, which also serves dim 64, 192 and 832 … 1024); any other dim in [1, 1536] a generic
+ * CBK_FLAG_RERANK_KSPLIT selects the older K-split mma.sync kernel, which also serves dim 64); any other dim in [1, 1536] a generic
  * CUDA-core kernel with the same results contract (fp32 arithmetic; CBK_FLAG_RERANK_GENERIC forces it).  pids are range-checked on
  * the device; an out-of-range pid yields NaN at its position.
  * ------------------------------------------------------------------------------------------------ */
