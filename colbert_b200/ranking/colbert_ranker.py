@@ -295,6 +295,14 @@ class ColbertRanker:
             Qp = kernels.mask_cast_rows(Q.reshape(-1, self.dim), None, torch.float16).reshape(Q.size(0), Q.size(1), self.dim)
             Dp = self.tensor[: n_docs * d].view(n_docs, d, self.dim)
             return kernels.score_allpairs_fwd(Qp, Dp, want_argmax=False)[0]
+        if self.dim != 128:
+            # Any other store the query-batched kernels do not take (ragged documents at a wide width, bf16 multi-view
+            # stores): every document becomes a candidate of every query and the rerank kernel of that width scores them —
+            # the store is read once per query instead of once per batch, which is the HBM-bound optimum for a single query.
+            B, n_docs = Q.size(0), int(self.doclens.numel())
+            cand = (torch.arange(n_docs, dtype=torch.int64, device=self.device) + self.pid_base).repeat(B)
+            rowptr = torch.arange(0, (B + 1) * n_docs, n_docs, dtype=torch.int64, device=self.device)
+            return self.score_candidates(Q, cand, rowptr).view(B, n_docs)
         if getattr(self, "_doc_end_bits", None) is None:
             nonempty = self.doclens > 0
             if bool(nonempty.all()):

@@ -183,3 +183,24 @@ def test_exhaustive_on_a_wide_multiview_store(dim, d_view, q_view):
         assert (np.abs(dense[b] - ref) / np.maximum(np.abs(ref), 1.0)).max() <= SCORE_RTOL
         rp, rs = O.topk_desc(ref, pids_all, k)
         check_topk(p[b].cpu().numpy(), s[b].cpu().numpy(), rp, rs, SCORE_RTOL, *O.topk_desc(ref, pids_all, None))
+
+
+@pytest.mark.parametrize("dt", [torch.float16, torch.bfloat16], ids=["fp16", "bf16"])
+def test_exhaustive_on_a_wide_ragged_store(dt):
+    """ragged documents at dim 768 (and bf16 stores): score_all falls back to the rerank kernel of that width with every
+    document as a candidate of every query"""
+    from colbert_b200 import synthetic
+    from colbert_b200.ranking import ColbertRanker
+    dim, n_docs, nq, k = 768, 1500, 3, 40
+    doclens = np.random.default_rng(2200).integers(1, 150, size=n_docs).astype(np.int64)
+    index = synthetic.make_index(2201, n_docs, dim=dim, doclens=doclens)
+    emb = torch.from_numpy(index.emb).to(dt)
+    ranker = ColbertRanker.from_tensors(emb, index.doclens.tolist(), device=DEV, store_dtype=dt)
+    Q = synthetic.make_queries(2202, nq, 32, dim)
+    store, pf = O.pad_store(emb.float().numpy()), O.doclens_pfxsum(index.doclens)
+    pids_all = np.arange(n_docs, dtype=np.int64)
+    p, s = ranker.rank_exhaustive(torch.from_numpy(Q), k=k)
+    for b in range(nq):
+        ref = O.maxsim_exact(store, index.doclens, pf, ranker.strides, Q[b], pids_all)
+        rp, rs = O.topk_desc(ref, pids_all, k)
+        check_topk(p[b].cpu().numpy(), s[b].cpu().numpy(), rp, rs, SCORE_RTOL, *O.topk_desc(ref, pids_all, None))
