@@ -64,3 +64,38 @@ def test_empty_documents_score_zero_in_both_formulations():
     assert np.all(exact[index.doclens == 0] == 0.0)
     _, _, ref = O.rank_forward(store, index.doclens, pf, strides, Q.T[None], pids, depth=None, return_all_scores=True)
     np.testing.assert_allclose(exact, ref, rtol=1e-5, atol=1e-5)
+
+
+def test_score_allpairs_grad_is_the_derivative_of_score_allpairs():
+    """central differences of the oracle's forward against the oracle's backward (away from arg-max ties the score is
+    piecewise linear in Q and D, so the difference quotient is exact up to rounding); linear in the upstream gradient W"""
+    import numpy as np
+    from oracle import maxsim_oracle as O
+    rng = np.random.default_rng(5)
+    nq, m, nd, n, h = 2, 3, 3, 4, 5
+    Q = rng.standard_normal((nq, m, h))
+    D = rng.standard_normal((nd, n, h))
+    qm = np.array([[1, 1, 0], [1, 1, 1]])
+    dm = np.array([[1, 1, 1, 0], [1, 0, 0, 0], [1, 1, 1, 1]])
+    W = rng.standard_normal((nq, nd)).astype(np.float32)
+    _, dQ, dD, _ = O.score_allpairs_grad(Q, D, qm, dm, W)
+
+    def loss(Qx, Dx):
+        Qm, Dm = Qx * qm[..., None], Dx * dm[..., None]
+        sim = np.einsum("qmh,dnh->qdmn", Qm, Dm)
+        return float((sim.max(-1).sum(-1) * W).sum())
+
+    eps = 1e-6
+    for idx in [(0, 0, 1), (1, 2, 4), (0, 2, 0)]:
+        Qp, Qn = Q.copy(), Q.copy()
+        Qp[idx] += eps
+        Qn[idx] -= eps
+        assert abs((loss(Qp, D) - loss(Qn, D)) / (2 * eps) - dQ[idx]) < 1e-4
+    for idx in [(0, 0, 0), (1, 0, 3), (2, 3, 2), (0, 3, 1)]:
+        Dp, Dn = D.copy(), D.copy()
+        Dp[idx] += eps
+        Dn[idx] -= eps
+        assert abs((loss(Q, Dp) - loss(Q, Dn)) / (2 * eps) - dD[idx]) < 1e-4
+    _, dQ2, dD2, _ = O.score_allpairs_grad(Q, D, qm, dm, 2 * W)
+    np.testing.assert_allclose(dQ2, 2 * dQ, rtol=1e-6, atol=1e-7)
+    np.testing.assert_allclose(dD2, 2 * dD, rtol=1e-6, atol=1e-7)
